@@ -1,0 +1,243 @@
+/*
+ * fss.h -- C ABI of the B200-native falling-sand core.
+ *
+ * The reference (PieKing1215/FallingSandSurvival) has no plugin / FFI layer: `World` is a
+ * C++ class with public raw arrays (FallingSandSurvival/world.hpp:98-146) and the two hot
+ * functions `World::tick()` (world.cpp:1091-2041) and `World::tickTemperature()`
+ * (world.cpp:2043-2143).  This header is the boundary a maintainer binds instead of the
+ * bodies of those two functions: the grid lives on the GPU, the host keeps its
+ * `MaterialInstance tiles[]` mirror and syncs rectangles through fss_upload_rect /
+ * fss_download_rect.  INTEGRATION.md shows the reference-side shim.
+ *
+ * Conventions: every function returns 0 on success or a negative FSS_ERR_* code;
+ * fss_last_error() returns a human-readable description of the last failure on the calling
+ * thread.  No C++ types, exceptions or torch types cross this boundary.  A world is
+ * externally synchronised (one caller thread at a time, like the reference's main-thread
+ * `Game::tick`, Game.cpp:2428-2430, :2759-2761) and internally asynchronous on one CUDA
+ * stream; fss_download_* / fss_sync are the synchronisation points.
+ */
+#ifndef FSS_H
+#define FSS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSS_ABI_VERSION 1
+
+/* error codes */
+#define FSS_OK 0
+#define FSS_ERR_INVALID (-1)   /* bad argument */
+#define FSS_ERR_ALIGN (-2)     /* tick zone / strip not aligned to the micro-chunk grid */
+#define FSS_ERR_CUDA (-3)      /* CUDA runtime failure, see fss_last_error() */
+#define FSS_ERR_NO_DEVICE (-4) /* no usable sm_100 device: there is NO CPU fallback */
+#define FSS_ERR_STATE (-5)     /* call out of order (e.g. tick before materials) */
+#define FSS_ERR_RANGE (-6)     /* rectangle outside this world's storage */
+#define FSS_ERR_COMM (-7)      /* NCCL failure */
+
+/* micro-chunk geometry of the checkerboard schedule (the reference's CHUNK_W/CHUNK_H,
+ * Chunk.hpp:18-19, shrunk; see DESIGN.md "schedule") */
+#define FSS_CHUNK_W 4
+#define FSS_CHUNK_H 16
+#define FSS_ZONE_ALIGN_X 8  /* = 2*CHUNK_W: tick zone x, w are multiples of this */
+#define FSS_ZONE_ALIGN_Y 32 /* = 2*CHUNK_H: tick zone h and strip heights are multiples */
+#define FSS_ZONE_MARGIN 16  /* tick zone must stay this far from every world edge */
+
+/* PhysicsType.hpp:6-12 */
+enum {
+    FSS_PHYS_AIR = 0,
+    FSS_PHYS_SOLID = 1,
+    FSS_PHYS_SAND = 2,
+    FSS_PHYS_SOUP = 3,
+    FSS_PHYS_GAS = 4,
+    FSS_PHYS_PASSABLE = 5, /* == OBJECT */
+};
+
+/* Material.hpp:18-19 */
+#define FSS_REACT_TEMPERATURE_BELOW 4
+#define FSS_REACT_TEMPERATURE_ABOVE 5
+
+#define FSS_MAX_MATERIALS 256
+#define FSS_MAX_REACTIONS 2
+#define FSS_MAX_TEXTURES 32
+
+/* fss_material.flags */
+#define FSS_MAT_IS_FIRE 1u  /* `mat->id == Materials::FIRE.id`  (world.cpp:1171) */
+#define FSS_MAT_IS_STEAM 2u /* `mat->id == Materials::STEAM.id` (world.cpp:1965) */
+
+/* fss_material.create_kind: how Tiles::create(mat, x, y) (Tiles.cpp:190-268) colours a new cell */
+#define FSS_CREATE_FLAT 0    /* color = create_base                                   */
+#define FSS_CREATE_RAND 1    /* color = create_base + ((rand() % mod) << shift)        */
+#define FSS_CREATE_TEXTURE 2 /* color = texture[create_texture] at (x mod w, y mod h)   */
+
+/* One cell in the host exchange format (row-major arrays of these).
+ * Mirrors MaterialInstance (MaterialInstance.hpp:12-29) minus `id`, the host-only unique
+ * counter (MaterialInstance.cpp:7), with `Material* mat` replaced by its id. */
+typedef struct fss_cell {
+    uint16_t material;       /* Material::id */
+    uint8_t moved;           /* MaterialInstance::moved (sand: friction released; liquid: settled) */
+    uint8_t settle_count;    /* MaterialInstance::settleCount */
+    uint32_t color;          /* MaterialInstance::color */
+    int32_t temperature;     /* MaterialInstance::temperature */
+    float fluid_amount;      /* MaterialInstance::fluidAmount (constructor default 2.0f) */
+    float fluid_amount_diff; /* MaterialInstance::fluidAmountDiff */
+} fss_cell;
+
+typedef struct fss_reaction {
+    int32_t type;  /* FSS_REACT_TEMPERATURE_BELOW / _ABOVE (MaterialInteraction::type) */
+    int32_t data1; /* temperature threshold */
+    int32_t data2; /* target material id */
+} fss_reaction;
+
+/* One row of Materials::MATERIALS (Material.hpp:29-59, Materials.cpp:4-199) plus the
+ * colour recipe of the matching Tiles::create* factory. */
+typedef struct fss_material {
+    int32_t physics_type;
+    int32_t iterations;
+    int32_t slipperyness;
+    float density;
+    uint32_t add_temp; /* Uint32 in the reference (Material.hpp:40) */
+    float conduction_self;
+    float conduction_other;
+    uint32_t color; /* Material::color */
+    uint32_t flags; /* FSS_MAT_IS_* */
+    int32_t n_reactions; /* evaluated only if `react` (we store 0 when react is false) */
+    fss_reaction reactions[FSS_MAX_REACTIONS];
+    int32_t create_kind;
+    uint32_t create_base;
+    uint32_t create_rand_mod;
+    uint32_t create_rand_shift;
+    uint32_t create_rand_site; /* RNG site of the colour draw (FSS_SITE_TILES + Tiles.cpp line) */
+    int32_t create_texture;    /* index given to fss_set_texture */
+    int32_t create_temperature; /* Tiles::createWater -1023, createLava 1024, else 0 */
+} fss_material;
+
+/* fss_config.flags */
+#define FSS_PARTICLES_EMIT 1u /* reference behaviour: free-falling sand/liquid and fire sparks leave the
+                                 grid as Particle spawn records (world.cpp:1180, :1288-1294, :1352-1374).
+                                 Without it those three sites are disabled and cells keep falling in-grid. */
+
+typedef struct fss_config {
+    uint32_t struct_size; /* sizeof(fss_config), for ABI evolution */
+    uint32_t width;       /* world width in cells (reference: uint16_t, world.hpp:106) */
+    uint32_t height;      /* GLOBAL world height */
+    uint32_t seed;        /* RNG seed, see fss_rng.h */
+    int32_t device;       /* CUDA device ordinal */
+    uint32_t flags;
+    uint32_t particle_capacity; /* max spawn records kept per drain interval (0 = default 1<<20) */
+    /* row-strip sharding (one world object per GPU).  strip_rows == 0 means the whole world. */
+    uint32_t strip_y0;   /* first owned global row, multiple of FSS_ZONE_ALIGN_Y from the zone origin */
+    uint32_t strip_rows; /* owned rows */
+    /* steam condensation product (world.cpp:1967 Tiles::createWater()) */
+    int32_t condense_material; /* material id created when blocked steam condenses; -1 disables */
+} fss_config;
+
+/* particle spawn record: the host builds its Particle objects from these with the reference's
+ * velocity formulas (world.cpp:1180, :1291, :1366) and fss_rand(cellkey, site, k). */
+typedef struct fss_particle_spawn {
+    uint32_t x, y;     /* cell that spawned it (the reference spawns at y-1 / y+1, site tells which) */
+    uint32_t site;     /* 1180 fire spark, 1291 falling sand, 1366 falling liquid */
+    uint32_t cell_key; /* fss_rng_cell_key of the visit, for the velocity draws */
+    uint32_t tick_iter; /* tickCt * 8 + iter */
+    fss_cell cell;     /* the cell that left the grid (fire sparks: the fire cell itself) */
+} fss_particle_spawn;
+
+typedef struct fss_world fss_world;
+
+/* ---- lifecycle -------------------------------------------------------------------------------
+ * replaces the array part of World::init / ~World (world.cpp:86-88, :145-184, :3617-3711) */
+int fss_create(const fss_config* cfg, fss_world** out);
+int fss_destroy(fss_world* w);
+const char* fss_last_error(void);
+int fss_abi_version(void);
+
+/* run all work of this world on an existing CUDA stream (a cudaStream_t passed as void*);
+ * NULL restores the world's own stream.  Lets a host time the path with its own events. */
+int fss_set_stream(fss_world* w, void* cuda_stream);
+
+/* ---- material table: call after Materials::init() (Game.cpp:521) and whenever it changes ---- */
+int fss_set_materials(fss_world* w, const fss_material* table, int n);
+int fss_set_texture(fss_world* w, int texture_index, const uint32_t* argb, int tex_w, int tex_h);
+
+/* ---- World::tickZone (world.hpp:132, set by Game.cpp:2216) ---------------------------------- */
+int fss_set_tick_zone(fss_world* w, int x, int y, int width, int height);
+
+/* ---- host mirror <-> device, rectangles in GLOBAL cell coordinates ---------------------------
+ * `pitch_cells` = cells per row of the host array.  Replaces the direct `tiles[]` indexing of
+ * Game.cpp (brush :1147, rigid-body stamping :2355-2372, chunk merge world.cpp:2530-2543, ...). */
+int fss_upload_rect(fss_world* w, int x, int y, int width, int height, const fss_cell* host, size_t pitch_cells);
+int fss_download_rect(fss_world* w, int x, int y, int width, int height, fss_cell* host, size_t pitch_cells);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+/* one World::tick(): 6 iter x 4 tk checkerboard sub-steps x 3 scans (world.cpp:1108-2011);
+ * `tick_ct` is World::tickCt (world.cpp:2017), the RNG key.  Asynchronous.  For a strip-sharded
+ * world with a communicator attached this also performs the per-sub-step halo exchange. */
+int fss_tick(fss_world* w, uint32_t tick_ct);
+/* one sub-step (iter, tk) of the above without halo exchange */
+int fss_substep(fss_world* w, uint32_t tick_ct, int iter, int tk);
+/* one World::tickTemperature() (world.cpp:2043-2143).  Asynchronous. */
+int fss_tick_temperature(fss_world* w);
+
+/* ---- side outputs ---------------------------------------------------------------------------- */
+/* spawn records since the last drain, sorted by (tick_iter, y, x, site); *n_total = records produced
+ * (may exceed cap / capacity: then the surplus was dropped and the call returns FSS_ERR_RANGE). */
+int fss_drain_particles(fss_world* w, fss_particle_spawn* out, size_t cap, size_t* n_out, size_t* n_total);
+/* per-material cell counts over the owned rows (movingTiles replacement, Game.cpp:2579-2589) */
+int fss_histogram(fss_world* w, uint64_t* counts, int n_materials);
+/* order-independent digest (sum of fss_cell_digest over owned rows); k-GPU digests add up */
+int fss_hash(fss_world* w, uint64_t* digest);
+/* sum over owned rows of fluid_amount + fluid_amount_diff of SOUP cells, per material (double) */
+int fss_fluid_totals(fss_world* w, double* totals, int n_materials);
+int fss_sync(fss_world* w);
+
+/* ---- synthetic worlds for benchmarks ----------------------------------
+ * Fills every cell of this world's storage: cells within `border` of a world edge become
+ * material `border_material`; every other cell draws r = fss_fmix32(seed ^ fss_rng_cell_key(..)) % 100
+ * and takes the first entry i with r < cumulative_percent[i]; remaining cells are material 0.
+ * Cells are initialised like Tiles::create(mat,x,y) with the table's create_* recipe. */
+typedef struct fss_fill_spec {
+    uint32_t seed;
+    uint32_t border;
+    int32_t border_material;
+    int32_t n_entries;
+    int32_t material[16];
+    int32_t cumulative_percent[16];
+    /* optional: rows >= solid_from_row are all `solid_material` (config 5, mostly settled) */
+    uint32_t solid_from_row; /* 0 = off */
+    int32_t solid_material;
+    /* optional: entries apply only inside boxes; outside, sparse_material with probability
+     * sparse_per_mille/1000 (config 5).  n_boxes == 0 = entries apply everywhere. */
+    int32_t n_boxes;
+    uint32_t box_size;
+    int32_t sparse_material;
+    uint32_t sparse_per_mille;
+} fss_fill_spec;
+int fss_fill_synthetic(fss_world* w, const fss_fill_spec* spec);
+
+/* ---- row-strip sharding over NCCL (one process per GPU) --------------------------------------
+ * rank r owns strip r; neighbours are r-1 (above, smaller y) and r+1 (below).  The unique id is
+ * 128 bytes produced on rank 0 and distributed by the host (torch.distributed, MPI, a file...). */
+int fss_comm_unique_id(void* id128);
+int fss_comm_attach(fss_world* w, const void* id128, int rank, int n_ranks);
+/* explicit halo exchange after sub-step tk (what fss_tick does internally), and for temperature */
+int fss_exchange_halo(fss_world* w, int tk);
+int fss_exchange_halo_temperature(fss_world* w);
+
+/* ---- introspection used by benchmarks -------------------------------------------------------- */
+typedef struct fss_stats {
+    uint64_t kernel_launches;   /* kernels of this library launched since creation */
+    uint64_t substeps;          /* movement sub-steps executed */
+    uint64_t storage_bytes;     /* device bytes held by the planes */
+    uint32_t storage_pitch;     /* cells per stored row */
+    uint32_t storage_rows;
+    uint32_t storage_y0;        /* global row of the first stored row */
+} fss_stats;
+int fss_get_stats(fss_world* w, fss_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSS_H */
