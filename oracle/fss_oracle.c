@@ -1,0 +1,720 @@
+/*
+ * fss_oracle.c -- plain-C restatement of the reference's per-tick cellular automaton.
+ *
+ * TEST INFRASTRUCTURE ONLY (see fss_oracle.h).  Straight-line, array-of-structs, one cell at a
+ * time, in the reference's scan order; no attempt at speed beyond an OpenMP loop over the
+ * micro-chunks of one phase (which the schedule makes independent).
+ *
+ * Every function cites the reference lines it follows; F/ = /root/reference/FallingSandSurvival/.
+ * Schedule = F/world.cpp:1108-1141 with CHUNK_W x CHUNK_H = FSS_CHUNK_W x FSS_CHUNK_H (4 x 16)
+ * and rand() replaced by fss_rand() (include/fss_rng.h), exactly what oracle/_ref compiles.
+ */
+#include "fss_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/fss_rng.h"
+
+#define CW FSS_CHUNK_W
+#define CH FSS_CHUNK_H
+
+/* F/world.hpp:76-87 */
+#define FLUID_MaxValue 0.5f
+#define FLUID_MinValue 0.0005f
+#define FLUID_MaxCompression 0.1f
+#define FLUID_MinFlow 0.05f
+#define FLUID_MaxFlow 8.0f
+#define FLUID_FlowSpeed 1.0f
+
+typedef struct {
+    uint32_t* px;
+    int w, h;
+} texture_t;
+
+struct fsso_world {
+    int width, height;
+    int zx, zy, zw, zh;
+    uint32_t seed;
+    uint32_t flags;
+    int condense_material;
+    fss_cell* cells;
+    int32_t* new_temps;
+    fss_material mat[FSS_MAX_MATERIALS];
+    int max_stability[FSS_MAX_MATERIALS];
+    int n_mat;
+    int fire_id;
+    texture_t tex[FSS_MAX_TEXTURES];
+    fss_particle_spawn* parts;
+    size_t n_parts, cap_parts;
+};
+
+/* per-visit RNG state: one key per cell visit, one counter per site (fss_rng.h) */
+typedef struct {
+    uint32_t cellkey;
+    int n;
+    uint32_t site[8];
+    uint32_t count[8];
+} rng_t;
+
+static uint32_t rnd(rng_t* r, uint32_t site) {
+    uint32_t k = 0;
+    int i;
+    for(i = 0; i < r->n; i++) {
+        if(r->site[i] == site) {
+            k = ++r->count[i];
+            break;
+        }
+    }
+    if(i == r->n && r->n < 8) {
+        r->site[r->n] = site;
+        r->count[r->n] = 0;
+        r->n++;
+    }
+    return fss_rand(r->cellkey, site, k);
+}
+
+/* one micro-chunk's view of the sub-step */
+typedef struct {
+    fsso_world* w;
+    int cx, cy;
+    uint32_t tick_ct;
+    int iter;
+    uint32_t tkey;
+    uint8_t vis[CH][CW]; /* tickVisited restricted to the chunk: flags set outside are never read
+                            (the other buffer is cleared before reuse, F/world.cpp:1125-1131, :1998) */
+} chunk_t;
+
+static inline fss_cell* at(fsso_world* w, int x, int y) { return &w->cells[(size_t)y * w->width + x]; }
+static inline int phys(fsso_world* w, const fss_cell* c) { return w->mat[c->material].physics_type; }
+/* World::getTile, F/world.cpp:1053-1056: out of bounds reads Tiles::TEST_SOLID */
+static inline int phys_get(fsso_world* w, int x, int y) {
+    if(x < 0 || x >= w->width || y < 0 || y >= w->height) return FSS_PHYS_SOLID;
+    return phys(w, at(w, x, y));
+}
+static inline void mark(chunk_t* c, int x, int y) {
+    int dx = x - c->cx, dy = y - c->cy;
+    if(dx >= 0 && dx < CW && dy >= 0 && dy < CH) c->vis[dy][dx] = 1;
+}
+
+/* Tiles::NOTHING, F/Tiles.cpp:7; fluidAmount keeps the constructor default 2.0f (F/MaterialInstance.hpp:21) */
+static fss_cell nothing(void) {
+    fss_cell c;
+    memset(&c, 0, sizeof c);
+    c.fluid_amount = 2.0f;
+    return c;
+}
+
+/* Tiles::create(mat, x, y), F/Tiles.cpp:190-268, from the table's recipe */
+static fss_cell create_cell(fsso_world* w, int m, int x, int y, rng_t* r) {
+    const fss_material* d = &w->mat[m];
+    fss_cell c = nothing();
+    c.material = (uint16_t)m;
+    c.temperature = d->create_temperature;
+    if(d->create_kind == FSS_CREATE_RAND) {
+        c.color = d->create_base + ((rnd(r, d->create_rand_site) % d->create_rand_mod) << d->create_rand_shift);
+    } else if(d->create_kind == FSS_CREATE_TEXTURE && d->create_texture >= 0 && w->tex[d->create_texture].px) {
+        texture_t* t = &w->tex[d->create_texture];
+        c.color = t->px[(y % t->h) * t->w + (x % t->w)];
+    } else {
+        c.color = d->create_base;
+    }
+    return c;
+}
+
+/* `MaterialInstance(tile.mat, tile.color, tile.temperature)` + fluidAmount = 0  (F/world.cpp:1399-1400 etc.) */
+static fss_cell liquid_seed(const fss_cell* tile) {
+    fss_cell c = nothing();
+    c.material = tile->material;
+    c.color = tile->color;
+    c.temperature = tile->temperature;
+    c.fluid_amount = 0.0f;
+    return c;
+}
+
+static void emit(chunk_t* c, int x, int y, uint32_t site, uint32_t cellkey, const fss_cell* cell) {
+    fsso_world* w = c->w;
+    if(!(w->flags & FSS_PARTICLES_EMIT)) return;
+#pragma omp critical(fsso_parts)
+    {
+        if(w->n_parts == w->cap_parts) {
+            w->cap_parts = w->cap_parts ? w->cap_parts * 2 : 1024;
+            w->parts = (fss_particle_spawn*)realloc(w->parts, w->cap_parts * sizeof(fss_particle_spawn));
+        }
+        fss_particle_spawn* p = &w->parts[w->n_parts++];
+        p->x = (uint32_t)x;
+        p->y = (uint32_t)y;
+        p->site = site;
+        p->cell_key = cellkey;
+        p->tick_iter = c->tick_ct * 8u + (uint32_t)c->iter;
+        p->cell = *cell;
+    }
+}
+
+/* F/world.cpp:1075-1088 */
+static float vertical_flow(float remaining, float dest) {
+    float sum = remaining + dest;
+    float value;
+    if(sum <= FLUID_MaxValue) {
+        value = FLUID_MaxValue;
+    } else if(sum < 2 * FLUID_MaxValue + FLUID_MaxCompression) {
+        value = (FLUID_MaxValue * FLUID_MaxValue + sum * FLUID_MaxCompression) / (FLUID_MaxValue + FLUID_MaxCompression);
+    } else {
+        value = (sum + FLUID_MaxCompression) / 2.0f;
+    }
+    return value;
+}
+
+/* the clamp every flow goes through: `flow = std::max(flow, 0.0f); if(flow > std::min(MaxFlow, lim)) flow = ...` */
+static float clamp_flow(float flow, float lim) {
+    float cap;
+    if(flow < 0.0f) flow = 0.0f;
+    cap = lim < FLUID_MaxFlow ? lim : FLUID_MaxFlow;
+    if(flow > cap) flow = cap;
+    return flow;
+}
+
+static int can_move_into(fsso_world* w, const fss_cell* dst, const fss_cell* self) {
+    int t = phys(w, dst);
+    return t == FSS_PHYS_AIR || (t != FSS_PHYS_SOLID && w->mat[dst->material].density < w->mat[self->material].density);
+}
+
+/* ---- scan 1, F/world.cpp:1154-1665 ----------------------------------------------------------- */
+static void scan1_cell(chunk_t* c, int x, int y) {
+    fsso_world* w = c->w;
+    int particles = (w->flags & FSS_PARTICLES_EMIT) != 0;
+    fss_cell* self = at(w, x, y);
+    fss_cell tile;
+    int type, dx = x - c->cx, dy = y - c->cy;
+    rng_t r;
+
+    if(c->vis[dy][dx]) return;                              /* :1161 */
+    if(c->iter >= w->mat[self->material].iterations) {      /* :1163-1166 */
+        c->vis[dy][dx] = 1;
+        return;
+    }
+    tile = *self;                                           /* :1167 */
+    type = phys(w, &tile);
+    r.cellkey = fss_rng_cell_key(c->tkey, (uint32_t)x, (uint32_t)y);
+    r.n = 0;
+
+    if(w->mat[tile.material].flags & FSS_MAT_IS_FIRE) {     /* :1171-1216 */
+        if(rnd(&r, 1172) % 10 == 0) {                       /* recolours the local copy only */
+            tile.color = (((255u << 8) + 100 + rnd(&r, 1174) % 50) << 8) + 50;
+        }
+        if(rnd(&r, 1179) % 10 == 0) emit(c, x, y, 1180, r.cellkey, &tile); /* spark, no grid effect */
+        if(rnd(&r, 1191) % 150 == 0) {
+            *self = nothing();
+            c->vis[dy][dx] = 1;
+        } else {
+            int found = 0, xx, yy;
+            for(xx = -2; xx <= 2; xx++) {
+                for(yy = -2; yy <= 2; yy++) {
+                    fss_cell* n = at(w, x + xx, y + yy);
+                    if(phys(w, n) == FSS_PHYS_SOLID) {
+                        found = 1;
+                        if(rnd(&r, 1202) % 500 == 0) {
+                            *n = create_cell(w, w->fire_id, x + xx, y + yy, &r); /* Tiles::createFire() */
+                            mark(c, x + xx, y + yy);
+                        }
+                    }
+                }
+            }
+            if(!found && rnd(&r, 1210) % 120 == 0) {
+                *self = nothing();
+                c->vis[dy][dx] = 1;
+            }
+        }
+    }
+
+    if(type == FSS_PHYS_SAND) {                             /* :1218-1337 */
+        fss_cell below = *at(w, x, y + 1);
+        fss_cell bl, br;
+        const fss_material* m = &w->mat[tile.material];
+        int can_b, can_l, can_r, i;
+        /* :1223-1249 interactions: `interact` is false for every material (F/Materials.cpp:128,:144) */
+        if(m->n_reactions > 0) {                            /* :1251-1274 */
+            int react = 0;
+            for(i = 0; i < m->n_reactions; i++) {
+                const fss_reaction* in = &m->reactions[i];
+                if((in->type == FSS_REACT_TEMPERATURE_BELOW && tile.temperature < in->data1) ||
+                   (in->type == FSS_REACT_TEMPERATURE_ABOVE && tile.temperature > in->data1)) {
+                    *self = create_cell(w, in->data2, x, y, &r);
+                    self->temperature = tile.temperature;
+                    c->vis[dy][dx] = 1;
+                    react = 1;
+                }
+            }
+            if(react) return;
+        }
+        can_b = can_move_into(w, &below, &tile);            /* :1276 */
+        if(!can_b) return;
+        bl = *at(w, x - 1, y + 1);
+        br = *at(w, x + 1, y + 1);
+        can_l = can_move_into(w, &bl, &tile);
+        can_r = can_move_into(w, &br, &tile);
+        if(!((can_l || can_r) && rnd(&r, 1287) % 20 == 0)) { /* :1287 */
+            if(particles && phys(w, &below) == FSS_PHYS_AIR && phys_get(w, x, y + 2) == FSS_PHYS_AIR &&
+               phys_get(w, x, y + 3) == FSS_PHYS_AIR && phys_get(w, x, y + 4) == FSS_PHYS_AIR) {
+                *self = below;                              /* :1289 setTile(x, y, belowTile) */
+                emit(c, x, y, 1291, r.cellkey, &tile);
+            } else {
+                *self = below;                              /* :1296 */
+                if(rnd(&r, 1300) % 2 == 0) tile.moved = 1;
+                *at(w, x, y + 1) = tile;                    /* :1306 */
+                mark(c, x, y + 1);
+            }
+            if(rnd(&r, 1313) % 2 == 0) {                    /* :1313-1335 transmit movement */
+                if(x > 0 && phys(w, at(w, x - 1, y + 1)) == FSS_PHYS_SAND) {
+                    if(rnd(&r, 1316) % 2 == 0) at(w, x - 1, y + 1)->moved = 1;
+                }
+                if(x < w->width - 1 && phys(w, at(w, x + 1, y + 1)) == FSS_PHYS_SAND) {
+                    if(rnd(&r, 1327) % 2 == 0) at(w, x + 1, y + 1)->moved = 1;
+                }
+            }
+        }
+    } else if(type == FSS_PHYS_SOUP) {                      /* :1338-1537 */
+        float start, remaining, flow, dst;
+        fss_cell bottom, left, right, top;
+        int air_below, can_left, can_right;
+        if(tile.fluid_amount == 0.0f) return;               /* :1344 */
+        if(tile.fluid_amount < FLUID_MinValue) {            /* :1346-1350 */
+            tile.fluid_amount = 0.0f;
+            *self = tile;
+            return;
+        }
+        if(particles && (double)tile.fluid_amount > 0.005 && phys_get(w, x, y + 1) == FSS_PHYS_AIR &&
+           phys_get(w, x, y + 2) == FSS_PHYS_AIR && phys_get(w, x, y + 3) == FSS_PHYS_AIR &&
+           phys_get(w, x, y + 4) == FSS_PHYS_AIR) {         /* :1352-1374 */
+            int n = (int)(tile.fluid_amount / 4), i;
+            *self = nothing();
+            if(n < 1) n = 1;
+            for(i = 0; i < n; i++) {
+                fss_cell nt = liquid_seed(&tile);
+                nt.fluid_amount = tile.fluid_amount / n;
+                emit(c, x, y, 1366, r.cellkey, &nt);
+            }
+            return;
+        }
+        if(tile.moved) return;                              /* :1376 (moved == settled for liquids) */
+        start = tile.fluid_amount;
+        remaining = tile.fluid_amount;
+
+        bottom = *at(w, x, y + 1);                          /* :1381 */
+        air_below = phys(w, &bottom) == FSS_PHYS_AIR;
+        if((air_below && c->iter <= 2) || bottom.material == tile.material) { /* :1384-1405 */
+            dst = phys(w, &bottom) == FSS_PHYS_SOUP ? bottom.fluid_amount : 0.0f;
+            flow = vertical_flow(start, dst) - dst;
+            if(bottom.fluid_amount > 0 && flow > FLUID_MinFlow) flow *= FLUID_FlowSpeed;
+            flow = clamp_flow(flow, start);
+            if(flow != 0) {
+                remaining -= flow;
+                tile.fluid_amount_diff -= flow;
+                if(phys(w, &bottom) == FSS_PHYS_AIR) *at(w, x, y + 1) = liquid_seed(&tile);
+                at(w, x, y + 1)->fluid_amount_diff += flow;
+            }
+        } else if(c->iter == 0 && phys(w, &bottom) == FSS_PHYS_SOUP && bottom.material != tile.material) {
+            if(rnd(&r, 1407) % 10 == 0) {                   /* :1406-1412 */
+                *self = bottom;
+                *at(w, x, y + 1) = tile;
+                return;
+            }
+        }
+        if(remaining < FLUID_MinValue) {                    /* :1414-1418 */
+            tile.fluid_amount_diff -= remaining;
+            *self = tile;
+            return;
+        }
+
+        left = *at(w, x - 1, y);                            /* :1420-1424 */
+        can_left = (phys(w, &left) == FSS_PHYS_AIR || left.material == tile.material) && !air_below;
+        right = *at(w, x + 1, y);
+        can_right = (phys(w, &right) == FSS_PHYS_AIR || right.material == tile.material) && !air_below;
+
+        if(can_left) {                                      /* :1426-1448 */
+            dst = phys(w, &left) == FSS_PHYS_SOUP ? left.fluid_amount : 0.0f;
+            flow = (remaining - dst) / (can_right ? 3.0f : 2.0f);
+            if(flow > FLUID_MinFlow) flow *= FLUID_FlowSpeed;
+            flow = clamp_flow(flow, remaining);
+            if(flow != 0) {
+                remaining -= flow;
+                tile.fluid_amount_diff -= flow;
+                if(phys(w, &left) == FSS_PHYS_AIR) *at(w, x - 1, y) = liquid_seed(&tile);
+                at(w, x - 1, y)->fluid_amount_diff += flow;
+            }
+        }
+        if(remaining < FLUID_MinValue) {
+            tile.fluid_amount_diff -= remaining;
+            *self = tile;
+            return;
+        }
+        if(can_right) {                                     /* :1456-1478 (`canMoveLeft ? 2.0f : 2.0f`) */
+            dst = phys(w, &right) == FSS_PHYS_SOUP ? right.fluid_amount : 0.0f;
+            flow = (remaining - dst) / 2.0f;
+            if(flow > FLUID_MinFlow) flow *= FLUID_FlowSpeed;
+            flow = clamp_flow(flow, remaining);
+            if(flow != 0) {
+                remaining -= flow;
+                tile.fluid_amount_diff -= flow;
+                if(phys(w, &right) == FSS_PHYS_AIR) *at(w, x + 1, y) = liquid_seed(&tile);
+                at(w, x + 1, y)->fluid_amount_diff += flow;
+            }
+        }
+        if(remaining < FLUID_MinValue) {
+            tile.fluid_amount_diff -= remaining;
+            *self = tile;
+            return;
+        }
+        top = *at(w, x, y - 1);                             /* :1486-1516 */
+        if(phys(w, &top) == FSS_PHYS_AIR || top.material == tile.material) {
+            dst = phys(w, &top) == FSS_PHYS_SOUP ? top.fluid_amount : 0.0f;
+            flow = remaining - vertical_flow(remaining, dst);
+            if(flow > FLUID_MinFlow) flow *= FLUID_FlowSpeed;
+            flow = clamp_flow(flow, remaining);
+            if(flow != 0) {
+                remaining -= flow;
+                tile.fluid_amount_diff -= flow;
+                if(phys(w, &top) == FSS_PHYS_AIR) *at(w, x, y - 1) = liquid_seed(&tile);
+                at(w, x, y - 1)->fluid_amount_diff += flow;
+            }
+        } else if(c->iter == 0 && phys(w, &top) == FSS_PHYS_SOUP && top.material != tile.material) {
+            if(rnd(&r, 1511) % 10 == 0) {
+                *self = top;
+                *at(w, x, y - 1) = tile;
+                return;
+            }
+        }
+        if(remaining < FLUID_MinValue) {
+            tile.fluid_amount_diff -= remaining;
+            *self = tile;
+            return;
+        }
+        if(start == remaining) {                            /* :1524-1535 */
+            tile.settle_count++;
+            if(tile.settle_count >= 10) tile.moved = 1;
+        } else {
+            if(phys(w, &top) == FSS_PHYS_SOUP) at(w, x, y - 1)->moved = 0;
+            if(phys(w, &bottom) == FSS_PHYS_SOUP) at(w, x, y + 1)->moved = 0;
+            if(phys(w, &left) == FSS_PHYS_SOUP) at(w, x - 1, y)->moved = 0;
+            if(phys(w, &right) == FSS_PHYS_SOUP) at(w, x + 1, y)->moved = 0;
+        }
+        *self = tile;                                       /* :1537 */
+    } else if(type == FSS_PHYS_GAS) {                       /* :1647-1663 */
+        int above = phys(w, at(w, x, y - 1));
+        int above_l = phys(w, at(w, x - 1, y - 1));
+        int above_r = phys(w, at(w, x + 1, y - 1));
+        if(above == FSS_PHYS_AIR && !((above_l == FSS_PHYS_AIR || above_r == FSS_PHYS_AIR) && rnd(&r, 1654) % 2 == 0)) {
+            *self = *at(w, x, y - 1);
+            *at(w, x, y - 1) = tile;
+            mark(c, x, y - 1);
+        }
+    }
+}
+
+/* ---- scan 2, F/world.cpp:1669-1901 ----------------------------------------------------------- */
+static void scan2_cell(chunk_t* c, int x, int y) {
+    fsso_world* w = c->w;
+    fss_cell* self = at(w, x, y);
+    fss_cell tile;
+    int type, dx = x - c->cx, dy = y - c->cy;
+    rng_t r;
+    if(c->vis[dy][dx]) return;                              /* :1676 */
+    tile = *self;
+    type = phys(w, &tile);
+    r.cellkey = fss_rng_cell_key(c->tkey, (uint32_t)x, (uint32_t)y);
+    r.n = 0;
+
+    if(type == FSS_PHYS_SAND) {                             /* :1682-1807 */
+        fss_cell bl = *at(w, x - 1, y + 1), br = *at(w, x + 1, y + 1);
+        int can_l = can_move_into(w, &bl, &tile), can_r = can_move_into(w, &br, &tile);
+        int stopped = !tile.moved;
+        int slip = w->mat[tile.material].slipperyness;
+        int should_move;
+        if(stopped) {                                       /* :1697-1725 */
+            int drop = 0, pil, unstable;
+            for(pil = 0; pil < 10; pil++) {
+                if(phys(w, at(w, x - 1, y + 1 + pil)) == FSS_PHYS_AIR || phys(w, at(w, x + 1, y + 1 + pil)) == FSS_PHYS_AIR) drop++;
+            }
+            unstable = drop + 1 - w->max_stability[tile.material];
+            if(unstable > 0) {
+                int chance = 1000 / unstable;
+                if(chance < 1000) {
+                    if(rnd(&r, 1715) % (uint32_t)chance == 0) {
+                        stopped = 0;
+                        self->moved = 1; /* the grid cell; the local copy `tile` keeps moved == false */
+                    }
+                }
+            }
+        }
+        if(stopped || !(can_l || can_r)) {                  /* :1727-1734 */
+            self->moved = 0;
+            return;
+        }
+        should_move = rnd(&r, 1736) % (uint32_t)(2 * slip) != 0;
+        if(should_move && (can_l || can_r)) {               /* :1738-1753 */
+            if(rnd(&r, 1741) % 2 == 0) {
+                if(phys(w, at(w, x, y + 1)) == FSS_PHYS_SAND) {
+                    if(rnd(&r, 1744) % 2 == 0) at(w, x, y + 1)->moved = 1;
+                }
+            }
+        }
+        if(should_move && can_l && (!can_r || rnd(&r, 1755) % 2 == 0)) { /* :1755-1777 */
+            if(phys(w, at(w, x - 1, y)) == FSS_PHYS_AIR) {
+                *at(w, x - 1, y) = bl;
+                mark(c, x - 1, y);
+                *self = nothing();
+            } else {
+                *self = bl;
+                c->vis[dy][dx] = 1;
+            }
+            if(rnd(&r, 1768) % (uint32_t)(20 * slip) == 0) tile.moved = 0;
+            *at(w, x - 1, y + 1) = tile;
+            mark(c, x - 1, y + 1);
+        } else if(should_move && can_r) {                   /* :1778-1800: (x+1, y) is NOT marked visited */
+            if(phys(w, at(w, x + 1, y)) == FSS_PHYS_AIR) {
+                *at(w, x + 1, y) = br;
+                *self = nothing();
+            } else {
+                *self = br;
+                c->vis[dy][dx] = 1;
+            }
+            if(rnd(&r, 1791) % (uint32_t)(20 * slip) == 0) tile.moved = 0;
+            *at(w, x + 1, y + 1) = tile;
+            mark(c, x + 1, y + 1);
+        } else {
+            self->moved = 0;                                /* :1802 */
+        }
+    } else if(type == FSS_PHYS_SOUP) {                      /* :1808-1825 */
+        tile.fluid_amount += tile.fluid_amount_diff;
+        tile.fluid_amount_diff = 0.0f;
+        if(tile.fluid_amount < FLUID_MinValue) *self = nothing();
+        else *self = tile;
+        c->vis[dy][dx] = 1;
+    } else if(type == FSS_PHYS_GAS) {                       /* :1879-1899 */
+        int above_l = phys(w, at(w, x - 1, y - 1));
+        int above_r = phys(w, at(w, x + 1, y - 1));
+        if(above_l == FSS_PHYS_AIR && !(above_r == FSS_PHYS_AIR && rnd(&r, 1884) % 2 == 0)) {
+            *self = *at(w, x - 1, y - 1);
+            *at(w, x - 1, y - 1) = tile;
+            mark(c, x - 1, y - 1);
+        } else if(above_r == FSS_PHYS_AIR) {
+            *self = *at(w, x + 1, y - 1);
+            *at(w, x + 1, y - 1) = tile;
+            mark(c, x + 1, y - 1);
+        }
+    }
+}
+
+/* ---- scan 3, F/world.cpp:1905-1974 ----------------------------------------------------------- */
+static void scan3_cell(chunk_t* c, int x, int y) {
+    fsso_world* w = c->w;
+    fss_cell* self = at(w, x, y);
+    fss_cell tile;
+    int dx = x - c->cx, dy = y - c->cy;
+    rng_t r;
+    if(c->vis[dy][dx]) return;
+    tile = *self;
+    if(phys(w, &tile) != FSS_PHYS_GAS) return;              /* the SOUP branch is empty (:1918-1943) */
+    r.cellkey = fss_rng_cell_key(c->tkey, (uint32_t)x, (uint32_t)y);
+    r.n = 0;
+    {
+        int l = phys(w, at(w, x - 1, y)), rr = phys(w, at(w, x + 1, y));
+        if(l == FSS_PHYS_AIR && !(rr == FSS_PHYS_AIR && rnd(&r, 1950) % 2 == 0)) {
+            *self = *at(w, x - 1, y);
+            *at(w, x - 1, y) = tile;
+            mark(c, x - 1, y);
+        } else if(rr == FSS_PHYS_AIR) {
+            *self = *at(w, x + 1, y);
+            *at(w, x + 1, y) = tile;
+            mark(c, x + 1, y);
+        } else if((w->mat[tile.material].flags & FSS_MAT_IS_STEAM) && w->condense_material >= 0) {
+            if(rnd(&r, 1966) % 10 == 0) *self = create_cell(w, w->condense_material, x, y, &r); /* Tiles::createWater() */
+        }
+    }
+}
+
+static void chunk_substep(fsso_world* w, uint32_t tick_ct, int iter, uint32_t tkey, int cx, int cy) {
+    chunk_t c;
+    int dx, dy;
+    c.w = w;
+    c.cx = cx;
+    c.cy = cy;
+    c.tick_ct = tick_ct;
+    c.iter = iter;
+    c.tkey = tkey;
+    memset(c.vis, 0, sizeof c.vis);
+    for(dy = CH - 1; dy >= 0; dy--)
+        for(dx = 0; dx < CW; dx++) scan1_cell(&c, cx + dx, cy + dy);
+    for(dy = CH - 1; dy >= 0; dy--)
+        for(dx = 0; dx < CW; dx++) scan2_cell(&c, cx + dx, cy + dy);
+    for(dy = CH - 1; dy >= 0; dy--)
+        for(dx = 0; dx < CW; dx++) scan3_cell(&c, cx + dx, cy + dy);
+}
+
+/* F/world.cpp:1115-1141: phase tk activates chunks at zone + (tk%2, 1 - tk/2) * chunk + 2*chunk*(i, j) */
+void fsso_substep_rows(fsso_world* w, uint32_t tick_ct, int iter, int tk, int cy_from, int cy_to) {
+    int ofs_x = tk % 2, ofs_y = 1 - ((tk % 4) / 2);
+    uint32_t tkey = fss_rng_tick_key(w->seed, tick_ct, (uint32_t)iter);
+    int x_begin = w->zx + ofs_x * CW, x_end = w->zx + w->zw;
+    int y_begin = w->zy + ofs_y * CH, y_end = w->zy + w->zh;
+    int nx = x_begin < x_end ? (x_end - x_begin + 2 * CW - 1) / (2 * CW) : 0;
+    int ny = y_begin < y_end ? (y_end - y_begin + 2 * CH - 1) / (2 * CH) : 0;
+    int k;
+#pragma omp parallel for schedule(dynamic, 64)
+    for(k = 0; k < nx * ny; k++) {
+        int cx = x_begin + (k % nx) * 2 * CW;
+        int cy = y_begin + (k / nx) * 2 * CH;
+        if(cy < cy_from || cy >= cy_to) continue;
+        chunk_substep(w, tick_ct, iter, tkey, cx, cy);
+    }
+}
+
+/* F/world.cpp:1108-1119, :2017 (the caller owns tickCt) */
+void fsso_tick(fsso_world* w, uint32_t tick_ct) {
+    int iter, tk;
+    for(iter = 0; iter < 6; iter++)
+        for(tk = 0; tk < 4; tk++) fsso_substep_rows(w, tick_ct, iter, tk, -0x40000000, 0x40000000);
+}
+
+/* ---- World::tickTemperature, F/world.cpp:2043-2143 ------------------------------------------- */
+void fsso_tick_temperature_rows(fsso_world* w, int y_from, int y_to) {
+    static const int NX[9] = {-1, -1, -1, 0, 0, 0, 1, 1, 1}; /* :2072-2116 order: x offset outer, y offset inner */
+    static const int NY[9] = {-1, 0, 1, -1, 0, 1, -1, 0, 1};
+    int x, y, i;
+    int y0 = w->zy > y_from ? w->zy : y_from, y1 = (w->zy + w->zh) < y_to ? (w->zy + w->zh) : y_to;
+#pragma omp parallel for private(x, i)
+    for(y = y0; y < y1; y++) {
+        for(x = w->zx; x < w->zx + w->zw; x++) {
+            float n = 0.01f, v = 0.0f;
+            const fss_cell* self = at(w, x, y);
+            const fss_material* m = &w->mat[self->material];
+            int32_t out;
+            for(i = 0; i < 9; i++) {
+                const fss_cell* c = at(w, x + NX[i], y + NY[i]);
+                if(c->temperature) {
+                    float factor = abs(c->temperature) / 64.0f * w->mat[c->material].conduction_other;
+                    v += c->temperature * factor;
+                    n += factor;
+                }
+            }
+            if(v != 0) {                                    /* :2128-2132; addTemp is Uint32 */
+                out = (int32_t)(m->add_temp + (v / n * m->conduction_self) + (self->temperature * (1 - m->conduction_self)));
+            } else {
+                out = (int32_t)(m->add_temp + (uint32_t)self->temperature);
+            }
+            w->new_temps[(size_t)y * w->width + x] = out;
+        }
+    }
+#pragma omp parallel for private(x)
+    for(y = y0; y < y1; y++)                                /* :2137-2141 */
+        for(x = w->zx; x < w->zx + w->zw; x++) at(w, x, y)->temperature = w->new_temps[(size_t)y * w->width + x];
+}
+
+void fsso_tick_temperature(fsso_world* w) { fsso_tick_temperature_rows(w, -0x40000000, 0x40000000); }
+
+/* ---- bookkeeping ----------------------------------------------------------------------------- */
+fsso_world* fsso_create(int width, int height, uint32_t seed, uint32_t flags, int condense_material) {
+    fsso_world* w = (fsso_world*)calloc(1, sizeof *w);
+    size_t n = (size_t)width * height, i;
+    w->width = width;
+    w->height = height;
+    w->seed = seed;
+    w->flags = flags;
+    w->condense_material = condense_material;
+    w->cells = (fss_cell*)malloc(n * sizeof(fss_cell));
+    w->new_temps = (int32_t*)calloc(n, sizeof(int32_t));
+    for(i = 0; i < n; i++) w->cells[i] = nothing();
+    w->fire_id = -1;
+    return w;
+}
+
+void fsso_destroy(fsso_world* w) {
+    int i;
+    if(!w) return;
+    for(i = 0; i < FSS_MAX_TEXTURES; i++) free(w->tex[i].px);
+    free(w->cells);
+    free(w->new_temps);
+    free(w->parts);
+    free(w);
+}
+
+int fsso_set_materials(fsso_world* w, const fss_material* table, int n) {
+    int i;
+    if(n < 1 || n > FSS_MAX_MATERIALS) return FSS_ERR_INVALID;
+    memcpy(w->mat, table, (size_t)n * sizeof(fss_material));
+    w->n_mat = n;
+    w->fire_id = -1;
+    for(i = 0; i < n; i++) {
+        int slip = table[i].slipperyness;
+        /* `int maxStability = 8 / sqrt(slipperyness) + 1;`  F/world.cpp:1710 (double arithmetic) */
+        w->max_stability[i] = slip > 0 ? (int)(8 / sqrt((double)slip) + 1) : 0x3fffffff;
+        if((table[i].flags & FSS_MAT_IS_FIRE) && w->fire_id < 0) w->fire_id = i;
+        if(table[i].physics_type == FSS_PHYS_SAND && slip < 1) return FSS_ERR_INVALID;
+    }
+    return FSS_OK;
+}
+
+int fsso_set_texture(fsso_world* w, int index, const uint32_t* argb, int tw, int th) {
+    if(index < 0 || index >= FSS_MAX_TEXTURES || tw < 1 || th < 1) return FSS_ERR_INVALID;
+    free(w->tex[index].px);
+    w->tex[index].px = (uint32_t*)malloc((size_t)tw * th * 4);
+    memcpy(w->tex[index].px, argb, (size_t)tw * th * 4);
+    w->tex[index].w = tw;
+    w->tex[index].h = th;
+    return FSS_OK;
+}
+
+int fsso_set_tick_zone(fsso_world* w, int x, int y, int zw, int zh) {
+    if(x % FSS_ZONE_ALIGN_X || zw % FSS_ZONE_ALIGN_X || zh % FSS_ZONE_ALIGN_Y) return FSS_ERR_ALIGN;
+    if(x < FSS_ZONE_MARGIN || y < FSS_ZONE_MARGIN || x + zw > w->width - FSS_ZONE_MARGIN || y + zh > w->height - FSS_ZONE_MARGIN)
+        return FSS_ERR_ALIGN;
+    w->zx = x;
+    w->zy = y;
+    w->zw = zw;
+    w->zh = zh;
+    return FSS_OK;
+}
+
+fss_cell* fsso_cells(fsso_world* w) { return w->cells; }
+size_t fsso_num_particles(fsso_world* w) { return w->n_parts; }
+
+static int cmp_part(const void* a, const void* b) {
+    const fss_particle_spawn* p = (const fss_particle_spawn*)a;
+    const fss_particle_spawn* q = (const fss_particle_spawn*)b;
+    if(p->tick_iter != q->tick_iter) return p->tick_iter < q->tick_iter ? -1 : 1;
+    if(p->y != q->y) return p->y < q->y ? -1 : 1;
+    if(p->x != q->x) return p->x < q->x ? -1 : 1;
+    if(p->site != q->site) return p->site < q->site ? -1 : 1;
+    return 0;
+}
+
+size_t fsso_drain_particles(fsso_world* w, fss_particle_spawn* out, size_t cap) {
+    size_t n = w->n_parts < cap ? w->n_parts : cap;
+    qsort(w->parts, w->n_parts, sizeof(fss_particle_spawn), cmp_part);
+    memcpy(out, w->parts, n * sizeof(fss_particle_spawn));
+    w->n_parts = 0;
+    return n;
+}
+
+uint64_t fsso_hash_rows(const fss_cell* cells, int width, int x0, int y0, int w, int h, int global_y0) {
+    uint64_t sum = 0;
+    int x, y;
+    for(y = y0; y < y0 + h; y++) {
+        for(x = x0; x < x0 + w; x++) {
+            const fss_cell* c = &cells[(size_t)y * width + x];
+            uint32_t a, d, mms = (uint32_t)c->material | ((uint32_t)(c->moved != 0) << 16) | ((uint32_t)c->settle_count << 24);
+            memcpy(&a, &c->fluid_amount, 4);
+            memcpy(&d, &c->fluid_amount_diff, 4);
+            sum += fss_cell_digest((uint32_t)x, (uint32_t)(y + global_y0), mms, c->color, (uint32_t)c->temperature, a, d);
+        }
+    }
+    return sum;
+}
+
+void fsso_histogram(const fss_cell* cells, size_t n, uint64_t* counts, int n_materials) {
+    size_t i;
+    memset(counts, 0, (size_t)n_materials * sizeof(uint64_t));
+    for(i = 0; i < n; i++)
+        if(cells[i].material < n_materials) counts[cells[i].material]++;
+}

@@ -1,0 +1,75 @@
+#!/usr/bin/env python3
+"""Mint the golden fixtures from the reference's own tick (oracle/_ref, built by
+oracle/build_ref.py from /root/reference).  The reference ships no tests for this path
+(SURVEY.md section 4), so these are the known answers everything else is pinned to.
+
+  materials_srand1234.json  Materials::MATERIALS after srand(1234); Materials::init()
+  tick_hashes.json          {case -> digest}: fss_hash-style digest of the whole grid after N ticks
+  micro_*.npz               tiny before/after scenes per rule family (full cell records)
+
+Run:  python tests/golden/make_golden.py      (needs oracle/_ref)
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle import oraclesim, refsim  # noqa: E402
+
+CASES = [
+    # name, size, mix, seed, ticks, particles
+    ("c2_160x160_s1_t40", (160, 160), "c2", 1, 40, False),
+    ("c3_160x160_s2_t40", (160, 160), "c3", 2, 40, False),
+    ("c3_particles_160x128_s3_t30", (160, 128), "c3", 3, 30, True),
+    ("sand_192x160_s4_t60", (192, 160), "sand", 4, 60, False),
+    ("sand_particles_128x160_s5_t30", (128, 160), "sand", 5, 30, True),
+    ("liquids_160x160_s6_t40", (160, 160), "liquids", 6, 40, False),
+    ("gas_160x128_s7_t40", (160, 128), "gas", 7, 40, False),
+    ("fire_128x128_s8_t60", (128, 128), "fire", 8, 60, False),
+    ("randmats_160x160_s9_t40", (160, 160), "randmats", 9, 40, False),
+    ("settled_256x96_s10_t20", (256, 96), "settled", 10, 20, False),
+    ("c3_320x224_s11_t100", (320, 224), "c3", 11, 100, False),
+]
+
+
+def export_materials():
+    rows = []
+    for i, (m, name, inter) in enumerate(refsim.materials()):
+        rows.append(dict(id=i, name=name, physics_type=m.physics_type, iterations=m.iterations,
+                         slipperyness=m.slipperyness, density=float(m.density), add_temp=m.add_temp,
+                         conduction_self=float(m.conduction_self), conduction_other=float(m.conduction_other),
+                         color=m.color, flags=m.flags, interact=inter,
+                         reactions=[[m.reactions[j].type, m.reactions[j].data1, m.reactions[j].data2]
+                                    for j in range(m.n_reactions)]))
+    with open(os.path.join(HERE, "materials_srand1234.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+
+
+def main():
+    assert refsim.available(), "build oracle/_ref first: python oracle/build_ref.py"
+    export_materials()
+    import helpers
+    hashes = {}
+    for name, size, mix, seed, ticks, particles in CASES:
+        cells, zone = helpers.make_world(size, mix, seed)
+        r = refsim.RefWorld(cells, zone, particles=particles, seed=0xF55)
+        helpers.run_ticks(r, ticks)
+        out = r.cells()
+        hashes[name] = dict(size=list(size), mix=mix, seed=seed, ticks=ticks, particles=particles,
+                            digest=f"{oraclesim.hash_cells(out):016x}",
+                            histogram={str(k): int(v) for k, v in zip(*np.unique(out['material'], return_counts=True))})
+        if name.startswith(("fire", "gas", "sand_particles")):
+            np.savez_compressed(os.path.join(HERE, f"micro_{name}.npz"), before=cells, after=out, zone=np.array(zone))
+        r.close()
+        print(name, hashes[name]["digest"])
+    with open(os.path.join(HERE, "tick_hashes.json"), "w") as f:
+        json.dump(hashes, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
