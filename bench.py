@@ -1,0 +1,320 @@
+#!/usr/bin/env python3
+"""Benchmark of the World::tick hot path on B200 (contract: see the task statement, section 4).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c5] [--size S] [--impl b200|reference]
+
+One "step" = one full World::tick (6 iter x 4 tk checkerboard sub-steps x 3 scans, world.cpp:1091-2041) over
+the whole tick zone; workload c3 also runs World::tickTemperature every 4th step (Game.cpp:2759).
+metric = cell-updates/s = zone cells x steps / seconds, whole job (all ranks).
+
+N = 1   workload "c2" (BASELINE.json configs[1]): 16384 x 16384 zone, 25 % sand / 20 % water / 10 % stone.
+N > 1   weak scaling: every rank owns a 16384 x 16384 strip of a 16384 x (16384*N) zone, halo rows
+        exchanged over NCCL after tk 1 / tk 3 of every iter (one process per GPU under torchrun).
+The grid is generated on the device (fss_fill_synthetic); "data": "synthetic".
+
+Besides `value` (grid resident in HBM) the line carries
+  e2e          the same metric through the C ABI with HOST buffers: every step uploads the whole grid from
+               pinned host memory, ticks, and downloads the whole grid (the reference-side shim's worst case)
+  roofline     K1 (k_substep) against the measured HBM copy bandwidth, algorithmic bytes as DESIGN.md defines
+  cpu_baseline the reference's own tick (oracle/_ref) or the oracle port on this box's host cores, N = 1 only
+`--impl reference` times only that CPU implementation (rank 0), same metric and unit.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ZONE_PER_GPU = 16384
+BORDER = 16
+CELL_BYTES_PLANES = 20   # 5 planes x 4 B per cell in HBM
+ALGO_BYTES_PER_CELL_UPDATE = 32.0  # 16-B packed cell read once + written once per tick
+SUBSTEPS = 24
+CPU_SAMPLE_ZONE = (2048, 1024)
+
+
+def mixes():
+    from fallingsandsurvival_b200 import worlds
+    return {"c2": worlds.MIX_C2, "c3": worlds.MIX_C3, "c5": worlds.MIX_C2}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "B200_PROFILING.md fallback"
+
+
+# ---- the reference's CPU tick on a bounded sample ---------------------------------------------------------------
+def cpu_tick_throughput(workload, steps, warmup, temperature):
+    """cell-updates/s of the reference's own World::tick (oracle/_ref, fastest variant) or of the oracle port on a
+    2048x1024 zone of the same fill, all host threads."""
+    from fallingsandsurvival_b200 import worlds
+    from oracle import oraclesim, refsim
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    zw, zh = CPU_SAMPLE_ZONE
+    size = (zw + 2 * BORDER, zh + 2 * BORDER)
+    defs = helpers.full_table()
+    cells = worlds.synthetic_world(size[0], size[1], mixes()[workload], seed=0xF55, defs=defs)
+    zone = (BORDER, BORDER, zw, zh)
+    cores = os.cpu_count() or 1
+    if refsim.available("c128"):
+        kind, w = "reference", refsim.RefWorld(cells, zone, threads=cores, variant="c128")
+        what = "oracle/_ref c128: the reference's World::tick lines, CHUNK 128, keyed RNG"
+    else:
+        kind, w = "port", oraclesim.OracleWorld(cells, zone, defs=defs)
+        what = "oracle/fss_oracle.c (OpenMP)"
+    for t in range(warmup):
+        w.tick(t)
+    t0 = time.perf_counter()
+    for t in range(warmup, warmup + steps):
+        w.tick(t)
+        if temperature and t % 4 == 2:
+            w.tick_temperature()
+    dt = time.perf_counter() - t0
+    w.close()
+    return {"value": zw * zh * steps / dt, "unit": "cell-updates/s", "cores": cores, "kind": kind,
+            "sample": f"{steps} ticks of a {zw}x{zh} zone, same fill as the workload, after {warmup} warm-up ticks; {what}",
+            "ms_per_step": dt / steps * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workload = args.workload
+    r = cpu_tick_throughput(workload, args.steps, args.warmup, workload == "c3")
+    line = {
+        "impl": "reference", "metric": "cell-updates/sec", "value": r["value"], "unit": "cell-updates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic",
+        "config": workload_config(workload, args.gpus, args.size),
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(workload, n, size):
+    return {"workload": {"c2": "BASELINE.json configs[1]: synthetic random sand/water/stone world, movement-only tick",
+                         "c3": "BASELINE.json configs[2]: configs[1] + lava/fire/gold ore/steam/soft dirt, tickTemperature every 4th tick",
+                         "c5": "BASELINE.json configs[4]: mostly settled world with sparse active boxes"}[workload],
+            "zone_cells_per_gpu": [size, size], "zone_cells": [size, size * n], "strips": n,
+            "fill": "25% TEST_SAND / 20% WATER / 10% COBBLE_STONE" + (" + 3% LAVA 2% FIRE 3% GOLD_ORE 3% STEAM 5% SOFT_DIRT" if workload == "c3" else ""),
+            "particles": "off", "l2": "working set (5 planes x 4 B x cells) is far larger than the 126 MB L2; no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"])
+    ap.add_argument("--size", type=int, default=ZONE_PER_GPU, help="zone cells per GPU along each axis (multiple of 32)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from fallingsandsurvival_b200 import materials as M
+    from fallingsandsurvival_b200 import strips, world
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+
+    rank = int(os.environ.get("RANK", "0"))
+    n = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert n == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={n}: launch with torchrun --nproc-per-node {args.gpus}"
+    torch.cuda.set_device(local)
+    if n > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    S = args.size
+    W, H = S + 2 * BORDER, S * n + 2 * BORDER
+    zone = (BORDER, BORDER, S, S * n)
+    defs = helpers.full_table()
+    workload = args.workload
+    temperature = workload == "c3"
+
+    rw = strips.RankWorld((W, H), zone, rank, n, local, defs=defs)
+    g = rw.world
+    stream = torch.cuda.Stream()  # a real stream: handle 0 would mean "the world's own stream" to fss_set_stream
+    torch.cuda.set_stream(stream)
+    g.set_stream(stream.cuda_stream)
+    fill = dict(seed=0xF55, border=BORDER)
+    if workload == "c5":
+        fill.update(solid_from_row=int(H * 0.9), n_boxes=64 if S >= 4096 else 4, box_size=256, sparse_material=M.TEST_SAND, sparse_per_mille=1)
+    g.fill_synthetic(mixes()[workload], **fill)
+    g.sync()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if n > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    tick_ct = 0
+
+    def step():
+        nonlocal tick_ct
+        g.tick(tick_ct)
+        if temperature and tick_ct % 4 == 2:
+            g.tick_temperature()
+        tick_ct += 1
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = g.stats().kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = g.stats().kernel_launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # K1 alone, per launch, for the roofline: one more tick with an event pair around every sub-step launch
+    k1_ms = []
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(SUBSTEPS + 1)]
+    if n == 1:
+        evs[0].record(stream)
+        k = 0
+        for it in range(6):
+            for tk in range(4):
+                g.substep(tick_ct, it, tk)
+                k += 1
+                evs[k].record(stream)
+        tick_ct += 1
+        torch.cuda.synchronize()
+        k1_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(SUBSTEPS)]
+
+    # ---- e2e: host buffers through the C ABI --------------------------------------------------------------
+    y0, y1 = g.stored
+    rows = y1 - y0
+    host = torch.empty((rows, W, 20), dtype=torch.uint8, pin_memory=True).numpy().view(helpers.abi.CELL_DTYPE).reshape(rows, W)
+    g.download(0, y0, W, rows, out=host)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        g.upload(0, y0, host)
+        step()
+        g.download(0, y0, W, rows, out=host)
+    e1.record(stream)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    e2e_ms = max(e0.elapsed_time(e1), e2e_wall * 1e3)
+
+    def max_over_ranks(v):
+        if n == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms = max_over_ranks(ms)
+    e2e_ms = max_over_ranks(e2e_ms)
+    zone_cells = S * S * n
+    value = zone_cells * args.steps / (ms / 1e3)
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        line = {
+            "metric": "cell-updates/sec", "value": value, "unit": "cell-updates/s", "n_gpus": n, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic", "config": workload_config(workload, n, S),
+            "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": {"value": zone_cells * args.e2e_steps / (e2e_ms / 1e3), "unit": "cell-updates/s",
+                    "h2d_bytes_per_step": int(rows * W * 20), "d2h_bytes_per_step": int(rows * W * 20), "steps": args.e2e_steps,
+                    "ms_per_step": e2e_ms / args.e2e_steps,
+                    "what": "per step: fss_upload_rect(whole stored grid, pinned host) + fss_tick + fss_download_rect(whole stored grid)"},
+        }
+        if k1_ms:
+            avg = float(np.mean(k1_ms))
+            algo = ALGO_BYTES_PER_CELL_UPDATE * zone_cells / SUBSTEPS  # bytes per k_substep launch
+            sweep = 2.0 * CELL_BYTES_PLANES * zone_cells / 4            # active micro-chunks read + written once, all planes
+            line["roofline"] = {
+                "kernel": "k_substep", "bound": "hbm", "achieved": algo / (avg / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": algo / (avg / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "launch_ms_avg": avg, "launch_ms_by_iter": [float(np.sum(k1_ms[4 * i:4 * i + 4])) for i in range(6)],
+                "algorithmic_bytes_per_launch": algo,
+                "note": "algorithmic = 32 B per cell-update (whole tick) x zone cells / 24 launches per tick; the shipped schedule "
+                        "sweeps the active quarter of the grid once per launch: see sweep_*",
+                "sweep_bytes_per_launch": sweep, "sweep_achieved": sweep / (avg / 1e3) / 1e9, "sweep_frac": sweep / (avg / 1e3) / 1e9 / peak,
+            }
+        if n == 1 and not args.no_cpu:
+            try:
+                c = cpu_tick_throughput(workload, 10, 2, temperature)
+                line["cpu_baseline"] = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:  # the checker libraries are optional on a box without them
+                line["cpu_baseline"] = {"value": None, "unit": "cell-updates/s", "cores": os.cpu_count(), "kind": "port", "sample": f"unavailable: {e}"}
+        print(json.dumps(line), flush=True)
+    g.close()
+    if n > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,734 @@
+// fss_abi.cu -- the C ABI of include/fss.h on top of the kernels in fss_kernels.cuh.
+//
+// Host-side counterpart of the array part of `World` (FallingSandSurvival/world.hpp:98-146): owns the
+// device planes, the material table, the tick zone, the particle spawn buffer and (for strip-sharded
+// worlds) the NCCL communicator.  There is no CPU implementation of the path in this library: without
+// a CUDA device fss_create() fails with FSS_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "fss_kernels.cuh"
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if(e_ != cudaSuccess) return fail(FSS_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while(0)
+
+// ---- NCCL, bound lazily so that single-GPU users need no libnccl ------------------------------------------
+struct NcclId {
+    char internal[128];
+};
+typedef int (*nccl_get_unique_id_t)(NcclId*);
+typedef int (*nccl_comm_init_rank_t)(void**, int, NcclId, int);
+typedef int (*nccl_comm_destroy_t)(void*);
+typedef int (*nccl_send_t)(const void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_recv_t)(void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_group_t)(void);
+typedef const char* (*nccl_err_t)(int);
+static struct {
+    void* lib;
+    nccl_get_unique_id_t get_unique_id;
+    nccl_comm_init_rank_t comm_init_rank;
+    nccl_comm_destroy_t comm_destroy;
+    nccl_send_t send;
+    nccl_recv_t recv;
+    nccl_group_t group_start, group_end;
+    nccl_err_t err_string;
+} g_nccl;
+#define NCCL_UINT32 3 /* ncclUint32, nccl.h */
+
+static int nccl_bind() {
+    if(g_nccl.lib) return FSS_OK;
+    // RTLD_NOLOAD first: inside a torch process this picks up the libnccl torch already loaded
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if(!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+    if(!h) h = dlopen("libnccl.so", RTLD_NOW);
+    if(!h) return fail(FSS_ERR_COMM, "cannot load libnccl.so.2: %s", dlerror());
+    g_nccl.get_unique_id = (nccl_get_unique_id_t)dlsym(h, "ncclGetUniqueId");
+    g_nccl.comm_init_rank = (nccl_comm_init_rank_t)dlsym(h, "ncclCommInitRank");
+    g_nccl.comm_destroy = (nccl_comm_destroy_t)dlsym(h, "ncclCommDestroy");
+    g_nccl.send = (nccl_send_t)dlsym(h, "ncclSend");
+    g_nccl.recv = (nccl_recv_t)dlsym(h, "ncclRecv");
+    g_nccl.group_start = (nccl_group_t)dlsym(h, "ncclGroupStart");
+    g_nccl.group_end = (nccl_group_t)dlsym(h, "ncclGroupEnd");
+    g_nccl.err_string = (nccl_err_t)dlsym(h, "ncclGetErrorString");
+    if(!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.send || !g_nccl.recv || !g_nccl.group_start || !g_nccl.group_end)
+        return fail(FSS_ERR_COMM, "libnccl.so.2 lacks a required symbol");
+    g_nccl.lib = h;
+    return FSS_OK;
+}
+#define NC(call)                                                                                                   \
+    do {                                                                                                           \
+        int e_ = (call);                                                                                           \
+        if(e_ != 0) return fail(FSS_ERR_COMM, "%s: %s", #call, g_nccl.err_string ? g_nccl.err_string(e_) : "nccl error"); \
+    } while(0)
+
+// ---- the world ------------------------------------------------------------------------------------------
+struct fss_world {
+    fss_config cfg;
+    int device;
+    cudaStream_t own_stream, stream;
+    Grid g;
+    int32_t* temp2;
+    int own_lo, own_hi; // owned global rows
+    bool sharded;
+    int zx, zy, zw, zh;
+    bool zone_set, mats_set;
+    int n_mat, fire_id;
+    uint32_t nothing_mf;
+    DMat h_mats[FSS_MAX_MATERIALS];
+    DMat* d_mats;
+    DTex h_tex[FSS_MAX_TEXTURES];
+    DTex* d_tex;
+    fss_particle_spawn* d_parts;
+    unsigned long long* d_part_count;
+    uint32_t part_cap;
+    void* d_stage;
+    size_t stage_bytes;
+    unsigned long long* d_red; // FSS_MAX_MATERIALS u64 + FSS_MAX_MATERIALS f64
+    fss_stats stats;
+    // strips
+    void* comm;
+    int rank, n_ranks;
+};
+
+#define STAGE_BYTES ((size_t)64 << 20)
+
+static int use_device(fss_world* w) {
+    CU(cudaSetDevice(w->device));
+    return FSS_OK;
+}
+
+static size_t plane_cells(const fss_world* w) { return (size_t)w->g.rows * w->g.pitch; }
+
+extern "C" {
+
+int fss_abi_version(void) { return FSS_ABI_VERSION; }
+const char* fss_last_error(void) { return g_err.c_str(); }
+
+int fss_create(const fss_config* cfg, fss_world** out) {
+    if(!cfg || !out) return fail(FSS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if(cfg->struct_size != sizeof(fss_config)) return fail(FSS_ERR_INVALID, "fss_config.struct_size %u != %zu", cfg->struct_size, sizeof(fss_config));
+    if(cfg->width < 2 * FSS_ZONE_MARGIN + FSS_ZONE_ALIGN_X || cfg->height < 2 * FSS_ZONE_MARGIN + FSS_ZONE_ALIGN_Y)
+        return fail(FSS_ERR_INVALID, "world %ux%u too small", cfg->width, cfg->height);
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if(e != cudaSuccess || n_dev == 0) return fail(FSS_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if(cfg->device < 0 || cfg->device >= n_dev) return fail(FSS_ERR_NO_DEVICE, "device %d of %d", cfg->device, n_dev);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if(prop.major < 10) return fail(FSS_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+
+    fss_world* w = new fss_world();
+    memset(w, 0, sizeof *w);
+    w->cfg = *cfg;
+    w->device = cfg->device;
+    w->fire_id = -1;
+    w->sharded = cfg->strip_rows != 0;
+    if(w->sharded) {
+        if(cfg->strip_y0 + cfg->strip_rows > cfg->height || cfg->strip_rows < 2 * FSS_HALO_ROWS) {
+            delete w;
+            return fail(FSS_ERR_INVALID, "strip [%u, +%u): outside height %u or shorter than %d rows", cfg->strip_y0, cfg->strip_rows, cfg->height, 2 * FSS_HALO_ROWS);
+        }
+        w->own_lo = (int)cfg->strip_y0;
+        w->own_hi = (int)(cfg->strip_y0 + cfg->strip_rows);
+    } else {
+        w->own_lo = 0;
+        w->own_hi = (int)cfg->height;
+    }
+    const int s_lo = std::max(0, w->own_lo - FSS_HALO_ROWS), s_hi = std::min((int)cfg->height, w->own_hi + FSS_HALO_ROWS);
+    w->g.pitch = (cfg->width + FSS_BLOCK_COLS - 1) / FSS_BLOCK_COLS * FSS_BLOCK_COLS;
+    w->g.sy0 = s_lo;
+    w->g.rows = s_hi - s_lo;
+    w->part_cap = cfg->particle_capacity ? cfg->particle_capacity : (1u << 20);
+
+#define CUX(call)                                                                             \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if(e_ != cudaSuccess) {                                                               \
+            fail(FSS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));                      \
+            fss_destroy(w);                                                                   \
+            return FSS_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while(0)
+    CUX(cudaSetDevice(w->device));
+    CUX(cudaStreamCreateWithFlags(&w->own_stream, cudaStreamNonBlocking));
+    w->stream = w->own_stream;
+    const size_t n = plane_cells(w);
+    CUX(cudaMalloc(&w->g.mf, n * 4));
+    CUX(cudaMalloc(&w->g.col, n * 4));
+    CUX(cudaMalloc(&w->g.temp, n * 4));
+    CUX(cudaMalloc(&w->temp2, n * 4));
+    CUX(cudaMalloc(&w->g.amt, n * 4));
+    CUX(cudaMalloc(&w->g.dif, n * 4));
+    CUX(cudaMemsetAsync(w->g.mf, 0, n * 4, w->stream));
+    CUX(cudaMemsetAsync(w->g.col, 0, n * 4, w->stream));
+    CUX(cudaMemsetAsync(w->g.temp, 0, n * 4, w->stream));
+    CUX(cudaMemsetAsync(w->temp2, 0, n * 4, w->stream));
+    CUX(cudaMemsetAsync(w->g.amt, 0, n * 4, w->stream));
+    CUX(cudaMemsetAsync(w->g.dif, 0, n * 4, w->stream));
+    CUX(cudaMalloc(&w->d_mats, sizeof(DMat) * FSS_MAX_MATERIALS));
+    CUX(cudaMalloc(&w->d_tex, sizeof(DTex) * FSS_MAX_TEXTURES));
+    CUX(cudaMemsetAsync(w->d_tex, 0, sizeof(DTex) * FSS_MAX_TEXTURES, w->stream));
+    CUX(cudaMalloc(&w->d_parts, sizeof(fss_particle_spawn) * (size_t)w->part_cap));
+    CUX(cudaMalloc(&w->d_part_count, 8));
+    CUX(cudaMemsetAsync(w->d_part_count, 0, 8, w->stream));
+    CUX(cudaMalloc(&w->d_red, FSS_MAX_MATERIALS * 16));
+    w->stage_bytes = std::min(STAGE_BYTES, std::max((size_t)1 << 20, (size_t)cfg->width * 20 * 16));
+    CUX(cudaMalloc(&w->d_stage, w->stage_bytes));
+    CUX(cudaStreamSynchronize(w->stream));
+#undef CUX
+    w->stats.storage_bytes = n * 4 * 6;
+    w->stats.storage_pitch = w->g.pitch;
+    w->stats.storage_rows = (uint32_t)w->g.rows;
+    w->stats.storage_y0 = (uint32_t)w->g.sy0;
+    *out = w;
+    return FSS_OK;
+}
+
+int fss_destroy(fss_world* w) {
+    if(!w) return FSS_OK;
+    cudaSetDevice(w->device);
+    if(w->own_stream) cudaStreamSynchronize(w->own_stream);
+    if(w->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(w->comm);
+    cudaFree(w->g.mf);
+    cudaFree(w->g.col);
+    cudaFree(w->g.temp);
+    cudaFree(w->temp2);
+    cudaFree(w->g.amt);
+    cudaFree(w->g.dif);
+    cudaFree(w->d_mats);
+    for(int i = 0; i < FSS_MAX_TEXTURES; i++) cudaFree((void*)w->h_tex[i].px);
+    cudaFree(w->d_tex);
+    cudaFree(w->d_parts);
+    cudaFree(w->d_part_count);
+    cudaFree(w->d_red);
+    cudaFree(w->d_stage);
+    if(w->own_stream) cudaStreamDestroy(w->own_stream);
+    delete w;
+    return FSS_OK;
+}
+
+int fss_set_stream(fss_world* w, void* cuda_stream) {
+    if(!w) return fail(FSS_ERR_INVALID, "null world");
+    if(use_device(w)) return FSS_ERR_CUDA;
+    CU(cudaStreamSynchronize(w->stream));
+    w->stream = cuda_stream ? (cudaStream_t)cuda_stream : w->own_stream;
+    return FSS_OK;
+}
+
+int fss_sync(fss_world* w) {
+    if(!w) return fail(FSS_ERR_INVALID, "null world");
+    if(use_device(w)) return FSS_ERR_CUDA;
+    CU(cudaStreamSynchronize(w->stream));
+    CU(cudaGetLastError());
+    return FSS_OK;
+}
+
+// ---- material table -----------------------------------------------------------------------------------
+int fss_set_materials(fss_world* w, const fss_material* t, int n) {
+    if(!w || !t) return fail(FSS_ERR_INVALID, "null argument");
+    if(n < 1 || n > FSS_MAX_MATERIALS) return fail(FSS_ERR_INVALID, "%d materials (1..%d)", n, FSS_MAX_MATERIALS);
+    if(use_device(w)) return FSS_ERR_CUDA;
+    int fire_id = -1;
+    DMat tmp[FSS_MAX_MATERIALS];
+    memset(tmp, 0, sizeof tmp);
+    for(int i = 0; i < n; i++) {
+        const fss_material& m = t[i];
+        DMat& d = tmp[i];
+        if(m.physics_type < 0 || m.physics_type > FSS_PHYS_PASSABLE) return fail(FSS_ERR_INVALID, "material %d: physics type %d", i, m.physics_type);
+        if(m.physics_type == FSS_PHYS_SAND && (m.slipperyness < 1 || m.slipperyness > 0xFFFF))
+            return fail(FSS_ERR_INVALID, "material %d: SAND needs 1 <= slipperyness <= 65535 (rand() %% (2*slip), world.cpp:1736)", i);
+        if((m.flags & FSS_MAT_IS_FIRE) && m.physics_type != FSS_PHYS_PASSABLE)
+            return fail(FSS_ERR_INVALID, "material %d: the fire material must be PASSABLE like Materials::FIRE (Materials.cpp:42)", i);
+        if(m.n_reactions < 0 || m.n_reactions > FSS_MAX_REACTIONS) return fail(FSS_ERR_INVALID, "material %d: %d reactions", i, m.n_reactions);
+        if(m.create_kind == FSS_CREATE_RAND && m.create_rand_mod == 0) return fail(FSS_ERR_INVALID, "material %d: create_rand_mod == 0", i);
+        if(m.create_kind == FSS_CREATE_TEXTURE && m.create_texture >= FSS_MAX_TEXTURES) return fail(FSS_ERR_INVALID, "material %d: texture %d", i, m.create_texture);
+        d.density = m.density;
+        const int iters = m.iterations < 0 ? 0 : (m.iterations > 7 ? 7 : m.iterations); // iter < 6 always: clamping is exact
+        d.bits = ((uint32_t)m.physics_type << MF_TYPE_SHIFT) | ((uint32_t)iters << MF_ITERS_SHIFT) | ((m.flags & FSS_MAT_IS_FIRE) ? MF_FIRE : 0u);
+        d.flags = m.flags;
+        d.slip = m.slipperyness;
+        // `int maxStability = 8 / sqrt(slipperyness) + 1;` world.cpp:1710: double arithmetic, truncated
+        d.max_stability = m.slipperyness > 0 ? (int)(8 / sqrt((double)m.slipperyness) + 1) : 255;
+        d.n_react = m.n_reactions;
+        for(int r = 0; r < m.n_reactions; r++) {
+            if(m.reactions[r].data2 < 0 || m.reactions[r].data2 >= n) return fail(FSS_ERR_INVALID, "material %d: reaction target %d", i, m.reactions[r].data2);
+            d.r_type[r] = m.reactions[r].type;
+            d.r_thr[r] = m.reactions[r].data1;
+            d.r_target[r] = m.reactions[r].data2;
+        }
+        d.create_kind = m.create_kind;
+        d.create_base = m.create_base;
+        d.create_mod = m.create_rand_mod;
+        d.create_shift = m.create_rand_shift;
+        d.create_site = m.create_rand_site;
+        d.create_tex = m.create_texture;
+        d.create_temp = m.create_temperature;
+        d.add_temp = m.add_temp;
+        d.cond_self = m.conduction_self;
+        d.cond_other = m.conduction_other;
+        if((m.flags & FSS_MAT_IS_FIRE) && fire_id < 0) fire_id = i;
+    }
+    if(w->cfg.condense_material >= n) return fail(FSS_ERR_INVALID, "condense_material %d >= %d materials", w->cfg.condense_material, n);
+    memcpy(w->h_mats, tmp, sizeof tmp);
+    w->n_mat = n;
+    w->fire_id = fire_id;
+    w->nothing_mf = 0u | tmp[0].bits;
+    CU(cudaMemcpyAsync(w->d_mats, w->h_mats, sizeof(DMat) * FSS_MAX_MATERIALS, cudaMemcpyHostToDevice, w->stream));
+    k_rederive<<<148 * 8, 256, 0, w->stream>>>(w->g, w->d_mats, n, plane_cells(w));
+    w->stats.kernel_launches++;
+    CU(cudaStreamSynchronize(w->stream)); // h_mats may be rewritten by the next call
+    w->mats_set = true;
+    return FSS_OK;
+}
+
+int fss_set_texture(fss_world* w, int index, const uint32_t* argb, int tw, int th) {
+    if(!w || !argb) return fail(FSS_ERR_INVALID, "null argument");
+    if(index < 0 || index >= FSS_MAX_TEXTURES || tw < 1 || th < 1) return fail(FSS_ERR_INVALID, "texture %d (%dx%d)", index, tw, th);
+    if(use_device(w)) return FSS_ERR_CUDA;
+    CU(cudaStreamSynchronize(w->stream));
+    cudaFree((void*)w->h_tex[index].px);
+    uint32_t* d = nullptr;
+    CU(cudaMalloc(&d, (size_t)tw * th * 4));
+    CU(cudaMemcpy(d, argb, (size_t)tw * th * 4, cudaMemcpyHostToDevice));
+    w->h_tex[index].px = d;
+    w->h_tex[index].w = tw;
+    w->h_tex[index].h = th;
+    CU(cudaMemcpy(w->d_tex, w->h_tex, sizeof(DTex) * FSS_MAX_TEXTURES, cudaMemcpyHostToDevice));
+    return FSS_OK;
+}
+
+int fss_set_tick_zone(fss_world* w, int x, int y, int zw, int zh) {
+    if(!w) return fail(FSS_ERR_INVALID, "null world");
+    if(x % FSS_ZONE_ALIGN_X || zw % FSS_ZONE_ALIGN_X || zh % FSS_ZONE_ALIGN_Y || zw <= 0 || zh <= 0)
+        return fail(FSS_ERR_ALIGN, "tick zone (%d,%d,%d,%d): x and width must be multiples of %d, height of %d", x, y, zw, zh, FSS_ZONE_ALIGN_X, FSS_ZONE_ALIGN_Y);
+    if(x < FSS_ZONE_MARGIN || y < FSS_ZONE_MARGIN || x + zw > (int)w->cfg.width - FSS_ZONE_MARGIN || y + zh > (int)w->cfg.height - FSS_ZONE_MARGIN)
+        return fail(FSS_ERR_ALIGN, "tick zone (%d,%d,%d,%d) must stay %d cells inside the %ux%u world", x, y, zw, zh, FSS_ZONE_MARGIN, w->cfg.width, w->cfg.height);
+    if(w->sharded) {
+        // interior strip boundaries must fall on the phase pattern (multiples of 2*CHUNK_H from the zone origin)
+        const bool first = w->own_lo == 0, last = w->own_hi == (int)w->cfg.height;
+        if(!first && ((w->own_lo - y) % FSS_ZONE_ALIGN_Y || w->own_lo < y || w->own_lo > y + zh))
+            return fail(FSS_ERR_ALIGN, "strip start %d is not zone.y + k*%d inside the zone", w->own_lo, FSS_ZONE_ALIGN_Y);
+        if(!last && ((w->own_hi - y) % FSS_ZONE_ALIGN_Y || w->own_hi < y || w->own_hi > y + zh))
+            return fail(FSS_ERR_ALIGN, "strip end %d is not zone.y + k*%d inside the zone", w->own_hi, FSS_ZONE_ALIGN_Y);
+    }
+    w->zx = x;
+    w->zy = y;
+    w->zw = zw;
+    w->zh = zh;
+    w->zone_set = true;
+    return FSS_OK;
+}
+
+// ---- host mirror <-> device ------------------------------------------------------------------------------
+static int rect_clip(fss_world* w, int& x, int& y, int& rw, int& rh, size_t& skip_rows) {
+    if(rw <= 0 || rh <= 0 || x < 0 || y < 0 || (uint32_t)(x + rw) > w->cfg.width || (uint32_t)(y + rh) > w->cfg.height)
+        return fail(FSS_ERR_RANGE, "rectangle (%d,%d,%d,%d) outside the %ux%u world", x, y, rw, rh, w->cfg.width, w->cfg.height);
+    const int lo = std::max(y, w->g.sy0), hi = std::min(y + rh, w->g.sy0 + w->g.rows);
+    if(lo >= hi) return fail(FSS_ERR_RANGE, "rows [%d,%d) are not stored by this strip [%d,%d)", y, y + rh, w->g.sy0, w->g.sy0 + w->g.rows);
+    skip_rows = (size_t)(lo - y);
+    y = lo;
+    rh = hi - lo;
+    return FSS_OK;
+}
+
+static int rect_copy(fss_world* w, int x, int y, int rw, int rh, fss_cell* host, size_t pitch_cells, bool upload) {
+    if(!w || !host) return fail(FSS_ERR_INVALID, "null argument");
+    if(upload && !w->mats_set) return fail(FSS_ERR_STATE, "fss_upload_rect before fss_set_materials");
+    if(pitch_cells < (size_t)rw) return fail(FSS_ERR_INVALID, "pitch %zu < width %d", pitch_cells, rw);
+    if(use_device(w)) return FSS_ERR_CUDA;
+    size_t skip = 0;
+    int rc = rect_clip(w, x, y, rw, rh, skip);
+    if(rc) return rc;
+    host += skip * pitch_cells;
+    const int rows_per_pass = (int)std::max<size_t>(1, w->stage_bytes / ((size_t)rw * sizeof(fss_cell)));
+    const int nblk = ((x + rw - 1) >> 8) - (x >> 8) + 1;
+    for(int r0 = 0; r0 < rh; r0 += rows_per_pass) {
+        const int nr = std::min(rows_per_pass, rh - r0);
+        RectParams p;
+        p.g = w->g;
+        p.mats = w->d_mats;
+        p.n_mat = w->n_mat;
+        p.aos = (uint32_t*)w->d_stage;
+        p.rx = x;
+        p.ry = y + r0;
+        p.rw = rw;
+        p.rh = nr;
+        fss_cell* h = host + (size_t)r0 * pitch_cells;
+        if(upload) {
+            CU(cudaMemcpy2DAsync(w->d_stage, (size_t)rw * sizeof(fss_cell), h, pitch_cells * sizeof(fss_cell), (size_t)rw * sizeof(fss_cell), nr,
+                                 cudaMemcpyHostToDevice, w->stream));
+            k_upload<<<dim3(nblk, nr), 256, 0, w->stream>>>(p);
+        } else {
+            k_download<<<dim3(nblk, nr), 256, 0, w->stream>>>(p);
+            CU(cudaMemcpy2DAsync(h, pitch_cells * sizeof(fss_cell), w->d_stage, (size_t)rw * sizeof(fss_cell), (size_t)rw * sizeof(fss_cell), nr,
+                                 cudaMemcpyDeviceToHost, w->stream));
+        }
+        w->stats.kernel_launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(w->stream)); // the caller owns `host` again when we return
+    return FSS_OK;
+}
+
+int fss_upload_rect(fss_world* w, int x, int y, int width, int height, const fss_cell* host, size_t pitch_cells) {
+    return rect_copy(w, x, y, width, height, (fss_cell*)host, pitch_cells, true);
+}
+int fss_download_rect(fss_world* w, int x, int y, int width, int height, fss_cell* host, size_t pitch_cells) {
+    return rect_copy(w, x, y, width, height, host, pitch_cells, false);
+}
+
+// ---- the hot path -----------------------------------------------------------------------------------------
+static int ready(fss_world* w) {
+    if(!w) return fail(FSS_ERR_INVALID, "null world");
+    if(!w->mats_set) return fail(FSS_ERR_STATE, "call fss_set_materials first");
+    if(!w->zone_set) return fail(FSS_ERR_STATE, "call fss_set_tick_zone first");
+    return use_device(w);
+}
+
+static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk) {
+    // world.cpp:1115-1141: phase tk activates chunks at zone + (tk%2, 1 - tk/2) * chunk + 2*chunk*(i, j)
+    const int ofs_x = tk % 2, ofs_y = 1 - tk / 2;
+    // rows of active chunks owned by this strip (boundaries are multiples of 2*CHUNK_H from zone.y)
+    const int j_lo = w->own_lo <= w->zy ? 0 : (w->own_lo - w->zy) / FSS_ZONE_ALIGN_Y;
+    const int j_hi = w->own_hi >= w->zy + w->zh ? w->zh / FSS_ZONE_ALIGN_Y : (w->own_hi - w->zy) / FSS_ZONE_ALIGN_Y;
+    SubstepParams p;
+    p.g = w->g;
+    p.mats = w->d_mats;
+    p.tex = w->d_tex;
+    p.n_mat = w->n_mat;
+    p.x_begin = w->zx + ofs_x * FSS_CHUNK_W;
+    p.y_begin = w->zy + ofs_y * FSS_CHUNK_H + j_lo * FSS_ZONE_ALIGN_Y;
+    p.nx = w->zw / FSS_ZONE_ALIGN_X;
+    p.ny = j_hi - j_lo;
+    p.tkey = fss_rng_tick_key(w->cfg.seed, tick_ct, (uint32_t)iter);
+    p.iter = iter;
+    p.tick_iter = tick_ct * 8u + (uint32_t)iter;
+    p.flags = w->cfg.flags;
+    p.condense = w->cfg.condense_material;
+    p.fire_id = w->fire_id;
+    p.nothing_mf = w->nothing_mf;
+    p.parts = w->d_parts;
+    p.part_count = w->d_part_count;
+    p.part_cap = w->part_cap;
+    w->stats.substeps++;
+    if(p.ny <= 0 || p.nx <= 0) return FSS_OK;
+    k_substep<<<dim3((p.nx + K1_THREADS - 1) / K1_THREADS, p.ny), K1_THREADS, 0, w->stream>>>(p);
+    w->stats.kernel_launches++;
+    return FSS_OK;
+}
+
+int fss_substep(fss_world* w, uint32_t tick_ct, int iter, int tk) {
+    int rc = ready(w);
+    if(rc) return rc;
+    if(iter < 0 || iter > 5 || tk < 0 || tk > 3) return fail(FSS_ERR_INVALID, "sub-step (iter %d, tk %d)", iter, tk);
+    rc = launch_substep(w, tick_ct, iter, tk);
+    if(rc) return rc;
+    CU(cudaGetLastError());
+    return FSS_OK;
+}
+
+int fss_tick(fss_world* w, uint32_t tick_ct) {
+    int rc = ready(w);
+    if(rc) return rc;
+    if(w->sharded && !w->comm) return fail(FSS_ERR_STATE, "strip-sharded world without communicator: attach one, or drive fss_substep + fss_exchange_halo_peer");
+    for(int iter = 0; iter < 6; iter++) {
+        for(int tk = 0; tk < 4; tk++) {
+            rc = launch_substep(w, tick_ct, iter, tk);
+            if(rc) return rc;
+            if(w->comm && (tk == 1 || tk == 3)) {
+                rc = fss_exchange_halo(w, tk);
+                if(rc) return rc;
+            }
+        }
+    }
+    CU(cudaGetLastError());
+    return FSS_OK;
+}
+
+int fss_tick_temperature(fss_world* w) {
+    int rc = ready(w);
+    if(rc) return rc;
+    TempParams p;
+    p.g = w->g;
+    p.out = w->temp2;
+    p.mats = w->d_mats;
+    p.n_mat = w->n_mat;
+    p.zx = w->zx;
+    p.zy = w->zy;
+    p.zw = w->zw;
+    p.zh = w->zh;
+    p.own_lo = w->own_lo;
+    p.own_hi = w->own_hi;
+    const uint32_t groups = w->g.pitch / 8;
+    k_temperature<<<dim3((groups + TEMP_THREADS - 1) / TEMP_THREADS, (w->g.rows + TEMP_ROWS - 1) / TEMP_ROWS), TEMP_THREADS, 0, w->stream>>>(p);
+    w->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    std::swap(w->g.temp, w->temp2);
+    if(w->comm) return fss_exchange_halo_temperature(w);
+    return FSS_OK;
+}
+
+// ---- side outputs -------------------------------------------------------------------------------------------
+int fss_drain_particles(fss_world* w, fss_particle_spawn* out, size_t cap, size_t* n_out, size_t* n_total) {
+    if(!w || (!out && cap)) return fail(FSS_ERR_INVALID, "null argument");
+    if(use_device(w)) return FSS_ERR_CUDA;
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, w->d_part_count, 8, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    const size_t kept = (size_t)std::min<unsigned long long>(total, w->part_cap);
+    std::vector<fss_particle_spawn> v(kept);
+    if(kept) CU(cudaMemcpy(v.data(), w->d_parts, kept * sizeof(fss_particle_spawn), cudaMemcpyDeviceToHost));
+    CU(cudaMemsetAsync(w->d_part_count, 0, 8, w->stream));
+    std::sort(v.begin(), v.end(), [](const fss_particle_spawn& a, const fss_particle_spawn& b) {
+        if(a.tick_iter != b.tick_iter) return a.tick_iter < b.tick_iter;
+        if(a.y != b.y) return a.y < b.y;
+        if(a.x != b.x) return a.x < b.x;
+        return a.site < b.site;
+    });
+    const size_t n = std::min(kept, cap);
+    if(n) memcpy(out, v.data(), n * sizeof(fss_particle_spawn));
+    if(n_out) *n_out = n;
+    if(n_total) *n_total = (size_t)total;
+    if(total > kept || kept > cap) return fail(FSS_ERR_RANGE, "%llu spawn records produced, %zu kept, %zu returned", total, kept, n);
+    return FSS_OK;
+}
+
+static int reduce_params(fss_world* w, ReduceParams& p, int n_materials) {
+    if(use_device(w)) return FSS_ERR_CUDA;
+    p.g = w->g;
+    p.width = w->cfg.width;
+    p.own_lo = w->own_lo;
+    p.own_hi = w->own_hi;
+    p.n_mat = n_materials;
+    p.out_u64 = w->d_red;
+    p.out_f64 = nullptr;
+    p.mats = w->d_mats;
+    CU(cudaMemsetAsync(w->d_red, 0, FSS_MAX_MATERIALS * 16, w->stream));
+    return FSS_OK;
+}
+
+int fss_hash(fss_world* w, uint64_t* digest) {
+    if(!w || !digest) return fail(FSS_ERR_INVALID, "null argument");
+    ReduceParams p;
+    int rc = reduce_params(w, p, 0);
+    if(rc) return rc;
+    k_hash<<<148 * 8, 256, 0, w->stream>>>(p);
+    w->stats.kernel_launches++;
+    CU(cudaMemcpyAsync(digest, w->d_red, 8, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return FSS_OK;
+}
+
+int fss_histogram(fss_world* w, uint64_t* counts, int n_materials) {
+    if(!w || !counts || n_materials < 1 || n_materials > FSS_MAX_MATERIALS) return fail(FSS_ERR_INVALID, "bad argument");
+    ReduceParams p;
+    int rc = reduce_params(w, p, n_materials);
+    if(rc) return rc;
+    k_histogram<<<148 * 16, 256, 0, w->stream>>>(p);
+    w->stats.kernel_launches++;
+    CU(cudaMemcpyAsync(counts, w->d_red, 8 * (size_t)n_materials, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return FSS_OK;
+}
+
+int fss_fluid_totals(fss_world* w, double* totals, int n_materials) {
+    if(!w || !totals || n_materials < 1 || n_materials > FSS_MAX_MATERIALS) return fail(FSS_ERR_INVALID, "bad argument");
+    ReduceParams p;
+    int rc = reduce_params(w, p, n_materials);
+    if(rc) return rc;
+    p.out_f64 = (double*)(w->d_red + FSS_MAX_MATERIALS);
+    k_histogram<<<148 * 16, 256, 0, w->stream>>>(p);
+    w->stats.kernel_launches++;
+    CU(cudaMemcpyAsync(totals, p.out_f64, 8 * (size_t)n_materials, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return FSS_OK;
+}
+
+int fss_fill_synthetic(fss_world* w, const fss_fill_spec* spec) {
+    if(!w || !spec) return fail(FSS_ERR_INVALID, "null argument");
+    if(!w->mats_set) return fail(FSS_ERR_STATE, "fss_fill_synthetic before fss_set_materials");
+    if(spec->n_entries < 0 || spec->n_entries > 16 || spec->n_boxes < 0 || spec->n_boxes > 256) return fail(FSS_ERR_INVALID, "bad fill spec");
+    if(use_device(w)) return FSS_ERR_CUDA;
+    FillParams p;
+    p.g = w->g;
+    p.mats = w->d_mats;
+    p.tex = w->d_tex;
+    p.n_mat = w->n_mat;
+    p.width = w->cfg.width;
+    p.height = w->cfg.height;
+    p.spec = *spec;
+    k_fill<<<dim3(w->g.pitch / 256, w->g.rows), 256, 0, w->stream>>>(p);
+    w->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(w->temp2, w->g.temp, plane_cells(w) * 4, cudaMemcpyDeviceToDevice, w->stream));
+    return FSS_OK;
+}
+
+int fss_get_stats(fss_world* w, fss_stats* out) {
+    if(!w || !out) return fail(FSS_ERR_INVALID, "null argument");
+    *out = w->stats;
+    return FSS_OK;
+}
+
+// ---- row-strip sharding --------------------------------------------------------------------------------
+// Boundary B between an upper strip (rows < B) and the lower strip (rows >= B); B = zone.y + k*32.
+//   after tk 0,1 (the chunk row just above B was active: it wrote rows B, B+1 and changed B-2, B-1)
+//        upper -> lower : rows [B-2, B+2)
+//   after tk 2,3 (the chunk row just below B was active: it wrote rows B-2, B-1 and changed [B, B+18))
+//        lower -> upper : rows [B-2, B+10)   (10 = pillar probe depth, world.cpp:1700-1702)
+static const int DOWN_LO = -2, DOWN_HI = 2, UP_LO = -2, UP_HI = 10;
+
+static void plane_ptrs(fss_world* w, void* ptr[5]) {
+    ptr[0] = w->g.mf;
+    ptr[1] = w->g.col;
+    ptr[2] = w->g.temp;
+    ptr[3] = w->g.amt;
+    ptr[4] = w->g.dif;
+}
+
+int fss_exchange_halo_peer(fss_world* upper, fss_world* lower, int tk) {
+    if(!upper || !lower) return fail(FSS_ERR_INVALID, "null world");
+    if(upper->own_hi != lower->own_lo || upper->g.pitch != lower->g.pitch) return fail(FSS_ERR_INVALID, "worlds are not adjacent strips");
+    if(tk != 1 && tk != 3) return FSS_OK;
+    const int B = upper->own_hi;
+    fss_world* src = tk == 1 ? upper : lower;
+    fss_world* dst = tk == 1 ? lower : upper;
+    const int lo = B + (tk == 1 ? DOWN_LO : UP_LO), hi = B + (tk == 1 ? DOWN_HI : UP_HI);
+    void *ps[5], *pd[5];
+    plane_ptrs(src, ps);
+    plane_ptrs(dst, pd);
+    // order the copy after the producer's sub-step and before the consumer's next one
+    cudaEvent_t ev;
+    CU(cudaSetDevice(src->device));
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, src->stream));
+    CU(cudaSetDevice(dst->device));
+    CU(cudaStreamWaitEvent(dst->stream, ev, 0));
+    for(int k = 0; k < 5; k++) {
+        const char* s = (const char*)ps[k] + (size_t)(lo - src->g.sy0) * src->g.pitch * 4;
+        char* d = (char*)pd[k] + (size_t)(lo - dst->g.sy0) * dst->g.pitch * 4;
+        CU(cudaMemcpyPeerAsync(d, dst->device, s, src->device, (size_t)(hi - lo) * src->g.pitch * 4, dst->stream));
+    }
+    CU(cudaEventRecord(ev, dst->stream));
+    CU(cudaSetDevice(src->device));
+    CU(cudaStreamWaitEvent(src->stream, ev, 0)); // the source must not overwrite the rows while they are copied
+    CU(cudaEventDestroy(ev));
+    return FSS_OK;
+}
+
+int fss_exchange_halo_temperature_peer(fss_world* upper, fss_world* lower) {
+    if(!upper || !lower) return fail(FSS_ERR_INVALID, "null world");
+    if(upper->own_hi != lower->own_lo || upper->g.pitch != lower->g.pitch) return fail(FSS_ERR_INVALID, "worlds are not adjacent strips");
+    const int B = upper->own_hi;
+    CU(cudaSetDevice(upper->device));
+    CU(cudaStreamSynchronize(upper->stream));
+    CU(cudaSetDevice(lower->device));
+    CU(cudaStreamSynchronize(lower->stream));
+    const size_t rowb = (size_t)upper->g.pitch * 4;
+    // upper's rows [B-FSS_HALO_ROWS, B) -> lower's ghost; lower's rows [B, B+FSS_HALO_ROWS) -> upper's ghost
+    CU(cudaMemcpyPeer((char*)lower->g.temp + (size_t)(B - FSS_HALO_ROWS - lower->g.sy0) * rowb, lower->device,
+                      (char*)upper->g.temp + (size_t)(B - FSS_HALO_ROWS - upper->g.sy0) * rowb, upper->device, FSS_HALO_ROWS * rowb));
+    CU(cudaMemcpyPeer((char*)upper->g.temp + (size_t)(B - upper->g.sy0) * rowb, upper->device,
+                      (char*)lower->g.temp + (size_t)(B - lower->g.sy0) * rowb, lower->device, FSS_HALO_ROWS * rowb));
+    return FSS_OK;
+}
+
+int fss_comm_unique_id(void* id128) {
+    if(!id128) return fail(FSS_ERR_INVALID, "null argument");
+    int rc = nccl_bind();
+    if(rc) return rc;
+    NC(g_nccl.get_unique_id((NcclId*)id128));
+    return FSS_OK;
+}
+
+int fss_comm_attach(fss_world* w, const void* id128, int rank, int n_ranks) {
+    if(!w || !id128 || rank < 0 || rank >= n_ranks) return fail(FSS_ERR_INVALID, "bad argument");
+    int rc = nccl_bind();
+    if(rc) return rc;
+    if(use_device(w)) return FSS_ERR_CUDA;
+    NcclId id;
+    memcpy(&id, id128, sizeof id);
+    NC(g_nccl.comm_init_rank(&w->comm, n_ranks, id, rank));
+    w->rank = rank;
+    w->n_ranks = n_ranks;
+    return FSS_OK;
+}
+
+static int nccl_rows(fss_world* w, bool send, int peer, int lo, int hi, bool temp_only) {
+    void* ptr[5];
+    plane_ptrs(w, ptr);
+    const size_t count = (size_t)(hi - lo) * w->g.pitch;
+    for(int k = 0; k < 5; k++) {
+        if(temp_only && k != 2) continue;
+        char* a = (char*)ptr[k] + (size_t)(lo - w->g.sy0) * w->g.pitch * 4;
+        if(send) NC(g_nccl.send(a, count, NCCL_UINT32, peer, w->comm, w->stream));
+        else NC(g_nccl.recv(a, count, NCCL_UINT32, peer, w->comm, w->stream));
+    }
+    return FSS_OK;
+}
+
+int fss_exchange_halo(fss_world* w, int tk) {
+    if(!w) return fail(FSS_ERR_INVALID, "null world");
+    if(!w->comm) return fail(FSS_ERR_STATE, "no communicator attached");
+    if(tk != 1 && tk != 3) return FSS_OK;
+    if(use_device(w)) return FSS_ERR_CUDA;
+    const bool has_upper = w->rank > 0, has_lower = w->rank + 1 < w->n_ranks;
+    int rc = FSS_OK;
+    NC(g_nccl.group_start());
+    if(tk == 1) { // data flows down
+        if(has_lower) rc = nccl_rows(w, true, w->rank + 1, w->own_hi + DOWN_LO, w->own_hi + DOWN_HI, false);
+        if(!rc && has_upper) rc = nccl_rows(w, false, w->rank - 1, w->own_lo + DOWN_LO, w->own_lo + DOWN_HI, false);
+    } else { // data flows up
+        if(has_upper) rc = nccl_rows(w, true, w->rank - 1, w->own_lo + UP_LO, w->own_lo + UP_HI, false);
+        if(!rc && has_lower) rc = nccl_rows(w, false, w->rank + 1, w->own_hi + UP_LO, w->own_hi + UP_HI, false);
+    }
+    NC(g_nccl.group_end());
+    w->stats.kernel_launches++; // one fused NCCL send/recv kernel per group
+    return rc;
+}
+
+int fss_exchange_halo_temperature(fss_world* w) {
+    if(!w) return fail(FSS_ERR_INVALID, "null world");
+    if(!w->comm) return fail(FSS_ERR_STATE, "no communicator attached");
+    if(use_device(w)) return FSS_ERR_CUDA;
+    const bool has_upper = w->rank > 0, has_lower = w->rank + 1 < w->n_ranks;
+    int rc = FSS_OK;
+    NC(g_nccl.group_start());
+    if(has_lower) {
+        rc = nccl_rows(w, true, w->rank + 1, w->own_hi - FSS_HALO_ROWS, w->own_hi, true);
+        if(!rc) rc = nccl_rows(w, false, w->rank + 1, w->own_hi, w->own_hi + FSS_HALO_ROWS, true);
+    }
+    if(!rc && has_upper) {
+        rc = nccl_rows(w, true, w->rank - 1, w->own_lo, w->own_lo + FSS_HALO_ROWS, true);
+        if(!rc) rc = nccl_rows(w, false, w->rank - 1, w->own_lo - FSS_HALO_ROWS, w->own_lo, true);
+    }
+    NC(g_nccl.group_end());
+    w->stats.kernel_launches++;
+    return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,351 @@
+// fss_kernels.cuh -- the CUDA kernels of the falling-sand core (sm_100a).
+//   k_substep       K1  one (iter, tk) checkerboard sub-step of World::tick        world.cpp:1108-2011
+//   k_temperature   K2  World::tickTemperature as a register-tiled 9-point stencil  world.cpp:2043-2143
+//   k_upload / k_download   host exchange format (fss_cell, 20 B AoS) <-> permuted SoA planes
+//   k_fill          synthetic worlds generated on the device
+//   k_rederive / k_hash / k_histogram / k_fluid_totals   bookkeeping
+#pragma once
+#include "fss_rules.cuh"
+
+#define K1_THREADS 128
+
+// ---- K1: movement sub-step ---------------------------------------------------------------------------
+// grid = (ceil(nx / 128), ny); thread (bx*128 + t, by) owns the micro-chunk at
+// (x_begin + 8*(bx*128+t), y_begin + 32*by).  A warp therefore owns 32 micro-chunks that are 8 columns
+// apart: with the permuted layout its lanes read consecutive words.
+__global__ void __launch_bounds__(K1_THREADS) k_substep(const __grid_constant__ SubstepParams p) {
+    __shared__ float sden[FSS_MAX_MATERIALS];
+    __shared__ uint32_t sinfo[FSS_MAX_MATERIALS];
+    for(int m = threadIdx.x; m < p.n_mat; m += K1_THREADS) {
+        sden[m] = p.mats[m].density;
+        const DMat& d = p.mats[m];
+        uint32_t stab = d.max_stability > 255 ? 255u : (uint32_t)d.max_stability;
+        sinfo[m] = ((uint32_t)d.slip & 0xFFFFu) | (stab << 16) | (((uint32_t)d.n_react & 3u) << 24) |
+                   ((d.flags & FSS_MAT_IS_STEAM) ? HI_STEAM : 0u);
+    }
+    __syncthreads();
+    const int gi = blockIdx.x * K1_THREADS + threadIdx.x;
+    if(gi >= p.nx) return;
+    ChunkWalk w(p, sden, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y);
+    w.run();
+}
+
+// ---- K2: temperature stencil ---------------------------------------------------------------------------
+// One thread owns the 8 consecutive columns of one "group" (x >> 3) and walks TEMP_ROWS stored rows
+// top-down, keeping the conduction terms of rows y-1, y, y+1 (10 columns each: the group plus one column
+// either side) in registers.  Lanes of a warp own consecutive groups, so each of a thread's 8 (+2) loads per
+// row and plane is one fully used 128-byte line per warp.  The per-neighbour terms
+//   factor = abs(T)/64.0f * conductionOther;  v += T*factor;  n += factor      (world.cpp:2072-2116)
+// depend only on the neighbour, so they are computed once per loaded cell; a cell with T == 0 contributes
+// (+0.0f, +0.0f), which leaves the fp32 running sums bit-identical to the reference's `if(T != 0)` skip.
+// Output goes to the second temperature plane (Jacobi); cells outside tickZone are copied.
+#define TEMP_ROWS 32
+#define TEMP_THREADS 128
+
+struct TempParams {
+    Grid g;
+    int32_t* out;
+    const DMat* mats;
+    int n_mat;
+    int zx, zy, zw, zh;
+    int own_lo, own_hi; // global rows this world computes (owned rows); other stored rows are copied
+};
+
+struct TempRow {
+    float f[10], tf[10];
+};
+
+__device__ __forceinline__ void temp_load_row(const TempParams& p, const float* s_co, size_t rowbase, const uint32_t* col_ofs,
+                                              TempRow& r, int32_t* tc, uint32_t* mc) {
+#pragma unroll
+    for(int c = 0; c < 10; c++) {
+        const size_t i = rowbase + col_ofs[c];
+        const int32_t t = p.g.temp[i];
+        const uint32_t m = mf_mat(p.g.mf[i]);
+        float f = 0.0f, tf = 0.0f;
+        if(t != 0) {
+            f = abs(t) / 64.0f * s_co[m];
+            tf = t * f;
+        }
+        r.f[c] = f;
+        r.tf[c] = tf;
+        if(c >= 1 && c <= 8) {
+            tc[c - 1] = t;
+            mc[c - 1] = m;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TEMP_THREADS) k_temperature(const __grid_constant__ TempParams p) {
+    __shared__ float s_co[FSS_MAX_MATERIALS], s_cs[FSS_MAX_MATERIALS];
+    __shared__ uint32_t s_add[FSS_MAX_MATERIALS];
+    for(int m = threadIdx.x; m < p.n_mat; m += TEMP_THREADS) {
+        s_co[m] = p.mats[m].cond_other;
+        s_cs[m] = p.mats[m].cond_self;
+        s_add[m] = p.mats[m].add_temp;
+    }
+    __syncthreads();
+    const uint32_t grp = blockIdx.x * TEMP_THREADS + threadIdx.x;
+    if(grp >= p.g.pitch / 8) return;
+    const int x0 = (int)grp * 8;
+    const int sr0 = blockIdx.y * TEMP_ROWS;
+    const int sr1 = min(sr0 + TEMP_ROWS, p.g.rows);
+    const size_t pitch = p.g.pitch;
+    const uint32_t base = (grp >> 5) * 256u + (grp & 31u);
+    const bool in_zone_x = x0 >= p.zx && x0 + 8 <= p.zx + p.zw;
+    const int y_lo = max(p.zy, p.own_lo), y_hi = min(p.zy + p.zh, p.own_hi);
+
+    uint32_t col_ofs[10];
+#pragma unroll
+    for(int c = 0; c < 10; c++) col_ofs[c] = fss_perm((uint32_t)(x0 - 1 + c));
+
+    TempRow A, B, C;
+    int32_t tb[8], tcn[8];
+    uint32_t mb[8], mcn[8];
+    bool window = false; // A, B (and tb, mb) hold rows y-1, y
+#pragma unroll 1
+    for(int sr = sr0; sr < sr1; sr++) {
+        const int y = p.g.sy0 + sr;
+        const size_t rowbase = (size_t)sr * pitch;
+        if(!(in_zone_x && y >= y_lo && y < y_hi)) {
+#pragma unroll
+            for(int r = 0; r < 8; r++) p.out[rowbase + base + r * 32] = p.g.temp[rowbase + base + r * 32];
+            window = false;
+            continue;
+        }
+        if(!window) {
+            temp_load_row(p, s_co, rowbase - pitch, col_ofs, A, tcn, mcn);
+            temp_load_row(p, s_co, rowbase, col_ofs, B, tb, mb);
+            window = true;
+        }
+        temp_load_row(p, s_co, rowbase + pitch, col_ofs, C, tcn, mcn);
+#pragma unroll
+        for(int r = 0; r < 8; r++) {
+            // neighbour order of world.cpp:2072-2116: x offset -1, 0, +1 outer; y offset -1, 0, +1 inner
+            float n = 0.01f, v = 0.0f;
+#pragma unroll
+            for(int c = r; c < r + 3; c++) {
+                v += A.tf[c];
+                n += A.f[c];
+                v += B.tf[c];
+                n += B.f[c];
+                v += C.tf[c];
+                n += C.f[c];
+            }
+            const float cs = s_cs[mb[r]];
+            const uint32_t add = s_add[mb[r]];
+            int32_t o;
+            if(v != 0) { // :2128-2132; addTemp is Uint32 (Material.hpp:40)
+                o = (int32_t)(add + (v / n * cs) + (tb[r] * (1 - cs)));
+            } else {
+                o = (int32_t)(add + (uint32_t)tb[r]);
+            }
+            p.out[rowbase + base + r * 32] = o;
+        }
+        A = B;
+        B = C;
+#pragma unroll
+        for(int r = 0; r < 8; r++) {
+            tb[r] = tcn[r];
+            mb[r] = mcn[r];
+        }
+    }
+}
+
+// ---- host exchange format <-> planes ---------------------------------------------------------------------
+// One CTA converts one row of one aligned 256-column block.  The AoS side is read / written as a
+// contiguous run of words through shared memory, the plane side in permuted order: both coalesced.
+struct RectParams {
+    Grid g;
+    const DMat* mats;
+    int n_mat;
+    uint32_t* aos; // rw * rh cells of 5 words, row-major, packed
+    int rx, ry, rw, rh; // rectangle in global cell coordinates (already clipped to storage)
+};
+
+__global__ void __launch_bounds__(256) k_upload(const __grid_constant__ RectParams p) {
+    __shared__ uint32_t sw[256 * 5];
+    const int xb = (p.rx & ~255) + 256 * (int)blockIdx.x;
+    const int xs = max(xb, p.rx), xe = min(xb + 256, p.rx + p.rw);
+    const int row = blockIdx.y;
+    const int n = (xe - xs) * 5;
+    const uint32_t* src = p.aos + ((size_t)row * p.rw + (xs - p.rx)) * 5;
+    for(int k = threadIdx.x; k < n; k += 256) sw[k] = src[k];
+    __syncthreads();
+    const int x = xb + (int)fss_unperm(threadIdx.x);
+    if(x < xs || x >= xe) return;
+    const uint32_t* c = sw + (x - xs) * 5;
+    const size_t i = p.g.idx(x, p.ry + row);
+    const uint32_t w0 = c[0];
+    uint32_t mat = w0 & 0xFFFFu;
+    if((int)mat >= p.n_mat) mat = 0; // unknown material ids become Tiles::NOTHING's material
+    p.g.mf[i] = mf_pack(mat, (w0 >> 16) & 0xFFu, w0 >> 24, p.mats[mat].bits);
+    p.g.col[i] = c[1];
+    p.g.temp[i] = (int32_t)c[2];
+    p.g.amt[i] = __uint_as_float(c[3]);
+    p.g.dif[i] = __uint_as_float(c[4]);
+}
+
+__global__ void __launch_bounds__(256) k_download(const __grid_constant__ RectParams p) {
+    __shared__ uint32_t sw[256 * 5];
+    const int xb = (p.rx & ~255) + 256 * (int)blockIdx.x;
+    const int xs = max(xb, p.rx), xe = min(xb + 256, p.rx + p.rw);
+    const int row = blockIdx.y;
+    const int x = xb + (int)fss_unperm(threadIdx.x);
+    if(x >= xs && x < xe) {
+        uint32_t* c = sw + (x - xs) * 5;
+        const size_t i = p.g.idx(x, p.ry + row);
+        const uint32_t mf = p.g.mf[i];
+        c[0] = (mf & MF_MAT_MASK) | ((mf & MF_MOVED) ? 0x10000u : 0u) | (mf & 0xFF000000u);
+        c[1] = p.g.col[i];
+        c[2] = (uint32_t)p.g.temp[i];
+        c[3] = __float_as_uint(p.g.amt[i]);
+        c[4] = __float_as_uint(p.g.dif[i]);
+    }
+    __syncthreads();
+    const int n = (xe - xs) * 5;
+    uint32_t* dst = p.aos + ((size_t)row * p.rw + (xs - p.rx)) * 5;
+    for(int k = threadIdx.x; k < n; k += 256) dst[k] = sw[k];
+}
+
+// material table changed: refresh the cached type / iterations / fire bits of every stored cell
+__global__ void k_rederive(Grid g, const DMat* mats, int n_mat, size_t n) {
+    for(size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t mf = g.mf[i];
+        uint32_t mat = mf_mat(mf);
+        if((int)mat >= n_mat) mat = 0;
+        g.mf[i] = (mf & ~(MF_DERIVED_MASK | MF_MAT_MASK)) | mat | mats[mat].bits;
+    }
+}
+
+// ---- synthetic worlds (same definition as fallingsandsurvival_b200/worlds.py) -------------------------------
+struct FillParams {
+    Grid g;
+    const DMat* mats;
+    const DTex* tex;
+    int n_mat;
+    uint32_t width, height; // global
+    fss_fill_spec spec;
+};
+
+__device__ __forceinline__ bool fill_in_box(const fss_fill_spec& s, uint32_t width, uint32_t height, uint32_t x, uint32_t y) {
+    // box b has its corner at a position hashed from (seed, b), snapped to 32 cells
+    for(int b = 0; b < s.n_boxes; b++) {
+        const uint32_t h1 = fss_fmix32(s.seed ^ (0xB0C5u + 2u * (uint32_t)b));
+        const uint32_t h2 = fss_fmix32(s.seed ^ (0xB0C6u + 2u * (uint32_t)b) ^ 0x5bd1e995u);
+        const uint32_t span_x = width > s.box_size + 2 * s.border ? width - s.box_size - 2 * s.border : 1u;
+        const uint32_t span_y = height > s.box_size + 2 * s.border ? height - s.box_size - 2 * s.border : 1u;
+        const uint32_t bx = s.border + ((h1 % span_x) & ~31u), by = s.border + ((h2 % span_y) & ~31u);
+        if(x - bx < s.box_size && y - by < s.box_size) return true;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(256) k_fill(const __grid_constant__ FillParams p) {
+    const uint32_t pcol = blockIdx.x * 256u + threadIdx.x; // stored (permuted) column
+    const uint32_t sr = blockIdx.y;
+    if(pcol >= p.g.pitch) return;
+    const uint32_t x = fss_unperm(pcol), y = (uint32_t)p.g.sy0 + sr;
+    const size_t i = (size_t)sr * p.g.pitch + pcol;
+    const fss_fill_spec& s = p.spec;
+    int mat = 0;
+    const uint32_t key = fss_rng_cell_key(s.seed, x, y);
+    if(x < p.width) {
+        if(x < s.border || y < s.border || x >= p.width - s.border || y >= p.height - s.border) {
+            mat = s.border_material;
+        } else if(s.solid_from_row && y >= s.solid_from_row) {
+            mat = s.solid_material;
+        } else {
+            const uint32_t r = key % 100u;
+            if(s.n_boxes == 0 || fill_in_box(s, p.width, p.height, x, y)) {
+                for(int e = 0; e < s.n_entries; e++) {
+                    if(r < (uint32_t)s.cumulative_percent[e]) {
+                        mat = s.material[e];
+                        break;
+                    }
+                }
+            } else if((key >> 8) % 1000u < s.sparse_per_mille) {
+                mat = s.sparse_material;
+            }
+        }
+    }
+    if(mat < 0 || mat >= p.n_mat) mat = 0;
+    const DMat& d = p.mats[mat];
+    uint32_t col;
+    if(d.create_kind == FSS_CREATE_RAND) {
+        col = d.create_base + ((fss_rand(key, d.create_site, 0) % d.create_mod) << d.create_shift);
+    } else if(d.create_kind == FSS_CREATE_TEXTURE && d.create_tex >= 0 && p.tex[d.create_tex].px) {
+        const DTex t = p.tex[d.create_tex];
+        col = t.px[(y % t.h) * t.w + (x % t.w)];
+    } else {
+        col = d.create_base;
+    }
+    p.g.mf[i] = (uint32_t)mat | d.bits;
+    p.g.col[i] = col;
+    p.g.temp[i] = d.create_temp;
+    p.g.amt[i] = 2.0f;
+    p.g.dif[i] = 0.0f;
+}
+
+// ---- reductions over the owned rows ---------------------------------------------------------------------
+struct ReduceParams {
+    Grid g;
+    uint32_t width;
+    int own_lo, own_hi; // global rows
+    int n_mat;
+    unsigned long long* out_u64; // hash: [0]; histogram: [n_mat]
+    double* out_f64;             // fluid totals: [n_mat]
+    const DMat* mats;
+};
+
+__global__ void __launch_bounds__(256) k_hash(const __grid_constant__ ReduceParams p) {
+    unsigned long long sum = 0;
+    const size_t rows = (size_t)(p.own_hi - p.own_lo);
+    const size_t n = rows * p.g.pitch;
+    for(size_t k = blockIdx.x * (size_t)256 + threadIdx.x; k < n; k += (size_t)gridDim.x * 256) {
+        const uint32_t pcol = (uint32_t)(k % p.g.pitch);
+        const uint32_t x = fss_unperm(pcol);
+        if(x >= p.width) continue;
+        const int y = p.own_lo + (int)(k / p.g.pitch);
+        const size_t i = (size_t)(y - p.g.sy0) * p.g.pitch + pcol;
+        const uint32_t mf = p.g.mf[i];
+        sum += fss_cell_digest(x, (uint32_t)y, mf & ~MF_DERIVED_MASK, p.g.col[i], (uint32_t)p.g.temp[i], __float_as_uint(p.g.amt[i]),
+                               __float_as_uint(p.g.dif[i]));
+    }
+    for(int o = 16; o; o >>= 1) sum += __shfl_down_sync(0xFFFFFFFFu, sum, o);
+    __shared__ unsigned long long s[8];
+    if((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if(threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for(int q = 0; q < 8; q++) t += s[q];
+        atomicAdd(p.out_u64, t);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_histogram(const __grid_constant__ ReduceParams p) {
+    __shared__ unsigned int h[FSS_MAX_MATERIALS];
+    __shared__ double fl[FSS_MAX_MATERIALS];
+    for(int m = threadIdx.x; m < FSS_MAX_MATERIALS; m += 256) {
+        h[m] = 0;
+        fl[m] = 0.0;
+    }
+    __syncthreads();
+    const size_t rows = (size_t)(p.own_hi - p.own_lo);
+    const size_t n = rows * p.g.pitch;
+    // bounded trip count per block keeps the 32-bit shared counters from overflowing
+    for(size_t k = blockIdx.x * (size_t)256 + threadIdx.x; k < n; k += (size_t)gridDim.x * 256) {
+        const uint32_t pcol = (uint32_t)(k % p.g.pitch);
+        if(fss_unperm(pcol) >= p.width) continue;
+        const size_t i = ((size_t)(p.own_lo - p.g.sy0) + k / p.g.pitch) * p.g.pitch + pcol;
+        const uint32_t mf = p.g.mf[i];
+        const uint32_t m = mf_mat(mf);
+        atomicAdd(&h[m], 1u);
+        if(p.out_f64 && MF_IS(mf, FSS_PHYS_SOUP)) atomicAdd(&fl[m], (double)p.g.amt[i] + (double)p.g.dif[i]);
+    }
+    __syncthreads();
+    for(int m = threadIdx.x; m < p.n_mat; m += 256) {
+        if(h[m]) atomicAdd(&p.out_u64[m], (unsigned long long)h[m]);
+        if(p.out_f64 && fl[m] != 0.0) atomicAdd(&p.out_f64[m], fl[m]);
+    }
+}

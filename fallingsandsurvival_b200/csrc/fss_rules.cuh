@@ -1,0 +1,581 @@
+// fss_rules.cuh -- the movement rules of World::tick as device code.
+//
+// One thread owns one 4x16 micro-chunk of the current checkerboard phase and walks it exactly like
+// the reference walks a chunk (FallingSandSurvival/world.cpp:1154-1974): three sequential scans,
+// rows bottom-up, columns left-to-right.  All 32 lanes of a warp run the scans in lock step (same
+// (dx,dy) at the same time), so with the permuted column layout of fss_device.cuh every global
+// access of the warp falls into one 128-byte line per plane.  Cells are updated in place in HBM
+// (through L1/L2); the checkerboard gap makes the read/write windows of concurrently active
+// micro-chunks disjoint, so no two threads ever touch the same word in one launch.
+//
+// Every rule cites the reference lines it implements.  Copies vs. live reads follow the reference:
+// where the reference works on a by-value copy of a cell (`MaterialInstance tile = tiles[index]`)
+// the register copy is used, where it re-reads the grid the grid is re-read, unless no store of the
+// same cell visit can have changed the value in between.
+#pragma once
+#include "fss_device.cuh"
+
+#define FLUID_MaxValue 0.5f
+#define FLUID_MinValue 0.0005f
+#define FLUID_MaxCompression 0.1f
+#define FLUID_MinFlow 0.05f
+#define FLUID_MaxFlow 8.0f
+#define FLUID_FlowSpeed 1.0f
+
+struct SubstepParams {
+    Grid g;
+    const DMat* mats;
+    const DTex* tex;
+    int n_mat;
+    int x_begin, y_begin; // origin of the first active micro-chunk of this phase
+    int nx, ny;           // active micro-chunks per row / rows of active micro-chunks
+    uint32_t tkey;        // fss_rng_tick_key(seed, tickCt, iter)
+    int iter;
+    uint32_t tick_iter;   // tickCt * 8 + iter (particle records)
+    uint32_t flags;       // FSS_PARTICLES_EMIT
+    int condense;         // material created by condensing steam, -1 = off
+    int fire_id;          // first material flagged FSS_MAT_IS_FIRE, -1 = none
+    uint32_t nothing_mf;  // mf word of Tiles::NOTHING (material 0 + its derived bits)
+    fss_particle_spawn* parts;
+    unsigned long long* part_count;
+    uint32_t part_cap;
+};
+
+__device__ __forceinline__ Cell cell_nothing(uint32_t nothing_mf) {
+    // Tiles::NOTHING, Tiles.cpp:7; fluidAmount keeps the constructor default 2.0f (MaterialInstance.hpp:21)
+    Cell c;
+    c.mf = nothing_mf;
+    c.col = 0u;
+    c.temp = 0;
+    c.amt = 2.0f;
+    c.dif = 0.0f;
+    return c;
+}
+
+// world.cpp:1075-1088
+__device__ __forceinline__ float vertical_flow(float remaining, float dest) {
+    float sum = remaining + dest;
+    float value;
+    if(sum <= FLUID_MaxValue) {
+        value = FLUID_MaxValue;
+    } else if(sum < 2 * FLUID_MaxValue + FLUID_MaxCompression) {
+        value = (FLUID_MaxValue * FLUID_MaxValue + sum * FLUID_MaxCompression) / (FLUID_MaxValue + FLUID_MaxCompression);
+    } else {
+        value = (sum + FLUID_MaxCompression) / 2.0f;
+    }
+    return value;
+}
+
+// `flow = std::max(flow, 0.0f); if(flow > std::min(FLUID_MaxFlow, lim)) flow = std::min(...)`
+__device__ __forceinline__ float clamp_flow(float flow, float lim) {
+    if(flow < 0.0f) flow = 0.0f;
+    float cap = lim < FLUID_MaxFlow ? lim : FLUID_MaxFlow;
+    if(flow > cap) flow = cap;
+    return flow;
+}
+
+// Tiles::create(mat, x, y), Tiles.cpp:190-268, from the table's recipe; k = draws already made at the
+// recipe's RNG site during this cell visit (fss_rng.h)
+__device__ __noinline__ Cell create_cell(const SubstepParams& p, int m, int x, int y, uint32_t key, uint32_t k) {
+    const DMat& d = p.mats[m];
+    Cell c = cell_nothing(0u);
+    c.mf = (uint32_t)m | d.bits;
+    c.temp = d.create_temp;
+    if(d.create_kind == FSS_CREATE_RAND) {
+        c.col = d.create_base + ((fss_rand(key, d.create_site, k) % d.create_mod) << d.create_shift);
+    } else if(d.create_kind == FSS_CREATE_TEXTURE && d.create_tex >= 0 && p.tex[d.create_tex].px) {
+        const DTex t = p.tex[d.create_tex];
+        c.col = t.px[(y % t.h) * t.w + (x % t.w)];
+    } else {
+        c.col = d.create_base;
+    }
+    return c;
+}
+
+// Particle spawn record (world.cpp:1180, :1291, :1366): the cell leaves the grid for the host
+__device__ __noinline__ void emit_particle(const SubstepParams& p, int x, int y, uint32_t site, uint32_t key, Cell c) {
+    unsigned long long slot = atomicAdd(p.part_count, 1ull);
+    if(slot >= p.part_cap) return;
+    fss_particle_spawn* r = &p.parts[slot];
+    r->x = (uint32_t)x;
+    r->y = (uint32_t)y;
+    r->site = site;
+    r->cell_key = key;
+    r->tick_iter = p.tick_iter;
+    r->cell.material = (uint16_t)mf_mat(c.mf);
+    r->cell.moved = (c.mf & MF_MOVED) ? 1 : 0;
+    r->cell.settle_count = (uint8_t)mf_settle(c.mf);
+    r->cell.color = c.col;
+    r->cell.temperature = c.temp;
+    r->cell.fluid_amount = c.amt;
+    r->cell.fluid_amount_diff = c.dif;
+}
+
+// ---- FIRE, world.cpp:1171-1216 (matched by material id; its physics type is PASSABLE) ------------------
+// returns the tickVisited bits to set inside the caller's micro-chunk at (cx, cy)
+__device__ __noinline__ unsigned long long rule_fire(const SubstepParams& p, int cx, int cy, size_t i, int x, int y,
+                                                     unsigned long long bit) {
+    const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
+    unsigned long long vis = 0ull;
+    Cell tile = ld_cell(p.g, i);
+    if(fss_rand(key, 1172, 0) % 10 == 0) { // recolours the local copy only (never stored)
+        tile.col = (((255u << 8) + 100 + fss_rand(key, 1174, 0) % 50) << 8) + 50;
+    }
+    if(fss_rand(key, 1179, 0) % 10 == 0) {
+        if(p.flags & FSS_PARTICLES_EMIT) emit_particle(p, x, y, 1180, key, tile);
+    }
+    if(fss_rand(key, 1191, 0) % 150 == 0) {
+        st_cell(p.g, i, cell_nothing(p.nothing_mf));
+        return bit;
+    }
+    bool found = false;
+    uint32_t k1202 = 0, kcreate = 0;
+    for(int xx = -2; xx <= 2; xx++) {
+        for(int yy = -2; yy <= 2; yy++) {
+            const size_t in = p.g.idx(x + xx, y + yy);
+            if(MF_IS(p.g.mf[in], FSS_PHYS_SOLID)) {
+                found = true;
+                if(fss_rand(key, 1202, k1202++) % 500 == 0) {
+                    st_cell(p.g, in, create_cell(p, p.fire_id, x + xx, y + yy, key, kcreate++)); // Tiles::createFire()
+                    const unsigned dx = (unsigned)(x + xx - cx), dy = (unsigned)(y + yy - cy);
+                    if(dx < (unsigned)FSS_CHUNK_W && dy < (unsigned)FSS_CHUNK_H) vis |= 1ull << (dy * FSS_CHUNK_W + dx);
+                }
+            }
+        }
+    }
+    if(!found && fss_rand(key, 1210, 0) % 120 == 0) {
+        st_cell(p.g, i, cell_nothing(p.nothing_mf));
+        vis |= bit;
+    }
+    return vis;
+}
+
+// ---- SAND reactions, world.cpp:1251-1274 (only SAND evaluates them); true = the cell reacted ----------
+__device__ __noinline__ bool rule_sand_react(const SubstepParams& p, size_t i, int x, int y, uint32_t mf) {
+    const DMat& m = p.mats[mf_mat(mf)];
+    const int32_t temp = p.g.temp[i];
+    const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
+    bool react = false;
+    uint32_t site_seen[FSS_MAX_REACTIONS];
+    for(int r = 0; r < m.n_react && r < FSS_MAX_REACTIONS; r++) {
+        site_seen[r] = 0xFFFFFFFFu;
+        if((m.r_type[r] == FSS_REACT_TEMPERATURE_BELOW && temp < m.r_thr[r]) ||
+           (m.r_type[r] == FSS_REACT_TEMPERATURE_ABOVE && temp > m.r_thr[r])) {
+            const uint32_t site = p.mats[m.r_target[r]].create_site;
+            uint32_t k = 0;
+            for(int q = 0; q < r; q++) k += (site_seen[q] == site) ? 1u : 0u;
+            site_seen[r] = site;
+            Cell c = create_cell(p, m.r_target[r], x, y, key, k);
+            c.temp = temp;
+            st_cell(p.g, i, c);
+            react = true;
+        }
+    }
+    return react;
+}
+
+// ---- falling liquid leaves the grid as particles, world.cpp:1352-1374 ---------------------------------
+__device__ __noinline__ void rule_soup_free_fall(const SubstepParams& p, size_t i, int x, int y, uint32_t mf, float amt) {
+    const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
+    Cell nt;
+    nt.mf = mf & (MF_MAT_MASK | MF_DERIVED_MASK);
+    nt.col = p.g.col[i];
+    nt.temp = p.g.temp[i];
+    nt.dif = 0.0f;
+    int n = (int)(amt / 4);
+    if(n < 1) n = 1;
+    nt.amt = amt / n;
+    st_cell(p.g, i, cell_nothing(p.nothing_mf));
+    for(int k = 0; k < n; k++) emit_particle(p, x, y, 1366, key, nt);
+}
+
+// per-thread state of one micro-chunk visit
+struct ChunkWalk {
+    const SubstepParams& p;
+    const float* sden;     // shared: density per material
+    const uint32_t* sinfo; // shared: HI_* word per material
+    int cx, cy;
+    unsigned long long vis; // tickVisited restricted to the chunk, bit dy*4+dx (flags set outside the chunk are
+                            // never read back: the other buffer is cleared before reuse, world.cpp:1125-1131, :1998)
+
+    __device__ __forceinline__ ChunkWalk(const SubstepParams& p_, const float* sd, const uint32_t* si, int cx_, int cy_)
+        : p(p_), sden(sd), sinfo(si), cx(cx_), cy(cy_), vis(0ull) {}
+
+    __device__ __forceinline__ size_t I(int x, int y) const { return p.g.idx(x, y); }
+    __device__ __forceinline__ void mark(int x, int y) {
+        unsigned dx = (unsigned)(x - cx), dy = (unsigned)(y - cy);
+        if(dx < (unsigned)FSS_CHUNK_W && dy < (unsigned)FSS_CHUNK_H) vis |= 1ull << (dy * FSS_CHUNK_W + dx);
+    }
+    __device__ __forceinline__ bool can_move_into(uint32_t dst_mf, float self_density) const {
+        // world.cpp:1276-1285: AIR, or not SOLID and lighter
+        if(MF_IS(dst_mf, FSS_PHYS_AIR)) return true;
+        if(MF_IS(dst_mf, FSS_PHYS_SOLID)) return false;
+        return sden[mf_mat(dst_mf)] < self_density;
+    }
+    __device__ __forceinline__ void swap_cells(size_t a, size_t b) const {
+        Cell ca = ld_cell(p.g, a), cb = ld_cell(p.g, b);
+        st_cell(p.g, a, cb);
+        st_cell(p.g, b, ca);
+    }
+
+    // `neighbour created (copy of mat/colour/temperature, amount 0) if AIR; neighbour.diff += flow`
+    // (world.cpp:1399-1403, :1441-1445, :1471-1475, :1503-1507)
+    __device__ __forceinline__ void give(size_t in, uint32_t nmf, float flow, uint32_t self_mf, size_t i) const {
+        if(MF_IS(nmf, FSS_PHYS_AIR)) {
+            Cell s;
+            s.mf = self_mf & (MF_MAT_MASK | MF_DERIVED_MASK);
+            s.col = p.g.col[i];
+            s.temp = p.g.temp[i];
+            s.amt = 0.0f;
+            s.dif = 0.0f + flow;
+            st_cell(p.g, in, s);
+        } else {
+            p.g.dif[in] = p.g.dif[in] + flow;
+        }
+    }
+
+    // ---- SOUP, scan 1, world.cpp:1338-1537 -----------------------------------------------------------------
+    __device__ __forceinline__ void soup1(size_t i, int x, int y, uint32_t mf) {
+        const Grid& g = p.g;
+        const size_t pitch = g.pitch;
+        const float amt = g.amt[i];
+        if(amt == 0.0f) return;      // :1344
+        if(amt < FLUID_MinValue) {   // :1346-1350
+            g.amt[i] = 0.0f;
+            return;
+        }
+        if((p.flags & FSS_PARTICLES_EMIT) && (double)amt > 0.005 && MF_IS(g.mf[i + pitch], FSS_PHYS_AIR) &&
+           MF_IS(g.mf[i + 2 * pitch], FSS_PHYS_AIR) && MF_IS(g.mf[i + 3 * pitch], FSS_PHYS_AIR) &&
+           MF_IS(g.mf[i + 4 * pitch], FSS_PHYS_AIR)) {
+            rule_soup_free_fall(p, i, x, y, mf, amt);
+            return;
+        }
+        if(mf & MF_MOVED) return;    // :1376 (moved == settled for liquids)
+        const float start = amt;
+        float remaining = amt;
+        float tdif = g.dif[i];
+        const uint32_t mat = mf_mat(mf);
+        const int iter = p.iter;
+
+        const size_t ib = i + pitch; // :1381
+        const uint32_t bmf = g.mf[ib];
+        const bool air_below = MF_IS(bmf, FSS_PHYS_AIR);
+        if((air_below && iter <= 2) || mf_mat(bmf) == mat) { // :1384-1405
+            const float dst = MF_IS(bmf, FSS_PHYS_SOUP) ? g.amt[ib] : 0.0f;
+            float flow = vertical_flow(start, dst) - dst;
+            flow = clamp_flow(flow, start);
+            if(flow != 0) {
+                remaining -= flow;
+                tdif -= flow;
+                give(ib, bmf, flow, mf, i);
+            }
+        } else if(iter == 0 && MF_IS(bmf, FSS_PHYS_SOUP)) { // :1406-1412 (different material: the branch above failed)
+            const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
+            if(fss_rand(key, 1407, 0) % 10 == 0) {
+                swap_cells(i, ib);
+                return;
+            }
+        }
+        if(remaining < FLUID_MinValue) { // :1414-1418
+            g.dif[i] = tdif - remaining;
+            return;
+        }
+
+        const size_t il = I(x - 1, y), ir = I(x + 1, y); // :1420-1424
+        const uint32_t lmf = g.mf[il], rmf = g.mf[ir];
+        const bool can_left = (MF_IS(lmf, FSS_PHYS_AIR) || mf_mat(lmf) == mat) && !air_below;
+        const bool can_right = (MF_IS(rmf, FSS_PHYS_AIR) || mf_mat(rmf) == mat) && !air_below;
+        if(can_left) { // :1426-1448
+            const float dst = MF_IS(lmf, FSS_PHYS_SOUP) ? g.amt[il] : 0.0f;
+            float flow = (remaining - dst) / (can_right ? 3.0f : 2.0f);
+            flow = clamp_flow(flow, remaining);
+            if(flow != 0) {
+                remaining -= flow;
+                tdif -= flow;
+                give(il, lmf, flow, mf, i);
+            }
+        }
+        if(remaining < FLUID_MinValue) {
+            g.dif[i] = tdif - remaining;
+            return;
+        }
+        if(can_right) { // :1456-1478 (`canMoveLeft ? 2.0f : 2.0f`)
+            const float dst = MF_IS(rmf, FSS_PHYS_SOUP) ? g.amt[ir] : 0.0f;
+            float flow = (remaining - dst) / 2.0f;
+            flow = clamp_flow(flow, remaining);
+            if(flow != 0) {
+                remaining -= flow;
+                tdif -= flow;
+                give(ir, rmf, flow, mf, i);
+            }
+        }
+        if(remaining < FLUID_MinValue) {
+            g.dif[i] = tdif - remaining;
+            return;
+        }
+        const size_t it = i - pitch; // :1486-1516
+        const uint32_t tmf = g.mf[it];
+        if(MF_IS(tmf, FSS_PHYS_AIR) || mf_mat(tmf) == mat) {
+            const float dst = MF_IS(tmf, FSS_PHYS_SOUP) ? g.amt[it] : 0.0f;
+            float flow = remaining - vertical_flow(remaining, dst);
+            flow = clamp_flow(flow, remaining);
+            if(flow != 0) {
+                remaining -= flow;
+                tdif -= flow;
+                give(it, tmf, flow, mf, i);
+            }
+        } else if(iter == 0 && MF_IS(tmf, FSS_PHYS_SOUP)) {
+            const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
+            if(fss_rand(key, 1511, 0) % 10 == 0) {
+                Cell top = ld_cell(g, it);
+                Cell me = ld_cell(g, i);
+                me.dif = tdif;
+                st_cell(g, i, top);
+                st_cell(g, it, me);
+                return;
+            }
+        }
+        if(remaining < FLUID_MinValue) {
+            g.dif[i] = tdif - remaining;
+            return;
+        }
+        uint32_t nmf = mf;
+        if(start == remaining) { // :1524-1528
+            const uint32_t settle = (mf_settle(mf) + 1u) & 0xFFu;
+            nmf = (mf & 0x00FFFFFFu) | (settle << MF_SETTLE_SHIFT);
+            if(settle >= 10u) nmf |= MF_MOVED;
+        } else {                 // :1529-1535: the by-value copies decide (a neighbour seeded above still counts as AIR)
+            if(MF_IS(tmf, FSS_PHYS_SOUP) && (tmf & MF_MOVED)) g.mf[it] = tmf & ~MF_MOVED;
+            if(MF_IS(bmf, FSS_PHYS_SOUP) && (bmf & MF_MOVED)) g.mf[ib] = bmf & ~MF_MOVED;
+            if(MF_IS(lmf, FSS_PHYS_SOUP) && (lmf & MF_MOVED)) g.mf[il] = lmf & ~MF_MOVED;
+            if(MF_IS(rmf, FSS_PHYS_SOUP) && (rmf & MF_MOVED)) g.mf[ir] = rmf & ~MF_MOVED;
+        }
+        if(nmf != mf) g.mf[i] = nmf; // :1537 `tiles[index] = tile`
+        g.dif[i] = tdif;
+    }
+
+    // ---- SAND, scan 1, world.cpp:1218-1337 -----------------------------------------------------------------
+    __device__ __forceinline__ void sand1(size_t i, int x, int y, uint32_t mf, unsigned long long bit) {
+        const Grid& g = p.g;
+        const uint32_t mat = mf_mat(mf);
+        // :1223-1249 interactions: `interact` is false for every material (Materials.cpp:128, :144)
+        if(HI_NREACT(sinfo[mat])) {
+            if(rule_sand_react(p, i, x, y, mf)) {
+                vis |= bit;
+                return;
+            }
+        }
+        const size_t ib = i + g.pitch;
+        const uint32_t bmf = g.mf[ib];
+        const float dself = sden[mat];
+        if(!can_move_into(bmf, dself)) return; // :1276, :1287
+        const size_t ibl = I(x - 1, y + 1), ibr = I(x + 1, y + 1);
+        const uint32_t blmf = g.mf[ibl], brmf = g.mf[ibr];
+        const bool can_l = can_move_into(blmf, dself), can_r = can_move_into(brmf, dself);
+        const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
+        if((can_l || can_r) && fss_rand(key, 1287, 0) % 20 == 0) return;
+        Cell tile = ld_cell(g, i);
+        Cell below = ld_cell(g, ib);
+        st_cell(g, i, below); // :1289 / :1296
+        if((p.flags & FSS_PARTICLES_EMIT) && MF_IS(bmf, FSS_PHYS_AIR) && MF_IS(g.mf[ib + g.pitch], FSS_PHYS_AIR) &&
+           MF_IS(g.mf[ib + 2 * (size_t)g.pitch], FSS_PHYS_AIR) && MF_IS(g.mf[ib + 3 * (size_t)g.pitch], FSS_PHYS_AIR)) {
+            emit_particle(p, x, y, 1291, key, tile); // :1288-1294 free fall: the cell leaves the grid
+        } else {
+            if(fss_rand(key, 1300, 0) % 2 == 0) tile.mf |= MF_MOVED;
+            st_cell(g, ib, tile); // :1306
+            mark(x, y + 1);
+        }
+        if(fss_rand(key, 1313, 0) % 2 == 0) { // :1313-1335 transmit movement (x-1, x+1 are inside the world: zone margin)
+            if(MF_IS(blmf, FSS_PHYS_SAND) && fss_rand(key, 1316, 0) % 2 == 0 && !(blmf & MF_MOVED)) g.mf[ibl] = blmf | MF_MOVED;
+            if(MF_IS(brmf, FSS_PHYS_SAND) && fss_rand(key, 1327, 0) % 2 == 0 && !(brmf & MF_MOVED)) g.mf[ibr] = brmf | MF_MOVED;
+        }
+    }
+
+    // ---- scan 1, world.cpp:1154-1665 -------------------------------------------------------------------------
+    __device__ __forceinline__ void scan1_cell(int dx, int dy) {
+        const unsigned long long bit = 1ull << (dy * FSS_CHUNK_W + dx);
+        if(vis & bit) return; // :1161
+        const int x = cx + dx, y = cy + dy;
+        const size_t i = I(x, y);
+        const uint32_t mf = p.g.mf[i];
+        if(p.iter >= mf_iters(mf)) { // :1163-1166
+            vis |= bit;
+            return;
+        }
+        if(mf & MF_FIRE) { // fss_set_materials guarantees a fire material is PASSABLE: no other branch follows
+            vis |= rule_fire(p, cx, cy, i, x, y, bit);
+            return;
+        }
+        if(MF_IS(mf, FSS_PHYS_SAND)) {
+            sand1(i, x, y, mf, bit);
+        } else if(MF_IS(mf, FSS_PHYS_SOUP)) {
+            soup1(i, x, y, mf);
+        } else if(MF_IS(mf, FSS_PHYS_GAS)) { // :1647-1663
+            const Grid& g = p.g;
+            const size_t ia = i - g.pitch;
+            if(MF_IS(g.mf[ia], FSS_PHYS_AIR)) {
+                const bool open = MF_IS(g.mf[I(x - 1, y - 1)], FSS_PHYS_AIR) || MF_IS(g.mf[I(x + 1, y - 1)], FSS_PHYS_AIR);
+                if(!(open && fss_rand(fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y), 1654, 0) % 2 == 0)) {
+                    swap_cells(i, ia);
+                    mark(x, y - 1);
+                }
+            }
+        }
+    }
+
+    // ---- SAND, scan 2, world.cpp:1682-1807 -----------------------------------------------------------------
+    __device__ __forceinline__ void sand2(size_t i, int x, int y, uint32_t mf, unsigned long long bit) {
+        const Grid& g = p.g;
+        const size_t pitch = g.pitch;
+        const uint32_t mat = mf_mat(mf);
+        const size_t ibl = I(x - 1, y + 1), ibr = I(x + 1, y + 1);
+        const uint32_t blmf = g.mf[ibl], brmf = g.mf[ibr];
+        const float dself = sden[mat];
+        const bool can_l = can_move_into(blmf, dself), can_r = can_move_into(brmf, dself);
+        if(!(can_l || can_r)) {
+            // :1697-1734 with no open diagonal: whatever the pillar probe and its draw decide, `moved` ends up false
+            if(mf & MF_MOVED) g.mf[i] = mf & ~MF_MOVED;
+            return;
+        }
+        const uint32_t info = sinfo[mat];
+        const uint32_t slip = HI_SLIP(info);
+        const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
+        bool stopped = !(mf & MF_MOVED);
+        if(stopped) { // :1697-1725
+            int drop = (MF_IS(blmf, FSS_PHYS_AIR) || MF_IS(brmf, FSS_PHYS_AIR)) ? 1 : 0;
+            size_t jl = ibl, jr = ibr;
+#pragma unroll 1
+            for(int pil = 1; pil < 10; pil++) {
+                jl += pitch;
+                jr += pitch;
+                if(MF_IS(g.mf[jl], FSS_PHYS_AIR) || MF_IS(g.mf[jr], FSS_PHYS_AIR)) drop++;
+            }
+            const int unstable = drop + 1 - (int)HI_STAB(info);
+            if(unstable > 0) {
+                const int chance = 1000 / unstable;
+                if(chance < 1000 && fss_rand(key, 1715, 0) % (uint32_t)chance == 0) {
+                    // tiles[index].moved = true while the by-value copy keeps moved == false; every path below
+                    // either overwrites the grid cell or resets its flag (:1802), so the store is never observable
+                    stopped = false;
+                }
+            }
+            if(stopped) { // :1727-1734
+                return;   // moved is already false
+            }
+        }
+        const bool should_move = fss_rand(key, 1736, 0) % (2u * slip) != 0;
+        if(!should_move) { // :1802 `tiles[index].moved = false`
+            if(mf & MF_MOVED) g.mf[i] = mf & ~MF_MOVED;
+            return;
+        }
+        if(fss_rand(key, 1741, 0) % 2 == 0) { // :1738-1753
+            const uint32_t bmf = g.mf[i + pitch];
+            if(MF_IS(bmf, FSS_PHYS_SAND) && fss_rand(key, 1744, 0) % 2 == 0 && !(bmf & MF_MOVED)) g.mf[i + pitch] = bmf | MF_MOVED;
+        }
+        Cell tile = ld_cell(g, i);
+        tile.mf = mf;
+        if(can_l && (!can_r || fss_rand(key, 1755, 0) % 2 == 0)) { // :1755-1777
+            const size_t il = I(x - 1, y);
+            const Cell bl = ld_cell(g, ibl);
+            if(MF_IS(g.mf[il], FSS_PHYS_AIR)) {
+                st_cell(g, il, bl);
+                mark(x - 1, y);
+                st_cell(g, i, cell_nothing(p.nothing_mf));
+            } else {
+                st_cell(g, i, bl);
+                vis |= bit;
+            }
+            if(fss_rand(key, 1768, 0) % (20u * slip) == 0) tile.mf &= ~MF_MOVED;
+            st_cell(g, ibl, tile);
+            mark(x - 1, y + 1);
+        } else if(can_r) { // :1778-1800: (x+1, y) is NOT marked visited
+            const size_t ir = I(x + 1, y);
+            const Cell br = ld_cell(g, ibr);
+            if(MF_IS(g.mf[ir], FSS_PHYS_AIR)) {
+                st_cell(g, ir, br);
+                st_cell(g, i, cell_nothing(p.nothing_mf));
+            } else {
+                st_cell(g, i, br);
+                vis |= bit;
+            }
+            if(fss_rand(key, 1791, 0) % (20u * slip) == 0) tile.mf &= ~MF_MOVED;
+            st_cell(g, ibr, tile);
+            mark(x + 1, y + 1);
+        } else {
+            if(mf & MF_MOVED) g.mf[i] = mf & ~MF_MOVED; // :1802
+        }
+    }
+
+    // ---- scan 2, world.cpp:1669-1901 -------------------------------------------------------------------------
+    __device__ __forceinline__ void scan2_cell(int dx, int dy) {
+        const unsigned long long bit = 1ull << (dy * FSS_CHUNK_W + dx);
+        if(vis & bit) return; // :1676
+        const Grid& g = p.g;
+        const int x = cx + dx, y = cy + dy;
+        const size_t i = I(x, y);
+        const uint32_t mf = g.mf[i];
+        if(MF_IS(mf, FSS_PHYS_SAND)) {
+            sand2(i, x, y, mf, bit);
+        } else if(MF_IS(mf, FSS_PHYS_SOUP)) { // :1808-1825
+            const float amt = g.amt[i] + g.dif[i];
+            if(amt < FLUID_MinValue) {
+                st_cell(g, i, cell_nothing(p.nothing_mf));
+            } else {
+                g.amt[i] = amt;
+                g.dif[i] = 0.0f;
+            }
+            vis |= bit;
+        } else if(MF_IS(mf, FSS_PHYS_GAS)) { // :1879-1899
+            const size_t ial = I(x - 1, y - 1), iar = I(x + 1, y - 1);
+            const bool al = MF_IS(g.mf[ial], FSS_PHYS_AIR), ar = MF_IS(g.mf[iar], FSS_PHYS_AIR);
+            if(al && !(ar && fss_rand(fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y), 1884, 0) % 2 == 0)) {
+                swap_cells(i, ial);
+                mark(x - 1, y - 1);
+            } else if(ar) {
+                swap_cells(i, iar);
+                mark(x + 1, y - 1);
+            }
+        }
+    }
+
+    // ---- scan 3, world.cpp:1905-1974 (the SOUP branch is empty, :1918-1943) -----------------------------------
+    __device__ __forceinline__ void scan3_cell(int dx, int dy) {
+        const unsigned long long bit = 1ull << (dy * FSS_CHUNK_W + dx);
+        if(vis & bit) return;
+        const Grid& g = p.g;
+        const int x = cx + dx, y = cy + dy;
+        const size_t i = I(x, y);
+        const uint32_t mf = g.mf[i];
+        if(!MF_IS(mf, FSS_PHYS_GAS)) return;
+        const size_t il = I(x - 1, y), ir = I(x + 1, y);
+        const bool l = MF_IS(g.mf[il], FSS_PHYS_AIR), r = MF_IS(g.mf[ir], FSS_PHYS_AIR);
+        const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
+        if(l && !(r && fss_rand(key, 1950, 0) % 2 == 0)) { // :1944-1964
+            swap_cells(i, il);
+            mark(x - 1, y);
+        } else if(r) {
+            swap_cells(i, ir);
+            mark(x + 1, y);
+        } else if((sinfo[mf_mat(mf)] & HI_STEAM) && p.condense >= 0) { // :1965-1969
+            if(fss_rand(key, 1966, 0) % 10 == 0) st_cell(g, i, create_cell(p, p.condense, x, y, key, 0)); // Tiles::createWater()
+        }
+    }
+
+    __device__ __forceinline__ void run() {
+#pragma unroll 1
+        for(int dy = FSS_CHUNK_H - 1; dy >= 0; dy--) {
+#pragma unroll 1
+            for(int dx = 0; dx < FSS_CHUNK_W; dx++) scan1_cell(dx, dy);
+        }
+#pragma unroll 1
+        for(int dy = FSS_CHUNK_H - 1; dy >= 0; dy--) {
+#pragma unroll 1
+            for(int dx = 0; dx < FSS_CHUNK_W; dx++) scan2_cell(dx, dy);
+        }
+#pragma unroll 1
+        for(int dy = FSS_CHUNK_H - 1; dy >= 0; dy--) {
+#pragma unroll 1
+            for(int dx = 0; dx < FSS_CHUNK_W; dx++) scan3_cell(dx, dy);
+        }
+    }
+};

@@ -1,0 +1,284 @@
+"""Host-side mirror of the reference's `World` for the tick path, on top of the C ABI (include/fss.h).
+
+`World` keeps what the reference's `World` keeps for this path -- the tick zone (world.hpp:132), `tickCt`
+(world.cpp:2017), the material table -- and forwards `tick()` / `tick_temperature()` (world.cpp:1091, :2043)
+to libfss_b200.so, where the grid lives on the GPU.  Cells cross the boundary as numpy arrays of
+`abi.CELL_DTYPE` records (MaterialInstance minus the host-only `id`).
+
+There is no CPU implementation behind this class: if the CUDA library is missing or no sm_100 device is
+present, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from . import materials as M
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfss_b200.so")
+_lib = None
+
+
+class FssError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{abi.ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+def load():
+    """dlopen libfss_b200.so and declare the prototypes of include/fss.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FssError(-4, f"{LIB_PATH} is not built (python -m fallingsandsurvival_b200.build); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u32, sz = C.c_void_p, C.c_int, C.c_uint32, C.c_size_t
+    protos = {
+        "fss_create": [C.POINTER(abi.Config), C.POINTER(vp)],
+        "fss_destroy": [vp],
+        "fss_abi_version": [],
+        "fss_set_stream": [vp, vp],
+        "fss_set_materials": [vp, vp, i32],
+        "fss_set_texture": [vp, i32, vp, i32, i32],
+        "fss_set_tick_zone": [vp, i32, i32, i32, i32],
+        "fss_upload_rect": [vp, i32, i32, i32, i32, vp, sz],
+        "fss_download_rect": [vp, i32, i32, i32, i32, vp, sz],
+        "fss_tick": [vp, u32],
+        "fss_substep": [vp, u32, i32, i32],
+        "fss_tick_temperature": [vp],
+        "fss_drain_particles": [vp, vp, sz, C.POINTER(sz), C.POINTER(sz)],
+        "fss_histogram": [vp, vp, i32],
+        "fss_hash": [vp, C.POINTER(C.c_uint64)],
+        "fss_fluid_totals": [vp, vp, i32],
+        "fss_sync": [vp],
+        "fss_fill_synthetic": [vp, C.POINTER(abi.FillSpec)],
+        "fss_comm_unique_id": [vp],
+        "fss_comm_attach": [vp, vp, i32, i32],
+        "fss_exchange_halo": [vp, i32],
+        "fss_exchange_halo_temperature": [vp],
+        "fss_exchange_halo_peer": [vp, vp, i32],
+        "fss_exchange_halo_temperature_peer": [vp, vp],
+        "fss_get_stats": [vp, C.POINTER(abi.Stats)],
+    }
+    for name, args in protos.items():
+        f = getattr(L, name)
+        f.argtypes = args
+        f.restype = C.c_int
+    L.fss_last_error.restype = C.c_char_p
+    L.fss_last_error.argtypes = []
+    if L.fss_abi_version() != abi.FSS_ABI_VERSION:
+        raise FssError(-1, f"ABI version {L.fss_abi_version()} != {abi.FSS_ABI_VERSION}")
+    _lib = L
+    return L
+
+
+def _check(L, rc):
+    if rc != 0:
+        raise FssError(rc, L.fss_last_error().decode(errors="replace"))
+
+
+class World:
+    """One device-resident world (or one row strip of it).
+
+    cells: (H, W) array of abi.CELL_DTYPE to upload, or None to leave the grid empty (see fill_synthetic);
+    size:  (W, H) when cells is None;  zone: tickZone (x, y, w, h);
+    strip: (y0, rows) owned global rows of a strip-sharded world, None = the whole world.
+    """
+
+    def __init__(self, cells=None, zone=None, defs=None, textures=None, seed=0xF55, particles=False,
+                 condense_material=M.WATER, device=0, size=None, strip=None, particle_capacity=0):
+        self.L = load()
+        if cells is not None:
+            h, w = cells.shape
+        else:
+            w, h = size
+        self.w, self.h = w, h
+        self.defs = defs or M.named_materials()
+        self.textures = textures if textures is not None else [M.synthetic_texture(i) for i in range(M.N_TEXTURES)]
+        cfg = abi.Config()
+        cfg.struct_size = C.sizeof(abi.Config)
+        cfg.width, cfg.height, cfg.seed, cfg.device = w, h, seed, device
+        cfg.flags = abi.PARTICLES_EMIT if particles else 0
+        cfg.particle_capacity = particle_capacity
+        cfg.strip_y0, cfg.strip_rows = strip if strip is not None else (0, 0)
+        cfg.condense_material = condense_material
+        self.strip = strip
+        self.h_ = C.c_void_p()
+        _check(self.L, self.L.fss_create(C.byref(cfg), C.byref(self.h_)))
+        tbl = M.table_struct(self.defs)
+        _check(self.L, self.L.fss_set_materials(self.h_, C.byref(tbl), len(self.defs)))
+        for i, t in enumerate(self.textures):
+            t = np.ascontiguousarray(t, dtype=np.uint32)
+            _check(self.L, self.L.fss_set_texture(self.h_, i, t.ctypes.data, t.shape[1], t.shape[0]))
+        if zone is not None:
+            self.set_tick_zone(*zone)
+        st = self.stats()
+        self.stored = (st.storage_y0, st.storage_y0 + st.storage_rows)
+        if cells is not None:
+            y0, y1 = self.stored
+            self.upload(0, y0, cells[y0:y1])
+        self.tick_ct = 0
+
+    # ---- World::tickZone ----
+    def set_tick_zone(self, x, y, w, h):
+        _check(self.L, self.L.fss_set_tick_zone(self.h_, x, y, w, h))
+        self.zone = (x, y, w, h)
+
+    # ---- host mirror <-> device ----
+    def upload(self, x, y, cells):
+        cells = np.ascontiguousarray(cells, dtype=abi.CELL_DTYPE)
+        h, w = cells.shape
+        _check(self.L, self.L.fss_upload_rect(self.h_, x, y, w, h, cells.ctypes.data, w))
+
+    def download(self, x=0, y=None, w=None, h=None, out=None):
+        y0, y1 = self.stored
+        y = y0 if y is None else y
+        w = self.w - x if w is None else w
+        h = y1 - y if h is None else h
+        if out is None:
+            out = np.zeros((h, w), dtype=abi.CELL_DTYPE)
+        _check(self.L, self.L.fss_download_rect(self.h_, x, y, w, h, out.ctypes.data, out.strides[0] // abi.CELL_DTYPE.itemsize))
+        return out
+
+    def cells(self):
+        """the stored rows of this world (the whole grid unless strip-sharded)"""
+        return self.download()
+
+    # ---- the hot path ----
+    def tick(self, tick_ct=None):
+        if tick_ct is None:
+            tick_ct = self.tick_ct
+        _check(self.L, self.L.fss_tick(self.h_, tick_ct))
+        self.tick_ct = tick_ct + 1
+
+    def substep(self, tick_ct, iter_, tk):
+        _check(self.L, self.L.fss_substep(self.h_, tick_ct, iter_, tk))
+
+    def tick_temperature(self):
+        _check(self.L, self.L.fss_tick_temperature(self.h_))
+
+    def sync(self):
+        _check(self.L, self.L.fss_sync(self.h_))
+
+    def set_stream(self, cuda_stream):
+        _check(self.L, self.L.fss_set_stream(self.h_, C.c_void_p(cuda_stream)))
+
+    # ---- side outputs ----
+    def drain_particles(self, cap=1 << 20):
+        out = np.zeros(max(cap, 1), dtype=abi.PARTICLE_DTYPE)
+        n, total = C.c_size_t(), C.c_size_t()
+        _check(self.L, self.L.fss_drain_particles(self.h_, out.ctypes.data, cap, C.byref(n), C.byref(total)))
+        return out[: n.value]
+
+    def histogram(self):
+        counts = np.zeros(len(self.defs), dtype=np.uint64)
+        _check(self.L, self.L.fss_histogram(self.h_, counts.ctypes.data, len(self.defs)))
+        return counts
+
+    def hash(self):
+        d = C.c_uint64()
+        _check(self.L, self.L.fss_hash(self.h_, C.byref(d)))
+        return d.value
+
+    def fluid_totals(self):
+        t = np.zeros(len(self.defs), dtype=np.float64)
+        _check(self.L, self.L.fss_fluid_totals(self.h_, t.ctypes.data, len(self.defs)))
+        return t
+
+    def stats(self):
+        s = abi.Stats()
+        _check(self.L, self.L.fss_get_stats(self.h_, C.byref(s)))
+        return s
+
+    def fill_synthetic(self, mix, seed=0xF55, border=16, border_material=M.SOLID, solid_from_row=0,
+                       solid_material=M.COBBLE_STONE, n_boxes=0, box_size=0, sparse_material=0, sparse_per_mille=0):
+        """device-side twin of worlds.synthetic_world(); mix = [(material, percent), ...]"""
+        s = abi.FillSpec()
+        s.seed, s.border, s.border_material = seed, border, border_material
+        s.n_entries = len(mix)
+        cum = 0
+        for i, (m, pct) in enumerate(mix):
+            cum += pct
+            s.material[i], s.cumulative_percent[i] = m, cum
+        s.solid_from_row, s.solid_material = solid_from_row, solid_material
+        s.n_boxes, s.box_size, s.sparse_material, s.sparse_per_mille = n_boxes, box_size, sparse_material, sparse_per_mille
+        _check(self.L, self.L.fss_fill_synthetic(self.h_, C.byref(s)))
+
+    # ---- strips over NCCL ----
+    def comm_attach(self, unique_id: bytes, rank: int, n_ranks: int):
+        buf = C.create_string_buffer(unique_id, 128)
+        _check(self.L, self.L.fss_comm_attach(self.h_, buf, rank, n_ranks))
+
+    def close(self):
+        if getattr(self, "h_", None):
+            self.L.fss_destroy(self.h_)
+            self.h_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def comm_unique_id() -> bytes:
+    L = load()
+    buf = C.create_string_buffer(128)
+    _check(L, L.fss_comm_unique_id(buf))
+    return buf.raw
+
+
+class StripWorld:
+    """A world cut into row strips inside ONE process (one strip per entry of `devices`), halo rows moved by
+    peer copies (fss_exchange_halo_peer).  Same surface as World; used to check the strip schedule on a single
+    GPU and as the single-process multi-GPU mode.  The multi-process mode (one rank per GPU, NCCL) is
+    strips.RankWorld."""
+
+    def __init__(self, cells, zone, n_strips, devices=None, **kw):
+        from . import strips
+        h, w = cells.shape
+        self.w, self.h, self.zone = w, h, tuple(zone)
+        self.plan = strips.plan_strips(h, zone, n_strips)
+        devices = devices or [0] * n_strips
+        self.parts = [World(cells, zone, strip=s, device=d, **kw) for s, d in zip(self.plan, devices)]
+        self.L = self.parts[0].L
+        self.tick_ct = 0
+
+    def tick(self, tick_ct=None):
+        if tick_ct is None:
+            tick_ct = self.tick_ct
+        for it in range(6):
+            for tk in range(4):
+                for p in self.parts:
+                    p.substep(tick_ct, it, tk)
+                if tk in (1, 3):
+                    for a, b in zip(self.parts[:-1], self.parts[1:]):
+                        _check(self.L, self.L.fss_exchange_halo_peer(a.h_, b.h_, tk))
+        self.tick_ct = tick_ct + 1
+
+    def tick_temperature(self):
+        for p in self.parts:
+            p.tick_temperature()
+        for a, b in zip(self.parts[:-1], self.parts[1:]):
+            _check(self.L, self.L.fss_exchange_halo_temperature_peer(a.h_, b.h_))
+
+    def cells(self):
+        out = np.zeros((self.h, self.w), dtype=abi.CELL_DTYPE)
+        for p, (y0, rows) in zip(self.parts, self.plan):
+            p.download(0, y0, self.w, rows, out=out[y0:y0 + rows])
+        return out
+
+    def hash(self):
+        return sum(p.hash() for p in self.parts) & 0xFFFFFFFFFFFFFFFF
+
+    def drain_particles(self):
+        recs = np.concatenate([p.drain_particles() for p in self.parts])
+        order = np.lexsort((recs["site"], recs["x"], recs["y"], recs["tick_iter"]))
+        return recs[order]
+
+    def close(self):
+        for p in self.parts:
+            p.close()

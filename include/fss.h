@@ -195,7 +195,7 @@ int fss_sync(fss_world* w);
 
 /* ---- synthetic worlds for benchmarks ----------------------------------
  * Fills every cell of this world's storage: cells within `border` of a world edge become
- * material `border_material`; every other cell draws r = fss_fmix32(seed ^ fss_rng_cell_key(..)) % 100
+ * material `border_material`; every other cell draws key = fss_rng_cell_key(seed, x, y), r = key % 100
  * and takes the first entry i with r < cumulative_percent[i]; remaining cells are material 0.
  * Cells are initialised like Tiles::create(mat,x,y) with the table's create_* recipe. */
 typedef struct fss_fill_spec {
@@ -222,9 +222,15 @@ int fss_fill_synthetic(fss_world* w, const fss_fill_spec* spec);
  * 128 bytes produced on rank 0 and distributed by the host (torch.distributed, MPI, a file...). */
 int fss_comm_unique_id(void* id128);
 int fss_comm_attach(fss_world* w, const void* id128, int rank, int n_ranks);
-/* explicit halo exchange after sub-step tk (what fss_tick does internally), and for temperature */
+/* explicit halo exchange after sub-step tk (what fss_tick does internally: rows move after tk 1 and
+ * tk 3 only, other tk are no-ops), and of the temperature plane after fss_tick_temperature */
 int fss_exchange_halo(fss_world* w, int tk);
 int fss_exchange_halo_temperature(fss_world* w);
+/* the same two exchanges between two adjacent strip worlds of ONE process (same or different GPU),
+ * by peer copies instead of NCCL: `upper` owns the rows just above `lower`.  The caller drives the
+ * schedule with fss_substep(): for each iter, tk 0, tk 1, exchange(1), tk 2, tk 3, exchange(3). */
+int fss_exchange_halo_peer(fss_world* upper, fss_world* lower, int tk);
+int fss_exchange_halo_temperature_peer(fss_world* upper, fss_world* lower);
 
 /* ---- introspection used by benchmarks -------------------------------------------------------- */
 typedef struct fss_stats {

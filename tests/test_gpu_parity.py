@@ -1,0 +1,231 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle: bit-exact cells, particles, digests.
+
+All tests need a B200 (`-m gpu`).  The oracle (oracle/fss_oracle.c) is itself pinned to the reference's own
+lines by test_oracle_vs_reference.py; the golden digests / scenes in tests/golden were minted from the
+reference build, so `test_gpu_matches_golden_*` compare the GPU to the reference directly.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, MIXES, diff_report, full_table, make_world, run_ticks
+from fallingsandsurvival_b200 import abi, worlds
+from fallingsandsurvival_b200 import materials as M
+
+pytestmark = pytest.mark.gpu
+
+with open(os.path.join(GOLDEN, "tick_hashes.json")) as f:
+    HASHES = json.load(f)
+
+
+def gpu_world(cells, zone, **kw):
+    from fallingsandsurvival_b200 import world
+    return world.World(cells, zone, defs=full_table(), **kw)
+
+
+def oracle_world(cells, zone, **kw):
+    from oracle import oraclesim
+    return oraclesim.OracleWorld(cells, zone, defs=full_table(), **kw)
+
+
+def test_library_loaded_is_the_cuda_one():
+    from fallingsandsurvival_b200 import world
+    L = world.load()
+    assert L.fss_abi_version() == abi.FSS_ABI_VERSION
+    with open("/proc/self/maps") as f:
+        assert "libfss_b200.so" in f.read()
+
+
+@pytest.mark.parametrize("size", [(64, 64), (200, 176), (517, 301), (1031, 96)])
+def test_upload_download_roundtrip(size):
+    """ragged widths: not a multiple of the 256-column storage block, rectangles off the block grid"""
+    cells, zone = make_world(size, "c3", seed=3)
+    rng = np.random.default_rng(1)
+    cells["moved"] = rng.integers(0, 2, cells.shape)
+    cells["settle_count"] = rng.integers(0, 256, cells.shape)
+    cells["fluid_amount_diff"] = rng.random(cells.shape, dtype=np.float32)
+    g = gpu_world(cells, None)
+    assert g.cells().tobytes() == cells.tobytes()
+    # a rectangle in the middle
+    w, h = size
+    x0, y0, rw, rh = 5, 7, w - 11, h - 20
+    assert g.download(x0, y0, rw, rh).tobytes() == np.ascontiguousarray(cells[y0:y0 + rh, x0:x0 + rw]).tobytes()
+    patch = cells[y0:y0 + rh, x0:x0 + rw].copy()
+    patch["material"] = M.STONE
+    g.upload(x0, y0, patch)
+    cells[y0:y0 + rh, x0:x0 + rw] = patch
+    assert g.cells().tobytes() == cells.tobytes()
+    from oracle import oraclesim
+    assert g.hash() == oraclesim.hash_cells(cells)
+    hist = g.histogram()
+    ids, cnt = np.unique(cells["material"], return_counts=True)
+    assert {int(i): int(c) for i, c in zip(ids, cnt)} == {i: int(c) for i, c in enumerate(hist) if c}
+    g.close()
+
+
+@pytest.mark.parametrize("mix", sorted(MIXES))
+@pytest.mark.parametrize("particles", [False, True])
+def test_gpu_matches_oracle_every_tick(mix, particles):
+    cells, zone = make_world((200, 176), mix, seed=1000 + len(mix))
+    g = gpu_world(cells, zone, particles=particles)
+    o = oracle_world(cells, zone, particles=particles)
+    for t in range(24):
+        g.tick(t)
+        o.tick(t)
+        if t % 4 == 2:
+            g.tick_temperature()
+            o.tick_temperature()
+        a, b = o.cells(), g.cells()
+        assert a.tobytes() == b.tobytes(), f"tick {t}: " + diff_report(a, b)
+    if particles:
+        po, pg = o.drain_particles(), g.drain_particles()
+        assert len(po) == len(pg)
+        assert po.tobytes() == pg.tobytes()
+    g.close()
+    o.close()
+
+
+def test_gpu_matches_oracle_substep_by_substep():
+    """the finest granularity the ABI offers: one (iter, tk) phase at a time"""
+    cells, zone = make_world((264, 208), "c3", seed=99)
+    g = gpu_world(cells, zone, particles=True)
+    o = oracle_world(cells, zone, particles=True)
+    for t in range(3):
+        for it in range(6):
+            for tk in range(4):
+                g.substep(t, it, tk)
+                o.substep_rows(t, it, tk)
+                a, b = o.cells(), g.cells()
+                assert a.tobytes() == b.tobytes(), f"tick {t} iter {it} tk {tk}: " + diff_report(a, b)
+    g.close()
+    o.close()
+
+
+@pytest.mark.parametrize("name", sorted(HASHES))
+def test_gpu_matches_golden_digest(name):
+    """digests minted from the reference's own lines (tests/golden/make_golden.py)"""
+    gd = HASHES[name]
+    cells, zone = make_world(tuple(gd["size"]), gd["mix"], gd["seed"])
+    g = gpu_world(cells, zone, particles=gd["particles"])
+    run_ticks(g, gd["ticks"])
+    assert f"{g.hash():016x}" == gd["digest"]
+    hist = {str(i): int(c) for i, c in enumerate(g.histogram()) if c}
+    assert hist == gd["histogram"]
+    g.close()
+
+
+@pytest.mark.parametrize("name", ["fire_128x128_s8_t60", "gas_160x128_s7_t40", "sand_particles_128x160_s5_t30"])
+def test_gpu_matches_golden_scene(name):
+    gd = HASHES[name]
+    z = np.load(os.path.join(GOLDEN, f"micro_{name}.npz"))
+    g = gpu_world(z["before"], tuple(int(v) for v in z["zone"]), particles=gd["particles"])
+    run_ticks(g, gd["ticks"])
+    out = g.cells()
+    assert out.tobytes() == z["after"].tobytes(), diff_report(z["after"], out)
+    g.close()
+
+
+@pytest.mark.parametrize("mix,size,ticks", [("c3", (1040, 784), 40), ("c2", (2080, 1056), 16), ("liquids", (784, 528), 60)])
+def test_gpu_matches_oracle_larger(mix, size, ticks):
+    cells, zone = make_world(size, mix, seed=4242)
+    g = gpu_world(cells, zone, particles=(mix == "c3"))
+    o = oracle_world(cells, zone, particles=(mix == "c3"))
+    run_ticks(g, ticks)
+    run_ticks(o, ticks)
+    a, b = o.cells(), g.cells()
+    assert a.tobytes() == b.tobytes(), diff_report(a, b)
+    from oracle import oraclesim
+    assert g.hash() == oraclesim.hash_cells(a)
+    g.close()
+    o.close()
+
+
+def test_temperature_only_many_passes():
+    cells, zone = make_world((520, 272), "c3", seed=6)
+    rng = np.random.default_rng(0)
+    cells["temperature"] = rng.integers(-1100, 1100, cells.shape).astype(np.int32) * (rng.random(cells.shape) < 0.6)
+    g = gpu_world(cells, zone)
+    o = oracle_world(cells, zone)
+    for k in range(25):
+        g.tick_temperature()
+        o.tick_temperature()
+        a, b = o.cells(), g.cells()
+        assert a.tobytes() == b.tobytes(), f"pass {k}: " + diff_report(a["temperature"], b["temperature"])
+    g.close()
+    o.close()
+
+
+@pytest.mark.parametrize("n_strips", [2, 3])
+def test_strips_equal_whole_world(n_strips):
+    """row strips with ghost rows exchanged after tk 1 / tk 3 give the same grid as one world"""
+    from fallingsandsurvival_b200 import world
+    cells, zone = make_world((264, 336), "c3", seed=11)
+    whole = gpu_world(cells, zone, particles=True)
+    parts = world.StripWorld(cells, zone, n_strips, defs=full_table(), particles=True)
+    for t in range(16):
+        whole.tick(t)
+        parts.tick(t)
+        if t % 4 == 2:
+            whole.tick_temperature()
+            parts.tick_temperature()
+        a, b = whole.cells(), parts.cells()
+        assert a.tobytes() == b.tobytes(), f"tick {t}: " + diff_report(a, b)
+    assert whole.hash() == parts.hash()
+    pa, pb = whole.drain_particles(), parts.drain_particles()
+    assert pa.tobytes() == pb.tobytes()
+    whole.close()
+    parts.close()
+
+
+def test_device_fill_equals_host_fill():
+    from fallingsandsurvival_b200 import world
+    size = (776, 300)
+    for mix in (worlds.MIX_C2, worlds.MIX_C3):
+        host = worlds.synthetic_world(size[0], size[1], mix, seed=0xF55, defs=full_table())
+        g = world.World(None, None, defs=full_table(), size=size)
+        g.fill_synthetic(mix, seed=0xF55)
+        assert g.cells().tobytes() == host.tobytes()
+        g.close()
+
+
+def test_invariants_without_particles():
+    """with particles off and no fire / steam / reactive material, SAND, SOLID and GAS cell counts
+    are conserved and the liquid total never grows"""
+    mix = [(M.TEST_SAND, 25), (M.WATER, 20), (M.COBBLE_STONE, 10), (M.GAS, 5)]
+    cells, zone = make_world((520, 400), mix, seed=8)
+    g = gpu_world(cells, zone)
+    h0, f0 = g.histogram(), g.fluid_totals()
+    prev = f0[M.WATER]
+    for t in range(30):
+        g.tick(t)
+        f = g.fluid_totals()[M.WATER]
+        assert f <= prev + 1e-3
+        prev = f
+    h1 = g.histogram()
+    for m in (M.TEST_SAND, M.COBBLE_STONE, M.GAS, M.SOLID):
+        assert h0[m] == h1[m], m
+    assert prev > 0.9 * f0[M.WATER]
+    g.close()
+
+
+def test_error_paths():
+    from fallingsandsurvival_b200 import world
+    cells, zone = make_world((200, 176), "c2", seed=1)
+    g = gpu_world(cells, None)
+    with pytest.raises(world.FssError) as e:
+        g.tick(0)  # no tick zone yet
+    assert e.value.code == -5
+    with pytest.raises(world.FssError) as e:
+        g.set_tick_zone(17, 16, 160, 128)
+    assert e.value.code == -2
+    with pytest.raises(world.FssError) as e:
+        g.set_tick_zone(16, 16, 184, 128)  # reaches into the margin
+    assert e.value.code == -2
+    with pytest.raises(world.FssError) as e:
+        g.download(0, 0, 201, 10)
+    assert e.value.code == -6
+    g.close()
+    with pytest.raises(world.FssError):
+        world.World(None, None, size=(8, 8))
