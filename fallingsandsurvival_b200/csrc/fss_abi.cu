@@ -113,7 +113,7 @@ struct fss_world {
     int rank, n_ranks;
 };
 
-#define STAGE_BYTES ((size_t)64 << 20)
+#define STAGE_BYTES ((size_t)256 << 20)
 
 static int use_device(fss_world* w) {
     CU(cudaSetDevice(w->device));
@@ -196,7 +196,7 @@ int fss_create(const fss_config* cfg, fss_world** out) {
     CUX(cudaMalloc(&w->d_part_count, 8));
     CUX(cudaMemsetAsync(w->d_part_count, 0, 8, w->stream));
     CUX(cudaMalloc(&w->d_red, FSS_MAX_MATERIALS * 16));
-    w->stage_bytes = std::min(STAGE_BYTES, std::max((size_t)1 << 20, (size_t)cfg->width * 20 * 16));
+    w->stage_bytes = std::min(STAGE_BYTES, std::max((size_t)1 << 20, (size_t)cfg->width * sizeof(fss_cell) * (size_t)w->g.rows));
     CUX(cudaMalloc(&w->d_stage, w->stage_bytes));
     CUX(cudaStreamSynchronize(w->stream));
 #undef CUX

@@ -8,12 +8,15 @@
 #include "fss_rules.cuh"
 
 #define K1_THREADS 128
+#ifndef K1_MIN_BLOCKS
+#define K1_MIN_BLOCKS 8
+#endif
 
 // ---- K1: movement sub-step ---------------------------------------------------------------------------
 // grid = (ceil(nx / 128), ny); thread (bx*128 + t, by) owns the micro-chunk at
 // (x_begin + 8*(bx*128+t), y_begin + 32*by).  A warp therefore owns 32 micro-chunks that are 8 columns
 // apart: with the permuted layout its lanes read consecutive words.
-__global__ void __launch_bounds__(K1_THREADS) k_substep(const __grid_constant__ SubstepParams p) {
+__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_substep(const __grid_constant__ SubstepParams p) {
     __shared__ float sden[FSS_MAX_MATERIALS];
     __shared__ uint32_t sinfo[FSS_MAX_MATERIALS];
     for(int m = threadIdx.x; m < p.n_mat; m += K1_THREADS) {

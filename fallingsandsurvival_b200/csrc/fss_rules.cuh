@@ -195,11 +195,12 @@ struct ChunkWalk {
     const float* sden;     // shared: density per material
     const uint32_t* sinfo; // shared: HI_* word per material
     int cx, cy;
+    bool maybe_gas;         // an unvisited GAS cell may exist in the chunk (else scan 3 has nothing to do)
     unsigned long long vis; // tickVisited restricted to the chunk, bit dy*4+dx (flags set outside the chunk are
                             // never read back: the other buffer is cleared before reuse, world.cpp:1125-1131, :1998)
 
     __device__ __forceinline__ ChunkWalk(const SubstepParams& p_, const float* sd, const uint32_t* si, int cx_, int cy_)
-        : p(p_), sden(sd), sinfo(si), cx(cx_), cy(cy_), vis(0ull) {}
+        : p(p_), sden(sd), sinfo(si), cx(cx_), cy(cy_), maybe_gas(false), vis(0ull) {}
 
     __device__ __forceinline__ size_t I(int x, int y) const { return p.g.idx(x, y); }
     __device__ __forceinline__ void mark(int x, int y) {
@@ -220,7 +221,7 @@ struct ChunkWalk {
 
     // `neighbour created (copy of mat/colour/temperature, amount 0) if AIR; neighbour.diff += flow`
     // (world.cpp:1399-1403, :1441-1445, :1471-1475, :1503-1507)
-    __device__ __forceinline__ void give(size_t in, uint32_t nmf, float flow, uint32_t self_mf, size_t i) const {
+    __device__ __forceinline__ void give(size_t in, uint32_t nmf, float ndif, float flow, uint32_t self_mf, size_t i) const {
         if(MF_IS(nmf, FSS_PHYS_AIR)) {
             Cell s;
             s.mf = self_mf & (MF_MAT_MASK | MF_DERIVED_MASK);
@@ -230,7 +231,7 @@ struct ChunkWalk {
             s.dif = 0.0f + flow;
             st_cell(p.g, in, s);
         } else {
-            p.g.dif[in] = p.g.dif[in] + flow;
+            p.g.dif[in] = ndif + flow;
         }
     }
 
@@ -253,21 +254,26 @@ struct ChunkWalk {
         if(mf & MF_MOVED) return;    // :1376 (moved == settled for liquids)
         const float start = amt;
         float remaining = amt;
-        float tdif = g.dif[i];
         const uint32_t mat = mf_mat(mf);
         const int iter = p.iter;
+        // Everything the four flows can need, issued as one batch of independent loads (one exposed memory
+        // latency instead of a dozen chained ones).  None of these words is written by this visit before its use:
+        // each flow only stores to the neighbour it feeds.
+        const size_t ib = i + pitch, it = i - pitch, il = I(x - 1, y), ir = I(x + 1, y);
+        float tdif = g.dif[i];
+        const uint32_t bmf = g.mf[ib], lmf = g.mf[il], rmf = g.mf[ir], tmf = g.mf[it];
+        const float bamt = g.amt[ib], lamt = g.amt[il], ramt = g.amt[ir], tamt = g.amt[it];
+        const float bdif = g.dif[ib], ldif = g.dif[il], rdif = g.dif[ir], updif = g.dif[it];
 
-        const size_t ib = i + pitch; // :1381
-        const uint32_t bmf = g.mf[ib];
-        const bool air_below = MF_IS(bmf, FSS_PHYS_AIR);
+        const bool air_below = MF_IS(bmf, FSS_PHYS_AIR); // :1381
         if((air_below && iter <= 2) || mf_mat(bmf) == mat) { // :1384-1405
-            const float dst = MF_IS(bmf, FSS_PHYS_SOUP) ? g.amt[ib] : 0.0f;
+            const float dst = MF_IS(bmf, FSS_PHYS_SOUP) ? bamt : 0.0f;
             float flow = vertical_flow(start, dst) - dst;
             flow = clamp_flow(flow, start);
             if(flow != 0) {
                 remaining -= flow;
                 tdif -= flow;
-                give(ib, bmf, flow, mf, i);
+                give(ib, bmf, bdif, flow, mf, i);
             }
         } else if(iter == 0 && MF_IS(bmf, FSS_PHYS_SOUP)) { // :1406-1412 (different material: the branch above failed)
             const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
@@ -281,18 +287,17 @@ struct ChunkWalk {
             return;
         }
 
-        const size_t il = I(x - 1, y), ir = I(x + 1, y); // :1420-1424
-        const uint32_t lmf = g.mf[il], rmf = g.mf[ir];
+        // :1420-1424
         const bool can_left = (MF_IS(lmf, FSS_PHYS_AIR) || mf_mat(lmf) == mat) && !air_below;
         const bool can_right = (MF_IS(rmf, FSS_PHYS_AIR) || mf_mat(rmf) == mat) && !air_below;
         if(can_left) { // :1426-1448
-            const float dst = MF_IS(lmf, FSS_PHYS_SOUP) ? g.amt[il] : 0.0f;
+            const float dst = MF_IS(lmf, FSS_PHYS_SOUP) ? lamt : 0.0f;
             float flow = (remaining - dst) / (can_right ? 3.0f : 2.0f);
             flow = clamp_flow(flow, remaining);
             if(flow != 0) {
                 remaining -= flow;
                 tdif -= flow;
-                give(il, lmf, flow, mf, i);
+                give(il, lmf, ldif, flow, mf, i);
             }
         }
         if(remaining < FLUID_MinValue) {
@@ -300,29 +305,28 @@ struct ChunkWalk {
             return;
         }
         if(can_right) { // :1456-1478 (`canMoveLeft ? 2.0f : 2.0f`)
-            const float dst = MF_IS(rmf, FSS_PHYS_SOUP) ? g.amt[ir] : 0.0f;
+            const float dst = MF_IS(rmf, FSS_PHYS_SOUP) ? ramt : 0.0f;
             float flow = (remaining - dst) / 2.0f;
             flow = clamp_flow(flow, remaining);
             if(flow != 0) {
                 remaining -= flow;
                 tdif -= flow;
-                give(ir, rmf, flow, mf, i);
+                give(ir, rmf, rdif, flow, mf, i);
             }
         }
         if(remaining < FLUID_MinValue) {
             g.dif[i] = tdif - remaining;
             return;
         }
-        const size_t it = i - pitch; // :1486-1516
-        const uint32_t tmf = g.mf[it];
+        // :1486-1516
         if(MF_IS(tmf, FSS_PHYS_AIR) || mf_mat(tmf) == mat) {
-            const float dst = MF_IS(tmf, FSS_PHYS_SOUP) ? g.amt[it] : 0.0f;
+            const float dst = MF_IS(tmf, FSS_PHYS_SOUP) ? tamt : 0.0f;
             float flow = remaining - vertical_flow(remaining, dst);
             flow = clamp_flow(flow, remaining);
             if(flow != 0) {
                 remaining -= flow;
                 tdif -= flow;
-                give(it, tmf, flow, mf, i);
+                give(it, tmf, updif, flow, mf, i);
             }
         } else if(iter == 0 && MF_IS(tmf, FSS_PHYS_SOUP)) {
             const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
@@ -361,21 +365,21 @@ struct ChunkWalk {
         // :1223-1249 interactions: `interact` is false for every material (Materials.cpp:128, :144)
         if(HI_NREACT(sinfo[mat])) {
             if(rule_sand_react(p, i, x, y, mf)) {
-                vis |= bit;
+                vis |= bit; // (a product is marked visited, so even a GAS product gets no scan 2 / 3 visit)
                 return;
             }
         }
         const size_t ib = i + g.pitch;
-        const uint32_t bmf = g.mf[ib];
+        const size_t ibl = I(x - 1, y + 1), ibr = I(x + 1, y + 1);
+        const uint32_t bmf = g.mf[ib], blmf = g.mf[ibl], brmf = g.mf[ibr]; // one batch of loads
         const float dself = sden[mat];
         if(!can_move_into(bmf, dself)) return; // :1276, :1287
-        const size_t ibl = I(x - 1, y + 1), ibr = I(x + 1, y + 1);
-        const uint32_t blmf = g.mf[ibl], brmf = g.mf[ibr];
         const bool can_l = can_move_into(blmf, dself), can_r = can_move_into(brmf, dself);
         const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
         if((can_l || can_r) && fss_rand(key, 1287, 0) % 20 == 0) return;
         Cell tile = ld_cell(g, i);
         Cell below = ld_cell(g, ib);
+        if(MF_IS(bmf, FSS_PHYS_GAS)) maybe_gas = true;
         st_cell(g, i, below); // :1289 / :1296
         if((p.flags & FSS_PARTICLES_EMIT) && MF_IS(bmf, FSS_PHYS_AIR) && MF_IS(g.mf[ib + g.pitch], FSS_PHYS_AIR) &&
            MF_IS(g.mf[ib + 2 * (size_t)g.pitch], FSS_PHYS_AIR) && MF_IS(g.mf[ib + 3 * (size_t)g.pitch], FSS_PHYS_AIR)) {
@@ -402,6 +406,7 @@ struct ChunkWalk {
             vis |= bit;
             return;
         }
+        if(MF_IS(mf, FSS_PHYS_GAS)) maybe_gas = true;
         if(mf & MF_FIRE) { // fss_set_materials guarantees a fire material is PASSABLE: no other branch follows
             vis |= rule_fire(p, cx, cy, i, x, y, bit);
             return;
@@ -413,8 +418,9 @@ struct ChunkWalk {
         } else if(MF_IS(mf, FSS_PHYS_GAS)) { // :1647-1663
             const Grid& g = p.g;
             const size_t ia = i - g.pitch;
-            if(MF_IS(g.mf[ia], FSS_PHYS_AIR)) {
-                const bool open = MF_IS(g.mf[I(x - 1, y - 1)], FSS_PHYS_AIR) || MF_IS(g.mf[I(x + 1, y - 1)], FSS_PHYS_AIR);
+            const uint32_t amf = g.mf[ia], almf = g.mf[I(x - 1, y - 1)], armf = g.mf[I(x + 1, y - 1)];
+            if(MF_IS(amf, FSS_PHYS_AIR)) {
+                const bool open = MF_IS(almf, FSS_PHYS_AIR) || MF_IS(armf, FSS_PHYS_AIR);
                 if(!(open && fss_rand(fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y), 1654, 0) % 2 == 0)) {
                     swap_cells(i, ia);
                     mark(x, y - 1);
@@ -441,15 +447,16 @@ struct ChunkWalk {
         const uint32_t slip = HI_SLIP(info);
         const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
         bool stopped = !(mf & MF_MOVED);
-        if(stopped) { // :1697-1725
+        if(stopped) { // :1697-1725: the 18 probe loads are independent, issue them together
             int drop = (MF_IS(blmf, FSS_PHYS_AIR) || MF_IS(brmf, FSS_PHYS_AIR)) ? 1 : 0;
-            size_t jl = ibl, jr = ibr;
-#pragma unroll 1
+            uint32_t pl[9], pr[9];
+#pragma unroll
             for(int pil = 1; pil < 10; pil++) {
-                jl += pitch;
-                jr += pitch;
-                if(MF_IS(g.mf[jl], FSS_PHYS_AIR) || MF_IS(g.mf[jr], FSS_PHYS_AIR)) drop++;
+                pl[pil - 1] = g.mf[ibl + (size_t)pil * pitch];
+                pr[pil - 1] = g.mf[ibr + (size_t)pil * pitch];
             }
+#pragma unroll
+            for(int pil = 0; pil < 9; pil++) drop += (MF_IS(pl[pil], FSS_PHYS_AIR) || MF_IS(pr[pil], FSS_PHYS_AIR)) ? 1 : 0;
             const int unstable = drop + 1 - (int)HI_STAB(info);
             if(unstable > 0) {
                 const int chance = 1000 / unstable;
@@ -459,9 +466,7 @@ struct ChunkWalk {
                     stopped = false;
                 }
             }
-            if(stopped) { // :1727-1734
-                return;   // moved is already false
-            }
+            if(stopped) return; // :1727-1734, moved is already false
         }
         const bool should_move = fss_rand(key, 1736, 0) % (2u * slip) != 0;
         if(!should_move) { // :1802 `tiles[index].moved = false`
@@ -472,38 +477,35 @@ struct ChunkWalk {
             const uint32_t bmf = g.mf[i + pitch];
             if(MF_IS(bmf, FSS_PHYS_SAND) && fss_rand(key, 1744, 0) % 2 == 0 && !(bmf & MF_MOVED)) g.mf[i + pitch] = bmf | MF_MOVED;
         }
-        Cell tile = ld_cell(g, i);
+        // :1755-1800, both directions through one code path.  Left: `canMoveBelowLeft && (!canMoveBelowRight || rand()%2==0)`,
+        // marks (x-1, y) visited; right: marks nothing at (x+1, y) (the reference's asymmetry, :1759 vs :1780-1784)
+        const bool go_left = can_l && (!can_r || fss_rand(key, 1755, 0) % 2 == 0);
+        const int sx = go_left ? -1 : 1;
+        const size_t idiag = go_left ? ibl : ibr, iside = I(x + sx, y);
+        Cell tile, diag;
         tile.mf = mf;
-        if(can_l && (!can_r || fss_rand(key, 1755, 0) % 2 == 0)) { // :1755-1777
-            const size_t il = I(x - 1, y);
-            const Cell bl = ld_cell(g, ibl);
-            if(MF_IS(g.mf[il], FSS_PHYS_AIR)) {
-                st_cell(g, il, bl);
-                mark(x - 1, y);
-                st_cell(g, i, cell_nothing(p.nothing_mf));
-            } else {
-                st_cell(g, i, bl);
-                vis |= bit;
-            }
-            if(fss_rand(key, 1768, 0) % (20u * slip) == 0) tile.mf &= ~MF_MOVED;
-            st_cell(g, ibl, tile);
-            mark(x - 1, y + 1);
-        } else if(can_r) { // :1778-1800: (x+1, y) is NOT marked visited
-            const size_t ir = I(x + 1, y);
-            const Cell br = ld_cell(g, ibr);
-            if(MF_IS(g.mf[ir], FSS_PHYS_AIR)) {
-                st_cell(g, ir, br);
-                st_cell(g, i, cell_nothing(p.nothing_mf));
-            } else {
-                st_cell(g, i, br);
-                vis |= bit;
-            }
-            if(fss_rand(key, 1791, 0) % (20u * slip) == 0) tile.mf &= ~MF_MOVED;
-            st_cell(g, ibr, tile);
-            mark(x + 1, y + 1);
+        tile.col = g.col[i];
+        tile.temp = g.temp[i];
+        tile.amt = g.amt[i];
+        tile.dif = g.dif[i];
+        diag.mf = go_left ? blmf : brmf;
+        diag.col = g.col[idiag];
+        diag.temp = g.temp[idiag];
+        diag.amt = g.amt[idiag];
+        diag.dif = g.dif[idiag];
+        const uint32_t smf = g.mf[iside];
+        if(MF_IS(diag.mf, FSS_PHYS_GAS)) maybe_gas = true;
+        if(MF_IS(smf, FSS_PHYS_AIR)) {
+            st_cell(g, iside, diag);
+            if(go_left) mark(x - 1, y);
+            st_cell(g, i, cell_nothing(p.nothing_mf));
         } else {
-            if(mf & MF_MOVED) g.mf[i] = mf & ~MF_MOVED; // :1802
+            st_cell(g, i, diag);
+            vis |= bit;
         }
+        if(fss_rand(key, go_left ? 1768u : 1791u, 0) % (20u * slip) == 0) tile.mf &= ~MF_MOVED;
+        st_cell(g, idiag, tile);
+        mark(x + sx, y + 1);
     }
 
     // ---- scan 2, world.cpp:1669-1901 -------------------------------------------------------------------------
@@ -561,17 +563,40 @@ struct ChunkWalk {
         }
     }
 
+    static __device__ __forceinline__ void prefetch_l1(const void* q) { asm volatile("prefetch.global.L1 [%0];" ::"l"(q)); }
+
+    // first touch of the row above, issued one row early: the own four columns plus one either side
+    __device__ __forceinline__ void prefetch_row(int y, bool fluid) const {
+        const size_t rb = (size_t)(y - p.g.sy0) * p.g.pitch;
+#pragma unroll
+        for(int k = -1; k <= FSS_CHUNK_W; k++) {
+            const size_t j = rb + fss_perm((uint32_t)(cx + k));
+            prefetch_l1(p.g.mf + j);
+            if(fluid && k >= 0 && k < FSS_CHUNK_W) {
+                prefetch_l1(p.g.amt + j);
+                prefetch_l1(p.g.dif + j);
+            }
+        }
+    }
+
     __device__ __forceinline__ void run() {
 #pragma unroll 1
         for(int dy = FSS_CHUNK_H - 1; dy >= 0; dy--) {
+            prefetch_row(cy + dy - 1, true);
 #pragma unroll 1
             for(int dx = 0; dx < FSS_CHUNK_W; dx++) scan1_cell(dx, dy);
         }
+        // scan 2 and scan 3 only act on cells that are not marked visited: when every lane's chunk is fully
+        // visited (iter >= iterations everywhere: AIR, SOLID, spent SAND) the warp skips them
+        if(__all_sync(__activemask(), vis == ~0ull)) return;
 #pragma unroll 1
         for(int dy = FSS_CHUNK_H - 1; dy >= 0; dy--) {
+            prefetch_row(cy + dy - 1, true);
 #pragma unroll 1
             for(int dx = 0; dx < FSS_CHUNK_W; dx++) scan2_cell(dx, dy);
         }
+        // a GAS cell inside the chunk at scan 3 was GAS at its scan-1 visit or was swapped in by a SAND move
+        if(!__any_sync(__activemask(), maybe_gas)) return;
 #pragma unroll 1
         for(int dy = FSS_CHUNK_H - 1; dy >= 0; dy--) {
 #pragma unroll 1

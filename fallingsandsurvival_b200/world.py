@@ -17,7 +17,7 @@ from . import abi
 from . import materials as M
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfss_b200.so")
+LIB_PATH = os.environ.get("FSS_LIB") or os.path.join(HERE, "libfss_b200.so")  # FSS_LIB: kernel-tuning experiments only
 _lib = None
 
 
