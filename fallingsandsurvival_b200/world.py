@@ -248,15 +248,16 @@ class StripWorld:
         self.tick_ct = 0
 
     def tick(self, tick_ct=None):
+        from . import strips
         if tick_ct is None:
             tick_ct = self.tick_ct
-        for it in range(6):
-            for tk in range(4):
+        for op, it, tk in strips.tick_schedule():
+            if op == "substep":
                 for p in self.parts:
                     p.substep(tick_ct, it, tk)
-                if tk in (1, 3):
-                    for a, b in zip(self.parts[:-1], self.parts[1:]):
-                        _check(self.L, self.L.fss_exchange_halo_peer(a.h_, b.h_, tk))
+            else:
+                for a, b in zip(self.parts[:-1], self.parts[1:]):
+                    _check(self.L, self.L.fss_exchange_halo_peer(a.h_, b.h_, tk))
         self.tick_ct = tick_ct + 1
 
     def tick_temperature(self):

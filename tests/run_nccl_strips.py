@@ -1,0 +1,68 @@
+#!/usr/bin/env python3
+"""Strip-sharded world over NCCL == the same world on one GPU (bit-exact).  Launch with
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/run_nccl_strips.py
+Every rank owns one row strip on its own GPU; fss_tick exchanges ghost rows with ncclSend/ncclRecv.
+Rank 0 also runs the undivided world and compares cells, digest and particle records."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import helpers  # noqa: E402
+from fallingsandsurvival_b200 import abi, strips, world  # noqa: E402
+
+
+def main():
+    rank, n, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    size = (520, 64 * 4 * n + 32)
+    ticks = 12
+    cells, zone = helpers.make_world(size, "c3", seed=31)
+    rw = strips.RankWorld(size, zone, rank, n, local, cells=cells, defs=helpers.full_table(), particles=True)
+    for t in range(ticks):
+        rw.tick(t)
+        if t % 4 == 2:
+            rw.tick_temperature()
+    y0, rows = rw.strip
+    mine = rw.world.download(0, y0, size[0], rows)
+    digest = torch.tensor([rw.world.hash() & 0x7FFFFFFFFFFFFFFF, rw.world.hash() >> 63], dtype=torch.int64, device="cuda")
+    parts = rw.world.drain_particles()
+    gathered = [None] * n
+    dist.all_gather_object(gathered, (y0, rows, mine.tobytes(), rw.world.hash(), parts.tobytes()))
+    ok = True
+    if rank == 0:
+        whole = world.World(cells, zone, defs=helpers.full_table(), particles=True, device=local)
+        for t in range(ticks):
+            whole.tick(t)
+            if t % 4 == 2:
+                whole.tick_temperature()
+        ref = whole.cells()
+        out = np.zeros_like(ref)
+        hsum = 0
+        recs = []
+        for gy0, grows, raw, h, praw in gathered:
+            out[gy0:gy0 + grows] = np.frombuffer(raw, dtype=abi.CELL_DTYPE).reshape(grows, size[0])
+            hsum = (hsum + h) & 0xFFFFFFFFFFFFFFFF
+            recs.append(np.frombuffer(praw, dtype=abi.PARTICLE_DTYPE))
+        recs = np.concatenate(recs)
+        recs = recs[np.lexsort((recs["site"], recs["x"], recs["y"], recs["tick_iter"]))]
+        ok = out.tobytes() == ref.tobytes() and hsum == whole.hash() and recs.tobytes() == whole.drain_particles().tobytes()
+        print(f"nccl strips n={n}: cells {'==' if out.tobytes() == ref.tobytes() else '!='} single GPU, digest sum {hsum:016x} vs {whole.hash():016x}, "
+              f"{len(recs)} particle records -> {'OK' if ok else 'MISMATCH'}", flush=True)
+        whole.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    rw.world.close()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -229,3 +229,21 @@ def test_error_paths():
     g.close()
     with pytest.raises(world.FssError):
         world.World(None, None, size=(8, 8))
+
+
+def test_nccl_strips_equal_single_gpu():
+    """one process per GPU over NCCL (needs >= 2 visible GPUs; the 1-GPU box covers the same schedule through
+    test_strips_equal_whole_world's peer copies)"""
+    import subprocess
+    import sys
+
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    n = 2 if n < 4 else 4
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "run_nccl_strips.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29631", script], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "OK" in r.stdout
