@@ -151,7 +151,7 @@ def workload_config(workload, n, size):
                          "c5": "BASELINE.json configs[4]: mostly settled world with sparse active boxes"}[workload],
             "zone_cells_per_gpu": [size, size], "zone_cells": [size, size * n], "strips": n,
             "fill": "25% TEST_SAND / 20% WATER / 10% COBBLE_STONE" + (" + 3% LAVA 2% FIRE 3% GOLD_ORE 3% STEAM 5% SOFT_DIRT" if workload == "c3" else ""),
-            "particles": "off", "l2": "working set (5 planes x 4 B x cells) is far larger than the 126 MB L2; no flush needed"}
+            "particles": "off", "early_out": "on (chunks verified settled are skipped; results identical)", "l2": "working set (5 planes x 4 B x cells) is far larger than the 126 MB L2; no flush needed"}
 
 
 def main():
@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--size", type=int, default=ZONE_PER_GPU, help="zone cells per GPU along each axis (multiple of 32)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-early-out", action="store_true", help="visit every micro-chunk in every sub-step (FSS_NO_EARLY_OUT)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -191,7 +192,7 @@ def main():
     workload = args.workload
     temperature = workload == "c3"
 
-    rw = strips.RankWorld((W, H), zone, rank, n, local, defs=defs)
+    rw = strips.RankWorld((W, H), zone, rank, n, local, defs=defs, early_out=not args.no_early_out)
     g = rw.world
     stream = torch.cuda.Stream()  # a real stream: handle 0 would mean "the world's own stream" to fss_set_stream
     torch.cuda.set_stream(stream)

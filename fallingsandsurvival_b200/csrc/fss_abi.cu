@@ -108,6 +108,9 @@ struct fss_world {
     size_t stage_bytes;
     unsigned long long* d_red; // FSS_MAX_MATERIALS u64 + FSS_MAX_MATERIALS f64
     fss_stats stats;
+    // settled-chunk flags (SubstepParams::q): (q_h x q_w) bytes, chunk (ci, cj) of the zone at [(cj - q_cj0 + 1) * q_w + ci + 1]
+    uint8_t* d_q;
+    int q_w, q_h, q_cj0;
     // strips
     void* comm;
     int rank, n_ranks;
@@ -121,6 +124,29 @@ static int use_device(fss_world* w) {
 }
 
 static size_t plane_cells(const fss_world* w) { return (size_t)w->g.rows * w->g.pitch; }
+
+// rows of 32-row bands of the zone owned by this strip (boundaries are multiples of 2*CHUNK_H from zone.y)
+static void owned_bands(const fss_world* w, int& j_lo, int& j_hi) {
+    j_lo = w->own_lo <= w->zy ? 0 : (w->own_lo - w->zy) / FSS_ZONE_ALIGN_Y;
+    j_hi = w->own_hi >= w->zy + w->zh ? w->zh / FSS_ZONE_ALIGN_Y : (w->own_hi - w->zy) / FSS_ZONE_ALIGN_Y;
+}
+
+// Forget the "settled" verdict of every chunk whose read window ([-2,+5] columns, [-2,+25] rows around the chunk)
+// can see a cell of the rectangle (global cell coordinates; rw, rh < 0 = everything).
+static int dirty_chunks(fss_world* w, int rx, int ry, int rw, int rh) {
+    if(!w->d_q) return FSS_OK;
+    int c0 = 0, c1 = w->q_w, r0 = 0, r1 = w->q_h;
+    if(rw >= 0) {
+        auto fdiv = [](int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); };
+        c0 = std::max(0, fdiv(rx - 5 - w->zx, FSS_CHUNK_W) + 1);
+        c1 = std::min(w->q_w, fdiv(rx + rw - 1 + 2 - w->zx, FSS_CHUNK_W) + 2);
+        r0 = std::max(0, fdiv(ry - 25 - w->zy, FSS_CHUNK_H) - w->q_cj0 + 1);
+        r1 = std::min(w->q_h, fdiv(ry + rh - 1 + 2 - w->zy, FSS_CHUNK_H) - w->q_cj0 + 2);
+        if(c0 >= c1 || r0 >= r1) return FSS_OK;
+    }
+    CU(cudaMemset2DAsync(w->d_q + (size_t)r0 * w->q_w + c0, (size_t)w->q_w, 0xFF, (size_t)(c1 - c0), (size_t)(r1 - r0), w->stream));
+    return FSS_OK;
+}
 
 extern "C" {
 
@@ -163,6 +189,10 @@ int fss_create(const fss_config* cfg, fss_world** out) {
     w->g.sy0 = s_lo;
     w->g.rows = s_hi - s_lo;
     w->part_cap = cfg->particle_capacity ? cfg->particle_capacity : (1u << 20);
+    if(sizeof(cidx_t) == 4 && (unsigned long long)w->g.rows * w->g.pitch >= (1ull << 32)) {
+        delete w;
+        return fail(FSS_ERR_INVALID, "%d stored rows x pitch %u is 2^32 cells or more: shard the world into more strips", s_hi - s_lo, (cfg->width + FSS_BLOCK_COLS - 1) / FSS_BLOCK_COLS * FSS_BLOCK_COLS);
+    }
 
 #define CUX(call)                                                                             \
     do {                                                                                      \
@@ -226,6 +256,7 @@ int fss_destroy(fss_world* w) {
     cudaFree(w->d_part_count);
     cudaFree(w->d_red);
     cudaFree(w->d_stage);
+    cudaFree(w->d_q);
     if(w->own_stream) cudaStreamDestroy(w->own_stream);
     delete w;
     return FSS_OK;
@@ -302,6 +333,7 @@ int fss_set_materials(fss_world* w, const fss_material* t, int n) {
     w->stats.kernel_launches++;
     CU(cudaStreamSynchronize(w->stream)); // h_mats may be rewritten by the next call
     w->mats_set = true;
+    if(dirty_chunks(w, 0, 0, -1, -1)) return FSS_ERR_CUDA;
     return FSS_OK;
 }
 
@@ -335,11 +367,24 @@ int fss_set_tick_zone(fss_world* w, int x, int y, int zw, int zh) {
         if(!last && ((w->own_hi - y) % FSS_ZONE_ALIGN_Y || w->own_hi < y || w->own_hi > y + zh))
             return fail(FSS_ERR_ALIGN, "strip end %d is not zone.y + k*%d inside the zone", w->own_hi, FSS_ZONE_ALIGN_Y);
     }
+    if(use_device(w)) return FSS_ERR_CUDA;
     w->zx = x;
     w->zy = y;
     w->zw = zw;
     w->zh = zh;
     w->zone_set = true;
+    CU(cudaStreamSynchronize(w->stream));
+    cudaFree(w->d_q);
+    w->d_q = nullptr;
+    if(!(w->cfg.flags & FSS_NO_EARLY_OUT)) {
+        int j_lo, j_hi;
+        owned_bands(w, j_lo, j_hi);
+        w->q_w = zw / FSS_CHUNK_W + 2;
+        w->q_h = std::max(0, j_hi - j_lo) * 2 + 2;
+        w->q_cj0 = j_lo * 2;
+        CU(cudaMalloc(&w->d_q, (size_t)w->q_w * w->q_h));
+        if(dirty_chunks(w, 0, 0, -1, -1)) return FSS_ERR_CUDA;
+    }
     return FSS_OK;
 }
 
@@ -390,6 +435,7 @@ static int rect_copy(fss_world* w, int x, int y, int rw, int rh, fss_cell* host,
         w->stats.kernel_launches++;
         CU(cudaGetLastError());
     }
+    if(upload && dirty_chunks(w, x, y, rw, rh)) return FSS_ERR_CUDA;
     CU(cudaStreamSynchronize(w->stream)); // the caller owns `host` again when we return
     return FSS_OK;
 }
@@ -413,8 +459,8 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk) {
     // world.cpp:1115-1141: phase tk activates chunks at zone + (tk%2, 1 - tk/2) * chunk + 2*chunk*(i, j)
     const int ofs_x = tk % 2, ofs_y = 1 - tk / 2;
     // rows of active chunks owned by this strip (boundaries are multiples of 2*CHUNK_H from zone.y)
-    const int j_lo = w->own_lo <= w->zy ? 0 : (w->own_lo - w->zy) / FSS_ZONE_ALIGN_Y;
-    const int j_hi = w->own_hi >= w->zy + w->zh ? w->zh / FSS_ZONE_ALIGN_Y : (w->own_hi - w->zy) / FSS_ZONE_ALIGN_Y;
+    int j_lo, j_hi;
+    owned_bands(w, j_lo, j_hi);
     SubstepParams p;
     p.g = w->g;
     p.mats = w->d_mats;
@@ -434,6 +480,10 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk) {
     p.parts = w->d_parts;
     p.part_count = w->d_part_count;
     p.part_cap = w->part_cap;
+    p.q = w->d_q;
+    p.q_w = w->q_w;
+    p.ofs_x = ofs_x;
+    p.ofs_y = ofs_y;
     w->stats.substeps++;
     if(p.ny <= 0 || p.nx <= 0) return FSS_OK;
     k_substep<<<dim3((p.nx + K1_THREADS - 1) / K1_THREADS, p.ny), K1_THREADS, 0, w->stream>>>(p);
@@ -585,7 +635,7 @@ int fss_fill_synthetic(fss_world* w, const fss_fill_spec* spec) {
     w->stats.kernel_launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(w->temp2, w->g.temp, plane_cells(w) * 4, cudaMemcpyDeviceToDevice, w->stream));
-    return FSS_OK;
+    return dirty_chunks(w, 0, 0, -1, -1);
 }
 
 int fss_get_stats(fss_world* w, fss_stats* out) {
@@ -633,6 +683,7 @@ int fss_exchange_halo_peer(fss_world* upper, fss_world* lower, int tk) {
         char* d = (char*)pd[k] + (size_t)(lo - dst->g.sy0) * dst->g.pitch * 4;
         CU(cudaMemcpyPeerAsync(d, dst->device, s, src->device, (size_t)(hi - lo) * src->g.pitch * 4, dst->stream));
     }
+    if(dirty_chunks(dst, 0, lo, (int)dst->cfg.width, hi - lo)) return FSS_ERR_CUDA;
     CU(cudaEventRecord(ev, dst->stream));
     CU(cudaSetDevice(src->device));
     CU(cudaStreamWaitEvent(src->stream, ev, 0)); // the source must not overwrite the rows while they are copied
@@ -708,6 +759,10 @@ int fss_exchange_halo(fss_world* w, int tk) {
     }
     NC(g_nccl.group_end());
     w->stats.kernel_launches++; // one fused NCCL send/recv kernel per group
+    if(!rc) { // received rows replace cells that settled chunks may have looked at
+        if(tk == 1 && has_upper) rc = dirty_chunks(w, 0, w->own_lo + DOWN_LO, (int)w->cfg.width, DOWN_HI - DOWN_LO);
+        if(tk == 3 && has_lower) rc = dirty_chunks(w, 0, w->own_hi + UP_LO, (int)w->cfg.width, UP_HI - UP_LO);
+    }
     return rc;
 }
 

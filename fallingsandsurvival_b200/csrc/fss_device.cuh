@@ -82,6 +82,14 @@ struct DTex {
 #define HI_STEAM 0x04000000u
 
 // ---- the planes ----------------------------------------------------------------------------------
+// Cell index inside one GPU's planes.  64 bits by default (a 65536 x 65536 world on one GPU has 2^32 cells);
+// -DFSS_IDX32 was measured and is not faster (profiles/r01_tuning_log.md).
+#ifdef FSS_IDX32
+typedef uint32_t cidx_t;
+#else
+typedef size_t cidx_t;
+#endif
+
 struct Grid {
     uint32_t* mf;
     uint32_t* col;
@@ -91,8 +99,8 @@ struct Grid {
     uint32_t pitch; // cells per stored row (multiple of 256)
     int sy0;        // global row of stored row 0
     int rows;       // stored rows
-    __device__ __forceinline__ size_t idx(int x, int y) const {
-        return (size_t)(y - sy0) * pitch + fss_perm((uint32_t)x);
+    __device__ __forceinline__ cidx_t idx(int x, int y) const {
+        return (cidx_t)(y - sy0) * pitch + fss_perm((uint32_t)x);
     }
 };
 
@@ -104,7 +112,7 @@ struct Cell {
     float dif;
 };
 
-__device__ __forceinline__ Cell ld_cell(const Grid& g, size_t i) {
+__device__ __forceinline__ Cell ld_cell(const Grid& g, cidx_t i) {
     Cell c;
     c.mf = g.mf[i];
     c.col = g.col[i];
@@ -113,7 +121,7 @@ __device__ __forceinline__ Cell ld_cell(const Grid& g, size_t i) {
     c.dif = g.dif[i];
     return c;
 }
-__device__ __forceinline__ void st_cell(const Grid& g, size_t i, const Cell& c) {
+__device__ __forceinline__ void st_cell(const Grid& g, cidx_t i, const Cell& c) {
     g.mf[i] = c.mf;
     g.col[i] = c.col;
     g.temp[i] = c.temp;

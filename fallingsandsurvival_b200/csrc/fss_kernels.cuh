@@ -7,9 +7,11 @@
 #pragma once
 #include "fss_rules.cuh"
 
+#ifndef K1_THREADS
 #define K1_THREADS 128
+#endif
 #ifndef K1_MIN_BLOCKS
-#define K1_MIN_BLOCKS 8
+#define K1_MIN_BLOCKS 7
 #endif
 
 // ---- K1: movement sub-step ---------------------------------------------------------------------------
@@ -29,8 +31,15 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_substep(const __g
     __syncthreads();
     const int gi = blockIdx.x * K1_THREADS + threadIdx.x;
     if(gi >= p.nx) return;
+    uint8_t* qown = nullptr;
+#ifndef K1_NO_EARLY
+    if(p.q) {
+        qown = p.q + (size_t)(2 * (int)blockIdx.y + p.ofs_y + 1) * p.q_w + (2 * gi + p.ofs_x + 1);
+        if(*qown <= (uint8_t)p.iter) return; // verified settled: a warp whose 32 chunks are all settled ends here
+    }
+#endif
     ChunkWalk w(p, sden, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y);
-    w.run();
+    w.run(qown);
 }
 
 // ---- K2: temperature stencil ---------------------------------------------------------------------------

@@ -39,6 +39,12 @@ struct SubstepParams {
     fss_particle_spawn* parts;
     unsigned long long* part_count;
     uint32_t part_cap;
+    // settled-tile early-out (DESIGN.md "early-out"): one byte per micro-chunk of the zone, with a guard ring.
+    //   0xFF  must be processed;   v in 0..5  the chunk was verified at iter v to be left unchanged, without any
+    //   RNG draw, by a sub-step: while its read window stays untouched, every sub-step with iter >= v skips it.
+    uint8_t* q;   // nullptr = early-out disabled
+    int q_w;      // flags per row of chunks (zone chunks + 2 guards)
+    int ofs_x, ofs_y; // phase offsets in chunks: the chunk of thread (gi, by) is (2*gi + ofs_x, 2*by + ofs_y)
 };
 
 __device__ __forceinline__ Cell cell_nothing(uint32_t nothing_mf) {
@@ -113,7 +119,7 @@ __device__ __noinline__ void emit_particle(const SubstepParams& p, int x, int y,
 
 // ---- FIRE, world.cpp:1171-1216 (matched by material id; its physics type is PASSABLE) ------------------
 // returns the tickVisited bits to set inside the caller's micro-chunk at (cx, cy)
-__device__ __noinline__ unsigned long long rule_fire(const SubstepParams& p, int cx, int cy, size_t i, int x, int y,
+__device__ __noinline__ unsigned long long rule_fire(const SubstepParams& p, int cx, int cy, cidx_t i, int x, int y,
                                                      unsigned long long bit) {
     const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
     unsigned long long vis = 0ull;
@@ -132,7 +138,7 @@ __device__ __noinline__ unsigned long long rule_fire(const SubstepParams& p, int
     uint32_t k1202 = 0, kcreate = 0;
     for(int xx = -2; xx <= 2; xx++) {
         for(int yy = -2; yy <= 2; yy++) {
-            const size_t in = p.g.idx(x + xx, y + yy);
+            const cidx_t in = p.g.idx(x + xx, y + yy);
             if(MF_IS(p.g.mf[in], FSS_PHYS_SOLID)) {
                 found = true;
                 if(fss_rand(key, 1202, k1202++) % 500 == 0) {
@@ -151,7 +157,7 @@ __device__ __noinline__ unsigned long long rule_fire(const SubstepParams& p, int
 }
 
 // ---- SAND reactions, world.cpp:1251-1274 (only SAND evaluates them); true = the cell reacted ----------
-__device__ __noinline__ bool rule_sand_react(const SubstepParams& p, size_t i, int x, int y, uint32_t mf) {
+__device__ __noinline__ bool rule_sand_react(const SubstepParams& p, cidx_t i, int x, int y, uint32_t mf) {
     const DMat& m = p.mats[mf_mat(mf)];
     const int32_t temp = p.g.temp[i];
     const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
@@ -175,7 +181,7 @@ __device__ __noinline__ bool rule_sand_react(const SubstepParams& p, size_t i, i
 }
 
 // ---- falling liquid leaves the grid as particles, world.cpp:1352-1374 ---------------------------------
-__device__ __noinline__ void rule_soup_free_fall(const SubstepParams& p, size_t i, int x, int y, uint32_t mf, float amt) {
+__device__ __noinline__ void rule_soup_free_fall(const SubstepParams& p, cidx_t i, int x, int y, uint32_t mf, float amt) {
     const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
     Cell nt;
     nt.mf = mf & (MF_MAT_MASK | MF_DERIVED_MASK);
@@ -195,14 +201,35 @@ struct ChunkWalk {
     const float* sden;     // shared: density per material
     const uint32_t* sinfo; // shared: HI_* word per material
     int cx, cy;
+    // storage offsets: own column dx is at pb + 32*dx (the four own columns share one 8-column group, so
+    // they are 32 words apart in the permuted layout); pl / pr are the columns left of dx = 0 / right of dx = 3
+    uint32_t pb, pl, pr;
+    cidx_t row0; // offset of stored row cy
+    // the cell being visited: i = its index, il / ir = the indices of (x-1, y) / (x+1, y)
+    cidx_t il, ir;
+    bool busy;              // this visit stored to the grid or drew a random number (else it was the identity)
     bool maybe_gas;         // an unvisited GAS cell may exist in the chunk (else scan 3 has nothing to do)
     unsigned long long vis; // tickVisited restricted to the chunk, bit dy*4+dx (flags set outside the chunk are
                             // never read back: the other buffer is cleared before reuse, world.cpp:1125-1131, :1998)
 
     __device__ __forceinline__ ChunkWalk(const SubstepParams& p_, const float* sd, const uint32_t* si, int cx_, int cy_)
-        : p(p_), sden(sd), sinfo(si), cx(cx_), cy(cy_), maybe_gas(false), vis(0ull) {}
+        : p(p_), sden(sd), sinfo(si), cx(cx_), cy(cy_), busy(false), maybe_gas(false), vis(0ull) {
+        pb = fss_perm((uint32_t)cx);
+        pl = fss_perm((uint32_t)(cx - 1));
+        pr = fss_perm((uint32_t)(cx + FSS_CHUNK_W));
+        row0 = (cidx_t)(cy - p.g.sy0) * p.g.pitch;
+        il = ir = 0;
+    }
+    // index of (cx+dx, cy+dy) for dx in 0..3; also sets il / ir
+    __device__ __forceinline__ cidx_t locate(int dx, int dy) {
+        const cidx_t rb = row0 + (cidx_t)dy * p.g.pitch;
+        const uint32_t pc = pb + 32u * (uint32_t)dx;
+        il = rb + (dx > 0 ? pc - 32u : pl);
+        ir = rb + (dx < FSS_CHUNK_W - 1 ? pc + 32u : pr);
+        return rb + pc;
+    }
 
-    __device__ __forceinline__ size_t I(int x, int y) const { return p.g.idx(x, y); }
+    __device__ __forceinline__ cidx_t I(int x, int y) const { return p.g.idx(x, y); }
     __device__ __forceinline__ void mark(int x, int y) {
         unsigned dx = (unsigned)(x - cx), dy = (unsigned)(y - cy);
         if(dx < (unsigned)FSS_CHUNK_W && dy < (unsigned)FSS_CHUNK_H) vis |= 1ull << (dy * FSS_CHUNK_W + dx);
@@ -213,7 +240,7 @@ struct ChunkWalk {
         if(MF_IS(dst_mf, FSS_PHYS_SOLID)) return false;
         return sden[mf_mat(dst_mf)] < self_density;
     }
-    __device__ __forceinline__ void swap_cells(size_t a, size_t b) const {
+    __device__ __forceinline__ void swap_cells(cidx_t a, cidx_t b) const {
         Cell ca = ld_cell(p.g, a), cb = ld_cell(p.g, b);
         st_cell(p.g, a, cb);
         st_cell(p.g, b, ca);
@@ -221,7 +248,7 @@ struct ChunkWalk {
 
     // `neighbour created (copy of mat/colour/temperature, amount 0) if AIR; neighbour.diff += flow`
     // (world.cpp:1399-1403, :1441-1445, :1471-1475, :1503-1507)
-    __device__ __forceinline__ void give(size_t in, uint32_t nmf, float ndif, float flow, uint32_t self_mf, size_t i) const {
+    __device__ __forceinline__ void give(cidx_t in, uint32_t nmf, float ndif, float flow, uint32_t self_mf, cidx_t i) const {
         if(MF_IS(nmf, FSS_PHYS_AIR)) {
             Cell s;
             s.mf = self_mf & (MF_MAT_MASK | MF_DERIVED_MASK);
@@ -236,22 +263,25 @@ struct ChunkWalk {
     }
 
     // ---- SOUP, scan 1, world.cpp:1338-1537 -----------------------------------------------------------------
-    __device__ __forceinline__ void soup1(size_t i, int x, int y, uint32_t mf) {
+    __device__ __forceinline__ void soup1(cidx_t i, int x, int y, uint32_t mf) {
         const Grid& g = p.g;
-        const size_t pitch = g.pitch;
+        const cidx_t pitch = g.pitch;
         const float amt = g.amt[i];
         if(amt == 0.0f) return;      // :1344
         if(amt < FLUID_MinValue) {   // :1346-1350
+            busy = true;
             g.amt[i] = 0.0f;
             return;
         }
         if((p.flags & FSS_PARTICLES_EMIT) && (double)amt > 0.005 && MF_IS(g.mf[i + pitch], FSS_PHYS_AIR) &&
            MF_IS(g.mf[i + 2 * pitch], FSS_PHYS_AIR) && MF_IS(g.mf[i + 3 * pitch], FSS_PHYS_AIR) &&
            MF_IS(g.mf[i + 4 * pitch], FSS_PHYS_AIR)) {
+            busy = true;
             rule_soup_free_fall(p, i, x, y, mf, amt);
             return;
         }
         if(mf & MF_MOVED) return;    // :1376 (moved == settled for liquids)
+        busy = true; // an unsettled liquid cell always changes: it flows, or its settle counter advances
         const float start = amt;
         float remaining = amt;
         const uint32_t mat = mf_mat(mf);
@@ -259,7 +289,7 @@ struct ChunkWalk {
         // Everything the four flows can need, issued as one batch of independent loads (one exposed memory
         // latency instead of a dozen chained ones).  None of these words is written by this visit before its use:
         // each flow only stores to the neighbour it feeds.
-        const size_t ib = i + pitch, it = i - pitch, il = I(x - 1, y), ir = I(x + 1, y);
+        const cidx_t ib = i + pitch, it = i - pitch;
         float tdif = g.dif[i];
         const uint32_t bmf = g.mf[ib], lmf = g.mf[il], rmf = g.mf[ir], tmf = g.mf[it];
         const float bamt = g.amt[ib], lamt = g.amt[il], ramt = g.amt[ir], tamt = g.amt[it];
@@ -359,21 +389,23 @@ struct ChunkWalk {
     }
 
     // ---- SAND, scan 1, world.cpp:1218-1337 -----------------------------------------------------------------
-    __device__ __forceinline__ void sand1(size_t i, int x, int y, uint32_t mf, unsigned long long bit) {
+    __device__ __forceinline__ void sand1(cidx_t i, int x, int y, uint32_t mf, unsigned long long bit) {
         const Grid& g = p.g;
         const uint32_t mat = mf_mat(mf);
         // :1223-1249 interactions: `interact` is false for every material (Materials.cpp:128, :144)
         if(HI_NREACT(sinfo[mat])) {
+            busy = true; // its behaviour depends on the temperature plane, which tickTemperature rewrites
             if(rule_sand_react(p, i, x, y, mf)) {
                 vis |= bit; // (a product is marked visited, so even a GAS product gets no scan 2 / 3 visit)
                 return;
             }
         }
-        const size_t ib = i + g.pitch;
-        const size_t ibl = I(x - 1, y + 1), ibr = I(x + 1, y + 1);
+        const cidx_t ib = i + g.pitch;
+        const cidx_t ibl = il + p.g.pitch, ibr = ir + p.g.pitch;
         const uint32_t bmf = g.mf[ib], blmf = g.mf[ibl], brmf = g.mf[ibr]; // one batch of loads
         const float dself = sden[mat];
         if(!can_move_into(bmf, dself)) return; // :1276, :1287
+        busy = true;
         const bool can_l = can_move_into(blmf, dself), can_r = can_move_into(brmf, dself);
         const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
         if((can_l || can_r) && fss_rand(key, 1287, 0) % 20 == 0) return;
@@ -382,7 +414,7 @@ struct ChunkWalk {
         if(MF_IS(bmf, FSS_PHYS_GAS)) maybe_gas = true;
         st_cell(g, i, below); // :1289 / :1296
         if((p.flags & FSS_PARTICLES_EMIT) && MF_IS(bmf, FSS_PHYS_AIR) && MF_IS(g.mf[ib + g.pitch], FSS_PHYS_AIR) &&
-           MF_IS(g.mf[ib + 2 * (size_t)g.pitch], FSS_PHYS_AIR) && MF_IS(g.mf[ib + 3 * (size_t)g.pitch], FSS_PHYS_AIR)) {
+           MF_IS(g.mf[ib + 2 * g.pitch], FSS_PHYS_AIR) && MF_IS(g.mf[ib + 3 * g.pitch], FSS_PHYS_AIR)) {
             emit_particle(p, x, y, 1291, key, tile); // :1288-1294 free fall: the cell leaves the grid
         } else {
             if(fss_rand(key, 1300, 0) % 2 == 0) tile.mf |= MF_MOVED;
@@ -400,7 +432,7 @@ struct ChunkWalk {
         const unsigned long long bit = 1ull << (dy * FSS_CHUNK_W + dx);
         if(vis & bit) return; // :1161
         const int x = cx + dx, y = cy + dy;
-        const size_t i = I(x, y);
+        const cidx_t i = locate(dx, dy);
         const uint32_t mf = p.g.mf[i];
         if(p.iter >= mf_iters(mf)) { // :1163-1166
             vis |= bit;
@@ -408,6 +440,7 @@ struct ChunkWalk {
         }
         if(MF_IS(mf, FSS_PHYS_GAS)) maybe_gas = true;
         if(mf & MF_FIRE) { // fss_set_materials guarantees a fire material is PASSABLE: no other branch follows
+            busy = true;
             vis |= rule_fire(p, cx, cy, i, x, y, bit);
             return;
         }
@@ -417,9 +450,10 @@ struct ChunkWalk {
             soup1(i, x, y, mf);
         } else if(MF_IS(mf, FSS_PHYS_GAS)) { // :1647-1663
             const Grid& g = p.g;
-            const size_t ia = i - g.pitch;
-            const uint32_t amf = g.mf[ia], almf = g.mf[I(x - 1, y - 1)], armf = g.mf[I(x + 1, y - 1)];
+            const cidx_t ia = i - g.pitch;
+            const uint32_t amf = g.mf[ia], almf = g.mf[il - g.pitch], armf = g.mf[ir - g.pitch];
             if(MF_IS(amf, FSS_PHYS_AIR)) {
+                busy = true;
                 const bool open = MF_IS(almf, FSS_PHYS_AIR) || MF_IS(armf, FSS_PHYS_AIR);
                 if(!(open && fss_rand(fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y), 1654, 0) % 2 == 0)) {
                     swap_cells(i, ia);
@@ -430,17 +464,20 @@ struct ChunkWalk {
     }
 
     // ---- SAND, scan 2, world.cpp:1682-1807 -----------------------------------------------------------------
-    __device__ __forceinline__ void sand2(size_t i, int x, int y, uint32_t mf, unsigned long long bit) {
+    __device__ __forceinline__ void sand2(cidx_t i, int x, int y, uint32_t mf, unsigned long long bit) {
         const Grid& g = p.g;
-        const size_t pitch = g.pitch;
+        const cidx_t pitch = g.pitch;
         const uint32_t mat = mf_mat(mf);
-        const size_t ibl = I(x - 1, y + 1), ibr = I(x + 1, y + 1);
+        const cidx_t ibl = il + p.g.pitch, ibr = ir + p.g.pitch;
         const uint32_t blmf = g.mf[ibl], brmf = g.mf[ibr];
         const float dself = sden[mat];
         const bool can_l = can_move_into(blmf, dself), can_r = can_move_into(brmf, dself);
         if(!(can_l || can_r)) {
             // :1697-1734 with no open diagonal: whatever the pillar probe and its draw decide, `moved` ends up false
-            if(mf & MF_MOVED) g.mf[i] = mf & ~MF_MOVED;
+            if(mf & MF_MOVED) {
+                busy = true;
+                g.mf[i] = mf & ~MF_MOVED;
+            }
             return;
         }
         const uint32_t info = sinfo[mat];
@@ -452,14 +489,15 @@ struct ChunkWalk {
             uint32_t pl[9], pr[9];
 #pragma unroll
             for(int pil = 1; pil < 10; pil++) {
-                pl[pil - 1] = g.mf[ibl + (size_t)pil * pitch];
-                pr[pil - 1] = g.mf[ibr + (size_t)pil * pitch];
+                pl[pil - 1] = g.mf[ibl + (cidx_t)pil * pitch];
+                pr[pil - 1] = g.mf[ibr + (cidx_t)pil * pitch];
             }
 #pragma unroll
             for(int pil = 0; pil < 9; pil++) drop += (MF_IS(pl[pil], FSS_PHYS_AIR) || MF_IS(pr[pil], FSS_PHYS_AIR)) ? 1 : 0;
             const int unstable = drop + 1 - (int)HI_STAB(info);
             if(unstable > 0) {
                 const int chance = 1000 / unstable;
+                if(chance < 1000) busy = true; // a draw decides
                 if(chance < 1000 && fss_rand(key, 1715, 0) % (uint32_t)chance == 0) {
                     // tiles[index].moved = true while the by-value copy keeps moved == false; every path below
                     // either overwrites the grid cell or resets its flag (:1802), so the store is never observable
@@ -468,6 +506,7 @@ struct ChunkWalk {
             }
             if(stopped) return; // :1727-1734, moved is already false
         }
+        busy = true;
         const bool should_move = fss_rand(key, 1736, 0) % (2u * slip) != 0;
         if(!should_move) { // :1802 `tiles[index].moved = false`
             if(mf & MF_MOVED) g.mf[i] = mf & ~MF_MOVED;
@@ -481,7 +520,7 @@ struct ChunkWalk {
         // marks (x-1, y) visited; right: marks nothing at (x+1, y) (the reference's asymmetry, :1759 vs :1780-1784)
         const bool go_left = can_l && (!can_r || fss_rand(key, 1755, 0) % 2 == 0);
         const int sx = go_left ? -1 : 1;
-        const size_t idiag = go_left ? ibl : ibr, iside = I(x + sx, y);
+        const cidx_t idiag = go_left ? ibl : ibr, iside = go_left ? il : ir;
         Cell tile, diag;
         tile.mf = mf;
         tile.col = g.col[i];
@@ -514,12 +553,14 @@ struct ChunkWalk {
         if(vis & bit) return; // :1676
         const Grid& g = p.g;
         const int x = cx + dx, y = cy + dy;
-        const size_t i = I(x, y);
+        const cidx_t i = locate(dx, dy);
         const uint32_t mf = g.mf[i];
         if(MF_IS(mf, FSS_PHYS_SAND)) {
             sand2(i, x, y, mf, bit);
         } else if(MF_IS(mf, FSS_PHYS_SOUP)) { // :1808-1825
-            const float amt = g.amt[i] + g.dif[i];
+            const float dif = g.dif[i];
+            const float amt = g.amt[i] + dif;
+            if(__float_as_uint(dif) != 0u || amt < FLUID_MinValue) busy = true; // else the stores below rewrite the same bits
             if(amt < FLUID_MinValue) {
                 st_cell(g, i, cell_nothing(p.nothing_mf));
             } else {
@@ -528,8 +569,9 @@ struct ChunkWalk {
             }
             vis |= bit;
         } else if(MF_IS(mf, FSS_PHYS_GAS)) { // :1879-1899
-            const size_t ial = I(x - 1, y - 1), iar = I(x + 1, y - 1);
+            const cidx_t ial = il - g.pitch, iar = ir - g.pitch;
             const bool al = MF_IS(g.mf[ial], FSS_PHYS_AIR), ar = MF_IS(g.mf[iar], FSS_PHYS_AIR);
+            if(al || ar) busy = true;
             if(al && !(ar && fss_rand(fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y), 1884, 0) % 2 == 0)) {
                 swap_cells(i, ial);
                 mark(x - 1, y - 1);
@@ -546,12 +588,12 @@ struct ChunkWalk {
         if(vis & bit) return;
         const Grid& g = p.g;
         const int x = cx + dx, y = cy + dy;
-        const size_t i = I(x, y);
+        const cidx_t i = locate(dx, dy);
         const uint32_t mf = g.mf[i];
         if(!MF_IS(mf, FSS_PHYS_GAS)) return;
-        const size_t il = I(x - 1, y), ir = I(x + 1, y);
         const bool l = MF_IS(g.mf[il], FSS_PHYS_AIR), r = MF_IS(g.mf[ir], FSS_PHYS_AIR);
         const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
+        if(l || r || ((sinfo[mf_mat(mf)] & HI_STEAM) && p.condense >= 0)) busy = true;
         if(l && !(r && fss_rand(key, 1950, 0) % 2 == 0)) { // :1944-1964
             swap_cells(i, il);
             mark(x - 1, y);
@@ -565,33 +607,57 @@ struct ChunkWalk {
 
     static __device__ __forceinline__ void prefetch_l1(const void* q) { asm volatile("prefetch.global.L1 [%0];" ::"l"(q)); }
 
-    // first touch of the row above, issued one row early: the own four columns plus one either side
-    __device__ __forceinline__ void prefetch_row(int y, bool fluid) const {
-        const size_t rb = (size_t)(y - p.g.sy0) * p.g.pitch;
+    // first touch of a chunk row (dy may be -1 .. 15), issued ahead of the scan: own four columns of mf / amt / dif
+    // plus the mf of the column either side
+    __device__ __forceinline__ void prefetch_row(int dy) const {
+#ifndef K1_PF_LEVEL
+#define K1_PF_LEVEL 1
+#endif
+        if(K1_PF_LEVEL == 0) return;
+        const cidx_t rb = row0 + (cidx_t)((long long)dy * (long long)p.g.pitch); // dy may be -1
+        prefetch_l1(p.g.mf + rb + pl);
+        prefetch_l1(p.g.mf + rb + pr);
+        if(K1_PF_LEVEL >= 2) {
+            prefetch_l1(p.g.amt + rb + pl);
+            prefetch_l1(p.g.amt + rb + pr);
+            prefetch_l1(p.g.dif + rb + pl);
+            prefetch_l1(p.g.dif + rb + pr);
+        }
 #pragma unroll
-        for(int k = -1; k <= FSS_CHUNK_W; k++) {
-            const size_t j = rb + fss_perm((uint32_t)(cx + k));
+        for(int k = 0; k < FSS_CHUNK_W; k++) {
+            const cidx_t j = rb + pb + 32u * k;
             prefetch_l1(p.g.mf + j);
-            if(fluid && k >= 0 && k < FSS_CHUNK_W) {
-                prefetch_l1(p.g.amt + j);
-                prefetch_l1(p.g.dif + j);
+            prefetch_l1(p.g.amt + j);
+            prefetch_l1(p.g.dif + j);
+            if(K1_PF_LEVEL >= 3) {
+                prefetch_l1(p.g.col + j);
+                prefetch_l1(p.g.temp + j);
             }
         }
     }
 
-    __device__ __forceinline__ void run() {
+    __device__ __forceinline__ void scans() {
+#ifndef K1_NO_PF_BELOW
+        prefetch_row(FSS_CHUNK_H);
+        prefetch_row(FSS_CHUNK_H - 1);
+#endif
 #pragma unroll 1
         for(int dy = FSS_CHUNK_H - 1; dy >= 0; dy--) {
-            prefetch_row(cy + dy - 1, true);
+            prefetch_row(dy - 1);
 #pragma unroll 1
             for(int dx = 0; dx < FSS_CHUNK_W; dx++) scan1_cell(dx, dy);
         }
         // scan 2 and scan 3 only act on cells that are not marked visited: when every lane's chunk is fully
         // visited (iter >= iterations everywhere: AIR, SOLID, spent SAND) the warp skips them
         if(__all_sync(__activemask(), vis == ~0ull)) return;
+#ifndef K1_PF2
+#define K1_PF2 1 /* scan 2 is short per cell: its prefetch runs this many rows ahead */
+#endif
+#pragma unroll
+        for(int k = 1; k <= K1_PF2; k++) prefetch_row(FSS_CHUNK_H - k);
 #pragma unroll 1
         for(int dy = FSS_CHUNK_H - 1; dy >= 0; dy--) {
-            prefetch_row(cy + dy - 1, true);
+            if(dy >= K1_PF2) prefetch_row(dy - K1_PF2);
 #pragma unroll 1
             for(int dx = 0; dx < FSS_CHUNK_W; dx++) scan2_cell(dx, dy);
         }
@@ -601,6 +667,22 @@ struct ChunkWalk {
         for(int dy = FSS_CHUNK_H - 1; dy >= 0; dy--) {
 #pragma unroll 1
             for(int dx = 0; dx < FSS_CHUNK_W; dx++) scan3_cell(dx, dy);
+        }
+    }
+
+    // early-out bookkeeping after the three scans (see SubstepParams::q)
+    __device__ __forceinline__ void run(uint8_t* qown) {
+        scans();
+        if(!qown) return;
+        if(!busy) {
+            *qown = (uint8_t)p.iter;
+        } else {
+            // whatever this visit wrote lies inside its write window (+-2 columns, -2..+17 rows), which only the read
+            // windows of the 3x3 chunks around it can see: those (and this chunk) must be visited again
+#pragma unroll
+            for(int a = -1; a <= 1; a++)
+#pragma unroll
+                for(int b = -1; b <= 1; b++) qown[a * p.q_w + b] = 0xFF;
         }
     }
 };

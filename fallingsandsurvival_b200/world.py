@@ -89,7 +89,7 @@ class World:
     """
 
     def __init__(self, cells=None, zone=None, defs=None, textures=None, seed=0xF55, particles=False,
-                 condense_material=M.WATER, device=0, size=None, strip=None, particle_capacity=0):
+                 condense_material=M.WATER, device=0, size=None, strip=None, particle_capacity=0, early_out=True):
         self.L = load()
         if cells is not None:
             h, w = cells.shape
@@ -101,7 +101,7 @@ class World:
         cfg = abi.Config()
         cfg.struct_size = C.sizeof(abi.Config)
         cfg.width, cfg.height, cfg.seed, cfg.device = w, h, seed, device
-        cfg.flags = abi.PARTICLES_EMIT if particles else 0
+        cfg.flags = (abi.PARTICLES_EMIT if particles else 0) | (0 if early_out else abi.NO_EARLY_OUT)
         cfg.particle_capacity = particle_capacity
         cfg.strip_y0, cfg.strip_rows = strip if strip is not None else (0, 0)
         cfg.condense_material = condense_material

@@ -120,6 +120,9 @@ typedef struct fss_material {
                                  grid as Particle spawn records (world.cpp:1180, :1288-1294, :1352-1374).
                                  Without it those three sites are disabled and cells keep falling in-grid. */
 
+#define FSS_NO_EARLY_OUT 2u   /* visit every micro-chunk in every sub-step like the reference does, instead of skipping
+                                 chunks verified settled (results are identical either way; for measurements) */
+
 typedef struct fss_config {
     uint32_t struct_size; /* sizeof(fss_config), for ABI evolution */
     uint32_t width;       /* world width in cells (reference: uint16_t, world.hpp:106) */

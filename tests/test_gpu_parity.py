@@ -247,3 +247,58 @@ def test_nccl_strips_equal_single_gpu():
                         "--master-port", "29631", script], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "OK" in r.stdout
+
+
+@pytest.mark.parametrize("mix", ["settled", "c3", "liquids", "sand"])
+def test_early_out_is_result_preserving(mix):
+    """skipping chunks verified settled (the dirty-rect replacement) must not change a single bit: early-out on ==
+    early-out off == oracle, over a run long enough for large parts of the world to settle, with host edits
+    (uploads) in the middle that must wake the neighbourhood up again"""
+    cells, zone = make_world((392, 304), mix, seed=77)
+    on = gpu_world(cells, zone, particles=True, early_out=True)
+    off = gpu_world(cells, zone, particles=True, early_out=False)
+    o = oracle_world(cells, zone, particles=True)
+    rng = np.random.default_rng(5)
+    for t in range(70):
+        for w in (on, off, o):
+            w.tick(t)
+            if t % 4 == 2:
+                w.tick_temperature()
+        if t in (30, 50):  # a brush stroke of sand and one of water through the host mirror
+            x0, y0 = int(rng.integers(40, 300)), int(rng.integers(40, 200))
+            patch = on.download(x0, y0, 24, 12)
+            assert patch.tobytes() == off.download(x0, y0, 24, 12).tobytes()
+            patch["material"] = M.TEST_SAND if t == 30 else M.WATER
+            patch["fluid_amount"], patch["fluid_amount_diff"], patch["moved"], patch["settle_count"] = 2.0, 0.0, 0, 0
+            on.upload(x0, y0, patch)
+            off.upload(x0, y0, patch)
+            o.view()[y0:y0 + 12, x0:x0 + 24] = patch
+        if t % 10 == 9 or t in (30, 31, 50, 51):
+            a, b, c = o.cells(), on.cells(), off.cells()
+            assert a.tobytes() == c.tobytes(), f"tick {t} (early-out off): " + diff_report(a, c)
+            assert a.tobytes() == b.tobytes(), f"tick {t} (early-out on): " + diff_report(a, b)
+    assert on.drain_particles().tobytes() == o.drain_particles().tobytes()
+    for w in (on, off, o):
+        w.close()
+
+
+def test_early_out_sparse_world_long_run():
+    """the configs[4] shape in small: stone floor, sparse sand, a few active boxes; 200 ticks, on == off"""
+    from fallingsandsurvival_b200 import world
+    size = (1056, 784)
+    zone = worlds.default_zone(*size)
+    ws = []
+    for eo in (True, False):
+        g = world.World(None, zone, defs=full_table(), size=size, early_out=eo)
+        g.fill_synthetic(worlds.MIX_C2, seed=3, solid_from_row=int(size[1] * 0.8), n_boxes=3, box_size=128,
+                         sparse_material=M.TEST_SAND, sparse_per_mille=2)
+        ws.append(g)
+    assert ws[0].hash() == ws[1].hash()
+    for t in range(200):
+        for g in ws:
+            g.tick(t)
+        if t % 50 == 49:
+            assert ws[0].hash() == ws[1].hash(), t
+    assert ws[0].cells().tobytes() == ws[1].cells().tobytes()
+    for g in ws:
+        g.close()
