@@ -302,3 +302,93 @@ def test_early_out_sparse_world_long_run():
     assert ws[0].cells().tobytes() == ws[1].cells().tobytes()
     for g in ws:
         g.close()
+
+
+def material_test_world(size=(520, 400)):
+    """A small version of BASELINE configs[0]: the MaterialTestGenerator layout (cobble band, walled containers,
+    MaterialTestGenerator.cpp:32-48) with painted blobs of sand, water, steam and fire on soft dirt."""
+    w, h = size
+    cells = worlds.synthetic_world(w, h, [], seed=1)
+    defs = full_table()
+    key = worlds.cell_key_grid(1, w, h)
+    mat = np.zeros((h, w), dtype=np.uint16)
+    mat[int(h * 0.78):int(h * 0.9), :] = M.COBBLE_STONE
+    for k, m in enumerate([31, 33, 35, 38]):  # containers filled with one random `Mat_N` each
+        x0 = 40 + k * 110
+        mat[200:290, x0:x0 + 4] = M.COBBLE_STONE
+        mat[200:290, x0 + 76:x0 + 80] = M.COBBLE_STONE
+        mat[286:290, x0:x0 + 80] = M.COBBLE_STONE
+        mat[210:270, x0 + 4:x0 + 76] = m
+    mat[40:100, 60:130] = M.TEST_SAND
+    mat[40:100, 180:260] = M.WATER
+    mat[120:170, 300:360] = M.STEAM
+    mat[100:110, 380:470] = M.SOFT_DIRT
+    mat[96:100, 390:460] = M.FIRE
+    mat[30:36, 330:400] = M.GOLD_ORE
+    mat[:16, :] = mat[-16:, :] = M.SOLID
+    mat[:, :16] = mat[:, -16:] = M.SOLID
+    cells = worlds.cells_of_material(defs, [M.synthetic_texture(i) for i in range(M.N_TEXTURES)], mat, key)
+    cells["temperature"][mat == M.GOLD_ORE] = 700
+    return cells, worlds.default_zone(w, h)
+
+
+def test_thousand_ticks_bit_exact():
+    """the north star's acceptance line: bit-exact grids against the reference schedule after 1000 ticks"""
+    cells, zone = material_test_world()
+    g = gpu_world(cells, zone, particles=True)
+    o = oracle_world(cells, zone, particles=True)
+    for t in range(1000):
+        g.tick(t)
+        o.tick(t)
+        if t % 4 == 2:
+            g.tick_temperature()
+            o.tick_temperature()
+        if t in (99, 499, 999):
+            a, b = o.cells(), g.cells()
+            assert a.tobytes() == b.tobytes(), f"tick {t}: " + diff_report(a, b)
+    assert o.drain_particles().tobytes() == g.drain_particles(cap=1 << 22).tobytes()
+    g.close()
+    o.close()
+
+
+def test_full_size_properties():
+    """at BASELINE's 16384 x 16384 the oracle is out of reach; check what does not need it: the digest of a 2-strip
+    run equals the undivided run, early-out on equals off, and SAND / SOLID counts are conserved"""
+    import torch
+    from fallingsandsurvival_b200 import world
+    free, _ = torch.cuda.mem_get_info()
+    S = 16384 if free > 60e9 else 4096
+    size = (S + 32, S + 32)
+    zone = (16, 16, S, S)
+    digests, hists = [], []
+    for mode in ("whole", "off", "strips"):
+        if mode == "strips":
+            from fallingsandsurvival_b200 import strips
+            parts = [world.World(None, zone, defs=full_table(), size=size, strip=s) for s in strips.plan_strips(size[1], zone, 2)]
+            ws = parts
+        else:
+            ws = [world.World(None, zone, defs=full_table(), size=size, early_out=(mode != "off"))]
+        for p in ws:
+            p.fill_synthetic(worlds.MIX_C2, seed=0xF55)
+        if not hists:
+            hists.append(ws[0].histogram())
+        L = ws[0].L
+        for t in range(3):
+            if mode == "strips":
+                from fallingsandsurvival_b200 import strips
+                for op, it, tk in strips.tick_schedule():
+                    if op == "substep":
+                        for p in ws:
+                            p.substep(t, it, tk)
+                    else:
+                        assert L.fss_exchange_halo_peer(ws[0].h_, ws[1].h_, tk) == 0
+            else:
+                ws[0].tick(t)
+        digests.append(sum(p.hash() for p in ws) & 0xFFFFFFFFFFFFFFFF)
+        if mode == "whole":
+            hists.append(ws[0].histogram())
+        for p in ws:
+            p.close()
+    assert digests[0] == digests[1] == digests[2], [f"{d:016x}" for d in digests]
+    for m in (M.TEST_SAND, M.COBBLE_STONE, M.SOLID):
+        assert hists[0][m] == hists[1][m]
