@@ -42,7 +42,7 @@ CPU_SAMPLE_ZONE = (2048, 1024)
 
 def mixes():
     from fallingsandsurvival_b200 import worlds
-    return {"c2": worlds.MIX_C2, "c3": worlds.MIX_C3, "c5": worlds.MIX_C2}
+    return {"c2": worlds.MIX_C2, "c3": worlds.MIX_C3, "c4": worlds.MIX_C2, "c5": worlds.MIX_C2}
 
 
 class ClockSampler:
@@ -145,11 +145,13 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(workload, n, size):
-    return {"workload": {"c2": "BASELINE.json configs[1]: synthetic random sand/water/stone world, movement-only tick",
+def workload_config(workload, n, size, zone_wh=None):
+    zone_wh = zone_wh or (size, size * n)
+    return {"workload": {"c4": "BASELINE.json configs[3]: 65536 x 65536 world strip-sharded with per-sub-step halo exchange over NVLink (NCCL)",
+                         "c2": "BASELINE.json configs[1]: synthetic random sand/water/stone world, movement-only tick",
                          "c3": "BASELINE.json configs[2]: configs[1] + lava/fire/gold ore/steam/soft dirt, tickTemperature every 4th tick",
                          "c5": "BASELINE.json configs[4]: mostly settled world with sparse active boxes"}[workload],
-            "zone_cells_per_gpu": [size, size], "zone_cells": [size, size * n], "strips": n,
+            "zone_cells": list(zone_wh), "zone_cells_per_gpu": [zone_wh[0], zone_wh[1] // n], "strips": n,
             "fill": "25% TEST_SAND / 20% WATER / 10% COBBLE_STONE" + (" + 3% LAVA 2% FIRE 3% GOLD_ORE 3% STEAM 5% SOFT_DIRT" if workload == "c3" else ""),
             "particles": "off", "early_out": "on (chunks verified settled are skipped; results identical)", "l2": "working set (5 planes x 4 B x cells) is far larger than the 126 MB L2; no flush needed"}
 
@@ -160,7 +162,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="c4 = BASELINE configs[3]: ONE 65536 x 65536 zone cut into --gpus strips (strong scaling; needs >= 2 GPUs)")
     ap.add_argument("--size", type=int, default=ZONE_PER_GPU, help="zone cells per GPU along each axis (multiple of 32)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -186,8 +189,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     S = args.size
-    W, H = S + 2 * BORDER, S * n + 2 * BORDER
-    zone = (BORDER, BORDER, S, S * n)
+    ZW, ZH = S, S * n
+    if args.workload == "c4":
+        ZW = ZH = 65536 if args.size == ZONE_PER_GPU else args.size
+    W, H = ZW + 2 * BORDER, ZH + 2 * BORDER
+    zone = (BORDER, BORDER, ZW, ZH)
     defs = helpers.full_table()
     workload = args.workload
     temperature = workload == "c3"
@@ -251,6 +257,18 @@ def main():
         torch.cuda.synchronize()
         k1_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(SUBSTEPS)]
 
+    k2_ms = None
+    if temperature and n == 1:
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g.tick_temperature()
+        torch.cuda.synchronize()
+        t0e.record(stream)
+        for _ in range(3):
+            g.tick_temperature()
+        t1e.record(stream)
+        torch.cuda.synchronize()
+        k2_ms = t0e.elapsed_time(t1e) / 3
+
     # ---- e2e: host buffers through the C ABI --------------------------------------------------------------
     y0, y1 = g.stored
     rows = y1 - y0
@@ -278,14 +296,14 @@ def main():
 
     ms = max_over_ranks(ms)
     e2e_ms = max_over_ranks(e2e_ms)
-    zone_cells = S * S * n
+    zone_cells = ZW * ZH
     value = zone_cells * args.steps / (ms / 1e3)
     if rank == 0:
         peak, peak_src = measured_peak()
         line = {
             "metric": "cell-updates/sec", "value": value, "unit": "cell-updates/s", "n_gpus": n, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic", "config": workload_config(workload, n, S),
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if workload == "c4" else "weak",
+            "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic", "config": workload_config(workload, n, S, (ZW, ZH)),
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": zone_cells * args.e2e_steps / (e2e_ms / 1e3), "unit": "cell-updates/s",
                     "h2d_bytes_per_step": int(rows * W * 20), "d2h_bytes_per_step": int(rows * W * 20), "steps": args.e2e_steps,
@@ -305,6 +323,12 @@ def main():
                         "sweeps the active quarter of the grid once per launch: see sweep_*",
                 "sweep_bytes_per_launch": sweep, "sweep_achieved": sweep / (avg / 1e3) / 1e9, "sweep_frac": sweep / (avg / 1e3) / 1e9 / peak,
             }
+        if k2_ms is not None:
+            stored_cells = (y1 - y0) * g.stats().storage_pitch
+            line["roofline_k2"] = {"kernel": "k_temperature", "bound": "hbm", "launch_ms": k2_ms, "unit": "GB/s",
+                                   "achieved": 12.0 * stored_cells / (k2_ms / 1e3) / 1e9, "peak": peak,
+                                   "frac": 12.0 * stored_cells / (k2_ms / 1e3) / 1e9 / peak,
+                                   "note": "12 B per cell-temperature-update (read temp + mf, write temp) x stored cells"}
         if n == 1 and not args.no_cpu:
             try:
                 c = cpu_tick_throughput(workload, 10, 2, temperature)

@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -111,6 +112,7 @@ struct fss_world {
     // settled-chunk flags (SubstepParams::q): (q_h x q_w) bytes, chunk (ci, cj) of the zone at [(cj - q_cj0 + 1) * q_w + ci + 1]
     uint8_t* d_q;
     int q_w, q_h, q_cj0;
+    int k1_variant; // 0 = K1a lock-step (k_substep), 1 = K1b shared-memory decoupled (k_substep_sm)
     // strips
     void* comm;
     int rank, n_ranks;
@@ -189,6 +191,10 @@ int fss_create(const fss_config* cfg, fss_world** out) {
     w->g.sy0 = s_lo;
     w->g.rows = s_hi - s_lo;
     w->part_cap = cfg->particle_capacity ? cfg->particle_capacity : (1u << 20);
+    {
+        const char* v = getenv("FSS_K1"); // kernel selection for A/B measurements: "a" lock-step, "b" shared-memory
+        w->k1_variant = (v && (v[0] == 'b' || v[0] == 'B')) ? 1 : 0; // K1b is 3x slower (profiles/r01_tuning_log.md)
+    }
     if(sizeof(cidx_t) == 4 && (unsigned long long)w->g.rows * w->g.pitch >= (1ull << 32)) {
         delete w;
         return fail(FSS_ERR_INVALID, "%d stored rows x pitch %u is 2^32 cells or more: shard the world into more strips", s_hi - s_lo, (cfg->width + FSS_BLOCK_COLS - 1) / FSS_BLOCK_COLS * FSS_BLOCK_COLS);
@@ -486,7 +492,16 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk) {
     p.ofs_y = ofs_y;
     w->stats.substeps++;
     if(p.ny <= 0 || p.nx <= 0) return FSS_OK;
-    k_substep<<<dim3((p.nx + K1_THREADS - 1) / K1_THREADS, p.ny), K1_THREADS, 0, w->stream>>>(p);
+    if(w->k1_variant == 1) {
+        static bool carveout_set = false;
+        if(!carveout_set) {
+            cudaFuncSetAttribute(k_substep_sm, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carveout_set = true;
+        }
+        k_substep_sm<<<dim3((p.nx + 31) / 32, p.ny), 32, 0, w->stream>>>(p);
+    } else {
+        k_substep<<<dim3((p.nx + K1_THREADS - 1) / K1_THREADS, p.ny), K1_THREADS, 0, w->stream>>>(p);
+    }
     w->stats.kernel_launches++;
     return FSS_OK;
 }

@@ -6,6 +6,7 @@
 //   k_rederive / k_hash / k_histogram / k_fluid_totals   bookkeeping
 #pragma once
 #include "fss_rules.cuh"
+#include "fss_rules_sm.cuh"
 
 #ifndef K1_THREADS
 #define K1_THREADS 128
@@ -40,6 +41,39 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_substep(const __g
 #endif
     ChunkWalk w(p, sden, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y);
     w.run(qown);
+}
+
+// ---- K1b: movement sub-step, window in shared memory, lanes decoupled (fss_rules_sm.cuh) ---------------------
+// One warp per CTA; grid = (ceil(nx / 32), ny); lane l of CTA bx owns the micro-chunk at column x_begin + 8*(32*bx + l).
+#ifndef K1B_MIN_BLOCKS
+#define K1B_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(32, K1B_MIN_BLOCKS) k_substep_sm(const __grid_constant__ SubstepParams p) {
+    __shared__ uint32_t s_mf[SW_CELLS * 32];
+    __shared__ float s_amt[SW_CELLS * 32];
+    __shared__ float s_dif[SW_CELLS * 32];
+    __shared__ float sden[FSS_MAX_MATERIALS];
+    __shared__ uint32_t sinfo[FSS_MAX_MATERIALS];
+    const int lane = threadIdx.x;
+    for(int m = lane; m < p.n_mat; m += 32) {
+        const DMat& d = p.mats[m];
+        sden[m] = d.density;
+        uint32_t stab = d.max_stability > 255 ? 255u : (uint32_t)d.max_stability;
+        sinfo[m] = ((uint32_t)d.slip & 0xFFFFu) | (stab << 16) | (((uint32_t)d.n_react & 3u) << 24) |
+                   ((d.flags & FSS_MAT_IS_STEAM) ? HI_STEAM : 0u);
+    }
+    __syncwarp();
+    const int gi = blockIdx.x * 32 + lane;
+    if(gi >= p.nx) return;
+    uint8_t* qown = nullptr;
+    if(p.q) {
+        qown = p.q + (size_t)(2 * (int)blockIdx.y + p.ofs_y + 1) * p.q_w + (2 * gi + p.ofs_x + 1);
+        if(*qown <= (uint8_t)p.iter) return; // verified settled
+    }
+    const unsigned mask = __activemask();
+    ChunkWalkS w(p, sden, sinfo, s_mf + lane, s_amt + lane, s_dif + lane, p.x_begin + 2 * FSS_CHUNK_W * gi,
+                 p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y);
+    w.run(qown, mask);
 }
 
 // ---- K2: temperature stencil ---------------------------------------------------------------------------
