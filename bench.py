@@ -86,6 +86,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(workload, size):
+    """dram__bytes_read.sum + dram__bytes_write.sum per k_substep launch from the committed ncu capture of this very
+    workload (profiles/r01e_*), or None when the capture does not match the run"""
+    if workload != "c2" or size != ZONE_PER_GPU:
+        return None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01e_k_substep_traffic.json")) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_per_launch_mean"]), d["source"]
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -314,9 +327,12 @@ def main():
             avg = float(np.mean(k1_ms))
             algo = ALGO_BYTES_PER_CELL_UPDATE * zone_cells / SUBSTEPS  # bytes per k_substep launch
             sweep = 2.0 * CELL_BYTES_PLANES * zone_cells / 4            # active micro-chunks read + written once, all planes
+            traffic, traffic_src = ncu_traffic(workload, S)
             line["roofline"] = {
                 "kernel": "k_substep", "bound": "hbm", "achieved": algo / (avg / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": algo / (avg / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "frac": algo / (avg / 1e3) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "dram_achieved": (traffic / (avg / 1e3) / 1e9) if traffic else None,
+                "dram_frac": (traffic / (avg / 1e3) / 1e9 / peak) if traffic else None, "peak_source": peak_src,
                 "launch_ms_avg": avg, "launch_ms_by_iter": [float(np.sum(k1_ms[4 * i:4 * i + 4])) for i in range(6)],
                 "algorithmic_bytes_per_launch": algo,
                 "note": "algorithmic = 32 B per cell-update (whole tick) x zone cells / 24 launches per tick; the shipped schedule "

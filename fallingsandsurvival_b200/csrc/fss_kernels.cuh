@@ -87,6 +87,9 @@ __global__ void __launch_bounds__(32, K1B_MIN_BLOCKS) k_substep_sm(const __grid_
 // Output goes to the second temperature plane (Jacobi); cells outside tickZone are copied.
 #define TEMP_ROWS 32
 #define TEMP_THREADS 128
+#ifndef K2_MIN_BLOCKS
+#define K2_MIN_BLOCKS 1
+#endif
 
 struct TempParams {
     Grid g;
@@ -122,7 +125,7 @@ __device__ __forceinline__ void temp_load_row(const TempParams& p, const float* 
     }
 }
 
-__global__ void __launch_bounds__(TEMP_THREADS) k_temperature(const __grid_constant__ TempParams p) {
+__global__ void __launch_bounds__(TEMP_THREADS, K2_MIN_BLOCKS) k_temperature(const __grid_constant__ TempParams p) {
     __shared__ float s_co[FSS_MAX_MATERIALS], s_cs[FSS_MAX_MATERIALS];
     __shared__ uint32_t s_add[FSS_MAX_MATERIALS];
     for(int m = threadIdx.x; m < p.n_mat; m += TEMP_THREADS) {
