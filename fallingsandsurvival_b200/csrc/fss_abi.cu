@@ -653,6 +653,24 @@ int fss_fill_synthetic(fss_world* w, const fss_fill_spec* spec) {
     return dirty_chunks(w, 0, 0, -1, -1);
 }
 
+int fss_shift_grid(fss_world* w, int change_x, int change_y) {
+    if(!w) return fail(FSS_ERR_INVALID, "null world");
+    if(w->sharded) return fail(FSS_ERR_STATE, "fss_shift_grid on a strip-sharded world is not supported (rows would cross strips)");
+    if(change_x == 0 && change_y == 0) return FSS_OK;
+    if(use_device(w)) return FSS_ERR_CUDA;
+    // every plane goes through the spare temperature plane: shift into it, then swap the two pointers
+    uint32_t** planes[5] = {&w->g.mf, &w->g.col, (uint32_t**)&w->g.temp, (uint32_t**)&w->g.amt, (uint32_t**)&w->g.dif};
+    uint32_t* spare = (uint32_t*)w->temp2;
+    for(int k = 0; k < 5; k++) {
+        k_shift<<<dim3(w->g.pitch / 256, w->g.rows), 256, 0, w->stream>>>(*planes[k], spare, w->g.pitch, w->g.rows, (int)w->cfg.width, change_x, change_y);
+        w->stats.kernel_launches++;
+        std::swap(*planes[k], spare);
+    }
+    w->temp2 = (int32_t*)spare;
+    CU(cudaGetLastError());
+    return dirty_chunks(w, 0, 0, -1, -1);
+}
+
 int fss_get_stats(fss_world* w, fss_stats* out) {
     if(!w || !out) return fail(FSS_ERR_INVALID, "null argument");
     *out = w->stats;

@@ -336,6 +336,22 @@ __global__ void __launch_bounds__(256) k_fill(const __grid_constant__ FillParams
     p.g.dif[i] = 0.0f;
 }
 
+// ---- grid shift when the camera moves: World::tickChunks, world.cpp:2617-2630 ---------------------------------
+// tiles[new] = tiles[new - change] wherever the source lies inside the grid; every other cell keeps its content
+// (the reference's in-place loop never clears the vacated band).  One plane per launch, out of place.
+__global__ void __launch_bounds__(256) k_shift(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t pitch, int rows, int width,
+                                               int change_x, int change_y) {
+    const uint32_t pcol = blockIdx.x * 256u + threadIdx.x;
+    const int y = blockIdx.y;
+    if(pcol >= pitch) return;
+    const int x = (int)fss_unperm(pcol);
+    const int ox = x - change_x, oy = y - change_y;
+    const size_t i = (size_t)y * pitch + pcol;
+    uint32_t v = in[i];
+    if(x < width && ox >= 0 && ox < width && oy >= 0 && oy < rows) v = in[(size_t)oy * pitch + fss_perm((uint32_t)ox)];
+    out[i] = v;
+}
+
 // ---- reductions over the owned rows ---------------------------------------------------------------------
 struct ReduceParams {
     Grid g;

@@ -46,6 +46,7 @@ def load():
         "fss_set_tick_zone": [vp, i32, i32, i32, i32],
         "fss_upload_rect": [vp, i32, i32, i32, i32, vp, sz],
         "fss_download_rect": [vp, i32, i32, i32, i32, vp, sz],
+        "fss_shift_grid": [vp, i32, i32],
         "fss_tick": [vp, u32],
         "fss_substep": [vp, u32, i32, i32],
         "fss_tick_temperature": [vp],
@@ -146,6 +147,10 @@ class World:
     def cells(self):
         """the stored rows of this world (the whole grid unless strip-sharded)"""
         return self.download()
+
+    def shift_grid(self, change_x, change_y):
+        """World::tickChunks' camera shift (world.cpp:2617-2630)"""
+        _check(self.L, self.L.fss_shift_grid(self.h_, change_x, change_y))
 
     # ---- the hot path ----
     def tick(self, tick_ct=None):

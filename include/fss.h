@@ -174,6 +174,11 @@ int fss_set_tick_zone(fss_world* w, int x, int y, int width, int height);
 int fss_upload_rect(fss_world* w, int x, int y, int width, int height, const fss_cell* host, size_t pitch_cells);
 int fss_download_rect(fss_world* w, int x, int y, int width, int height, fss_cell* host, size_t pitch_cells);
 
+/* World::tickChunks' grid shift when the camera moves (world.cpp:2617-2630): every cell moves by (change_x, change_y);
+ * cells whose source would lie outside the grid keep their content, exactly like the reference's in-place loop.  The
+ * caller then uploads the freshly loaded chunks into the vacated band.  Not available on strip-sharded worlds. */
+int fss_shift_grid(fss_world* w, int change_x, int change_y);
+
 /* ---- the hot path ---------------------------------------------------------------------------- */
 /* one World::tick(): 6 iter x 4 tk checkerboard sub-steps x 3 scans (world.cpp:1108-2011);
  * `tick_ct` is World::tickCt (world.cpp:2017), the RNG key.  Asynchronous.  For a strip-sharded
