@@ -112,6 +112,12 @@ struct fss_world {
     // settled-chunk flags (SubstepParams::q): (q_h x q_w) bytes, chunk (ci, cj) of the zone at [(cj - q_cj0 + 1) * q_w + ci + 1]
     uint8_t* d_q;
     int q_w, q_h, q_cj0;
+    // which materials can be in the grid (only ever grows): decides from which iter on the liquid-only kernel is exact
+    bool present[FSS_MAX_MATERIALS];
+    bool present_all;
+    uint8_t* d_present;
+    int liq_from_iter;    // from this iter on only liquids can act
+    int nogas_from_iter;  // from this iter on no GAS / fire can act
     int k1_variant; // 0 = K1a lock-step (k_substep), 1 = K1b shared-memory decoupled (k_substep_sm)
     // strips
     void* comm;
@@ -131,6 +137,38 @@ static size_t plane_cells(const fss_world* w) { return (size_t)w->g.rows * w->g.
 static void owned_bands(const fss_world* w, int& j_lo, int& j_hi) {
     j_lo = w->own_lo <= w->zy ? 0 : (w->own_lo - w->zy) / FSS_ZONE_ALIGN_Y;
     j_hi = w->own_hi >= w->zy + w->zh ? w->zh / FSS_ZONE_ALIGN_Y : (w->own_hi - w->zy) / FSS_ZONE_ALIGN_Y;
+}
+
+// From which iter on can only liquids act?  A SAND / GAS / fire material m acts while iter < iterations(m); once iter has
+// passed the largest such count among the materials that can be present (initial content, uploads, and everything they
+// can turn into: reaction targets, condensed steam, fire), the liquid-only kernel k_substep<true> gives identical results.
+static void recompute_liq(fss_world* w) {
+    bool pres[FSS_MAX_MATERIALS];
+    for(int m = 0; m < FSS_MAX_MATERIALS; m++) pres[m] = m < w->n_mat && (w->present_all || w->present[m]);
+    for(bool grew = true; grew;) {
+        grew = false;
+        for(int m = 0; m < w->n_mat; m++) {
+            if(!pres[m]) continue;
+            const DMat& d = w->h_mats[m];
+            for(int r = 0; r < d.n_react; r++)
+                if(!pres[d.r_target[r]]) pres[d.r_target[r]] = grew = true;
+            if((d.flags & FSS_MAT_IS_STEAM) && w->cfg.condense_material >= 0 && !pres[w->cfg.condense_material]) pres[w->cfg.condense_material] = grew = true;
+        }
+    }
+    int from = 0;
+    bool gas_or_fire = false;
+    for(int m = 0; m < w->n_mat; m++) {
+        if(!pres[m]) continue;
+        const int type = mf_type(w->h_mats[m].bits), iters = std::min(mf_iters(w->h_mats[m].bits), 6);
+        const bool gf = type == FSS_PHYS_GAS || (w->h_mats[m].bits & MF_FIRE);
+        gas_or_fire = gas_or_fire || gf;
+        if(type == FSS_PHYS_SAND || gf) from = std::max(from, iters);
+    }
+    // While SAND moves, a GAS cell it displaces lands on an unvisited position and is then run by scans 2 and 3 whatever its
+    // own `iterations` (they have no such gate): the no-gas kernel is only exact when no GAS / fire material is present at all.
+    // The liquid-only kernel has no such case: nothing moves a cell there (SOUP-SOUP swaps at iter 0 aside).
+    w->nogas_from_iter = gas_or_fire ? 99 : 0;
+    w->liq_from_iter = from;
 }
 
 // Forget the "settled" verdict of every chunk whose read window ([-2,+5] columns, [-2,+25] rows around the chunk)
@@ -232,6 +270,9 @@ int fss_create(const fss_config* cfg, fss_world** out) {
     CUX(cudaMalloc(&w->d_part_count, 8));
     CUX(cudaMemsetAsync(w->d_part_count, 0, 8, w->stream));
     CUX(cudaMalloc(&w->d_red, FSS_MAX_MATERIALS * 16));
+    CUX(cudaMalloc(&w->d_present, FSS_MAX_MATERIALS));
+    CUX(cudaMemsetAsync(w->d_present, 0, FSS_MAX_MATERIALS, w->stream));
+    w->present[0] = true; // Tiles::NOTHING
     w->stage_bytes = std::min(STAGE_BYTES, std::max((size_t)1 << 20, (size_t)cfg->width * sizeof(fss_cell) * (size_t)w->g.rows));
     CUX(cudaMalloc(&w->d_stage, w->stage_bytes));
     CUX(cudaStreamSynchronize(w->stream));
@@ -263,6 +304,7 @@ int fss_destroy(fss_world* w) {
     cudaFree(w->d_red);
     cudaFree(w->d_stage);
     cudaFree(w->d_q);
+    cudaFree(w->d_present);
     if(w->own_stream) cudaStreamDestroy(w->own_stream);
     delete w;
     return FSS_OK;
@@ -339,6 +381,7 @@ int fss_set_materials(fss_world* w, const fss_material* t, int n) {
     w->stats.kernel_launches++;
     CU(cudaStreamSynchronize(w->stream)); // h_mats may be rewritten by the next call
     w->mats_set = true;
+    recompute_liq(w);
     if(dirty_chunks(w, 0, 0, -1, -1)) return FSS_ERR_CUDA;
     return FSS_OK;
 }
@@ -424,6 +467,7 @@ static int rect_copy(fss_world* w, int x, int y, int rw, int rh, fss_cell* host,
         p.mats = w->d_mats;
         p.n_mat = w->n_mat;
         p.aos = (uint32_t*)w->d_stage;
+        p.present = w->d_present;
         p.rx = x;
         p.ry = y + r0;
         p.rw = rw;
@@ -442,7 +486,14 @@ static int rect_copy(fss_world* w, int x, int y, int rw, int rh, fss_cell* host,
         CU(cudaGetLastError());
     }
     if(upload && dirty_chunks(w, x, y, rw, rh)) return FSS_ERR_CUDA;
+    uint8_t seen[FSS_MAX_MATERIALS];
+    if(upload) CU(cudaMemcpyAsync(seen, w->d_present, FSS_MAX_MATERIALS, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream)); // the caller owns `host` again when we return
+    if(upload) {
+        for(int m = 0; m < FSS_MAX_MATERIALS; m++) w->present[m] = w->present[m] || seen[m];
+        if(w->sharded) w->present_all = true; // what the other strips hold is unknown here
+        recompute_liq(w);
+    }
     return FSS_OK;
 }
 
@@ -500,7 +551,11 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk) {
         }
         k_substep_sm<<<dim3((p.nx + 31) / 32, p.ny), 32, 0, w->stream>>>(p);
     } else {
-        k_substep<<<dim3((p.nx + K1_THREADS - 1) / K1_THREADS, p.ny), K1_THREADS, 0, w->stream>>>(p);
+        const dim3 grid((p.nx + K1_THREADS - 1) / K1_THREADS, p.ny);
+        static const bool no_spec = getenv("FSS_NO_SPECIALISE") != nullptr; // measurements: always the general kernel
+        if(!no_spec && iter >= w->liq_from_iter) k_substep<K1_LIQUID><<<grid, K1_THREADS, 0, w->stream>>>(p);
+        else if(!no_spec && iter >= w->nogas_from_iter) k_substep<K1_NOGAS><<<grid, K1_THREADS, 0, w->stream>>>(p);
+        else k_substep<K1_GENERAL><<<grid, K1_THREADS, 0, w->stream>>>(p);
     }
     w->stats.kernel_launches++;
     return FSS_OK;
@@ -650,6 +705,12 @@ int fss_fill_synthetic(fss_world* w, const fss_fill_spec* spec) {
     w->stats.kernel_launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(w->temp2, w->g.temp, plane_cells(w) * 4, cudaMemcpyDeviceToDevice, w->stream));
+    auto mark_present = [&](int m) { if(m >= 0 && m < w->n_mat) w->present[m] = true; };
+    mark_present(spec->border_material);
+    for(int e = 0; e < spec->n_entries; e++) mark_present(spec->material[e]);
+    if(spec->solid_from_row) mark_present(spec->solid_material);
+    if(spec->n_boxes) mark_present(spec->sparse_material);
+    recompute_liq(w); // (every strip of a sharded world is filled from the same spec)
     return dirty_chunks(w, 0, 0, -1, -1);
 }
 

@@ -19,7 +19,15 @@
 // grid = (ceil(nx / 128), ny); thread (bx*128 + t, by) owns the micro-chunk at
 // (x_begin + 8*(bx*128+t), y_begin + 32*by).  A warp therefore owns 32 micro-chunks that are 8 columns
 // apart: with the permuted layout its lanes read consecutive words.
-__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_substep(const __grid_constant__ SubstepParams p) {
+#ifndef K1L_MIN_BLOCKS
+#define K1L_MIN_BLOCKS 9
+#endif
+#ifndef K1N_MIN_BLOCKS
+#define K1N_MIN_BLOCKS 7
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS : (MODE == K1_NOGAS ? K1N_MIN_BLOCKS : K1_MIN_BLOCKS))
+    k_substep(const __grid_constant__ SubstepParams p) {
     __shared__ float sden[FSS_MAX_MATERIALS];
     __shared__ uint32_t sinfo[FSS_MAX_MATERIALS];
     for(int m = threadIdx.x; m < p.n_mat; m += K1_THREADS) {
@@ -39,7 +47,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_substep(const __g
         if(*qown <= (uint8_t)p.iter) return; // verified settled: a warp whose 32 chunks are all settled ends here
     }
 #endif
-    ChunkWalk w(p, sden, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y);
+    ChunkWalk<MODE> w(p, sden, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y);
     w.run(qown);
 }
 
@@ -208,6 +216,7 @@ struct RectParams {
     Grid g;
     const DMat* mats;
     int n_mat;
+    uint8_t* present; // upload: present[m] = 1 for every material id seen (which materials can be in the world)
     uint32_t* aos; // rw * rh cells of 5 words, row-major, packed
     int rx, ry, rw, rh; // rectangle in global cell coordinates (already clipped to storage)
 };
@@ -228,6 +237,7 @@ __global__ void __launch_bounds__(256) k_upload(const __grid_constant__ RectPara
     const uint32_t w0 = c[0];
     uint32_t mat = w0 & 0xFFFFu;
     if((int)mat >= p.n_mat) mat = 0; // unknown material ids become Tiles::NOTHING's material
+    p.present[mat] = 1;
     p.g.mf[i] = mf_pack(mat, (w0 >> 16) & 0xFFu, w0 >> 24, p.mats[mat].bits);
     p.g.col[i] = c[1];
     p.g.temp[i] = (int32_t)c[2];

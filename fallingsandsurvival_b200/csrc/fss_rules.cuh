@@ -195,8 +195,20 @@ __device__ __noinline__ void rule_soup_free_fall(const SubstepParams& p, cidx_t 
     for(int k = 0; k < n; k++) emit_particle(p, x, y, 1366, key, nt);
 }
 
-// per-thread state of one micro-chunk visit
+// per-thread state of one micro-chunk visit.
+// MODE selects a specialisation that is exact for the sub-step it is launched for (fss_abi.cu tracks which materials can
+// be present in the world and picks the mode per iter):
+//   K1_GENERAL  every rule
+//   K1_NOGAS    no GAS and no fire material with `iterations > iter` can be present: SAND + SOUP only, no scan 3
+//   K1_LIQUID   additionally no SAND material: every cell that passes the `iter < iterations` gate is SOUP (or an inert
+//               SOLID / PASSABLE); a third of the instructions and registers.  4 of the 6 iters of a sand + water world.
+#define K1_GENERAL 0
+#define K1_NOGAS 1
+#define K1_LIQUID 2
+template <int MODE>
 struct ChunkWalk {
+    static constexpr bool LIQ = MODE == K1_LIQUID;
+    static constexpr bool GASFIRE = MODE == K1_GENERAL;
     const SubstepParams& p;
     const float* sden;     // shared: density per material
     const uint32_t* sinfo; // shared: HI_* word per material
@@ -411,7 +423,7 @@ struct ChunkWalk {
         if((can_l || can_r) && fss_rand(key, 1287, 0) % 20 == 0) return;
         Cell tile = ld_cell(g, i);
         Cell below = ld_cell(g, ib);
-        if(MF_IS(bmf, FSS_PHYS_GAS)) maybe_gas = true;
+        if(GASFIRE && MF_IS(bmf, FSS_PHYS_GAS)) maybe_gas = true;
         st_cell(g, i, below); // :1289 / :1296
         if((p.flags & FSS_PARTICLES_EMIT) && MF_IS(bmf, FSS_PHYS_AIR) && MF_IS(g.mf[ib + g.pitch], FSS_PHYS_AIR) &&
            MF_IS(g.mf[ib + 2 * g.pitch], FSS_PHYS_AIR) && MF_IS(g.mf[ib + 3 * g.pitch], FSS_PHYS_AIR)) {
@@ -438,8 +450,12 @@ struct ChunkWalk {
             vis |= bit;
             return;
         }
-        if(MF_IS(mf, FSS_PHYS_GAS)) maybe_gas = true;
-        if(mf & MF_FIRE) { // fss_set_materials guarantees a fire material is PASSABLE: no other branch follows
+        if(LIQ) {
+            if(MF_IS(mf, FSS_PHYS_SOUP)) soup1(i, x, y, mf);
+            return;
+        }
+        if(GASFIRE && MF_IS(mf, FSS_PHYS_GAS)) maybe_gas = true;
+        if(GASFIRE && (mf & MF_FIRE)) { // fss_set_materials guarantees a fire material is PASSABLE: no other branch follows
             busy = true;
             vis |= rule_fire(p, cx, cy, i, x, y, bit);
             return;
@@ -448,7 +464,7 @@ struct ChunkWalk {
             sand1(i, x, y, mf, bit);
         } else if(MF_IS(mf, FSS_PHYS_SOUP)) {
             soup1(i, x, y, mf);
-        } else if(MF_IS(mf, FSS_PHYS_GAS)) { // :1647-1663
+        } else if(GASFIRE && MF_IS(mf, FSS_PHYS_GAS)) { // :1647-1663
             const Grid& g = p.g;
             const cidx_t ia = i - g.pitch;
             const uint32_t amf = g.mf[ia], almf = g.mf[il - g.pitch], armf = g.mf[ir - g.pitch];
@@ -533,7 +549,7 @@ struct ChunkWalk {
         diag.amt = g.amt[idiag];
         diag.dif = g.dif[idiag];
         const uint32_t smf = g.mf[iside];
-        if(MF_IS(diag.mf, FSS_PHYS_GAS)) maybe_gas = true;
+        if(GASFIRE && MF_IS(diag.mf, FSS_PHYS_GAS)) maybe_gas = true;
         if(MF_IS(smf, FSS_PHYS_AIR)) {
             st_cell(g, iside, diag);
             if(go_left) mark(x - 1, y);
@@ -558,17 +574,8 @@ struct ChunkWalk {
         if(MF_IS(mf, FSS_PHYS_SAND)) {
             sand2(i, x, y, mf, bit);
         } else if(MF_IS(mf, FSS_PHYS_SOUP)) { // :1808-1825
-            const float dif = g.dif[i];
-            const float amt = g.amt[i] + dif;
-            if(__float_as_uint(dif) != 0u || amt < FLUID_MinValue) busy = true; // else the stores below rewrite the same bits
-            if(amt < FLUID_MinValue) {
-                st_cell(g, i, cell_nothing(p.nothing_mf));
-            } else {
-                g.amt[i] = amt;
-                g.dif[i] = 0.0f;
-            }
-            vis |= bit;
-        } else if(MF_IS(mf, FSS_PHYS_GAS)) { // :1879-1899
+            soup_apply(i, g.amt[i], g.dif[i], bit);
+        } else if(GASFIRE && MF_IS(mf, FSS_PHYS_GAS)) { // :1879-1899
             const cidx_t ial = il - g.pitch, iar = ir - g.pitch;
             const bool al = MF_IS(g.mf[ial], FSS_PHYS_AIR), ar = MF_IS(g.mf[iar], FSS_PHYS_AIR);
             if(al || ar) busy = true;
@@ -580,6 +587,20 @@ struct ChunkWalk {
                 mark(x + 1, y - 1);
             }
         }
+    }
+
+    // SOUP in scan 2, world.cpp:1808-1825: `fluidAmount += fluidAmountDiff; fluidAmountDiff = 0`, below MinValue -> NOTHING
+    __device__ __forceinline__ void soup_apply(cidx_t i, float amt0, float dif, unsigned long long bit) {
+        const Grid& g = p.g;
+        const float amt = amt0 + dif;
+        if(__float_as_uint(dif) != 0u || amt < FLUID_MinValue) busy = true; // else the stores below rewrite the same bits
+        if(amt < FLUID_MinValue) {
+            st_cell(g, i, cell_nothing(p.nothing_mf));
+        } else {
+            g.amt[i] = amt;
+            g.dif[i] = 0.0f;
+        }
+        vis |= bit;
     }
 
     // ---- scan 3, world.cpp:1905-1974 (the SOUP branch is empty, :1918-1943) -----------------------------------
@@ -655,12 +676,40 @@ struct ChunkWalk {
 #endif
 #pragma unroll
         for(int k = 1; k <= K1_PF2; k++) prefetch_row(FSS_CHUNK_H - k);
+        if(LIQ) {
+            // only SOUP cells can be unvisited, and a SOUP cell of scan 2 touches nothing but itself: the row's twelve words
+            // are loaded as one batch of independent loads (one exposed latency per row instead of up to eight)
 #pragma unroll 1
-        for(int dy = FSS_CHUNK_H - 1; dy >= 0; dy--) {
-            if(dy >= K1_PF2) prefetch_row(dy - K1_PF2);
+            for(int dy = FSS_CHUNK_H - 1; dy >= 0; dy--) {
+                if(dy >= K1_PF2) prefetch_row(dy - K1_PF2);
+                const unsigned rowvis = (unsigned)(vis >> (dy * FSS_CHUNK_W)) & 0xFu;
+                if(rowvis == 0xFu) continue;
+                const cidx_t rb = row0 + (cidx_t)dy * p.g.pitch + pb;
+                uint32_t m[FSS_CHUNK_W];
+                float a[FSS_CHUNK_W], d[FSS_CHUNK_W];
+#pragma unroll
+                for(int k = 0; k < FSS_CHUNK_W; k++) {
+                    m[k] = p.g.mf[rb + 32u * k];
+                    a[k] = p.g.amt[rb + 32u * k];
+                    d[k] = p.g.dif[rb + 32u * k];
+                }
+#pragma unroll
+                for(int k = 0; k < FSS_CHUNK_W; k++)
+                    if(!((rowvis >> k) & 1u) && MF_IS(m[k], FSS_PHYS_SOUP)) soup_apply(rb + 32u * k, a[k], d[k], 1ull << (dy * FSS_CHUNK_W + k));
+            }
+            // no GAS can be active: scan 3 has nothing to do
+        } else {
 #pragma unroll 1
-            for(int dx = 0; dx < FSS_CHUNK_W; dx++) scan2_cell(dx, dy);
+            for(int dy = FSS_CHUNK_H - 1; dy >= 0; dy--) {
+                if(dy >= K1_PF2) prefetch_row(dy - K1_PF2);
+#pragma unroll 1
+                for(int dx = 0; dx < FSS_CHUNK_W; dx++) scan2_cell(dx, dy);
+            }
+            if(GASFIRE) scan3();
         }
+    }
+
+    __device__ __forceinline__ void scan3() {
         // a GAS cell inside the chunk at scan 3 was GAS at its scan-1 visit or was swapped in by a SAND move
         if(!__any_sync(__activemask(), maybe_gas)) return;
 #pragma unroll 1

@@ -417,3 +417,42 @@ def test_shift_grid_matches_reference_loop(change):
     assert g.cells().tobytes() == o.cells().tobytes()
     g.close()
     o.close()
+
+
+def test_kernel_specialisation_follows_the_materials_present():
+    """k_substep<K1_LIQUID / K1_NOGAS / K1_GENERAL> are picked per iter from the set of materials that can be in the world.
+    Start with water + stone only (every iter runs the liquid-only kernel), then paint sand, then steam and fire through the
+    host mirror: each upload must widen the set, and the grid must stay bit-identical to the oracle throughout."""
+    cells, zone = make_world((328, 272), [(M.WATER, 30), (M.LAVA, 5), (M.COBBLE_STONE, 15)], seed=41)
+    g = gpu_world(cells, zone, particles=True)
+    o = oracle_world(cells, zone, particles=True)
+
+    def paint(t, mat, x0, y0, w=40, h=24, temp=None):
+        patch = g.download(x0, y0, w, h)
+        patch["material"] = mat
+        patch["fluid_amount"], patch["fluid_amount_diff"], patch["moved"], patch["settle_count"] = 2.0, 0.0, 0, 0
+        if temp is not None:
+            patch["temperature"] = temp
+        g.upload(x0, y0, patch)
+        o.view()[y0:y0 + h, x0:x0 + w] = patch
+
+    for t in range(40):
+        if t == 8:
+            paint(t, M.TEST_SAND, 60, 40)
+        if t == 16:
+            paint(t, M.STEAM, 150, 180)
+            paint(t, M.GOLD_ORE, 200, 40, temp=700)  # reacts into molten gold (a liquid)
+        if t == 24:
+            paint(t, M.SOFT_DIRT, 240, 100)
+            paint(t, M.FIRE, 244, 96, w=30, h=4)
+        g.tick(t)
+        o.tick(t)
+        if t % 4 == 2:
+            g.tick_temperature()
+            o.tick_temperature()
+        if t % 4 == 3:
+            a, b = o.cells(), g.cells()
+            assert a.tobytes() == b.tobytes(), f"tick {t}: " + diff_report(a, b)
+    assert o.drain_particles().tobytes() == g.drain_particles().tobytes()
+    g.close()
+    o.close()
