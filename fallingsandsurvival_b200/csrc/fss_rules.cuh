@@ -59,8 +59,18 @@ __device__ __forceinline__ Cell cell_nothing(uint32_t nothing_mf) {
 }
 
 // world.cpp:1075-1088
+template <bool BRANCH_FREE>
 __device__ __forceinline__ float vertical_flow(float remaining, float dest) {
-    float sum = remaining + dest;
+    const float sum = remaining + dest;
+    if(BRANCH_FREE) {
+        // The three cases computed and selected: lanes fall into different cases all the time and the branchy form
+        // serialises them.  Each case is the reference's own expression, so the selected value is bit-identical.  Used by
+        // the liquid-only kernel; in the general kernel the extra live values cost more (spills) than the branches.
+        const float mid = (FLUID_MaxValue * FLUID_MaxValue + sum * FLUID_MaxCompression) / (FLUID_MaxValue + FLUID_MaxCompression);
+        const float high = (sum + FLUID_MaxCompression) / 2.0f;
+        const float value = sum < 2 * FLUID_MaxValue + FLUID_MaxCompression ? mid : high;
+        return sum <= FLUID_MaxValue ? FLUID_MaxValue : value;
+    }
     float value;
     if(sum <= FLUID_MaxValue) {
         value = FLUID_MaxValue;
@@ -310,7 +320,7 @@ struct ChunkWalk {
         const bool air_below = MF_IS(bmf, FSS_PHYS_AIR); // :1381
         if((air_below && iter <= 2) || mf_mat(bmf) == mat) { // :1384-1405
             const float dst = MF_IS(bmf, FSS_PHYS_SOUP) ? bamt : 0.0f;
-            float flow = vertical_flow(start, dst) - dst;
+            float flow = vertical_flow<LIQ>(start, dst) - dst;
             flow = clamp_flow(flow, start);
             if(flow != 0) {
                 remaining -= flow;
@@ -363,7 +373,7 @@ struct ChunkWalk {
         // :1486-1516
         if(MF_IS(tmf, FSS_PHYS_AIR) || mf_mat(tmf) == mat) {
             const float dst = MF_IS(tmf, FSS_PHYS_SOUP) ? tamt : 0.0f;
-            float flow = remaining - vertical_flow(remaining, dst);
+            float flow = remaining - vertical_flow<LIQ>(remaining, dst);
             flow = clamp_flow(flow, remaining);
             if(flow != 0) {
                 remaining -= flow;

@@ -310,7 +310,7 @@ struct ChunkWalkS {
         const bool air_below = MF_IS(bmf, FSS_PHYS_AIR);
         if((air_below && iter <= 2) || mf_mat(bmf) == mat) {
             const float dst = MF_IS(bmf, FSS_PHYS_SOUP) ? AMT(hb) : 0.0f;
-            float flow = vertical_flow(start, dst) - dst;
+            float flow = vertical_flow<false>(start, dst) - dst;
             flow = clamp_flow(flow, start);
             if(flow != 0) {
                 remaining -= flow;
@@ -360,7 +360,7 @@ struct ChunkWalkS {
         }
         if(MF_IS(tmf, FSS_PHYS_AIR) || mf_mat(tmf) == mat) {
             const float dst = MF_IS(tmf, FSS_PHYS_SOUP) ? AMT(ht) : 0.0f;
-            float flow = remaining - vertical_flow(remaining, dst);
+            float flow = remaining - vertical_flow<false>(remaining, dst);
             flow = clamp_flow(flow, remaining);
             if(flow != 0) {
                 remaining -= flow;
