@@ -111,3 +111,21 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oraclesim" not in text and "refsim" not in text and "fss_oracle" not in text, f
+
+
+def build_c_caller(tmp_path):
+    exe = tmp_path / "abi_smoke"
+    pkg = os.path.join(ROOT, "fallingsandsurvival_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", str(exe),
+                           os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-L", pkg, "-lfss_b200", f"-Wl,-rpath,{pkg}"])
+    return exe
+
+
+def test_plain_c_program_links_against_the_library(lib, tmp_path):
+    """the header is C (not C++), and a C caller links: the reference-side shim needs nothing else"""
+    exe = build_c_caller(tmp_path)
+    import torch
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr  # FSS_ERR_NO_DEVICE, loudly

@@ -456,3 +456,42 @@ def test_kernel_specialisation_follows_the_materials_present():
     assert o.drain_particles().tobytes() == g.drain_particles().tobytes()
     g.close()
     o.close()
+
+
+def test_plain_c_caller_matches_python_binding(tmp_path):
+    """tests/c/abi_smoke.c drives the C ABI directly (create, materials, fill, rect edit, tick, temperature, digest);
+    the same sequence through the Python binding, checked against the oracle, must give the same digest"""
+    import re
+    import subprocess
+
+    from test_abi import build_c_caller
+    from fallingsandsurvival_b200 import world
+    exe = build_c_caller(tmp_path)
+    r = subprocess.run([str(exe), "8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    c_digest = int(re.search(r"digest ([0-9a-f]{16})", r.stdout).group(1), 16)
+    c_particles = int(re.search(r"particles (\d+)", r.stdout).group(1))
+
+    A, SO, SA, LQ, G = abi.PHYS_AIR, abi.PHYS_SOLID, abi.PHYS_SAND, abi.PHYS_SOUP, abi.PHYS_GAS
+    D = M.MaterialDef
+    defs = [D(0, "air", A, 0, 255, 0.0, 0, conduction_self=0.8, conduction_other=0.8, color=0, create_base=0),
+            D(1, "solid", SO, 0, 255, 1.0, 0, create_base=0x808080, color=0),
+            D(2, "sand", SA, 20, 255, 10.0, 2, color=0, create_kind=abi.CREATE_RAND, create_base=(220 << 16) + (155 << 8) + 100,
+              create_rand_mod=30, create_rand_shift=8, create_rand_site=abi.SITE_TILES + 16),
+            D(3, "water", LQ, 0, 255, 1.5, 6, color=0, create_base=0x00B69F, create_temperature=-1023),
+            D(4, "steam", G, 0, 255, -1.0, 1, color=0, flags=abi.MAT_IS_STEAM, create_base=0x666666)]
+    size, zone = (264, 208), (16, 16, 232, 160)
+    g = world.World(None, zone, defs=defs, textures=[], size=size, particles=True, condense_material=3)
+    g.fill_synthetic([(2, 25), (3, 20), (1, 10), (4, 5)], seed=7, border=16, border_material=1)
+    patch = g.download(100, 60, 20, 10)
+    patch["material"], patch["fluid_amount"], patch["fluid_amount_diff"], patch["moved"] = 2, 2.0, 0.0, 0
+    g.upload(100, 60, patch)
+    from oracle import oraclesim
+    o = oraclesim.OracleWorld(g.cells(), zone, defs=defs, textures=[], particles=True, condense_material=3)
+    run_ticks(g, 8)
+    run_ticks(o, 8)
+    assert g.cells().tobytes() == o.cells().tobytes()
+    assert g.hash() == c_digest
+    assert len(g.drain_particles()) == c_particles
+    g.close()
+    o.close()
