@@ -108,7 +108,7 @@ def measured_peak():
 
 
 # ---- the reference's CPU tick on a bounded sample ---------------------------------------------------------------
-def cpu_tick_throughput(workload, steps, warmup, temperature):
+def cpu_tick_throughput(workload, steps, warmup, temperature, variants=False):
     """cell-updates/s of the reference's own World::tick (oracle/_ref, fastest variant) or of the oracle port on a
     2048x1024 zone of the same fill, all host threads."""
     from fallingsandsurvival_b200 import worlds
@@ -136,9 +136,24 @@ def cpu_tick_throughput(workload, steps, warmup, temperature):
             w.tick_temperature()
     dt = time.perf_counter() - t0
     w.close()
-    return {"value": zw * zh * steps / dt, "unit": "cell-updates/s", "cores": cores, "kind": kind,
-            "sample": f"{steps} ticks of a {zw}x{zh} zone, same fill as the workload, after {warmup} warm-up ticks; {what}",
-            "ms_per_step": dt / steps * 1e3}
+    out = {"value": zw * zh * steps / dt, "unit": "cell-updates/s", "cores": cores, "kind": kind,
+           "sample": f"{steps} ticks of a {zw}x{zh} zone, same fill as the workload, after {warmup} warm-up ticks; {what}",
+           "ms_per_step": dt / steps * 1e3}
+    if variants and kind == "reference":
+        # the other two CPU variants, always labelled (few ticks each: they are slow)
+        out["variants"] = {"counter-RNG CHUNK 128 (value above)": out["value"]}
+        for name, variant, threads, nt in (("as shipped: libc rand(), CHUNK 128, 6 threads (world.cpp:64)", "shipped", 6, 3),
+                                           (f"parity oracle schedule: counter-RNG CHUNK 4x16, {cores} threads", "c4x16", cores, 5)):
+            if not refsim.available(variant):
+                continue
+            v = refsim.RefWorld(cells, zone, threads=threads, variant=variant)
+            v.tick(0)
+            t0 = time.perf_counter()
+            for t in range(1, 1 + nt):
+                v.tick(t)
+            out["variants"][name] = zw * zh * nt / (time.perf_counter() - t0)
+            v.close()
+    return out
 
 
 def run_reference(args):
@@ -285,36 +300,39 @@ def main():
     # ---- e2e: host buffers through the C ABI --------------------------------------------------------------
     y0, y1 = g.stored
     rows = y1 - y0
-    host = torch.empty((rows, W, 20), dtype=torch.uint8, pin_memory=True).numpy().view(helpers.abi.CELL_DTYPE).reshape(rows, W)
-    g.download(0, y0, W, rows, out=host)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        g.upload(0, y0, host)
-        step()
+    e2e_ms = e2e_win_ms = None
+    ww = wh = 0
+    if args.e2e_steps > 0:
+        host = torch.empty((rows, W, 20), dtype=torch.uint8, pin_memory=True).numpy().view(helpers.abi.CELL_DTYPE).reshape(rows, W)
         g.download(0, y0, W, rows, out=host)
-    e1.record(stream)
-    barrier()
-    e2e_wall = time.perf_counter() - t0
-    e2e_ms = max(e0.elapsed_time(e1), e2e_wall * 1e3)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            g.upload(0, y0, host)
+            step()
+            g.download(0, y0, W, rows, out=host)
+        e1.record(stream)
+        barrier()
+        e2e_wall = time.perf_counter() - t0
+        e2e_ms = max(e0.elapsed_time(e1), e2e_wall * 1e3)
 
-    # the same loop with the rectangle the reference game itself keeps loaded (1024 x 768 cells, Game.cpp:450-452)
-    # instead of the whole grid: what a shim that tracks its edits pays per tick
-    wx, wy, ww, wh = BORDER, max(y0, BORDER), min(1024, W - 2 * BORDER), min(768, rows - 2 * BORDER)
-    win = torch.empty((wh, ww, 20), dtype=torch.uint8, pin_memory=True).numpy().view(helpers.abi.CELL_DTYPE).reshape(wh, ww)
-    g.download(wx, wy, ww, wh, out=win)
-    barrier()
-    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0.record(stream)
-    for _ in range(args.e2e_steps):
-        g.upload(wx, wy, win)
-        step()
+        # the same loop with the rectangle the reference game itself keeps loaded (1024 x 768 cells, Game.cpp:450-452)
+        # instead of the whole grid: what a shim that tracks its edits pays per tick
+        wx, wy, ww, wh = BORDER, max(y0, BORDER), min(1024, W - 2 * BORDER), min(768, rows - 2 * BORDER)
+        win = torch.empty((wh, ww, 20), dtype=torch.uint8, pin_memory=True).numpy().view(helpers.abi.CELL_DTYPE).reshape(wh, ww)
         g.download(wx, wy, ww, wh, out=win)
-    w1.record(stream)
-    barrier()
-    e2e_win_ms = w0.elapsed_time(w1)
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record(stream)
+        for _ in range(args.e2e_steps):
+            g.upload(wx, wy, win)
+            step()
+            g.download(wx, wy, ww, wh, out=win)
+        w1.record(stream)
+        barrier()
+        e2e_win_ms = w0.elapsed_time(w1)
 
     def max_over_ranks(v):
         if n == 1:
@@ -324,8 +342,9 @@ def main():
         return float(t.item())
 
     ms = max_over_ranks(ms)
-    e2e_ms = max_over_ranks(e2e_ms)
-    e2e_win_ms = max_over_ranks(e2e_win_ms)
+    if e2e_ms is not None:
+        e2e_ms = max_over_ranks(e2e_ms)
+        e2e_win_ms = max_over_ranks(e2e_win_ms)
     zone_cells = ZW * ZH
     value = zone_cells * args.steps / (ms / 1e3)
     if rank == 0:
@@ -335,14 +354,15 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if workload == "c4" else "weak",
             "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic", "config": workload_config(workload, n, S, (ZW, ZH)),
             "gpu_launches": int(launches), "clocks": clocks,
-            "e2e": {"value": zone_cells * args.e2e_steps / (e2e_ms / 1e3), "unit": "cell-updates/s",
+        }
+        if e2e_ms is not None:
+            line["e2e"] = {"value": zone_cells * args.e2e_steps / (e2e_ms / 1e3), "unit": "cell-updates/s",
                     "h2d_bytes_per_step": int(rows * W * 20), "d2h_bytes_per_step": int(rows * W * 20), "steps": args.e2e_steps,
                     "ms_per_step": e2e_ms / args.e2e_steps,
-                    "what": "per step: fss_upload_rect(whole stored grid, pinned host) + fss_tick + fss_download_rect(whole stored grid)"},
-            "e2e_window": {"value": zone_cells * args.e2e_steps / (e2e_win_ms / 1e3), "unit": "cell-updates/s", "ms_per_step": e2e_win_ms / args.e2e_steps,
+                    "what": "per step: fss_upload_rect(whole stored grid, pinned host) + fss_tick + fss_download_rect(whole stored grid)"}
+            line["e2e_window"] = {"value": zone_cells * args.e2e_steps / (e2e_win_ms / 1e3), "unit": "cell-updates/s", "ms_per_step": e2e_win_ms / args.e2e_steps,
                            "h2d_bytes_per_step": int(ww * wh * 20), "d2h_bytes_per_step": int(ww * wh * 20),
-                           "what": "same, but only a 1024 x 768 rectangle (the reference game's loaded window) crosses PCIe each step"},
-        }
+                           "what": "same, but only a 1024 x 768 rectangle (the reference game's loaded window) crosses PCIe each step"}
         if k1_ms:
             avg = float(np.mean(k1_ms))
             algo = ALGO_BYTES_PER_CELL_UPDATE * zone_cells / SUBSTEPS  # bytes per k_substep launch
@@ -367,8 +387,8 @@ def main():
                                    "note": "12 B per cell-temperature-update (read temp + mf, write temp) x stored cells"}
         if n == 1 and not args.no_cpu:
             try:
-                c = cpu_tick_throughput(workload, 10, 2, temperature)
-                line["cpu_baseline"] = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                c = cpu_tick_throughput(workload, 10, 2, temperature, variants=True)
+                line["cpu_baseline"] = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample", "variants") if k in c}
             except Exception as e:  # the checker libraries are optional on a box without them
                 line["cpu_baseline"] = {"value": None, "unit": "cell-updates/s", "cores": os.cpu_count(), "kind": "port", "sample": f"unavailable: {e}"}
         print(json.dumps(line), flush=True)
