@@ -458,7 +458,7 @@ static int rect_copy(fss_world* w, int x, int y, int rw, int rh, fss_cell* host,
     int rc = rect_clip(w, x, y, rw, rh, skip);
     if(rc) return rc;
     host += skip * pitch_cells;
-    const int rows_per_pass = (int)std::max<size_t>(1, w->stage_bytes / ((size_t)rw * sizeof(fss_cell)));
+    const int rows_per_pass = (int)std::min<size_t>(65535, std::max<size_t>(1, w->stage_bytes / ((size_t)rw * sizeof(fss_cell)))); // gridDim.y
     const int nblk = ((x + rw - 1) >> 8) - (x >> 8) + 1;
     for(int r0 = 0; r0 < rh; r0 += rows_per_pass) {
         const int nr = std::min(rows_per_pass, rh - r0);
@@ -701,7 +701,7 @@ int fss_fill_synthetic(fss_world* w, const fss_fill_spec* spec) {
     p.width = w->cfg.width;
     p.height = w->cfg.height;
     p.spec = *spec;
-    k_fill<<<dim3(w->g.pitch / 256, w->g.rows), 256, 0, w->stream>>>(p);
+    k_fill<<<dim3(w->g.rows, w->g.pitch / 256), 256, 0, w->stream>>>(p);
     w->stats.kernel_launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(w->temp2, w->g.temp, plane_cells(w) * 4, cudaMemcpyDeviceToDevice, w->stream));
@@ -723,7 +723,7 @@ int fss_shift_grid(fss_world* w, int change_x, int change_y) {
     uint32_t** planes[5] = {&w->g.mf, &w->g.col, (uint32_t**)&w->g.temp, (uint32_t**)&w->g.amt, (uint32_t**)&w->g.dif};
     uint32_t* spare = (uint32_t*)w->temp2;
     for(int k = 0; k < 5; k++) {
-        k_shift<<<dim3(w->g.pitch / 256, w->g.rows), 256, 0, w->stream>>>(*planes[k], spare, w->g.pitch, w->g.rows, (int)w->cfg.width, change_x, change_y);
+        k_shift<<<dim3(w->g.rows, w->g.pitch / 256), 256, 0, w->stream>>>(*planes[k], spare, w->g.pitch, w->g.rows, (int)w->cfg.width, change_x, change_y);
         w->stats.kernel_launches++;
         std::swap(*planes[k], spare);
     }

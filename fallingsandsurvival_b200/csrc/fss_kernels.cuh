@@ -301,8 +301,8 @@ __device__ __forceinline__ bool fill_in_box(const fss_fill_spec& s, uint32_t wid
 }
 
 __global__ void __launch_bounds__(256) k_fill(const __grid_constant__ FillParams p) {
-    const uint32_t pcol = blockIdx.x * 256u + threadIdx.x; // stored (permuted) column
-    const uint32_t sr = blockIdx.y;
+    const uint32_t pcol = blockIdx.y * 256u + threadIdx.x; // stored (permuted) column
+    const uint32_t sr = blockIdx.x;                        // stored row (grid.x: a 65536-row world exceeds gridDim.y)
     if(pcol >= p.g.pitch) return;
     const uint32_t x = fss_unperm(pcol), y = (uint32_t)p.g.sy0 + sr;
     const size_t i = (size_t)sr * p.g.pitch + pcol;
@@ -351,8 +351,8 @@ __global__ void __launch_bounds__(256) k_fill(const __grid_constant__ FillParams
 // (the reference's in-place loop never clears the vacated band).  One plane per launch, out of place.
 __global__ void __launch_bounds__(256) k_shift(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t pitch, int rows, int width,
                                                int change_x, int change_y) {
-    const uint32_t pcol = blockIdx.x * 256u + threadIdx.x;
-    const int y = blockIdx.y;
+    const uint32_t pcol = blockIdx.y * 256u + threadIdx.x;
+    const int y = blockIdx.x;
     if(pcol >= pitch) return;
     const int x = (int)fss_unperm(pcol);
     const int ox = x - change_x, oy = y - change_y;
