@@ -495,3 +495,32 @@ def test_plain_c_caller_matches_python_binding(tmp_path):
     assert len(g.drain_particles()) == c_particles
     g.close()
     o.close()
+
+
+def test_tall_world_beyond_grid_dim_limits():
+    """a 66000-row world: rows beyond gridDim.y's 65535 in every kernel that walks rows (fill, upload, download,
+    shift, hash), and a couple of ticks against the oracle"""
+    from fallingsandsurvival_b200 import world
+    size = (264, 66016)
+    zone = worlds.default_zone(*size)
+    g = world.World(None, zone, defs=full_table(), size=size)
+    g.fill_synthetic(worlds.MIX_C2, seed=9)
+    host = worlds.synthetic_world(size[0], size[1], worlds.MIX_C2, seed=9, defs=full_table())
+    got = g.cells()
+    assert got.tobytes() == host.tobytes()
+    g2 = gpu_world(host, zone)  # the upload path
+    from oracle import oraclesim
+    assert g.hash() == g2.hash() == oraclesim.hash_cells(host)
+    o = oracle_world(host, zone)
+    for t in range(2):
+        g.tick(t)
+        g2.tick(t)
+        o.tick(t)
+    a = o.cells()
+    assert a.tobytes() == g.cells().tobytes() == g2.cells().tobytes()
+    g.shift_grid(0, 65540)
+    want = a.copy()
+    want[65540:] = a[:size[1] - 65540]
+    assert g.cells().tobytes() == want.tobytes()
+    for w in (g, g2, o):
+        w.close()
