@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS
         if(*qown <= (uint8_t)p.iter) return; // verified settled: a warp whose 32 chunks are all settled ends here
     }
 #endif
-    ChunkWalk<MODE> w(p, sden, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y);
+    ChunkWalk<MODE> w(p, sden, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y,
+                      MODE == K1_GENERAL ? __activemask() : 0u);
     w.run(qown);
 }
 
