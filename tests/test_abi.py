@@ -129,3 +129,22 @@ def test_plain_c_program_links_against_the_library(lib, tmp_path):
         return
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 3 and "no CPU fallback" in r.stderr  # FSS_ERR_NO_DEVICE, loudly
+
+
+def build_cpp_shim_test(tmp_path):
+    exe = tmp_path / "world_shim_test"
+    pkg = os.path.join(ROOT, "fallingsandsurvival_b200")
+    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", str(exe),
+                           os.path.join(ROOT, "tests", "cpp", "world_shim_test.cpp"), "-L", pkg, "-lfss_b200", f"-Wl,-rpath,{pkg}"])
+    return exe
+
+
+def test_cpp_world_mirror_compiles_as_cxx14(lib, tmp_path):
+    """include/fss_world.hpp (the C++ mirror of the reference's World for this path) builds with the reference's own
+    language level (C++14, CMakeLists.txt:325) and fails loudly without a GPU"""
+    exe = build_cpp_shim_test(tmp_path)
+    import torch
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr

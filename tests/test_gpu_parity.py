@@ -524,3 +524,39 @@ def test_tall_world_beyond_grid_dim_limits():
     assert g.cells().tobytes() == want.tobytes()
     for w in (g, g2, o):
         w.close()
+
+
+def test_cpp_world_mirror_matches_oracle(tmp_path):
+    """tests/cpp/world_shim_test.cpp plays a short game script against fss::World (include/fss_world.hpp); the oracle
+    replays the same script (same initial grid, same brush stroke) and must produce the same tiles[]"""
+    import subprocess
+
+    from test_abi import build_cpp_shim_test
+    exe = build_cpp_shim_test(tmp_path)
+    r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    W, H = 328, 240
+    initial = np.fromfile(tmp_path / "initial.bin", dtype=abi.CELL_DTYPE).reshape(H, W)
+    final = np.fromfile(tmp_path / "final.bin", dtype=abi.CELL_DTYPE).reshape(H, W)
+    A, SO, SA, LQ, G = abi.PHYS_AIR, abi.PHYS_SOLID, abi.PHYS_SAND, abi.PHYS_SOUP, abi.PHYS_GAS
+    D = M.MaterialDef
+    defs = [D(0, "_AIR", A, 0, 255, 0.0, 0, color=0, conduction_self=0.8, conduction_other=0.8),
+            D(1, "Cobblestone", SO, 0, 255, 1.0, 0, color=0x808080, conduction_self=0.01, conduction_other=0.4),
+            D(2, "Test Sand", SA, 20, 255, 10.0, 2, color=0xDC9B64),
+            D(3, "Water", LQ, 0, 255, 1.5, 6, color=0x00B69F, create_temperature=-1023),
+            D(4, "Steam", G, 0, 255, -1.0, 1, color=0x666666, flags=abi.MAT_IS_STEAM),
+            D(5, "Lava", LQ, 0, 255, 2.0, 1, color=0xFF7C00, add_temp=2, conduction_self=0.5, conduction_other=0.7, create_temperature=1024)]
+    from oracle import oraclesim
+    o = oraclesim.OracleWorld(initial, (16, 16, W - 32, H - 48), defs=defs, textures=[], particles=True, condense_material=3)
+    for t in range(12):
+        if t == 5:
+            patch = np.zeros((12, 40), dtype=abi.CELL_DTYPE)
+            patch["material"], patch["color"], patch["fluid_amount"] = 2, 0xABCDEF, 2.0
+            o.view()[40:52, 100:140] = patch
+        o.tick(t)
+        if t % 4 == 2:
+            o.tick_temperature()
+    want = o.cells()
+    assert final.tobytes() == want.tobytes(), diff_report(want, final)
+    assert f"digest {oraclesim.hash_cells(want):016x}" in r.stdout
+    o.close()
