@@ -560,3 +560,32 @@ def test_cpp_world_mirror_matches_oracle(tmp_path):
     assert final.tobytes() == want.tobytes(), diff_report(want, final)
     assert f"digest {oraclesim.hash_cells(want):016x}" in r.stdout
     o.close()
+
+
+@pytest.mark.parametrize("size,zone,mix,seed", [
+    ((300, 210), (24, 19, 248, 160), "c3", 1),      # zone origin off the 16-cell grid, y odd
+    ((517, 301), (40, 33, 432, 224), "liquids", 2),  # ragged world width, zone well inside
+    ((1031, 130), (16, 17, 992, 96), "sand", 3),     # wide and flat: one band of 3 chunk rows
+    ((136, 700), (64, 250, 56, 416), "gas", 4),      # tall and narrow, zone narrower than one warp
+    ((264, 264), (120, 120, 24, 32), "fire", 5),     # the smallest legal zone class: 3 x 2 chunks
+    ((776, 520), (256, 16, 496, 480), "c3", 6),      # zone starting on a 256-column storage block
+])
+def test_odd_geometries(size, zone, mix, seed):
+    """tick zones that are not the default one: offsets, sizes and aspect ratios that exercise the block / warp / chunk
+    boundaries of the permuted layout.  Cells outside the zone are live material too (no solid border)."""
+    w, h = size
+    cells = worlds.synthetic_world(w, h, MIXES[mix], seed=seed, defs=full_table(), border=0)
+    g = gpu_world(cells, zone, particles=True)
+    o = oracle_world(cells, zone, particles=True)
+    for t in range(20):
+        g.tick(t)
+        o.tick(t)
+        if t % 4 == 2:
+            g.tick_temperature()
+            o.tick_temperature()
+        if t % 5 == 4:
+            a, b = o.cells(), g.cells()
+            assert a.tobytes() == b.tobytes(), f"tick {t}: " + diff_report(a, b)
+    assert o.drain_particles().tobytes() == g.drain_particles().tobytes()
+    g.close()
+    o.close()
