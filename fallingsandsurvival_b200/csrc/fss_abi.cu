@@ -150,8 +150,9 @@ static void recompute_liq(fss_world* w) {
         for(int m = 0; m < w->n_mat; m++) {
             if(!pres[m]) continue;
             const DMat& d = w->h_mats[m];
-            for(int r = 0; r < d.n_react; r++)
-                if(!pres[d.r_target[r]]) pres[d.r_target[r]] = grew = true;
+            if(mf_type(d.bits) == FSS_PHYS_SAND) // only SAND evaluates its reactions (world.cpp:1251-1274)
+                for(int r = 0; r < d.n_react; r++)
+                    if(!pres[d.r_target[r]]) pres[d.r_target[r]] = grew = true;
             if((d.flags & FSS_MAT_IS_STEAM) && w->cfg.condense_material >= 0 && !pres[w->cfg.condense_material]) pres[w->cfg.condense_material] = grew = true;
         }
     }
@@ -169,6 +170,12 @@ static void recompute_liq(fss_world* w) {
     // The liquid-only kernel has no such case: nothing moves a cell there (SOUP-SOUP swaps at iter 0 aside).
     w->nogas_from_iter = gas_or_fire ? 99 : 0;
     w->liq_from_iter = from;
+    if(getenv("FSS_DEBUG")) {
+        fprintf(stderr, "[fss] materials that can be present:");
+        for(int m = 0; m < w->n_mat; m++)
+            if(pres[m]) fprintf(stderr, " %d", m);
+        fprintf(stderr, " -> liquid-only kernel from iter %d, no-gas kernel %s\n", w->liq_from_iter, gas_or_fire ? "never" : "for the other iters");
+    }
 }
 
 // Forget the "settled" verdict of every chunk whose read window ([-2,+5] columns, [-2,+25] rows around the chunk)

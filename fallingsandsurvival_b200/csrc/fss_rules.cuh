@@ -471,23 +471,29 @@ struct ChunkWalk {
 
     __device__ __forceinline__ void scan1_cell(int dx, int dy) {
         const unsigned long long bit = 1ull << (dy * FSS_CHUNK_W + dx);
-        if(GASFIRE) {
-            // all lanes of the warp stay together until the fire neighbourhoods are gathered
+        if(!LIQ) {
+            // All lanes of the warp go through the prologue together and meet again (ballot / syncwarp) before the
+            // divergent rule bodies: measured 14 % faster than letting early-returning lanes drift ahead inside a row
+            // (they then issue their loads separately and the lock step that makes accesses coalesce is lost).
             const int x = cx + dx, y = cy + dy;
             const bool seen = (vis & bit) != 0ull; // :1161
             const cidx_t i = locate(dx, dy);
             const uint32_t mf = seen ? 0u : p.g.mf[i];
             const bool active = !seen && p.iter < mf_iters(mf);
-            const unsigned fire_lanes = __ballot_sync(wmask, active && (mf & MF_FIRE));
             uint32_t solid_nb = 0u;
-            if(fire_lanes) solid_nb = coop_fire_scan(fire_lanes, x, y);
+            if(GASFIRE) {
+                const unsigned fire_lanes = __ballot_sync(wmask, active && (mf & MF_FIRE));
+                if(fire_lanes) solid_nb = coop_fire_scan(fire_lanes, x, y);
+            } else {
+                __syncwarp(wmask);
+            }
             if(seen) return;
             if(!active) { // :1163-1166
                 vis |= bit;
                 return;
             }
             scan1_body(i, x, y, mf, bit, solid_nb);
-        } else { // no GAS, no fire: the plain sequential prologue (kept as one straight-line function: it compiles to 4 % faster code)
+        } else {
             if(vis & bit) return; // :1161
             const int x = cx + dx, y = cy + dy;
             const cidx_t i = locate(dx, dy);
@@ -496,13 +502,7 @@ struct ChunkWalk {
                 vis |= bit;
                 return;
             }
-            if(LIQ) {
-                if(MF_IS(mf, FSS_PHYS_SOUP)) soup1(i, x, y, mf);
-            } else if(MF_IS(mf, FSS_PHYS_SAND)) {
-                sand1(i, x, y, mf, bit);
-            } else if(MF_IS(mf, FSS_PHYS_SOUP)) {
-                soup1(i, x, y, mf);
-            }
+            if(MF_IS(mf, FSS_PHYS_SOUP)) soup1(i, x, y, mf);
         }
     }
 
@@ -623,9 +623,9 @@ struct ChunkWalk {
     // ---- scan 2, world.cpp:1669-1901 -------------------------------------------------------------------------
     __device__ __forceinline__ void scan2_cell(int dx, int dy) {
         const unsigned long long bit = 1ull << (dy * FSS_CHUNK_W + dx);
-        if(vis & bit) return; // :1676
         const Grid& g = p.g;
         const int x = cx + dx, y = cy + dy;
+        if(vis & bit) return; // :1676 (meeting the warp here like scan1_cell does was measured: no gain)
         const cidx_t i = locate(dx, dy);
         const uint32_t mf = g.mf[i];
         if(MF_IS(mf, FSS_PHYS_SAND)) {
@@ -643,6 +643,43 @@ struct ChunkWalk {
                 swap_cells(i, iar);
                 mark(x + 1, y - 1);
             }
+        }
+    }
+
+    // Scan 2's SOUP step (`fluidAmount += fluidAmountDiff`, :1808-1825) for chunk row r, run right after scan 1 has finished
+    // row r-1, while the row's amt / dif lines are still in L1 (by scan 2 proper they have been evicted and come back from
+    // L2 / HBM: 26 % of the liquid kernel's stall samples).  Exact because
+    //  * after scan 1 of row r-1 nothing in scan 1 reads or writes the amt / dif of a SOUP cell in row r any more (the
+    //    rules reach one row up and down; fire reaches further but only turns SOLID cells into fire);
+    //  * an unvisited SOUP cell is not touched by any other cell's scan-2 visit before its own (SAND displaces cells of the
+    //    row BELOW the moving cell, which scan 2 has already passed; GAS and SAND only move into AIR cells);
+    //  * no scan-2 rule reads another cell's amt / dif, only types, and a cell that survives its update keeps its type.
+    // A cell whose update would delete it (amount < MinValue -> NOTHING) changes type, which SAND / GAS neighbours to its
+    // left test (`== AIR`) before scan 2 reaches it: those are left for scan 2, in the reference's order.
+    __device__ __forceinline__ void early_apply_row(int r) {
+        const unsigned rowvis = (unsigned)(vis >> (r * FSS_CHUNK_W)) & 0xFu;
+        if(rowvis == 0xFu) return;
+        const Grid& g = p.g;
+        const cidx_t rb = row0 + (cidx_t)r * g.pitch + pb;
+        uint32_t m[FSS_CHUNK_W];
+        float a[FSS_CHUNK_W], d[FSS_CHUNK_W];
+#pragma unroll
+        for(int k = 0; k < FSS_CHUNK_W; k++) {
+            m[k] = g.mf[rb + 32u * k];
+            a[k] = g.amt[rb + 32u * k];
+            d[k] = g.dif[rb + 32u * k];
+        }
+#pragma unroll
+        for(int k = 0; k < FSS_CHUNK_W; k++) {
+            if(((rowvis >> k) & 1u) || !MF_IS(m[k], FSS_PHYS_SOUP)) continue;
+            const float amt = a[k] + d[k];
+            if(amt < FLUID_MinValue) continue; // deleted by its update: scan 2 does it in order
+            if(__float_as_uint(d[k]) != 0u) {
+                busy = true;
+                g.amt[rb + 32u * k] = amt;
+                g.dif[rb + 32u * k] = 0.0f;
+            }
+            vis |= 1ull << (r * FSS_CHUNK_W + k);
         }
     }
 
@@ -724,7 +761,10 @@ struct ChunkWalk {
             prefetch_row(dy - 1);
 #pragma unroll 1
             for(int dx = 0; dx < FSS_CHUNK_W; dx++) scan1_cell(dx, dy);
+            // (not in the general kernel: measured on c3 it costs the fire / gas iter more than it saves)
+            if(!GASFIRE && dy < FSS_CHUNK_H - 1) early_apply_row(dy + 1);
         }
+        if(!GASFIRE) early_apply_row(0);
         // scan 2 and scan 3 only act on cells that are not marked visited: when every lane's chunk is fully
         // visited (iter >= iterations everywhere: AIR, SOLID, spent SAND) the warp skips them
         if(__all_sync(__activemask(), vis == ~0ull)) return;
