@@ -728,6 +728,9 @@ struct ChunkWalk {
 #ifndef K1_PF_LEVEL
 #define K1_PF_LEVEL 1
 #endif
+#ifndef K1_PF_PAYLOAD
+#define K1_PF_PAYLOAD 1
+#endif
         if(K1_PF_LEVEL == 0) return;
         const cidx_t rb = row0 + (cidx_t)((long long)dy * (long long)p.g.pitch); // dy may be -1
         prefetch_l1(p.g.mf + rb + pl);
@@ -744,7 +747,7 @@ struct ChunkWalk {
             prefetch_l1(p.g.mf + j);
             prefetch_l1(p.g.amt + j);
             prefetch_l1(p.g.dif + j);
-            if(K1_PF_LEVEL >= 3) {
+            if(K1_PF_LEVEL >= 3 || (K1_PF_PAYLOAD && !LIQ)) { // cells only move where SAND / GAS act: their colour and temperature
                 prefetch_l1(p.g.col + j);
                 prefetch_l1(p.g.temp + j);
             }
