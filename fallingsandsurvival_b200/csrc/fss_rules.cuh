@@ -735,7 +735,7 @@ struct ChunkWalk {
         const cidx_t rb = row0 + (cidx_t)((long long)dy * (long long)p.g.pitch); // dy may be -1
         prefetch_l1(p.g.mf + rb + pl);
         prefetch_l1(p.g.mf + rb + pr);
-        if(K1_PF_LEVEL >= 2) {
+        if(K1_PF_LEVEL >= 2 || LIQ) { // liquids flow sideways out of the chunk: the side columns' amounts (measured: helps K1_LIQUID only)
             prefetch_l1(p.g.amt + rb + pl);
             prefetch_l1(p.g.amt + rb + pr);
             prefetch_l1(p.g.dif + rb + pl);
