@@ -256,10 +256,10 @@ struct ChunkWalk {
         if(dx < (unsigned)FSS_CHUNK_W && dy < (unsigned)FSS_CHUNK_H) vis |= 1ull << (dy * FSS_CHUNK_W + dx);
     }
     __device__ __forceinline__ bool can_move_into(uint32_t dst_mf, float self_density) const {
-        // world.cpp:1276-1285: AIR, or not SOLID and lighter
-        if(MF_IS(dst_mf, FSS_PHYS_AIR)) return true;
-        if(MF_IS(dst_mf, FSS_PHYS_SOLID)) return false;
-        return sden[mf_mat(dst_mf)] < self_density;
+        // world.cpp:1276-1285: AIR, or not SOLID and lighter.  The density is looked up unconditionally (no branch in front
+        // of the shared-memory load), so the two or three tests of one visit have their lookups in flight together.
+        const float d = sden[mf_mat(dst_mf)];
+        return MF_IS(dst_mf, FSS_PHYS_AIR) || (!MF_IS(dst_mf, FSS_PHYS_SOLID) && d < self_density);
     }
     __device__ __forceinline__ void swap_cells(cidx_t a, cidx_t b) const {
         Cell ca = ld_cell(p.g, a), cb = ld_cell(p.g, b);
@@ -425,9 +425,9 @@ struct ChunkWalk {
         const cidx_t ibl = il + p.g.pitch, ibr = ir + p.g.pitch;
         const uint32_t bmf = g.mf[ib], blmf = g.mf[ibl], brmf = g.mf[ibr]; // one batch of loads
         const float dself = sden[mat];
-        if(!can_move_into(bmf, dself)) return; // :1276, :1287
+        const bool can_b = can_move_into(bmf, dself), can_l = can_move_into(blmf, dself), can_r = can_move_into(brmf, dself);
+        if(!can_b) return; // :1276, :1287
         busy = true;
-        const bool can_l = can_move_into(blmf, dself), can_r = can_move_into(brmf, dself);
         const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
         if((can_l || can_r) && fss_rand(key, 1287, 0) % 20 == 0) return;
         Cell tile = ld_cell(g, i);
