@@ -428,10 +428,12 @@ struct ChunkWalk {
         const bool can_b = can_move_into(bmf, dself), can_l = can_move_into(blmf, dself), can_r = can_move_into(brmf, dself);
         if(!can_b) return; // :1276, :1287
         busy = true;
-        const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
-        if((can_l || can_r) && fss_rand(key, 1287, 0) % 20 == 0) return;
+        // the cell will move in 19 of 20 cases: its words and those of the cell below are requested now, so that the loads
+        // are in flight while the draw is computed
         Cell tile = ld_cell(g, i);
         Cell below = ld_cell(g, ib);
+        const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
+        if((can_l || can_r) && fss_rand(key, 1287, 0) % 20 == 0) return;
         if(GASFIRE && MF_IS(bmf, FSS_PHYS_GAS)) maybe_gas = true;
         st_cell(g, i, below); // :1289 / :1296
         if((p.flags & FSS_PARTICLES_EMIT) && MF_IS(bmf, FSS_PHYS_AIR) && MF_IS(g.mf[ib + g.pitch], FSS_PHYS_AIR) &&
@@ -580,6 +582,12 @@ struct ChunkWalk {
             if(stopped) return; // :1727-1734, moved is already false
         }
         busy = true;
+        Cell tile; // requested before the draws below: the cell moves unless `should_move` fails (1 in 2*slip)
+        tile.mf = mf;
+        tile.col = g.col[i];
+        tile.temp = g.temp[i];
+        tile.amt = g.amt[i];
+        tile.dif = g.dif[i];
         const bool should_move = fss_rand(key, 1736, 0) % (2u * slip) != 0;
         if(!should_move) { // :1802 `tiles[index].moved = false`
             if(mf & MF_MOVED) g.mf[i] = mf & ~MF_MOVED;
@@ -594,12 +602,7 @@ struct ChunkWalk {
         const bool go_left = can_l && (!can_r || fss_rand(key, 1755, 0) % 2 == 0);
         const int sx = go_left ? -1 : 1;
         const cidx_t idiag = go_left ? ibl : ibr, iside = go_left ? il : ir;
-        Cell tile, diag;
-        tile.mf = mf;
-        tile.col = g.col[i];
-        tile.temp = g.temp[i];
-        tile.amt = g.amt[i];
-        tile.dif = g.dif[i];
+        Cell diag;
         diag.mf = go_left ? blmf : brmf;
         diag.col = g.col[idiag];
         diag.temp = g.temp[idiag];
