@@ -92,3 +92,7 @@ class FillSpec(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("substeps", C.c_uint64), ("storage_bytes", C.c_uint64),
                 ("storage_pitch", C.c_uint32), ("storage_rows", C.c_uint32), ("storage_y0", C.c_uint32)]
+
+
+# fss_tile_record == MaterialInstanceData (Chunk.hpp:27-31): 12 bytes, 2 bytes of padding after `index`
+RECORD_DTYPE = np.dtype({"names": ["index", "color", "temperature"], "formats": ["<u2", "<u4", "<i4"], "offsets": [0, 4, 8], "itemsize": 12})

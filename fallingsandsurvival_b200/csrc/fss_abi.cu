@@ -721,6 +721,57 @@ int fss_fill_synthetic(fss_world* w, const fss_fill_spec* spec) {
     return dirty_chunks(w, 0, 0, -1, -1);
 }
 
+static int chunk_records(fss_world* w, int x0, int y0, int cw, int ch, fss_tile_record* recs, bool merge) {
+    if(!w || !recs) return fail(FSS_ERR_INVALID, "null argument");
+    if(!w->mats_set) return fail(FSS_ERR_STATE, "chunk records before fss_set_materials");
+    if(cw <= 0 || ch <= 0 || (size_t)cw * ch * sizeof(fss_tile_record) > w->stage_bytes) return fail(FSS_ERR_INVALID, "chunk %dx%d", cw, ch);
+    static_assert(sizeof(fss_tile_record) == 12, "MaterialInstanceData is 12 bytes (Chunk.hpp:27-31)");
+    if(use_device(w)) return FSS_ERR_CUDA;
+    const size_t bytes = (size_t)cw * ch * sizeof(fss_tile_record);
+    ChunkParams p;
+    p.g = w->g;
+    p.mats = w->d_mats;
+    p.n_mat = w->n_mat;
+    p.recs = (uint32_t*)w->d_stage;
+    p.x0 = x0;
+    p.y0 = y0;
+    p.cw = cw;
+    p.ch = ch;
+    p.width = (int)w->cfg.width;
+    p.y_lo = w->g.sy0;
+    p.y_hi = w->g.sy0 + w->g.rows;
+    p.present = w->d_present;
+    const int blocks = (cw * ch + 255) / 256;
+    if(merge) {
+        CU(cudaMemcpyAsync(w->d_stage, recs, bytes, cudaMemcpyHostToDevice, w->stream));
+        k_merge_records<<<blocks, 256, 0, w->stream>>>(p);
+        w->stats.kernel_launches++;
+        CU(cudaGetLastError());
+        const int cx0 = std::max(x0, 0), cy0 = std::max(y0, 0), cx1 = std::min(x0 + cw, (int)w->cfg.width), cy1 = std::min(y0 + ch, (int)w->cfg.height);
+        if(cx1 > cx0 && cy1 > cy0 && dirty_chunks(w, cx0, cy0, cx1 - cx0, cy1 - cy0)) return FSS_ERR_CUDA;
+        uint8_t seen[FSS_MAX_MATERIALS];
+        CU(cudaMemcpyAsync(seen, w->d_present, FSS_MAX_MATERIALS, cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+        for(int m = 0; m < FSS_MAX_MATERIALS; m++) w->present[m] = w->present[m] || seen[m];
+        if(w->sharded) w->present_all = true;
+        recompute_liq(w);
+    } else {
+        k_read_records<<<blocks, 256, 0, w->stream>>>(p);
+        w->stats.kernel_launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(recs, w->d_stage, bytes, cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+    }
+    return FSS_OK;
+}
+
+int fss_merge_chunk_records(fss_world* w, int x0, int y0, int chunk_w, int chunk_h, const fss_tile_record* records) {
+    return chunk_records(w, x0, y0, chunk_w, chunk_h, (fss_tile_record*)records, true);
+}
+int fss_read_chunk_records(fss_world* w, int x0, int y0, int chunk_w, int chunk_h, fss_tile_record* records) {
+    return chunk_records(w, x0, y0, chunk_w, chunk_h, records, false);
+}
+
 int fss_shift_grid(fss_world* w, int change_x, int change_y) {
     if(!w) return fail(FSS_ERR_INVALID, "null world");
     if(w->sharded) return fail(FSS_ERR_STATE, "fss_shift_grid on a strip-sharded world is not supported (rows would cross strips)");

@@ -377,6 +377,49 @@ __global__ void __launch_bounds__(256) k_shift(const uint32_t* __restrict__ in, 
     out[i] = v;
 }
 
+// ---- chunk records <-> planes (Chunk.cpp:139-156, :189-281; world.cpp:2526-2546) -----------------------------
+struct ChunkParams {
+    Grid g;
+    const DMat* mats;
+    int n_mat;
+    uint32_t* recs; // chunk_w * chunk_h records of 3 words {index (low 16 bits), color, temperature}
+    int x0, y0, cw, ch;
+    int width, y_lo, y_hi; // world width; stored rows [y_lo, y_hi)
+    uint8_t* present;
+};
+
+__global__ void __launch_bounds__(256) k_merge_records(const __grid_constant__ ChunkParams p) {
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if(k >= p.cw * p.ch) return;
+    const int x = p.x0 + k % p.cw, y = p.y0 + k / p.cw;
+    if(x < 0 || x >= p.width || y < p.y_lo || y >= p.y_hi) return;
+    const uint32_t* r = p.recs + 3 * (size_t)k;
+    uint32_t mat = r[0] & 0xFFFFu;
+    if((int)mat >= p.n_mat) mat = 0;
+    const size_t i = p.g.idx(x, y);
+    p.g.mf[i] = mat | p.mats[mat].bits;
+    p.g.col[i] = r[1];
+    p.g.temp[i] = (int32_t)r[2];
+    p.g.amt[i] = 2.0f; // MaterialInstance.hpp:21
+    p.g.dif[i] = 0.0f;
+    p.present[mat] = 1;
+}
+
+__global__ void __launch_bounds__(256) k_read_records(const __grid_constant__ ChunkParams p) {
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if(k >= p.cw * p.ch) return;
+    const int x = p.x0 + k % p.cw, y = p.y0 + k / p.cw;
+    uint32_t* r = p.recs + 3 * (size_t)k;
+    if(x < 0 || x >= p.width || y < p.y_lo || y >= p.y_hi) {
+        r[0] = r[1] = r[2] = 0u;
+        return;
+    }
+    const size_t i = p.g.idx(x, y);
+    r[0] = mf_mat(p.g.mf[i]);
+    r[1] = p.g.col[i];
+    r[2] = (uint32_t)p.g.temp[i];
+}
+
 // ---- reductions over the owned rows ---------------------------------------------------------------------
 struct ReduceParams {
     Grid g;

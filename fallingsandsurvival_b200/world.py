@@ -47,6 +47,8 @@ def load():
         "fss_upload_rect": [vp, i32, i32, i32, i32, vp, sz],
         "fss_download_rect": [vp, i32, i32, i32, i32, vp, sz],
         "fss_shift_grid": [vp, i32, i32],
+        "fss_merge_chunk_records": [vp, i32, i32, i32, i32, vp],
+        "fss_read_chunk_records": [vp, i32, i32, i32, i32, vp],
         "fss_tick": [vp, u32],
         "fss_substep": [vp, u32, i32, i32],
         "fss_tick_temperature": [vp],
@@ -147,6 +149,17 @@ class World:
     def cells(self):
         """the stored rows of this world (the whole grid unless strip-sharded)"""
         return self.download()
+
+    def merge_chunk_records(self, x0, y0, records):
+        """Chunk::read + the merge loop of World::frame for the tiles layer: records = (h, w) array of abi.RECORD_DTYPE"""
+        records = np.ascontiguousarray(records, dtype=abi.RECORD_DTYPE)
+        h, w = records.shape
+        _check(self.L, self.L.fss_merge_chunk_records(self.h_, x0, y0, w, h, records.ctypes.data))
+
+    def read_chunk_records(self, x0, y0, w, h):
+        out = np.zeros((h, w), dtype=abi.RECORD_DTYPE)
+        _check(self.L, self.L.fss_read_chunk_records(self.h_, x0, y0, w, h, out.ctypes.data))
+        return out
 
     def shift_grid(self, change_x, change_y):
         """World::tickChunks' camera shift (world.cpp:2617-2630)"""

@@ -174,6 +174,21 @@ int fss_set_tick_zone(fss_world* w, int x, int y, int width, int height);
 int fss_upload_rect(fss_world* w, int x, int y, int width, int height, const fss_cell* host, size_t pitch_cells);
 int fss_download_rect(fss_world* w, int x, int y, int width, int height, fss_cell* host, size_t pitch_cells);
 
+/* ---- chunk records: the reference's on-disk cell format (after LZ4, which stays on the host) ----------------
+ * MaterialInstanceData, Chunk.hpp:27-31: 12 bytes per cell.  fss_merge_chunk_records does what Chunk::read
+ * (Chunk.cpp:139-156) + the merge loop of World::frame (world.cpp:2526-2546) do for the `tiles` layer: the cell at
+ * (x0 + i, y0 + j) becomes MaterialInstance(MATERIALS[index], color, temperature) with the constructor's defaults for
+ * the fields the file does not store (moved = false, fluidAmount = 2.0, fluidAmountDiff = 0, settleCount = 0); cells
+ * outside the world are skipped (`if(tx < 0 || tx >= width ...) continue`).  fss_read_chunk_records is the way back
+ * for Chunk::write (Chunk.cpp:189-281); cells outside the world read as material 0. */
+typedef struct fss_tile_record {
+    uint16_t index;      /* Material::id */
+    uint32_t color;
+    int32_t temperature;
+} fss_tile_record;
+int fss_merge_chunk_records(fss_world* w, int x0, int y0, int chunk_w, int chunk_h, const fss_tile_record* records);
+int fss_read_chunk_records(fss_world* w, int x0, int y0, int chunk_w, int chunk_h, fss_tile_record* records);
+
 /* World::tickChunks' grid shift when the camera moves (world.cpp:2617-2630): every cell moves by (change_x, change_y);
  * cells whose source would lie outside the grid keep their content, exactly like the reference's in-place loop.  The
  * caller then uploads the freshly loaded chunks into the vacated band.  Not available on strip-sharded worlds. */

@@ -79,6 +79,7 @@ int main(void) {
   S(fss_particle_spawn); O(fss_particle_spawn, cell);
   S(fss_fill_spec); O(fss_fill_spec, cumulative_percent); O(fss_fill_spec, solid_from_row); O(fss_fill_spec, sparse_per_mille);
   S(fss_stats); O(fss_stats, storage_pitch);
+  S(fss_tile_record); O(fss_tile_record, color); O(fss_tile_record, temperature);
   printf("CHUNK %d %d %d %d %d\n", FSS_CHUNK_W, FSS_CHUNK_H, FSS_ZONE_ALIGN_X, FSS_ZONE_ALIGN_Y, FSS_ZONE_MARGIN);
   return 0;
 }'''
@@ -90,6 +91,9 @@ int main(void) {
     out = {k: int(v) for k, v in out.items()}
     py = {"fss_cell": abi.CellStruct, "fss_reaction": abi.Reaction, "fss_material": abi.Material, "fss_config": abi.Config,
           "fss_particle_spawn": abi.ParticleSpawn, "fss_fill_spec": abi.FillSpec, "fss_stats": abi.Stats}
+    assert abi.RECORD_DTYPE.itemsize == out.pop("fss_tile_record") == 12
+    assert abi.RECORD_DTYPE.fields["color"][1] == out.pop("fss_tile_record.color")
+    assert abi.RECORD_DTYPE.fields["temperature"][1] == out.pop("fss_tile_record.temperature")
     for key, val in out.items():
         if "." in key:
             t, f = key.split(".")

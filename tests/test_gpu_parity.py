@@ -589,3 +589,39 @@ def test_odd_geometries(size, zone, mix, seed):
     assert o.drain_particles().tobytes() == g.drain_particles().tobytes()
     g.close()
     o.close()
+
+
+@pytest.mark.parametrize("origin", [(64, 48), (-40, 100), (300, -20), (450, 250)])
+def test_chunk_records_merge_and_read(origin):
+    """the reference's on-disk cell records (MaterialInstanceData, Chunk.hpp:27-31) merged into / read back from the device
+    grid like Chunk::read + World::frame / Chunk::write do, including chunks that hang over the world's edge"""
+    cells, zone = make_world((520, 336), "c3", seed=17)
+    g = gpu_world(cells, zone)
+    rng = np.random.default_rng(3)
+    recs = np.zeros((128, 128), dtype=abi.RECORD_DTYPE)
+    recs["index"] = rng.choice([M.AIR, M.STONE, M.TEST_SAND, M.WATER, M.LAVA, M.STEAM], size=recs.shape)
+    recs["color"] = rng.integers(0, 1 << 32, recs.shape, dtype=np.uint64).astype(np.uint32)
+    recs["temperature"] = rng.integers(-1023, 1025, recs.shape)
+    x0, y0 = origin
+    g.merge_chunk_records(x0, y0, recs)
+    want = cells.copy()
+    h, w = cells.shape
+    xs0, ys0, xs1, ys1 = max(x0, 0), max(y0, 0), min(x0 + 128, w), min(y0 + 128, h)
+    sub = recs[ys0 - y0:ys1 - y0, xs0 - x0:xs1 - x0]
+    blk = np.zeros(sub.shape, dtype=abi.CELL_DTYPE)
+    blk["material"], blk["color"], blk["temperature"], blk["fluid_amount"] = sub["index"], sub["color"], sub["temperature"], 2.0
+    want[ys0:ys1, xs0:xs1] = blk
+    assert g.cells().tobytes() == want.tobytes()
+    back = g.read_chunk_records(x0, y0, 128, 128)
+    exp = np.zeros((128, 128), dtype=abi.RECORD_DTYPE)
+    exp[ys0 - y0:ys1 - y0, xs0 - x0:xs1 - x0] = sub
+    for f in ("index", "color", "temperature"):
+        assert (back[f] == exp[f]).all(), f
+    # and the merged world ticks like the oracle (the new materials widened the kernel selection)
+    o = oracle_world(want, zone)
+    for t in range(4):
+        g.tick(t)
+        o.tick(t)
+    assert g.cells().tobytes() == o.cells().tobytes()
+    g.close()
+    o.close()
