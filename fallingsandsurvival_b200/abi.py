@@ -23,6 +23,7 @@ MAT_IS_STEAM = 2
 CREATE_FLAT, CREATE_RAND, CREATE_TEXTURE = 0, 1, 2
 PARTICLES_EMIT = 1
 NO_EARLY_OUT = 2
+TRACK_FLOW = 4
 SITE_TILES = 10000
 
 ERRORS = {0: "FSS_OK", -1: "FSS_ERR_INVALID", -2: "FSS_ERR_ALIGN", -3: "FSS_ERR_CUDA", -4: "FSS_ERR_NO_DEVICE",

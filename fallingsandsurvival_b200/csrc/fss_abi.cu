@@ -270,6 +270,16 @@ int fss_create(const fss_config* cfg, fss_world** out) {
     CUX(cudaMemsetAsync(w->temp2, 0, n * 4, w->stream));
     CUX(cudaMemsetAsync(w->g.amt, 0, n * 4, w->stream));
     CUX(cudaMemsetAsync(w->g.dif, 0, n * 4, w->stream));
+    if(cfg->flags & FSS_TRACK_FLOW) {
+        if(w->k1_variant == 1) {
+            fss_destroy(w);
+            return fail(FSS_ERR_INVALID, "FSS_TRACK_FLOW is not supported by the experimental FSS_K1=b kernel");
+        }
+        CUX(cudaMalloc(&w->g.fx, n * 4));
+        CUX(cudaMalloc(&w->g.fy, n * 4));
+        CUX(cudaMemsetAsync(w->g.fx, 0, n * 4, w->stream));
+        CUX(cudaMemsetAsync(w->g.fy, 0, n * 4, w->stream));
+    }
     CUX(cudaMalloc(&w->d_mats, sizeof(DMat) * FSS_MAX_MATERIALS));
     CUX(cudaMalloc(&w->d_tex, sizeof(DTex) * FSS_MAX_TEXTURES));
     CUX(cudaMemsetAsync(w->d_tex, 0, sizeof(DTex) * FSS_MAX_TEXTURES, w->stream));
@@ -303,6 +313,8 @@ int fss_destroy(fss_world* w) {
     cudaFree(w->temp2);
     cudaFree(w->g.amt);
     cudaFree(w->g.dif);
+    cudaFree(w->g.fx);
+    cudaFree(w->g.fy);
     cudaFree(w->d_mats);
     for(int i = 0; i < FSS_MAX_TEXTURES; i++) cudaFree((void*)w->h_tex[i].px);
     cudaFree(w->d_tex);
@@ -560,9 +572,17 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk) {
     } else {
         const dim3 grid((p.nx + K1_THREADS - 1) / K1_THREADS, p.ny);
         static const bool no_spec = getenv("FSS_NO_SPECIALISE") != nullptr; // measurements: always the general kernel
-        if(!no_spec && iter >= w->liq_from_iter) k_substep<K1_LIQUID><<<grid, K1_THREADS, 0, w->stream>>>(p);
-        else if(!no_spec && iter >= w->nogas_from_iter) k_substep<K1_NOGAS><<<grid, K1_THREADS, 0, w->stream>>>(p);
-        else k_substep<K1_GENERAL><<<grid, K1_THREADS, 0, w->stream>>>(p);
+        const int mode = no_spec ? K1_GENERAL : (iter >= w->liq_from_iter ? K1_LIQUID : (iter >= w->nogas_from_iter ? K1_NOGAS : K1_GENERAL));
+        const bool flow = w->g.fx != nullptr;
+#define FSS_LAUNCH_K1(M, F) k_substep<M, F><<<grid, K1_THREADS, 0, w->stream>>>(p)
+        if(mode == K1_LIQUID) {
+            if(flow) FSS_LAUNCH_K1(K1_LIQUID, true); else FSS_LAUNCH_K1(K1_LIQUID, false);
+        } else if(mode == K1_NOGAS) {
+            if(flow) FSS_LAUNCH_K1(K1_NOGAS, true); else FSS_LAUNCH_K1(K1_NOGAS, false);
+        } else {
+            if(flow) FSS_LAUNCH_K1(K1_GENERAL, true); else FSS_LAUNCH_K1(K1_GENERAL, false);
+        }
+#undef FSS_LAUNCH_K1
     }
     w->stats.kernel_launches++;
     return FSS_OK;
@@ -770,6 +790,38 @@ int fss_merge_chunk_records(fss_world* w, int x0, int y0, int chunk_w, int chunk
 }
 int fss_read_chunk_records(fss_world* w, int x0, int y0, int chunk_w, int chunk_h, fss_tile_record* records) {
     return chunk_records(w, x0, y0, chunk_w, chunk_h, records, false);
+}
+
+int fss_download_flow(fss_world* w, int x, int y, int width, int height, float* flow_x, float* flow_y, size_t pitch) {
+    if(!w || !flow_x || !flow_y) return fail(FSS_ERR_INVALID, "null argument");
+    if(!w->g.fx) return fail(FSS_ERR_STATE, "the world was created without FSS_TRACK_FLOW");
+    if(pitch < (size_t)width) return fail(FSS_ERR_INVALID, "pitch %zu < width %d", pitch, width);
+    if(use_device(w)) return FSS_ERR_CUDA;
+    size_t skip = 0;
+    int rc = rect_clip(w, x, y, width, height, skip);
+    if(rc) return rc;
+    const int rows_per_pass = (int)std::max<size_t>(1, w->stage_bytes / ((size_t)width * 4));
+    for(int pass = 0; pass < 2; pass++) {
+        const float* plane = pass ? w->g.fy : w->g.fx;
+        float* host = (pass ? flow_y : flow_x) + skip * pitch;
+        for(int r0 = 0; r0 < height; r0 += rows_per_pass) {
+            const int nr = std::min(rows_per_pass, height - r0);
+            k_download_plane<<<(width * nr + 255) / 256, 256, 0, w->stream>>>(plane, (float*)w->d_stage, w->g.pitch, w->g.sy0, x, y + r0, width, nr);
+            w->stats.kernel_launches++;
+            CU(cudaMemcpy2DAsync(host + (size_t)r0 * pitch, pitch * 4, w->d_stage, (size_t)width * 4, (size_t)width * 4, nr, cudaMemcpyDeviceToHost, w->stream));
+            CU(cudaStreamSynchronize(w->stream)); // the staging buffer is reused by the next pass
+        }
+    }
+    return FSS_OK;
+}
+
+int fss_clear_flow(fss_world* w) {
+    if(!w) return fail(FSS_ERR_INVALID, "null world");
+    if(!w->g.fx) return fail(FSS_ERR_STATE, "the world was created without FSS_TRACK_FLOW");
+    if(use_device(w)) return FSS_ERR_CUDA;
+    CU(cudaMemsetAsync(w->g.fx, 0, plane_cells(w) * 4, w->stream));
+    CU(cudaMemsetAsync(w->g.fy, 0, plane_cells(w) * 4, w->stream));
+    return FSS_OK;
 }
 
 int fss_shift_grid(fss_world* w, int change_x, int change_y) {

@@ -96,6 +96,8 @@ struct Grid {
     int32_t* temp;
     float* amt;
     float* dif;
+    float* fx; // World::flowX / flowY, nullptr unless FSS_TRACK_FLOW
+    float* fy;
     uint32_t pitch; // cells per stored row (multiple of 256)
     int sy0;        // global row of stored row 0
     int rows;       // stored rows

@@ -39,7 +39,7 @@ __global__ void k_code_pad(int* out) {
 #ifndef K1N_MIN_BLOCKS
 #define K1N_MIN_BLOCKS 7
 #endif
-template <int MODE>
+template <int MODE, bool FLOW>
 __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS : (MODE == K1_NOGAS ? K1N_MIN_BLOCKS : K1_MIN_BLOCKS))
     k_substep(const __grid_constant__ SubstepParams p) {
     __shared__ float sden[FSS_MAX_MATERIALS];
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS
         if(*qown <= (uint8_t)p.iter) return; // verified settled: a warp whose 32 chunks are all settled ends here
     }
 #endif
-    ChunkWalk<MODE> w(p, sden, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y,
+    ChunkWalk<MODE, FLOW> w(p, sden, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y,
                       __activemask());
     w.run(qown);
 }
@@ -418,6 +418,15 @@ __global__ void __launch_bounds__(256) k_read_records(const __grid_constant__ Ch
     r[0] = mf_mat(p.g.mf[i]);
     r[1] = p.g.col[i];
     r[2] = (uint32_t)p.g.temp[i];
+}
+
+// one float plane of a rectangle, permuted storage -> row-major staging
+__global__ void __launch_bounds__(256) k_download_plane(const float* __restrict__ plane, float* __restrict__ out, uint32_t pitch, int sy0,
+                                                        int rx, int ry, int rw, int rh) {
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if(k >= rw * rh) return;
+    const int x = rx + k % rw, y = ry + k / rw;
+    out[k] = plane[(size_t)(y - sy0) * pitch + fss_perm((uint32_t)x)];
 }
 
 // ---- reductions over the owned rows ---------------------------------------------------------------------

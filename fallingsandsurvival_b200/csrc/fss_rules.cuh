@@ -213,7 +213,9 @@ __device__ __noinline__ void rule_soup_free_fall(const SubstepParams& p, cidx_t 
 #define K1_GENERAL 0
 #define K1_NOGAS 1
 #define K1_LIQUID 2
-template <int MODE>
+// FLOW: also keep World::flowX / flowY (FSS_TRACK_FLOW); a compile-time switch because the four extra read-modify-writes
+// sit in the hottest rule and cost 10 % of the liquid kernel even when a run-time test skips them.
+template <int MODE, bool FLOW = false>
 struct ChunkWalk {
     static constexpr bool LIQ = MODE == K1_LIQUID;
     static constexpr bool GASFIRE = MODE == K1_GENERAL;
@@ -326,6 +328,7 @@ struct ChunkWalk {
                 tdif -= flow;
                 give(ib, bmf, bdif, flow, mf, i);
             }
+            if(FLOW) g.fy[i] = g.fy[i] + flow; // :1405 flowY[index] += flow
         } else if(iter == 0 && MF_IS(bmf, FSS_PHYS_SOUP)) { // :1406-1412 (different material: the branch above failed)
             const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
             if(fss_rand(key, 1407, 0) % 10 == 0) {
@@ -350,6 +353,7 @@ struct ChunkWalk {
                 tdif -= flow;
                 give(il, lmf, ldif, flow, mf, i);
             }
+            if(FLOW) g.fx[i] = g.fx[i] - flow; // :1447
         }
         if(remaining < FLUID_MinValue) {
             g.dif[i] = tdif - remaining;
@@ -364,6 +368,7 @@ struct ChunkWalk {
                 tdif -= flow;
                 give(ir, rmf, rdif, flow, mf, i);
             }
+            if(FLOW) g.fx[i] = g.fx[i] + flow; // :1477
         }
         if(remaining < FLUID_MinValue) {
             g.dif[i] = tdif - remaining;
@@ -379,6 +384,7 @@ struct ChunkWalk {
                 tdif -= flow;
                 give(it, tmf, updif, flow, mf, i);
             }
+            if(FLOW) g.fy[i] = g.fy[i] - flow; // :1509
         } else if(iter == 0 && MF_IS(tmf, FSS_PHYS_SOUP)) {
             const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
             if(fss_rand(key, 1511, 0) % 10 == 0) {

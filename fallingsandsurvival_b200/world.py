@@ -47,6 +47,8 @@ def load():
         "fss_upload_rect": [vp, i32, i32, i32, i32, vp, sz],
         "fss_download_rect": [vp, i32, i32, i32, i32, vp, sz],
         "fss_shift_grid": [vp, i32, i32],
+        "fss_download_flow": [vp, i32, i32, i32, i32, vp, vp, sz],
+        "fss_clear_flow": [vp],
         "fss_merge_chunk_records": [vp, i32, i32, i32, i32, vp],
         "fss_read_chunk_records": [vp, i32, i32, i32, i32, vp],
         "fss_tick": [vp, u32],
@@ -92,7 +94,7 @@ class World:
     """
 
     def __init__(self, cells=None, zone=None, defs=None, textures=None, seed=0xF55, particles=False,
-                 condense_material=M.WATER, device=0, size=None, strip=None, particle_capacity=0, early_out=True):
+                 condense_material=M.WATER, device=0, size=None, strip=None, particle_capacity=0, early_out=True, track_flow=False):
         self.L = load()
         if cells is not None:
             h, w = cells.shape
@@ -104,7 +106,7 @@ class World:
         cfg = abi.Config()
         cfg.struct_size = C.sizeof(abi.Config)
         cfg.width, cfg.height, cfg.seed, cfg.device = w, h, seed, device
-        cfg.flags = (abi.PARTICLES_EMIT if particles else 0) | (0 if early_out else abi.NO_EARLY_OUT)
+        cfg.flags = (abi.PARTICLES_EMIT if particles else 0) | (0 if early_out else abi.NO_EARLY_OUT) | (abi.TRACK_FLOW if track_flow else 0)
         cfg.particle_capacity = particle_capacity
         cfg.strip_y0, cfg.strip_rows = strip if strip is not None else (0, 0)
         cfg.condense_material = condense_material
@@ -160,6 +162,17 @@ class World:
         out = np.zeros((h, w), dtype=abi.RECORD_DTYPE)
         _check(self.L, self.L.fss_read_chunk_records(self.h_, x0, y0, w, h, out.ctypes.data))
         return out
+
+    def flow(self):
+        """World::flowX, flowY of the stored rows as (rows, W) float32 arrays (needs track_flow=True)"""
+        y0, y1 = self.stored
+        fx = np.zeros((y1 - y0, self.w), dtype=np.float32)
+        fy = np.zeros((y1 - y0, self.w), dtype=np.float32)
+        _check(self.L, self.L.fss_download_flow(self.h_, 0, y0, self.w, y1 - y0, fx.ctypes.data, fy.ctypes.data, self.w))
+        return fx, fy
+
+    def clear_flow(self):
+        _check(self.L, self.L.fss_clear_flow(self.h_))
 
     def shift_grid(self, change_x, change_y):
         """World::tickChunks' camera shift (world.cpp:2617-2630)"""

@@ -123,6 +123,10 @@ typedef struct fss_material {
 #define FSS_NO_EARLY_OUT 2u   /* visit every micro-chunk in every sub-step like the reference does, instead of skipping
                                  chunks verified settled (results are identical either way; for measurements) */
 
+#define FSS_TRACK_FLOW 4u     /* keep World::flowX / flowY (world.hpp:99-100): the SOUP rule adds every flow it moves to the source
+                                 cell's entry (world.cpp:1405, :1447, :1477, :1509); the renderer reads and zeroes them
+                                 (Game.cpp:2631-2646).  Two more 4-byte planes; off by default. */
+
 typedef struct fss_config {
     uint32_t struct_size; /* sizeof(fss_config), for ABI evolution */
     uint32_t width;       /* world width in cells (reference: uint16_t, world.hpp:106) */
@@ -203,6 +207,11 @@ int fss_tick(fss_world* w, uint32_t tick_ct);
 int fss_substep(fss_world* w, uint32_t tick_ct, int iter, int tk);
 /* one World::tickTemperature() (world.cpp:2043-2143).  Asynchronous. */
 int fss_tick_temperature(fss_world* w);
+
+/* World::flowX / flowY of a rectangle (needs FSS_TRACK_FLOW), row-major floats, `pitch` floats per host row; and the
+ * reset the consumer does after reading them (Game.cpp:2644-2645) */
+int fss_download_flow(fss_world* w, int x, int y, int width, int height, float* flow_x, float* flow_y, size_t pitch);
+int fss_clear_flow(fss_world* w);
 
 /* ---- side outputs ---------------------------------------------------------------------------- */
 /* spawn records since the last drain, sorted by (tick_iter, y, x, site); *n_total = records produced

@@ -40,6 +40,7 @@ struct fsso_world {
     uint32_t flags;
     int condense_material;
     fss_cell* cells;
+    float *flow_x, *flow_y; /* World::flowX / flowY (F/world.hpp:99-100) */
     int32_t* new_temps;
     fss_material mat[FSS_MAX_MATERIALS];
     int max_stability[FSS_MAX_MATERIALS];
@@ -187,6 +188,7 @@ static void scan1_cell(chunk_t* c, int x, int y) {
     fss_cell* self = at(w, x, y);
     fss_cell tile;
     int type, dx = x - c->cx, dy = y - c->cy;
+    size_t index = (size_t)y * w->width + x;
     rng_t r;
 
     if(c->vis[dy][dx]) return;                              /* :1161 */
@@ -314,6 +316,7 @@ static void scan1_cell(chunk_t* c, int x, int y) {
                 if(phys(w, &bottom) == FSS_PHYS_AIR) *at(w, x, y + 1) = liquid_seed(&tile);
                 at(w, x, y + 1)->fluid_amount_diff += flow;
             }
+            w->flow_y[index] += flow;                       /* :1405 */
         } else if(c->iter == 0 && phys(w, &bottom) == FSS_PHYS_SOUP && bottom.material != tile.material) {
             if(rnd(&r, 1407) % 10 == 0) {                   /* :1406-1412 */
                 *self = bottom;
@@ -343,6 +346,7 @@ static void scan1_cell(chunk_t* c, int x, int y) {
                 if(phys(w, &left) == FSS_PHYS_AIR) *at(w, x - 1, y) = liquid_seed(&tile);
                 at(w, x - 1, y)->fluid_amount_diff += flow;
             }
+            w->flow_x[index] -= flow;                       /* :1447 */
         }
         if(remaining < FLUID_MinValue) {
             tile.fluid_amount_diff -= remaining;
@@ -360,6 +364,7 @@ static void scan1_cell(chunk_t* c, int x, int y) {
                 if(phys(w, &right) == FSS_PHYS_AIR) *at(w, x + 1, y) = liquid_seed(&tile);
                 at(w, x + 1, y)->fluid_amount_diff += flow;
             }
+            w->flow_x[index] += flow;                       /* :1477 */
         }
         if(remaining < FLUID_MinValue) {
             tile.fluid_amount_diff -= remaining;
@@ -378,6 +383,7 @@ static void scan1_cell(chunk_t* c, int x, int y) {
                 if(phys(w, &top) == FSS_PHYS_AIR) *at(w, x, y - 1) = liquid_seed(&tile);
                 at(w, x, y - 1)->fluid_amount_diff += flow;
             }
+            w->flow_y[index] -= flow;                       /* :1509 */
         } else if(c->iter == 0 && phys(w, &top) == FSS_PHYS_SOUP && top.material != tile.material) {
             if(rnd(&r, 1511) % 10 == 0) {
                 *self = top;
@@ -624,6 +630,8 @@ fsso_world* fsso_create(int width, int height, uint32_t seed, uint32_t flags, in
     w->condense_material = condense_material;
     w->cells = (fss_cell*)malloc(n * sizeof(fss_cell));
     w->new_temps = (int32_t*)calloc(n, sizeof(int32_t));
+    w->flow_x = (float*)calloc(n, sizeof(float));
+    w->flow_y = (float*)calloc(n, sizeof(float));
     for(i = 0; i < n; i++) w->cells[i] = nothing();
     w->fire_id = -1;
     return w;
@@ -635,6 +643,8 @@ void fsso_destroy(fsso_world* w) {
     for(i = 0; i < FSS_MAX_TEXTURES; i++) free(w->tex[i].px);
     free(w->cells);
     free(w->new_temps);
+    free(w->flow_x);
+    free(w->flow_y);
     free(w->parts);
     free(w);
 }
@@ -677,6 +687,8 @@ int fsso_set_tick_zone(fsso_world* w, int x, int y, int zw, int zh) {
 }
 
 fss_cell* fsso_cells(fsso_world* w) { return w->cells; }
+float* fsso_flow_x(fsso_world* w) { return w->flow_x; }
+float* fsso_flow_y(fsso_world* w) { return w->flow_y; }
 size_t fsso_num_particles(fsso_world* w) { return w->n_parts; }
 
 static int cmp_part(const void* a, const void* b) {

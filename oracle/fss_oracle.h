@@ -27,6 +27,8 @@ int fsso_set_materials(fsso_world* w, const fss_material* table, int n);
 int fsso_set_texture(fsso_world* w, int index, const uint32_t* argb, int tw, int th);
 int fsso_set_tick_zone(fsso_world* w, int x, int y, int zw, int zh);
 fss_cell* fsso_cells(fsso_world* w); /* row-major width*height, owned by the world */
+float* fsso_flow_x(fsso_world* w);   /* World::flowX / flowY, row-major width*height: the caller zeroes them when it consumes them */
+float* fsso_flow_y(fsso_world* w);
 
 void fsso_tick(fsso_world* w, uint32_t tick_ct);
 /* one (iter, tk) sub-step restricted to micro-chunks whose first row lies in [cy_from, cy_to) */

@@ -39,6 +39,10 @@ def load():
     L.fsso_set_tick_zone.argtypes = [C.c_void_p] + [C.c_int] * 4
     L.fsso_cells.restype = C.c_void_p
     L.fsso_cells.argtypes = [C.c_void_p]
+    L.fsso_flow_x.restype = C.c_void_p
+    L.fsso_flow_x.argtypes = [C.c_void_p]
+    L.fsso_flow_y.restype = C.c_void_p
+    L.fsso_flow_y.argtypes = [C.c_void_p]
     L.fsso_tick.argtypes = [C.c_void_p, C.c_uint32]
     L.fsso_substep_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int]
     L.fsso_tick_temperature.argtypes = [C.c_void_p]
@@ -91,6 +95,14 @@ class OracleWorld:
 
     def cells(self):
         return self._view.copy()
+
+    def flow(self):
+        """World::flowX, flowY as (H, W) float32 copies"""
+        out = []
+        for f in (self.L.fsso_flow_x, self.L.fsso_flow_y):
+            a = np.ctypeslib.as_array(C.cast(f(self.h_), C.POINTER(C.c_float)), shape=(self.h * self.w,))
+            out.append(a.reshape(self.h, self.w).copy())
+        return out[0], out[1]
 
     def view(self):
         return self._view

@@ -259,6 +259,15 @@ int fssref_set_cells(void* h, const fss_cell* cells) {
     return 0;
 }
 
+/* World::flowX / flowY (world.hpp:99-100), accumulated by the SOUP rule (world.cpp:1405, :1447, :1477, :1509) */
+int fssref_get_flow(void* h, float* fx, float* fy) {
+    World& W = ((RefWorld*)h)->w;
+    size_t n = (size_t)W.width * W.height;
+    memcpy(fx, W.flowX, n * sizeof(float));
+    memcpy(fy, W.flowY, n * sizeof(float));
+    return 0;
+}
+
 int fssref_get_cells(void* h, fss_cell* cells) {
     World& W = ((RefWorld*)h)->w;
     size_t n = (size_t)W.width * W.height;

@@ -36,6 +36,7 @@ def load(variant="c4x16"):
     L.fssref_world_destroy.argtypes = [C.c_void_p]
     L.fssref_set_cells.argtypes = [C.c_void_p, C.c_void_p]
     L.fssref_get_cells.argtypes = [C.c_void_p, C.c_void_p]
+    L.fssref_get_flow.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.fssref_tick.restype = C.c_double
     L.fssref_tick.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int]
     L.fssref_tick_temperature.restype = C.c_double
@@ -98,6 +99,13 @@ class RefWorld:
         out = np.zeros((self.h, self.w), dtype=abi.CELL_DTYPE)
         self.L.fssref_get_cells(self.h_, out.ctypes.data)
         return out
+
+    def flow(self):
+        """World::flowX, flowY as (H, W) float32 arrays"""
+        fx = np.zeros((self.h, self.w), dtype=np.float32)
+        fy = np.zeros((self.h, self.w), dtype=np.float32)
+        self.L.fssref_get_flow(self.h_, fx.ctypes.data, fy.ctypes.data)
+        return fx, fy
 
     def tick(self, tick_ct=None):
         """one World::tick(); returns seconds inside it"""

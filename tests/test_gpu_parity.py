@@ -625,3 +625,28 @@ def test_chunk_records_merge_and_read(origin):
     assert g.cells().tobytes() == o.cells().tobytes()
     g.close()
     o.close()
+
+
+@pytest.mark.parametrize("mix", ["c2", "liquids", "c3"])
+def test_flow_side_output_matches_oracle(mix):
+    """World::flowX / flowY (FSS_TRACK_FLOW): bit-identical float accumulators, and the consumer's reset"""
+    cells, zone = make_world((264, 208), mix, seed=23)
+    g = gpu_world(cells, zone, track_flow=True)
+    o = oracle_world(cells, zone)
+    for t in range(12):
+        g.tick(t)
+        o.tick(t)
+    (gx, gy), (ox, oy) = g.flow(), o.flow()
+    assert np.abs(ox).sum() > 0 and np.abs(oy).sum() > 0
+    assert gx.tobytes() == ox.tobytes() and gy.tobytes() == oy.tobytes()
+    assert g.cells().tobytes() == o.cells().tobytes()
+    g.clear_flow()
+    gx, gy = g.flow()
+    assert not gx.any() and not gy.any()
+    from fallingsandsurvival_b200 import world
+    plain = gpu_world(cells, zone)
+    with pytest.raises(world.FssError) as e:
+        plain.flow()
+    assert e.value.code == -5
+    for w in (g, o, plain):
+        w.close()

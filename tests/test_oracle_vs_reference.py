@@ -98,3 +98,22 @@ def test_temperature_rows_split_equals_whole():
     bot = b.cells()
     merged = np.concatenate([top[:80], bot[80:]])
     assert merged.tobytes() == a.cells().tobytes()
+
+
+@pytest.mark.parametrize("mix", ["c2", "liquids", "c3"])
+def test_oracle_flow_matches_reference_build(mix, have_ref):
+    """World::flowX / flowY, the SOUP rule's side output for the water shader (world.cpp:1405, :1447, :1477, :1509)"""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from oracle import refsim
+    cells, zone = make_world((200, 176), mix, seed=31)
+    r = refsim.RefWorld(cells, zone)
+    o = oraclesim.OracleWorld(cells, zone, defs=full_table())
+    for t in range(10):
+        r.tick(t)
+        o.tick(t)
+    (rx, ry), (ox, oy) = r.flow(), o.flow()
+    assert np.abs(rx).sum() > 0 and np.abs(ry).sum() > 0
+    assert rx.tobytes() == ox.tobytes() and ry.tobytes() == oy.tobytes()
+    r.close()
+    o.close()
