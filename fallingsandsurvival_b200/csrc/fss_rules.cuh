@@ -321,7 +321,7 @@ struct ChunkWalk {
         const bool air_below = MF_IS(bmf, FSS_PHYS_AIR); // :1381
         if((air_below && iter <= 2) || mf_mat(bmf) == mat) { // :1384-1405
             const float dst = MF_IS(bmf, FSS_PHYS_SOUP) ? bamt : 0.0f;
-            float flow = vertical_flow<LIQ>(start, dst) - dst;
+            float flow = vertical_flow<!GASFIRE>(start, dst) - dst;
             flow = clamp_flow(flow, start);
             if(flow != 0) {
                 remaining -= flow;
@@ -377,7 +377,7 @@ struct ChunkWalk {
         // :1486-1516
         if(MF_IS(tmf, FSS_PHYS_AIR) || mf_mat(tmf) == mat) {
             const float dst = MF_IS(tmf, FSS_PHYS_SOUP) ? tamt : 0.0f;
-            float flow = remaining - vertical_flow<LIQ>(remaining, dst);
+            float flow = remaining - vertical_flow<!GASFIRE>(remaining, dst);
             flow = clamp_flow(flow, remaining);
             if(flow != 0) {
                 remaining -= flow;
@@ -565,7 +565,16 @@ struct ChunkWalk {
         const uint32_t slip = HI_SLIP(info);
         const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
         bool stopped = !(mf & MF_MOVED);
-        if(stopped) { // :1697-1725: the 18 probe loads are independent, issue them together
+        // :1697-1725.  The probe only matters if `rand() % chance == 0`, chance = 1000 / unstable, unstable in 2..10.  When the
+        // visit is already known not to be idle (busy), the draw is looked at first: if it is not a multiple of ANY of the
+        // nine possible chances the cell stays stopped whatever the probe would count, and its 18 loads are skipped (19 in 20).
+        // (While busy is still false the probe runs, so that "no draw could matter here" stays an exact statement for the
+        // settled-chunk flags.)
+        if(stopped && busy) {
+            const uint32_t r = fss_rand(key, 1715, 0);
+            if(r % 500u && r % 333u && r % 250u && r % 200u && r % 166u && r % 142u && r % 125u && r % 111u && r % 100u) return;
+        }
+        if(stopped) { // the 18 probe loads are independent, issue them together
             int drop = (MF_IS(blmf, FSS_PHYS_AIR) || MF_IS(brmf, FSS_PHYS_AIR)) ? 1 : 0;
             uint32_t pl[9], pr[9];
 #pragma unroll
