@@ -549,6 +549,17 @@ struct ChunkWalk {
         const Grid& g = p.g;
         const cidx_t pitch = g.pitch;
         const uint32_t mat = mf_mat(mf);
+        const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
+        // A stopped cell (moved == false) only changes if its pillar draw hits: `rand() % chance == 0`, chance = 1000 / unstable,
+        // unstable in 2..10 (:1710-1716); with no open diagonal it stays as it is as well.  So when the visit is already known
+        // not to be idle (busy), the draw is looked at first: if it is not a multiple of ANY of the nine possible chances the
+        // cell stays stopped whatever the probe would count, and the visit ends before anything is loaded (19 visits in 20).
+        // (While busy is still false everything below runs, so that "no draw could matter here" stays an exact statement
+        // for the settled-chunk flags.)
+        if(!(mf & MF_MOVED) && busy) {
+            const uint32_t r = fss_rand(key, 1715, 0);
+            if(r % 500u && r % 333u && r % 250u && r % 200u && r % 166u && r % 142u && r % 125u && r % 111u && r % 100u) return;
+        }
         const cidx_t ibl = il + p.g.pitch, ibr = ir + p.g.pitch;
         const uint32_t blmf = g.mf[ibl], brmf = g.mf[ibr];
         const float dself = sden[mat];
@@ -563,18 +574,8 @@ struct ChunkWalk {
         }
         const uint32_t info = sinfo[mat];
         const uint32_t slip = HI_SLIP(info);
-        const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
         bool stopped = !(mf & MF_MOVED);
-        // :1697-1725.  The probe only matters if `rand() % chance == 0`, chance = 1000 / unstable, unstable in 2..10.  When the
-        // visit is already known not to be idle (busy), the draw is looked at first: if it is not a multiple of ANY of the
-        // nine possible chances the cell stays stopped whatever the probe would count, and its 18 loads are skipped (19 in 20).
-        // (While busy is still false the probe runs, so that "no draw could matter here" stays an exact statement for the
-        // settled-chunk flags.)
-        if(stopped && busy) {
-            const uint32_t r = fss_rand(key, 1715, 0);
-            if(r % 500u && r % 333u && r % 250u && r % 200u && r % 166u && r % 142u && r % 125u && r % 111u && r % 100u) return;
-        }
-        if(stopped) { // the 18 probe loads are independent, issue them together
+        if(stopped) { // :1697-1725: the 18 probe loads are independent, issue them together
             int drop = (MF_IS(blmf, FSS_PHYS_AIR) || MF_IS(brmf, FSS_PHYS_AIR)) ? 1 : 0;
             uint32_t pl[9], pr[9];
 #pragma unroll
