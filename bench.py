@@ -88,11 +88,11 @@ class ClockSampler:
 
 def ncu_traffic(workload, size):
     """dram__bytes_read.sum + dram__bytes_write.sum per k_substep launch from the committed ncu capture of this very
-    workload (profiles/r01j_*), or None when the capture does not match the run"""
+    workload (profiles/r01k_*), or None when the capture does not match the run"""
     if workload != "c2" or size != ZONE_PER_GPU:
         return None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01j_k_substep_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01k_k_substep_traffic.json")) as f:
             d = json.load(f)
         return float(d["dram_bytes_per_launch_mean"]), d["source"]
     except (OSError, KeyError, ValueError):
