@@ -80,6 +80,34 @@ PARTICLE_DTYPE = np.dtype([("x", "<u4"), ("y", "<u4"), ("site", "<u4"), ("cell_k
 assert PARTICLE_DTYPE.itemsize == C.sizeof(ParticleSpawn) == 40
 
 
+def spawn_order(recs, zone):
+    """argsort of spawn records into the order World::tick appends them to World::particles (fss_spawn_order_key, fss.h)"""
+    zx, zy = int(zone[0]), int(zone[1])
+    x = recs["x"].astype(np.uint64) - np.uint64(zx)
+    y = recs["y"].astype(np.uint64) - np.uint64(zy)
+    ci, cj, dx, dy = x // np.uint64(4), y // np.uint64(16), x % np.uint64(4), y % np.uint64(16)
+    tk = (ci & np.uint64(1)) + np.uint64(2) * (np.uint64(1) - (cj & np.uint64(1)))
+    key = ((recs["tick_iter"].astype(np.uint64) & np.uint64(0x3FFFFFFF)) << np.uint64(34)) | (tk << np.uint64(32)) | \
+          ((ci & np.uint64(0x3FFF)) << np.uint64(18)) | ((cj & np.uint64(0xFFF)) << np.uint64(6)) | \
+          ((np.uint64(15) - dy) << np.uint64(2)) | dx
+    return np.argsort(key, kind="stable")
+
+
+class Particle(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("vx", C.c_float), ("vy", C.c_float), ("ax", C.c_float),
+                ("ay", C.c_float), ("target_x", C.c_float), ("target_y", C.c_float), ("target_force", C.c_float),
+                ("lifetime", C.c_int32), ("fade_time", C.c_int32), ("in_object_state", C.c_uint16),
+                ("phase", C.c_uint8), ("temporary", C.c_uint8), ("tile", CellStruct)]
+
+
+# fss_particle == Particle (Particle.hpp:12-31) without the callback
+LIVE_PARTICLE_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("vx", "<f4"), ("vy", "<f4"), ("ax", "<f4"), ("ay", "<f4"),
+                                ("target_x", "<f4"), ("target_y", "<f4"), ("target_force", "<f4"),
+                                ("lifetime", "<i4"), ("fade_time", "<i4"), ("in_object_state", "<u2"),
+                                ("phase", "u1"), ("temporary", "u1"), ("tile", CELL_DTYPE)])
+assert LIVE_PARTICLE_DTYPE.itemsize == C.sizeof(Particle) == 68
+
+
 class FillSpec(C.Structure):
     _fields_ = [
         ("seed", C.c_uint32), ("border", C.c_uint32), ("border_material", C.c_int32), ("n_entries", C.c_int32),

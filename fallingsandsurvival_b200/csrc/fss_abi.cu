@@ -16,7 +16,11 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+
 #include "fss_kernels.cuh"
+#include "fss_particles.cuh"
 
 static thread_local std::string g_err;
 
@@ -119,6 +123,20 @@ struct fss_world {
     int liq_from_iter;    // from this iter on only liquids can act
     int nogas_from_iter;  // from this iter on no GAS / fire can act
     int k1_variant; // 0 = K1a lock-step (k_substep), 1 = K1b shared-memory decoupled (k_substep_sm)
+    // World::particles (fss_particles.cuh): the list, its scratch copy and the per-particle round state, all `pl_cap` long
+    fss_particle *pl_list, *pl_next;
+    uint8_t *pl_decided, *pl_keep, *pl_sure;
+    int4 *pl_act, *pl_seen, *pl_reach;
+    uint32_t pl_n, pl_cap;
+    uint32_t* pl_res_cell; // hashed cell reservations, pl_res_mask + 1 entries
+    uint32_t pl_res_mask;
+    uint32_t* pl_res_tile; // one entry per 16 x 16 tile of the world
+    uint32_t* pl_ctl;      // [0] left undecided, [1] cutoff, [2] list length after compaction
+    uint64_t *pl_key[2];   // spawn order keys / indices, `part_cap` long, for the sort
+    uint32_t *pl_idx[2];
+    void* pl_tmp; // cub scratch
+    size_t pl_tmp_bytes;
+    uint64_t pl_rounds; // rounds of the last fss_tick_particles
     // strips
     void* comm;
     int rank, n_ranks;
@@ -193,6 +211,12 @@ static int dirty_chunks(fss_world* w, int rx, int ry, int rw, int rh) {
     }
     CU(cudaMemset2DAsync(w->d_q + (size_t)r0 * w->q_w + c0, (size_t)w->q_w, 0xFF, (size_t)(c1 - c0), (size_t)(r1 - r0), w->stream));
     return FSS_OK;
+}
+
+static void particles_free(fss_world* w) {
+    void* ptrs[] = {w->pl_list, w->pl_next, w->pl_decided, w->pl_keep, w->pl_sure, w->pl_act, w->pl_seen, w->pl_reach,
+                    w->pl_res_cell, w->pl_res_tile, w->pl_ctl, w->pl_key[0], w->pl_key[1], w->pl_idx[0], w->pl_idx[1], w->pl_tmp};
+    for(void* p : ptrs) cudaFree(p);
 }
 
 extern "C" {
@@ -324,6 +348,7 @@ int fss_destroy(fss_world* w) {
     cudaFree(w->d_stage);
     cudaFree(w->d_q);
     cudaFree(w->d_present);
+    particles_free(w);
     if(w->own_stream) cudaStreamDestroy(w->own_stream);
     delete w;
     return FSS_OK;
@@ -650,17 +675,220 @@ int fss_drain_particles(fss_world* w, fss_particle_spawn* out, size_t cap, size_
     std::vector<fss_particle_spawn> v(kept);
     if(kept) CU(cudaMemcpy(v.data(), w->d_parts, kept * sizeof(fss_particle_spawn), cudaMemcpyDeviceToHost));
     CU(cudaMemsetAsync(w->d_part_count, 0, 8, w->stream));
-    std::sort(v.begin(), v.end(), [](const fss_particle_spawn& a, const fss_particle_spawn& b) {
-        if(a.tick_iter != b.tick_iter) return a.tick_iter < b.tick_iter;
-        if(a.y != b.y) return a.y < b.y;
-        if(a.x != b.x) return a.x < b.x;
-        return a.site < b.site;
+    const int zx = w->zx, zy = w->zy; // the order World::tick pushes them (fss_spawn_order_key); equal keys are identical records
+    std::stable_sort(v.begin(), v.end(), [zx, zy](const fss_particle_spawn& a, const fss_particle_spawn& b) {
+        return fss_spawn_order_key(a.tick_iter, a.x, a.y, zx, zy) < fss_spawn_order_key(b.tick_iter, b.x, b.y, zx, zy);
     });
     const size_t n = std::min(kept, cap);
     if(n) memcpy(out, v.data(), n * sizeof(fss_particle_spawn));
     if(n_out) *n_out = n;
     if(n_total) *n_total = (size_t)total;
     if(total > kept || kept > cap) return fail(FSS_ERR_RANGE, "%llu spawn records produced, %zu kept, %zu returned", total, kept, n);
+    return FSS_OK;
+}
+
+
+// ---- World::particles on the device (fss_particles.cuh) -----------------------------------------------------
+static int particles_reserve(fss_world* w, size_t need) {
+    if(need > 0x7FFFFFF0u) return fail(FSS_ERR_RANGE, "%zu particles", need);
+    if(!w->pl_ctl) {
+        CU(cudaMalloc(&w->pl_ctl, 4 * sizeof(uint32_t)));
+        const size_t tiles = (size_t)((w->cfg.width + FSS_PTILE - 1) / FSS_PTILE) * ((w->cfg.height + FSS_PTILE - 1) / FSS_PTILE);
+        CU(cudaMalloc(&w->pl_res_tile, tiles * sizeof(uint32_t)));
+    }
+    if(need <= w->pl_cap) return FSS_OK;
+    size_t cap = std::max<size_t>(w->pl_cap ? (size_t)w->pl_cap * 2 : 4096, need);
+    fss_particle *list = nullptr, *next = nullptr;
+    CU(cudaMalloc(&list, cap * sizeof(fss_particle)));
+    CU(cudaMalloc(&next, cap * sizeof(fss_particle)));
+    if(w->pl_n) CU(cudaMemcpyAsync(list, w->pl_list, (size_t)w->pl_n * sizeof(fss_particle), cudaMemcpyDeviceToDevice, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    void* old[] = {w->pl_list, w->pl_next, w->pl_decided, w->pl_keep, w->pl_sure, w->pl_act, w->pl_seen, w->pl_reach, w->pl_res_cell};
+    for(void* p : old) cudaFree(p);
+    w->pl_list = list;
+    w->pl_next = next;
+    CU(cudaMalloc(&w->pl_decided, cap));
+    CU(cudaMalloc(&w->pl_keep, cap));
+    CU(cudaMalloc(&w->pl_sure, cap));
+    CU(cudaMalloc(&w->pl_act, cap * sizeof(int4)));
+    CU(cudaMalloc(&w->pl_seen, cap * sizeof(int4)));
+    CU(cudaMalloc(&w->pl_reach, cap * sizeof(int4)));
+    size_t slots = 4096; // >= 8 slots per particle keeps chance collisions (which only delay a particle by a round) rare
+    while(slots < cap * 8) slots *= 2;
+    CU(cudaMalloc(&w->pl_res_cell, slots * sizeof(uint32_t)));
+    w->pl_res_mask = (uint32_t)(slots - 1);
+    w->pl_cap = (uint32_t)cap;
+    return FSS_OK;
+}
+
+static int cub_scratch(fss_world* w, size_t bytes) {
+    if(bytes <= w->pl_tmp_bytes) return FSS_OK;
+    cudaFree(w->pl_tmp);
+    w->pl_tmp = nullptr;
+    w->pl_tmp_bytes = 0;
+    CU(cudaMalloc(&w->pl_tmp, bytes));
+    w->pl_tmp_bytes = bytes;
+    return FSS_OK;
+}
+
+// what World::tick's `particles.insert(particles.end(), pts.begin(), pts.end())` (world.cpp:1989-1994) did for the ticks
+// since the last call: the spawn records, in push order, become Particles at the end of the list
+static int particles_adopt(fss_world* w) {
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, w->d_part_count, 8, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    if(total == 0) return FSS_OK;
+    if(total > w->part_cap) return fail(FSS_ERR_RANGE, "%llu spawn records produced, capacity %u (fss_config.particle_capacity)", total, w->part_cap);
+    const uint32_t n = (uint32_t)total;
+    if(int rc = particles_reserve(w, (size_t)w->pl_n + n)) return rc;
+    if(!w->pl_key[0]) {
+        for(int k = 0; k < 2; k++) {
+            CU(cudaMalloc(&w->pl_key[k], (size_t)w->part_cap * sizeof(uint64_t)));
+            CU(cudaMalloc(&w->pl_idx[k], (size_t)w->part_cap * sizeof(uint32_t)));
+        }
+    }
+    AdoptParams A;
+    A.spawn = w->d_parts;
+    A.key = w->pl_key[0];
+    A.idx = w->pl_idx[0];
+    A.key_sorted = w->pl_key[1];
+    A.idx_sorted = w->pl_idx[1];
+    A.dst = w->pl_list + w->pl_n;
+    A.n = n;
+    A.zx = w->zx;
+    A.zy = w->zy;
+    k_spawn_keys<<<(n + 255) / 256, 256, 0, w->stream>>>(A);
+    size_t bytes = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, bytes, w->pl_key[0], w->pl_key[1], w->pl_idx[0], w->pl_idx[1], (int)n, 0, 64, w->stream));
+    if(int rc = cub_scratch(w, bytes)) return rc;
+    CU(cub::DeviceRadixSort::SortPairs(w->pl_tmp, bytes, w->pl_key[0], w->pl_key[1], w->pl_idx[0], w->pl_idx[1], (int)n, 0, 64, w->stream));
+    k_spawn_to_particles<<<(n + 255) / 256, 256, 0, w->stream>>>(A);
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(w->d_part_count, 0, 8, w->stream));
+    w->stats.kernel_launches += 2;
+    w->pl_n += n;
+    return FSS_OK;
+}
+
+int fss_particles_add(fss_world* w, const fss_particle* particles, size_t n) {
+    if(!w || (!particles && n)) return fail(FSS_ERR_INVALID, "null argument");
+    if(use_device(w)) return FSS_ERR_CUDA;
+    if(w->sharded) return fail(FSS_ERR_STATE, "device particles are not available on strip-sharded worlds");
+    if(!w->mats_set) return fail(FSS_ERR_STATE, "fss_set_materials first");
+    for(size_t i = 0; i < n; i++)
+        if(particles[i].tile.material >= w->n_mat) return fail(FSS_ERR_INVALID, "particle %zu: material %u of %d", i, particles[i].tile.material, w->n_mat);
+    if(n == 0) return FSS_OK;
+    if(int rc = particles_adopt(w)) return rc; // host pushes come after what the ticks so far pushed
+    if(int rc = particles_reserve(w, (size_t)w->pl_n + n)) return rc;
+    CU(cudaMemcpyAsync(w->pl_list + w->pl_n, particles, n * sizeof(fss_particle), cudaMemcpyHostToDevice, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    w->pl_n += (uint32_t)n;
+    bool grew = false;
+    for(size_t i = 0; i < n; i++) {
+        grew = grew || !w->present[particles[i].tile.material];
+        w->present[particles[i].tile.material] = true;
+    }
+    if(grew) recompute_liq(w);
+    return FSS_OK;
+}
+
+int fss_particles_count(fss_world* w, size_t* n) {
+    if(!w || !n) return fail(FSS_ERR_INVALID, "null argument");
+    *n = w->pl_n;
+    return FSS_OK;
+}
+
+int fss_particles_download(fss_world* w, fss_particle* out, size_t cap, size_t* n_out) {
+    if(!w || (!out && cap)) return fail(FSS_ERR_INVALID, "null argument");
+    if(use_device(w)) return FSS_ERR_CUDA;
+    const size_t n = std::min<size_t>(cap, w->pl_n);
+    if(n) CU(cudaMemcpyAsync(out, w->pl_list, n * sizeof(fss_particle), cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    if(n_out) *n_out = n;
+    return n < w->pl_n ? fail(FSS_ERR_RANGE, "%u particles, room for %zu", w->pl_n, cap) : FSS_OK;
+}
+
+int fss_particles_clear(fss_world* w) {
+    if(!w) return fail(FSS_ERR_INVALID, "null world");
+    w->pl_n = 0;
+    return FSS_OK;
+}
+
+int fss_particles_rounds(fss_world* w, uint64_t* rounds) {
+    if(!w || !rounds) return fail(FSS_ERR_INVALID, "null argument");
+    *rounds = w->pl_rounds;
+    return FSS_OK;
+}
+
+int fss_tick_particles(fss_world* w) {
+    if(!w) return fail(FSS_ERR_INVALID, "null world");
+    if(use_device(w)) return FSS_ERR_CUDA;
+    if(w->sharded) return fail(FSS_ERR_STATE, "device particles are not available on strip-sharded worlds");
+    if(!w->zone_set || !w->mats_set) return fail(FSS_ERR_STATE, "fss_set_materials and fss_set_tick_zone first");
+    if(int rc = particles_adopt(w)) return rc;
+    w->pl_rounds = 0;
+    const uint32_t n = w->pl_n;
+    if(n == 0) return FSS_OK;
+    if(int rc = particles_reserve(w, n)) return rc;
+    ParticleParams P;
+    P.g = w->g;
+    P.mats = w->d_mats;
+    P.n_mat = w->n_mat;
+    P.width = (int)w->cfg.width;
+    P.height = (int)w->cfg.height;
+    P.zx = w->zx;
+    P.zy = w->zy;
+    P.zw = w->zw;
+    P.zh = w->zh;
+    P.in = w->pl_list;
+    P.out = w->pl_next;
+    P.decided = w->pl_decided;
+    P.keep = w->pl_keep;
+    P.sure = w->pl_sure;
+    P.act = w->pl_act;
+    P.seen = w->pl_seen;
+    P.reach = w->pl_reach;
+    P.res_cell = w->pl_res_cell;
+    P.res_mask = w->pl_res_mask;
+    P.res_tile = w->pl_res_tile;
+    P.tiles_w = (int)((w->cfg.width + FSS_PTILE - 1) / FSS_PTILE);
+    P.tiles_h = (int)((w->cfg.height + FSS_PTILE - 1) / FSS_PTILE);
+    P.ctl = w->pl_ctl;
+    P.n = n;
+    P.q = (w->cfg.flags & FSS_NO_EARLY_OUT) ? nullptr : w->d_q;
+    P.q_w = w->q_w;
+    P.q_h = w->q_h;
+    P.q_cj0 = w->q_cj0;
+    const unsigned blocks = (n + 127) / 128;
+    CU(cudaMemsetAsync(w->pl_decided, 0, n, w->stream));
+    for(uint32_t left = n; left;) {
+        const uint32_t ctl0[2] = {0u, 0xFFFFFFFFu};
+        CU(cudaMemcpyAsync(w->pl_ctl, ctl0, sizeof ctl0, cudaMemcpyHostToDevice, w->stream));
+        CU(cudaMemsetAsync(w->pl_res_cell, 0xFF, ((size_t)w->pl_res_mask + 1) * sizeof(uint32_t), w->stream));
+        CU(cudaMemsetAsync(w->pl_res_tile, 0xFF, (size_t)P.tiles_w * P.tiles_h * sizeof(uint32_t), w->stream));
+        k_particles_speculate<<<blocks, 128, 0, w->stream>>>(P);
+        k_particles_check_cells<<<blocks, 128, 0, w->stream>>>(P);
+        k_particles_check_tiles<false><<<blocks, 128, 0, w->stream>>>(P);
+        k_particles_check_tiles<true><<<blocks, 128, 0, w->stream>>>(P);
+        k_particles_commit<<<blocks, 128, 0, w->stream>>>(P);
+        CU(cudaGetLastError());
+        w->stats.kernel_launches += 5;
+        w->pl_rounds++;
+        uint32_t now = 0;
+        CU(cudaMemcpyAsync(&now, w->pl_ctl, sizeof now, cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+        if(now >= left) return fail(FSS_ERR_CUDA, "particle round %llu retired nobody (%u left)", (unsigned long long)w->pl_rounds, now);
+        left = now;
+    }
+    // particles.erase(std::remove_if(...)): the survivors, in order
+    size_t bytes = 0;
+    CU(cub::DeviceSelect::Flagged(nullptr, bytes, w->pl_next, w->pl_keep, w->pl_list, w->pl_ctl + 2, (int)n, w->stream));
+    if(int rc = cub_scratch(w, bytes)) return rc;
+    CU(cub::DeviceSelect::Flagged(w->pl_tmp, bytes, w->pl_next, w->pl_keep, w->pl_list, w->pl_ctl + 2, (int)n, w->stream));
+    uint32_t kept = 0;
+    CU(cudaMemcpyAsync(&kept, w->pl_ctl + 2, sizeof kept, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    w->pl_n = kept;
     return FSS_OK;
 }
 

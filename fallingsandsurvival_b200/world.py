@@ -55,6 +55,12 @@ def load():
         "fss_substep": [vp, u32, i32, i32],
         "fss_tick_temperature": [vp],
         "fss_drain_particles": [vp, vp, sz, C.POINTER(sz), C.POINTER(sz)],
+        "fss_tick_particles": [vp],
+        "fss_particles_add": [vp, vp, sz],
+        "fss_particles_count": [vp, C.POINTER(sz)],
+        "fss_particles_download": [vp, vp, sz, C.POINTER(sz)],
+        "fss_particles_clear": [vp],
+        "fss_particles_rounds": [vp, C.POINTER(C.c_uint64)],
         "fss_histogram": [vp, vp, i32],
         "fss_hash": [vp, C.POINTER(C.c_uint64)],
         "fss_fluid_totals": [vp, vp, i32],
@@ -204,6 +210,35 @@ class World:
         _check(self.L, self.L.fss_drain_particles(self.h_, out.ctypes.data, cap, C.byref(n), C.byref(total)))
         return out[: n.value]
 
+    # ---- World::particles on the device (world.cpp:2171-2311) ----
+    def tick_particles(self):
+        """World::tickParticles() after adopting the spawn records of the ticks since the last call"""
+        _check(self.L, self.L.fss_tick_particles(self.h_))
+
+    def add_particles(self, parts):
+        parts = np.ascontiguousarray(parts, dtype=abi.LIVE_PARTICLE_DTYPE)
+        _check(self.L, self.L.fss_particles_add(self.h_, parts.ctypes.data, parts.size))
+
+    def particles_count(self):
+        n = C.c_size_t()
+        _check(self.L, self.L.fss_particles_count(self.h_, C.byref(n)))
+        return n.value
+
+    def particle_list(self):
+        n = self.particles_count()
+        out = np.zeros(max(n, 1), dtype=abi.LIVE_PARTICLE_DTYPE)
+        got = C.c_size_t()
+        _check(self.L, self.L.fss_particles_download(self.h_, out.ctypes.data, n, C.byref(got)))
+        return out[: got.value]
+
+    def particle_rounds(self):
+        r = C.c_uint64()
+        _check(self.L, self.L.fss_particles_rounds(self.h_, C.byref(r)))
+        return r.value
+
+    def clear_particles(self):
+        _check(self.L, self.L.fss_particles_clear(self.h_))
+
     def histogram(self):
         counts = np.zeros(len(self.defs), dtype=np.uint64)
         _check(self.L, self.L.fss_histogram(self.h_, counts.ctypes.data, len(self.defs)))
@@ -308,7 +343,7 @@ class StripWorld:
 
     def drain_particles(self):
         recs = np.concatenate([p.drain_particles() for p in self.parts])
-        order = np.lexsort((recs["site"], recs["x"], recs["y"], recs["tick_iter"]))
+        order = abi.spawn_order(recs, self.zone)
         return recs[order]
 
     def close(self):

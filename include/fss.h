@@ -214,9 +214,63 @@ int fss_download_flow(fss_world* w, int x, int y, int width, int height, float* 
 int fss_clear_flow(fss_world* w);
 
 /* ---- side outputs ---------------------------------------------------------------------------- */
-/* spawn records since the last drain, sorted by (tick_iter, y, x, site); *n_total = records produced
- * (may exceed cap / capacity: then the surplus was dropped and the call returns FSS_ERR_RANGE). */
+/* spawn records since the last drain in the order World::tick appends them to World::particles
+ * (fss_spawn_order_key below); *n_total = records produced (may exceed cap / capacity: then the surplus
+ * was dropped and the call returns FSS_ERR_RANGE). */
 int fss_drain_particles(fss_world* w, fss_particle_spawn* out, size_t cap, size_t* n_out, size_t* n_total);
+
+/* The order of World::particles after a tick: per sub-step (iter, tk) the chunk futures are collected in launch order
+ * (cx outer, cy inner: world.cpp:1140-1141, :1989-1994) and every chunk pushes in visit order (rows bottom-up, columns
+ * left to right: world.cpp:1154-1157).  Ascending key = that order; equal keys are the n records of one falling
+ * liquid cell (world.cpp:1358-1371), whose j-th record is the j-th push.  Ticks enter modulo 2^27. */
+#if defined(__CUDACC__)
+#define FSS_INLINE __host__ __device__ static inline
+#else
+#define FSS_INLINE static inline
+#endif
+FSS_INLINE uint64_t fss_spawn_order_key(uint32_t tick_iter, uint32_t x, uint32_t y, int zone_x, int zone_y) {
+    const uint32_t ci = (x - (uint32_t)zone_x) / FSS_CHUNK_W, cj = (y - (uint32_t)zone_y) / FSS_CHUNK_H;
+    const uint32_t dx = (x - (uint32_t)zone_x) % FSS_CHUNK_W, dy = (y - (uint32_t)zone_y) % FSS_CHUNK_H;
+    const uint32_t tk = (ci & 1u) + 2u * (1u - (cj & 1u)); /* chOfsX = tk % 2, chOfsY = 1 - tk / 2 (world.cpp:1118-1119) */
+    return ((uint64_t)(tick_iter & 0x3FFFFFFFu) << 34) | ((uint64_t)tk << 32) | ((uint64_t)(ci & 0x3FFFu) << 18) |
+           ((uint64_t)(cj & 0xFFFu) << 6) | ((uint64_t)(FSS_CHUNK_H - 1u - dy) << 2) | dx;
+}
+
+/* ---- World::particles on the device ---------------------------------------------------------
+ * One Particle (Particle.hpp:12-31) without its killCallback: particles that need a host callback stay on the host. */
+typedef struct fss_particle {
+    float x, y, vx, vy, ax, ay;
+    float target_x, target_y, target_force;
+    int32_t lifetime;
+    int32_t fade_time;
+    uint16_t in_object_state;
+    uint8_t phase;
+    uint8_t temporary;
+    fss_cell tile;
+} fss_particle;
+
+/* How a spawn record becomes a Particle (world.cpp:1180-1183, :1291, :1366; `r(k)` = fss_rand(cell_key, site, k); g++ evaluates
+ * the constructor's arguments right to left, so the vy draw is the first call at the site and the vx draw the second;
+ * j = index of the record among those of the same cell visit):
+ *   site 1180  Particle(tile, x, y - 1, (r(1) % 10 - 5) / 20.0f, -((r(0) % 10) / 10.0f) / 3.0f + -0.5f, 0, 0.01f), temporary, lifetime 30, fadeTime 10
+ *   site 1291  Particle(tile, x, y + 1, (r(1) % 10 - 5) / 20.0f, -((r(0) % 2) + 3) / 10.0f + 1.5f, 0, 0.1f)
+ *   site 1366  Particle(nt,   x, y + 1, (r(2j+1) % 10 - 5) / 30.0f, -((r(2j) % 2) + 3) / 10.0f + 1.0f, 0, 0.1f)
+ *
+ * fss_tick_particles = one World::tickParticles() (world.cpp:2171-2311) on the device list, after moving the spawn records
+ * of the ticks since the last call to its end (so fss_drain_particles then returns nothing).  Particles act in list
+ * order exactly like the reference's remove_if loop; the kernels find the particles whose outcome cannot depend on an
+ * earlier, still undecided one and retire those together, round after round.  The 32 x 32 landing search
+ * (world.cpp:2251-2283) indexes tiles[] without a bounds test in the reference; here positions outside the world are
+ * skipped.  Not available on strip-sharded worlds. */
+int fss_tick_particles(fss_world* w);
+/* particles.push_back(...) by host code (tools, explosions: Game.cpp) */
+int fss_particles_add(fss_world* w, const fss_particle* particles, size_t n);
+int fss_particles_count(fss_world* w, size_t* n);
+/* the list in order, for World::renderParticles (world.cpp:2145-2169) */
+int fss_particles_download(fss_world* w, fss_particle* out, size_t cap, size_t* n_out);
+int fss_particles_clear(fss_world* w);
+/* how many retire rounds the last fss_tick_particles needed (1 when no particle depended on another) */
+int fss_particles_rounds(fss_world* w, uint64_t* rounds);
 /* per-material cell counts over the owned rows (movingTiles replacement, Game.cpp:2579-2589) */
 int fss_histogram(fss_world* w, uint64_t* counts, int n_materials);
 /* order-independent digest (sum of fss_cell_digest over owned rows); k-GPU digests add up */

@@ -12,7 +12,7 @@ path needs none of that.  Recipe:
     Materials.cpp, Tiles.cpp, Particle.cpp and lib/CTPL-ctpl_v.0.0.2/ctpl_stl.h;
   * FallingSandSurvival/world.cpp lines 1053-1062 (getTile/setTile), 1075-1088
     (CalculateVerticalFlowValue), 1091-2018 + 2027-2041 (World::tick minus the Box2D physicsCheck
-    block) and 2043-2143 (World::tickTemperature) are extracted into
+    block), 2043-2143 (World::tickTemperature) and 2171-2338 (World::tickParticles) are extracted into
     oracle/_ref/gen/tick_lines.inc behind #line directives (so __LINE__, our RNG site id, keeps the
     reference's numbering) with three single-line instrumentation edits listed in PATCHES;
   * shims (oracle/ref_shim/): SDL typedefs, a cut-down `World` declaration, the C API.
@@ -36,7 +36,7 @@ F = os.path.join(REF, "FallingSandSurvival")
 OUT = os.path.join(HERE, "_ref")
 GEN = os.path.join(OUT, "gen")
 
-RANGES = [(1053, 1062), (1075, 1088), (1091, 2018), (2027, 2041), (2043, 2143)]
+RANGES = [(1053, 1062), (1075, 1088), (1091, 2018), (2027, 2041), (2043, 2143), (2171, 2338)]
 
 # (line number, exact text that must be present, replacement) -- all keep the line count
 PATCHES = [

@@ -49,6 +49,8 @@ struct fsso_world {
     texture_t tex[FSS_MAX_TEXTURES];
     fss_particle_spawn* parts;
     size_t n_parts, cap_parts;
+    fss_particle* plist; /* World::particles */
+    size_t n_plist, cap_plist;
 };
 
 /* per-visit RNG state: one key per cell visit, one counter per site (fss_rng.h) */
@@ -646,6 +648,7 @@ void fsso_destroy(fsso_world* w) {
     free(w->flow_x);
     free(w->flow_y);
     free(w->parts);
+    free(w->plist);
     free(w);
 }
 
@@ -691,22 +694,190 @@ float* fsso_flow_x(fsso_world* w) { return w->flow_x; }
 float* fsso_flow_y(fsso_world* w) { return w->flow_y; }
 size_t fsso_num_particles(fsso_world* w) { return w->n_parts; }
 
+/* the order World::tick appends to World::particles, see fss_spawn_order_key (F/world.cpp:1140-1157, :1989-1994) */
+static int g_cmp_zx, g_cmp_zy;
 static int cmp_part(const void* a, const void* b) {
     const fss_particle_spawn* p = (const fss_particle_spawn*)a;
     const fss_particle_spawn* q = (const fss_particle_spawn*)b;
-    if(p->tick_iter != q->tick_iter) return p->tick_iter < q->tick_iter ? -1 : 1;
-    if(p->y != q->y) return p->y < q->y ? -1 : 1;
-    if(p->x != q->x) return p->x < q->x ? -1 : 1;
-    if(p->site != q->site) return p->site < q->site ? -1 : 1;
-    return 0;
+    uint64_t kp = fss_spawn_order_key(p->tick_iter, p->x, p->y, g_cmp_zx, g_cmp_zy);
+    uint64_t kq = fss_spawn_order_key(q->tick_iter, q->x, q->y, g_cmp_zx, g_cmp_zy);
+    return kp < kq ? -1 : kp > kq ? 1 : 0;
+}
+
+static void sort_spawned(fsso_world* w) {
+    g_cmp_zx = w->zx;
+    g_cmp_zy = w->zy;
+    qsort(w->parts, w->n_parts, sizeof(fss_particle_spawn), cmp_part); /* equal keys are identical records */
 }
 
 size_t fsso_drain_particles(fsso_world* w, fss_particle_spawn* out, size_t cap) {
     size_t n = w->n_parts < cap ? w->n_parts : cap;
-    qsort(w->parts, w->n_parts, sizeof(fss_particle_spawn), cmp_part);
+    sort_spawned(w);
     memcpy(out, w->parts, n * sizeof(fss_particle_spawn));
     w->n_parts = 0;
     return n;
+}
+
+/* ---- World::particles, F/world.cpp:2171-2311 ----------------------------------------------------------- */
+static void plist_reserve(fsso_world* w, size_t extra) {
+    if(w->n_plist + extra > w->cap_plist) {
+        while(w->n_plist + extra > w->cap_plist) w->cap_plist = w->cap_plist ? w->cap_plist * 2 : 1024;
+        w->plist = (fss_particle*)realloc(w->plist, w->cap_plist * sizeof(fss_particle));
+    }
+}
+
+static void adopt_spawned(fsso_world* w);
+
+/* a host-side particles.push_back: lands behind everything the ticks so far appended */
+void fsso_particles_add(fsso_world* w, const fss_particle* p, size_t n) {
+    adopt_spawned(w);
+    plist_reserve(w, n);
+    memcpy(w->plist + w->n_plist, p, n * sizeof(fss_particle));
+    w->n_plist += n;
+}
+
+fss_particle* fsso_particles(fsso_world* w, size_t* n) {
+    *n = w->n_plist;
+    return w->plist;
+}
+
+/* `new Particle(...)` at F/world.cpp:1180-1183, :1291, :1366 (the DO_MULTITHREADING branches, F/world.cpp:1097).  The two
+ * rand() calls of one constructor expression: g++ evaluates the arguments right to left, so vy draws first. */
+static void particle_from_spawn(const fss_particle_spawn* s, uint32_t j, fss_particle* p) {
+    uint32_t ry = fss_rand(s->cell_key, s->site, 2u * j), rx = fss_rand(s->cell_key, s->site, 2u * j + 1u);
+    memset(p, 0, sizeof *p);
+    p->tile = s->cell;
+    p->x = (float)(int)s->x;
+    p->fade_time = 60; /* F/Particle.hpp:27 */
+    if(s->site == 1180) {
+        p->y = (float)((int)s->y - 1);
+        p->vx = (float)((int)(rx % 10) - 5) / 20.0f;
+        p->vy = -((float)(int)(ry % 10) / 10.0f) / 3.0f + -0.5f;
+        p->ay = 0.01f;
+        p->temporary = 1;
+        p->lifetime = 30;
+        p->fade_time = 10;
+    } else if(s->site == 1291) {
+        p->y = (float)((int)s->y + 1);
+        p->vx = (float)((int)(rx % 10) - 5) / 20.0f;
+        p->vy = (float)(-((int)(ry % 2) + 3)) / 10.0f + 1.5f;
+        p->ay = 0.1f;
+    } else {
+        p->y = (float)((int)s->y + 1);
+        p->vx = (float)((int)(rx % 10) - 5) / 30.0f;
+        p->vy = (float)(-((int)(ry % 2) + 3)) / 10.0f + 1.0f;
+        p->ay = 0.1f;
+    }
+}
+
+/* what World::tick's `particles.insert(...)` did for the ticks since the last call */
+static void adopt_spawned(fsso_world* w) {
+    size_t i;
+    uint32_t j = 0;
+    sort_spawned(w);
+    plist_reserve(w, w->n_parts);
+    for(i = 0; i < w->n_parts; i++) {
+        const fss_particle_spawn* s = &w->parts[i];
+        j = (i > 0 && s[-1].tick_iter == s->tick_iter && s[-1].x == s->x && s[-1].y == s->y) ? j + 1 : 0;
+        particle_from_spawn(s, j, &w->plist[w->n_plist++]);
+    }
+    w->n_parts = 0;
+}
+
+/* the lambda of the remove_if, F/world.cpp:2179-2310; returns 1 when the particle leaves the list */
+static int particle_step(fsso_world* w, fss_particle* cur) {
+    int lx, ly, div, i;
+    float dvx, dvy;
+    if(cur->temporary && cur->lifetime <= 0) return 1; /* :2182-2186 */
+    if(cur->target_force != 0) {                       /* :2188-2201 */
+        float tdx = cur->target_x - cur->x;
+        float tdy = cur->target_y - cur->y;
+        float normFac = sqrtf(tdx * tdx + tdy * tdy);
+        cur->vx += tdx / normFac * cur->target_force;
+        cur->vy += tdy / normFac * cur->target_force;
+        if(normFac < 100) {
+            cur->vx *= 0.95f;
+            cur->vy *= 0.95f;
+        }
+    }
+    lx = (int)cur->x;
+    ly = (int)cur->y;
+    if(cur->x < 0 || (int)(cur->x) >= w->width || cur->y < 0 || (int)(cur->y) >= w->height) return 1; /* :2206-2209 */
+    if(!(lx >= w->zx && ly >= w->zy && lx < w->zx + w->zw && ly < w->zy + w->zh)) return 0;               /* :2211 */
+    cur->vx += cur->ax;
+    cur->vy += cur->ay;
+    div = (int)((fabsf(cur->vx) + fabsf(cur->vy)) + 1); /* :2216 */
+    dvx = cur->vx / div;
+    dvy = cur->vy / div;
+    for(i = 0; i < div; i++) {
+        fss_cell* hit;
+        cur->x += dvx;
+        cur->y += dvy;
+        if(cur->x < 0 || (int)(cur->x) >= w->width || cur->y < 0 || (int)(cur->y) >= w->height) return 1; /* :2225-2228 */
+        hit = at(w, (int)cur->x, (int)cur->y);
+        if(!cur->phase && phys(w, hit) != FSS_PHYS_AIR) { /* :2230 */
+            int isObject = phys(w, hit) == FSS_PHYS_PASSABLE; /* PhysicsType::OBJECT */
+            switch(cur->in_object_state) {                    /* :2234-2246 */
+            case 0: cur->in_object_state = isObject ? 1 : 2; break;
+            case 1: if(!isObject) cur->in_object_state = 2; break;
+            }
+            if(!isObject || cur->in_object_state == 2) {
+                if(cur->temporary) return 1; /* :2249-2253 */
+                if(phys(w, at(w, lx, ly)) != FSS_PHYS_AIR) {
+                    /* square spiral around the particle, first AIR cell (or, for a liquid, first cell of its own
+                     * material) takes it: :2263-2290 */
+                    int succeeded = 0;
+                    int X = 32, Y = 32, x = 0, y = 0, dx = 0, dy = -1, t = X > Y ? X : Y, maxI = t * t, j;
+                    for(j = 0; j < maxI; j++) {
+                        if((-X / 2 <= x) && (x <= X / 2) && (-Y / 2 <= y) && (y <= Y / 2)) {
+                            int px = (int)(cur->x + x), py = (int)(cur->y + y);
+                            /* the reference indexes tiles[] unchecked here; outside the world we skip (fss.h) */
+                            if(px >= 0 && px < w->width && py >= 0 && py < w->height) {
+                                fss_cell* c = at(w, px, py);
+                                if(phys(w, c) == FSS_PHYS_AIR) {
+                                    *c = cur->tile;
+                                    succeeded = 1;
+                                    break;
+                                } else if(w->mat[cur->tile.material].physics_type == FSS_PHYS_SOUP && cur->tile.material == c->material) {
+                                    c->fluid_amount += cur->tile.fluid_amount;
+                                    succeeded = 1;
+                                    break;
+                                }
+                            }
+                        }
+                        if((x == y) || ((x < 0) && (x == -y)) || ((x > 0) && (x == 1 - y))) {
+                            t = dx;
+                            dx = -dy;
+                            dy = t;
+                        }
+                        x += dx;
+                        y += dy;
+                    }
+                    if(succeeded) return 1;
+                    cur->vy = -4; /* :2296-2299 */
+                    cur->y -= 16;
+                    return 0;
+                } else {
+                    *at(w, lx, ly) = cur->tile; /* :2301-2306 */
+                    return 1;
+                }
+            }
+        }
+    }
+    if(cur->lifetime > 0) cur->lifetime--; /* :2311-2313 */
+    return 0;
+}
+
+void fsso_tick_particles(fsso_world* w) {
+    size_t i, out = 0;
+    adopt_spawned(w);
+    for(i = 0; i < w->n_plist; i++) {
+        if(!particle_step(w, &w->plist[i])) {
+            if(out != i) w->plist[out] = w->plist[i];
+            out++;
+        }
+    }
+    w->n_plist = out;
 }
 
 uint64_t fsso_hash_rows(const fss_cell* cells, int width, int x0, int y0, int w, int h, int global_y0) {

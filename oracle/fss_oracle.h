@@ -39,6 +39,10 @@ void fsso_tick_temperature_rows(fsso_world* w, int y_from, int y_to);
 
 size_t fsso_num_particles(fsso_world* w);
 size_t fsso_drain_particles(fsso_world* w, fss_particle_spawn* out, size_t cap); /* sorted like fss_drain_particles */
+/* World::particles and World::tickParticles (F/world.cpp:2171-2311); the tick first adopts the spawn records */
+void fsso_particles_add(fsso_world* w, const fss_particle* p, size_t n);
+fss_particle* fsso_particles(fsso_world* w, size_t* n);
+void fsso_tick_particles(fsso_world* w);
 
 uint64_t fsso_hash_rows(const fss_cell* cells, int width, int x0, int y0, int w, int h, int global_y0);
 void fsso_histogram(const fss_cell* cells, size_t n, uint64_t* counts, int n_materials);

@@ -51,6 +51,10 @@ def load():
     L.fsso_num_particles.argtypes = [C.c_void_p]
     L.fsso_drain_particles.restype = C.c_size_t
     L.fsso_drain_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.fsso_particles_add.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.fsso_particles.restype = C.c_void_p
+    L.fsso_particles.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+    L.fsso_tick_particles.argtypes = [C.c_void_p]
     L.fsso_hash_rows.restype = C.c_uint64
     L.fsso_hash_rows.argtypes = [C.c_void_p] + [C.c_int] * 6
     L.fsso_histogram.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
@@ -127,6 +131,22 @@ class OracleWorld:
         out = np.zeros(max(n, 1), dtype=abi.PARTICLE_DTYPE)
         m = self.L.fsso_drain_particles(self.h_, out.ctypes.data, n)
         return out[:m]
+
+    def tick_particles(self):
+        """World::tickParticles() after adopting the spawn records of the ticks since the last call"""
+        self.L.fsso_tick_particles(self.h_)
+
+    def add_particles(self, parts):
+        parts = np.ascontiguousarray(parts, dtype=abi.LIVE_PARTICLE_DTYPE)
+        self.L.fsso_particles_add(self.h_, parts.ctypes.data, parts.size)
+
+    def particle_list(self):
+        n = C.c_size_t(0)
+        p = self.L.fsso_particles(self.h_, C.byref(n))
+        if n.value == 0:
+            return np.zeros(0, dtype=abi.LIVE_PARTICLE_DTYPE)
+        raw = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value * abi.LIVE_PARTICLE_DTYPE.itemsize,))
+        return raw.view(abi.LIVE_PARTICLE_DTYPE).copy()
 
     def close(self):
         if self.h_:

@@ -5,7 +5,7 @@
  * legs may load the library built from this file (oracle/_ref/libfss_ref_*.so).
  *
  * The rule lines are not in this repository: oracle/build_ref.py extracts
- * FallingSandSurvival/world.cpp:1053-1062, :1075-1088, :1091-2018, :2027-2041, :2043-2143
+ * FallingSandSurvival/world.cpp:1053-1062, :1075-1088, :1091-2018, :2027-2041, :2043-2143, :2171-2338
  * into oracle/_ref/gen/tick_lines.inc (with #line directives so __LINE__ keeps the reference's
  * numbering) and this file #includes it.  Instrumentation, all outside the rule lines:
  *   - CHUNK_W / CHUNK_H come from -D (the reference hard-codes 128, Chunk.hpp:18-19);
@@ -83,6 +83,7 @@ int fss_ref_rand(int site) {
 }
 
 /* ---- the reference's lines ------------------------------------------------------------------- */
+using std::max; /* world.cpp:2258 `max(X, Y)` */
 #include "tick_lines.inc"
 
 /* ---- C API ----------------------------------------------------------------------------------- */
@@ -100,6 +101,7 @@ struct RefParticle {
 struct RefWorld {
     World w;
     std::vector<RefParticle> parts;
+    bool keep = false; /* leave World::particles alone after a tick (for World::tickParticles) */
 };
 
 static void to_cell(const MaterialInstance& m, fss_cell* c) {
@@ -300,7 +302,7 @@ double fssref_tick(void* h, uint32_t seed, int tick_ct, int particles) {
     auto t0 = std::chrono::steady_clock::now();
     r->w.tick();
     auto t1 = std::chrono::steady_clock::now();
-    collect_particles(r);
+    if(!r->keep) collect_particles(r);
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
@@ -328,6 +330,55 @@ size_t fssref_drain_particles(void* h, float* xyv, fss_cell* cells, int32_t* tem
     }
     r->parts.clear();
     return n;
+}
+
+/* ---- World::particles kept alive for World::tickParticles (world.cpp:2171-2338) ------------------------ */
+void fssref_keep_particles(void* h, int on) { ((RefWorld*)h)->keep = on != 0; }
+
+double fssref_tick_particles(void* h) {
+    RefWorld* r = (RefWorld*)h;
+    auto t0 = std::chrono::steady_clock::now();
+    r->w.tickParticles();
+    auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+size_t fssref_live_particles(void* h) { return ((RefWorld*)h)->w.particles.size(); }
+
+size_t fssref_get_particles(void* h, fss_particle* out, size_t cap) {
+    World& W = ((RefWorld*)h)->w;
+    size_t n = W.particles.size() < cap ? W.particles.size() : cap;
+    for(size_t i = 0; i < n; i++) {
+        const Particle* p = W.particles[i];
+        fss_particle& q = out[i];
+        memset(&q, 0, sizeof q);
+        q.x = p->x; q.y = p->y; q.vx = p->vx; q.vy = p->vy; q.ax = p->ax; q.ay = p->ay;
+        q.target_x = p->targetX; q.target_y = p->targetY; q.target_force = p->targetForce;
+        q.lifetime = p->lifetime; q.fade_time = p->fadeTime;
+        q.in_object_state = p->inObjectState; q.phase = p->phase ? 1 : 0; q.temporary = p->temporary ? 1 : 0;
+        to_cell(p->tile, &q.tile);
+    }
+    return n;
+}
+
+int fssref_add_particles(void* h, const fss_particle* in, size_t n) {
+    World& W = ((RefWorld*)h)->w;
+    int nm = (int)Materials::MATERIALS.size();
+    for(size_t i = 0; i < n; i++) {
+        const fss_particle& q = in[i];
+        if(q.tile.material >= nm) return -1;
+        MaterialInstance m(Materials::MATERIALS[q.tile.material], q.tile.color, q.tile.temperature);
+        m.moved = q.tile.moved != 0;
+        m.settleCount = q.tile.settle_count;
+        m.fluidAmount = q.tile.fluid_amount;
+        m.fluidAmountDiff = q.tile.fluid_amount_diff;
+        Particle* p = new Particle(m, q.x, q.y, q.vx, q.vy, q.ax, q.ay);
+        p->targetX = q.target_x; p->targetY = q.target_y; p->targetForce = q.target_force;
+        p->lifetime = q.lifetime; p->fadeTime = q.fade_time;
+        p->inObjectState = q.in_object_state; p->phase = q.phase != 0; p->temporary = q.temporary != 0;
+        W.particles.push_back(p);
+    }
+    return 0;
 }
 
 } /* extern "C" */

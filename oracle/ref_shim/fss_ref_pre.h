@@ -4,6 +4,9 @@
  * Test infrastructure; not part of the product. */
 #ifndef FSS_REF_PRE_H
 #define FSS_REF_PRE_H
+#include <math.h> /* like box2d/b2_math.h in the game: brings the float overloads of abs() into the global namespace */
+#include <stdlib.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>

@@ -1,5 +1,5 @@
 /* Cut-down declaration of the reference's `World` (FallingSandSurvival/world.hpp:89-211):
- * only the members that world.cpp:1053-1062, :1075-1088, :1091-2041 and :2043-2143 use.
+ * only the members that world.cpp:1053-1062, :1075-1088, :1091-2041, :2043-2143 and :2171-2338 use.
  * The method BODIES are never restated here: oracle/build_ref.py extracts them from
  * /root/reference at build time.  Test infrastructure; not part of the product. */
 #pragma once
@@ -47,4 +47,5 @@ public:
     void setTile(int x, int y, MaterialInstance type);
     void tick();
     void tickTemperature();
+    void tickParticles();
 };

@@ -45,6 +45,14 @@ def load(variant="c4x16"):
     L.fssref_num_particles.argtypes = [C.c_void_p]
     L.fssref_drain_particles.restype = C.c_size_t
     L.fssref_drain_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.fssref_keep_particles.argtypes = [C.c_void_p, C.c_int]
+    L.fssref_tick_particles.restype = C.c_double
+    L.fssref_tick_particles.argtypes = [C.c_void_p]
+    L.fssref_live_particles.restype = C.c_size_t
+    L.fssref_live_particles.argtypes = [C.c_void_p]
+    L.fssref_get_particles.restype = C.c_size_t
+    L.fssref_get_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.fssref_add_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.fssref_texture_pixel.restype = C.c_uint32
     L.fssref_texture_pixel.argtypes = [C.c_int, C.c_int, C.c_int]
     L.fssref_init(1234)
@@ -125,6 +133,24 @@ class RefWorld:
         temp = np.zeros(max(n, 1), dtype=np.int32)
         m = self.L.fssref_drain_particles(self.h_, xyv.ctypes.data, cells.ctypes.data, temp.ctypes.data, n)
         return xyv[:m], cells[:m], temp[:m]
+
+    def keep_particles(self, on=True):
+        """leave World::particles in place after tick() so that tick_particles() can run on them"""
+        self.L.fssref_keep_particles(self.h_, 1 if on else 0)
+
+    def tick_particles(self):
+        """one World::tickParticles(); returns seconds inside it"""
+        return self.L.fssref_tick_particles(self.h_)
+
+    def add_particles(self, parts):
+        parts = np.ascontiguousarray(parts, dtype=abi.LIVE_PARTICLE_DTYPE)
+        assert self.L.fssref_add_particles(self.h_, parts.ctypes.data, parts.size) == 0
+
+    def particle_list(self):
+        n = self.L.fssref_live_particles(self.h_)
+        out = np.zeros(max(n, 1), dtype=abi.LIVE_PARTICLE_DTYPE)
+        m = self.L.fssref_get_particles(self.h_, out.ctypes.data, n)
+        return out[:m]
 
     def close(self):
         if self.h_:

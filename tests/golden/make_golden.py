@@ -6,6 +6,8 @@ oracle/build_ref.py from /root/reference).  The reference ships no tests for thi
   materials_srand1234.json  Materials::MATERIALS after srand(1234); Materials::init()
   tick_hashes.json          {case -> digest}: fss_hash-style digest of the whole grid after N ticks
   micro_*.npz               tiny before/after scenes per rule family (full cell records)
+  particle_scene.json       World::tick + World::tickParticles on helpers.particle_scene(): per tick the list length and
+                            sha256 of the particle list and of the grid
 
 Run:  python tests/golden/make_golden.py      (needs oracle/_ref)
 """
@@ -69,6 +71,30 @@ def main():
         print(name, hashes[name]["digest"])
     with open(os.path.join(HERE, "tick_hashes.json"), "w") as f:
         json.dump(hashes, f, indent=1)
+    particle_scene(helpers)
+
+
+PARTICLE_SCENE_TICKS = 16
+
+
+def particle_scene(helpers):
+    import hashlib
+    cells, zone, parts = helpers.particle_scene()
+    r = refsim.RefWorld(cells, zone, particles=True, seed=0xF55)
+    r.keep_particles()
+    r.add_particles(parts)
+    rows = []
+    for t in range(PARTICLE_SCENE_TICKS):
+        r.tick(t)
+        r.tick_particles()
+        pl = r.particle_list()
+        rows.append(dict(tick=t, n=int(len(pl)), particles=hashlib.sha256(pl.tobytes()).hexdigest(),
+                         cells=hashlib.sha256(r.cells().tobytes()).hexdigest(),
+                         bounced=int((pl["vy"] == -4).sum()), in_object=int((pl["in_object_state"] == 1).sum())))
+    r.close()
+    with open(os.path.join(HERE, "particle_scene.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+    print("particle_scene", rows[-1]["n"], rows[-1]["particles"][:16])
 
 
 if __name__ == "__main__":

@@ -57,3 +57,77 @@ def diff_report(a, b, limit=5):
     for y, x in bad[:limit]:
         lines.append(f"  ({x},{y}): {a[y, x]} vs {b[y, x]}")
     return "\n".join(lines)
+
+
+def particle_scene(seed=3, size=(256, 224)):
+    """A world plus hand-made particles that drive every branch of World::tickParticles (world.cpp:2171-2311):
+    target force, `phase`, temporary lifetimes, the in-object states, landing in the start cell, the 32 x 32 landing
+    search (free cell / same liquid / nothing found -> bounce), leaving the world, frozen outside the tick zone, and
+    columns of particles that land on top of each other in one tick."""
+    rng = np.random.default_rng(seed)
+    w, h = size
+    cells, zone = make_world(size, [(M.TEST_SAND, 6), (M.WATER, 5), (M.COBBLE_STONE, 4), (M.FIRE, 1), (M.SOFT_DIRT, 2)], seed=seed)
+    defs = full_table()
+
+    def stamp(x0, y0, x1, y1, mat):
+        cells[y0:y1, x0:x1] = _flat_cells(mat, (y1 - y0, x1 - x0), defs)
+
+    stamp(40, 40, 100, 100, M.COBBLE_STONE)   # bigger than the landing search: particles inside it bounce
+    stamp(120, 40, 150, 70, M.OBJECT)         # PhysicsType::OBJECT
+    stamp(120, 70, 150, 74, M.COBBLE_STONE)
+    stamp(170, 60, 230, 64, M.WATER)          # a pool to pour into
+    stamp(170, 64, 230, 100, M.COBBLE_STONE)
+    stamp(24, 180, 232, 184, M.COBBLE_STONE)  # a floor
+    cells[150:180, 24:232] = _flat_cells(M.AIR, (30, 208), defs)  # open air above the floor
+
+    parts = []
+
+    def add(x, y, vx, vy, mat=M.TEST_SAND, ay=0.1, **kw):
+        p = np.zeros((), dtype=abi.LIVE_PARTICLE_DTYPE)
+        p["x"], p["y"], p["vx"], p["vy"], p["ay"] = x, y, vx, vy, ay
+        p["fade_time"] = 60
+        t = _flat_cells(mat, (1, 1), defs)[0, 0]
+        t["color"] = 0x123456 + len(parts)
+        t["fluid_amount"] = kw.pop("amount", 2.0)
+        p["tile"] = t
+        for k, v in kw.items():
+            p[k] = v
+        parts.append(p)
+
+    for k in range(12):                                   # columns that land on each other, on the floor
+        for c in range(6):
+            add(60 + 3 * c + 0.5, 150 + 2.5 * k, 0.0, 2.0 + 0.25 * c)
+    for k in range(8):                                    # the same start cell for several particles
+        add(130.25, 160.5, 0.1 * k - 0.3, 3.0)
+    for k in range(10):                                   # inside the big stone block: nothing free within reach
+        add(70 + k * 0.7, 70 + k * 0.3, 0.3, 0.4)
+    for k in range(10):                                   # inside stone, near its edge: the search finds air
+        add(42.5 + k, 43.5, 0.2, 0.3, mat=M.WATER if k % 2 else M.TEST_SAND)
+    for k in range(10):                                   # water started inside the pool's stone: pours into the pool
+        add(175.5 + 4 * k, 66.5, 0.05, -0.2, mat=M.WATER, amount=0.25 + 0.125 * k)
+    for k in range(6):                                    # born inside an object, leaves it, then hits stone
+        add(125.5 + 3 * k, 60.5 + k, 0.0, 1.5)
+    for k in range(4):                                    # born in air, flies into the object: state 2, lands at once
+        add(125.5 + 4 * k, 30.5, 0.0, 4.0)
+    for k in range(6):                                    # attracted to a point
+        add(30.0 + 5 * k, 160.0, 0.0, 0.0, ay=0.0, target_x=128.0, target_y=120.0 + 10 * k, target_force=0.4)
+    for k in range(4):                                    # phase: goes through everything
+        add(50.0 + 10 * k, 30.0, 0.5, 3.0, phase=1)
+    for k in range(6):                                    # temporary: dies on contact or when its lifetime is over
+        add(200.0 + 3 * k, 150.0 + k, 0.2, -0.5, ay=0.01, temporary=1, lifetime=2 + 3 * k, fade_time=10)
+    add(5.5, 100.0, -2.0, 0.0)                            # outside the tick zone: frozen
+    add(w - 20.5, 100.0, 30.0, 0.0)                       # leaves the world in one tick
+    add(100.5, 20.5, 0.0, -30.0)
+    for _ in range(200):                                  # a random crowd over the open area
+        add(rng.uniform(30, 226), rng.uniform(120, 176), rng.uniform(-1.5, 1.5), rng.uniform(-1, 4),
+            mat=M.WATER if rng.random() < 0.4 else M.TEST_SAND, amount=float(rng.uniform(0.1, 2.0)))
+    return cells, zone, np.array(parts, dtype=abi.LIVE_PARTICLE_DTYPE)
+
+
+def _flat_cells(mat, shape, defs):
+    """cells of one material as the MaterialInstance constructor leaves them (colour = Material::color)"""
+    c = np.zeros(shape, dtype=abi.CELL_DTYPE)
+    c["material"] = mat
+    c["color"] = defs[mat].color
+    c["fluid_amount"] = 2.0
+    return c

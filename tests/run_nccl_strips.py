@@ -52,7 +52,7 @@ def main():
             hsum = (hsum + h) & 0xFFFFFFFFFFFFFFFF
             recs.append(np.frombuffer(praw, dtype=abi.PARTICLE_DTYPE))
         recs = np.concatenate(recs)
-        recs = recs[np.lexsort((recs["site"], recs["x"], recs["y"], recs["tick_iter"]))]
+        recs = recs[abi.spawn_order(recs, zone)]
         ok = out.tobytes() == ref.tobytes() and hsum == whole.hash() and recs.tobytes() == whole.drain_particles().tobytes()
         print(f"nccl strips n={n}: cells {'==' if out.tobytes() == ref.tobytes() else '!='} single GPU, digest sum {hsum:016x} vs {whole.hash():016x}, "
               f"{len(recs)} particle records -> {'OK' if ok else 'MISMATCH'}", flush=True)

@@ -650,3 +650,120 @@ def test_flow_side_output_matches_oracle(mix):
     assert e.value.code == -5
     for w in (g, o, plain):
         w.close()
+
+
+# ---- World::particles on the device: fss_tick_particles against the oracle's serial loop ----------------
+def _same_particles(t, g, o):
+    a, b = g.particle_list(), o.particle_list()
+    assert len(a) == len(b), f"tick {t}: {len(a)} particles on the device, {len(b)} in the oracle"
+    if a.tobytes() != b.tobytes():
+        bad = [i for i in range(len(a)) if a[i].tobytes() != b[i].tobytes()]
+        raise AssertionError(f"tick {t}: {len(bad)} particles differ, first at {bad[0]}: {a[bad[0]]} vs {b[bad[0]]}")
+    ca, cb = g.cells(), o.cells()
+    assert ca.tobytes() == cb.tobytes(), f"tick {t}: " + diff_report(ca, cb)
+
+
+def test_device_particles_scene_matches_oracle_and_golden():
+    """the hand-made scene that drives every branch of World::tickParticles; also against the hashes minted from the
+    reference's own lines"""
+    import hashlib
+    from helpers import particle_scene
+    with open(os.path.join(GOLDEN, "particle_scene.json")) as f:
+        rows = json.load(f)
+    cells, zone, parts = particle_scene()
+    g = gpu_world(cells, zone, particles=True)
+    o = oracle_world(cells, zone, particles=True)
+    g.add_particles(parts)
+    o.add_particles(parts)
+    assert g.particles_count() == len(parts)
+    assert g.particle_list().tobytes() == parts.tobytes()
+    for row in rows:
+        t = row["tick"]
+        g.tick(t)
+        o.tick(t)
+        g.tick_particles()
+        o.tick_particles()
+        _same_particles(t, g, o)
+        assert g.particles_count() == row["n"]
+        assert hashlib.sha256(g.particle_list().tobytes()).hexdigest() == row["particles"]
+        assert hashlib.sha256(g.cells().tobytes()).hexdigest() == row["cells"]
+    assert len(g.drain_particles()) == 0  # the spawn records were adopted
+    g.close()
+    o.close()
+
+
+@pytest.mark.parametrize("mix", ["c3", "sand", "liquids", "fire"])
+def test_device_particles_with_tick_match_oracle(mix):
+    """World::tick feeds the list, World::tickParticles lands it again; temperature every 4th tick"""
+    cells, zone = make_world((264, 240), mix, seed=3000 + len(mix))
+    g = gpu_world(cells, zone, particles=True)
+    o = oracle_world(cells, zone, particles=True)
+    for t in range(40):
+        g.tick(t)
+        o.tick(t)
+        g.tick_particles()
+        o.tick_particles()
+        if t % 4 == 2:
+            g.tick_temperature()
+            o.tick_temperature()
+        _same_particles(t, g, o)
+    g.close()
+    o.close()
+
+
+def test_device_particles_every_other_tick_and_host_pushes():
+    """spawn records of two ticks adopted at once; host pushes land behind them; early-out off gives the same"""
+    from helpers import particle_scene
+    cells, zone, parts = particle_scene(seed=9)
+    worlds_ = [gpu_world(cells, zone, particles=True), gpu_world(cells, zone, particles=True, early_out=False),
+               oracle_world(cells, zone, particles=True)]
+    for t in range(12):
+        for w in worlds_:
+            w.tick(t)
+            if t % 2 == 1:
+                w.tick_particles()
+            if t == 3:
+                w.add_particles(parts[:100])
+            if t == 6:
+                w.add_particles(parts[100:])
+        if t % 2 == 1:
+            _same_particles(t, worlds_[0], worlds_[2])
+            _same_particles(t, worlds_[1], worlds_[2])
+    for w in worlds_:
+        w.close()
+
+
+def test_device_particles_dense_rain():
+    """many particles landing on each other in every column: long chains of rounds; digest + list against the oracle"""
+    size = (1040, 544)
+    cells, zone = make_world(size, [(M.TEST_SAND, 35), (M.WATER, 15), (M.COBBLE_STONE, 3)], seed=5)
+    g = gpu_world(cells, zone, particles=True, particle_capacity=1 << 21)
+    o = oracle_world(cells, zone, particles=True)
+    for t in range(10):
+        g.tick(t)
+        o.tick(t)
+        g.tick_particles()
+        o.tick_particles()
+        a, b = g.particle_list(), o.particle_list()
+        assert len(a) == len(b) and a.tobytes() == b.tobytes(), f"tick {t}"
+        from oracle import oraclesim
+        assert g.hash() == oraclesim.hash_cells(o.cells()), f"tick {t}"
+    g.close()
+    o.close()
+
+
+def test_device_particles_error_paths():
+    from fallingsandsurvival_b200 import world
+    cells, zone = make_world((264, 336), "c2", seed=1)
+    parts = world.StripWorld(cells, zone, 2, defs=full_table(), particles=True)
+    with pytest.raises(world.FssError):
+        parts.parts[0].tick_particles()
+    parts.close()
+    g = gpu_world(cells, zone, particles=True)
+    bad = np.zeros(1, dtype=abi.LIVE_PARTICLE_DTYPE)
+    bad["tile"]["material"] = 999
+    with pytest.raises(world.FssError):
+        g.add_particles(bad)
+    g.tick_particles()  # empty list: nothing to do
+    assert g.particles_count() == 0
+    g.close()

@@ -69,6 +69,54 @@ def test_oracle_matches_reference_build(mix, particles, have_ref):
     o.close()
 
 
+def test_oracle_particle_tick_matches_golden():
+    """World::tick + World::tickParticles (world.cpp:2171-2311) on the hand-made scene that drives every branch; the
+    golden hashes were minted from the reference's own lines (tests/golden/make_golden.py)"""
+    import hashlib
+    import json
+    from helpers import GOLDEN, particle_scene
+    with open(os.path.join(GOLDEN, "particle_scene.json")) as f:
+        rows = json.load(f)
+    cells, zone, parts = particle_scene()
+    o = oraclesim.OracleWorld(cells, zone, defs=full_table(), particles=True)
+    o.add_particles(parts)
+    assert rows[0]["bounced"] > 0 and rows[0]["in_object"] > 0
+    for row in rows:
+        o.tick(row["tick"])
+        o.tick_particles()
+        pl = o.particle_list()
+        assert len(pl) == row["n"], f"tick {row['tick']}"
+        assert hashlib.sha256(pl.tobytes()).hexdigest() == row["particles"], f"tick {row['tick']}"
+        assert hashlib.sha256(o.cells().tobytes()).hexdigest() == row["cells"], f"tick {row['tick']}"
+    o.close()
+
+
+@pytest.mark.parametrize("mix", ["c3", "sand", "liquids", "fire"])
+def test_oracle_particle_tick_matches_reference_build(mix, have_ref):
+    """the list (order, positions, velocities, tiles) and the grid, every tick, with World::tick feeding the list"""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from oracle import refsim
+    cells, zone = make_world((200, 176), mix, seed=2000 + len(mix))
+    r = refsim.RefWorld(cells, zone, particles=True)
+    r.keep_particles()
+    o = oraclesim.OracleWorld(cells, zone, defs=full_table(), particles=True)
+    seen = 0
+    for t in range(30):
+        r.tick(t)
+        o.tick(t)
+        r.tick_particles()
+        o.tick_particles()
+        a, b = r.particle_list(), o.particle_list()
+        assert len(a) == len(b) and a.tobytes() == b.tobytes(), f"tick {t}: particle lists differ"
+        ca, cb = r.cells(), o.cells()
+        assert ca.tobytes() == cb.tobytes(), f"tick {t}: " + diff_report(ca, cb)
+        seen += len(a)
+    assert seen > 0
+    r.close()
+    o.close()
+
+
 def test_reference_build_is_thread_count_independent(have_ref):
     """the 4x16 checkerboard is race-free: 1, 3 and 8 pool threads give the same grid"""
     if not have_ref:

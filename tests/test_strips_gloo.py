@@ -124,7 +124,7 @@ def test_gloo_ranks_reproduce_the_undivided_world(n, tmp_path):
     assert got.shape == ref.shape
     assert got.tobytes() == ref.tobytes(), f"{int((got != ref).sum())} cells differ"
     parts = np.concatenate([np.load(tmp_path / f"parts{r}.npy") for r in range(n)])
-    parts = parts[np.lexsort((parts["site"], parts["x"], parts["y"], parts["tick_iter"]))]
+    parts = parts[abi.spawn_order(parts, zone)]
     assert parts.tobytes() == whole.drain_particles().tobytes()
 
 
