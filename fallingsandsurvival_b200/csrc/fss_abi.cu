@@ -125,10 +125,11 @@ struct fss_world {
     int k1_variant; // 0 = K1a lock-step (k_substep), 1 = K1b shared-memory decoupled (k_substep_sm)
     // World::particles (fss_particles.cuh): the list, its scratch copy and the per-particle round state, all `pl_cap` long
     fss_particle *pl_list, *pl_next;
-    uint8_t *pl_decided, *pl_keep, *pl_sure;
+    uint8_t *pl_decided, *pl_keep, *pl_sure, *pl_big;
+    uint32_t *pl_ran, *pl_listed;
     int4 *pl_act, *pl_seen, *pl_reach;
     uint32_t pl_n, pl_cap;
-    uint32_t* pl_res_cell; // hashed cell reservations, pl_res_mask + 1 entries
+    uint32_t* pl_res_cell; // four hashed cell tables (W_act, R_act, W_pot, R_pot) of pl_res_mask + 1 entries each
     uint32_t pl_res_mask;
     uint32_t* pl_res_tile; // one entry per 16 x 16 tile of the world
     uint32_t* pl_ctl;      // [0] left undecided, [1] cutoff, [2] list length after compaction
@@ -136,7 +137,7 @@ struct fss_world {
     uint32_t *pl_idx[2];
     void* pl_tmp; // cub scratch
     size_t pl_tmp_bytes;
-    uint64_t pl_rounds; // rounds of the last fss_tick_particles
+    uint64_t pl_rounds, pl_passes; // rounds / cascade passes of the last fss_tick_particles
     // strips
     void* comm;
     int rank, n_ranks;
@@ -214,7 +215,7 @@ static int dirty_chunks(fss_world* w, int rx, int ry, int rw, int rh) {
 }
 
 static void particles_free(fss_world* w) {
-    void* ptrs[] = {w->pl_list, w->pl_next, w->pl_decided, w->pl_keep, w->pl_sure, w->pl_act, w->pl_seen, w->pl_reach,
+    void* ptrs[] = {w->pl_list, w->pl_next, w->pl_decided, w->pl_keep, w->pl_sure, w->pl_big, w->pl_ran, w->pl_listed, w->pl_act, w->pl_seen, w->pl_reach,
                     w->pl_res_cell, w->pl_res_tile, w->pl_ctl, w->pl_key[0], w->pl_key[1], w->pl_idx[0], w->pl_idx[1], w->pl_tmp};
     for(void* p : ptrs) cudaFree(p);
 }
@@ -689,12 +690,14 @@ int fss_drain_particles(fss_world* w, fss_particle_spawn* out, size_t cap, size_
 
 
 // ---- World::particles on the device (fss_particles.cuh) -----------------------------------------------------
+static int particles_spiral_init();
 static int particles_reserve(fss_world* w, size_t need) {
     if(need > 0x7FFFFFF0u) return fail(FSS_ERR_RANGE, "%zu particles", need);
     if(!w->pl_ctl) {
-        CU(cudaMalloc(&w->pl_ctl, 4 * sizeof(uint32_t)));
+        if(int rc = particles_spiral_init()) return rc;
+        CU(cudaMalloc(&w->pl_ctl, 8 * sizeof(uint32_t)));
         const size_t tiles = (size_t)((w->cfg.width + FSS_PTILE - 1) / FSS_PTILE) * ((w->cfg.height + FSS_PTILE - 1) / FSS_PTILE);
-        CU(cudaMalloc(&w->pl_res_tile, tiles * sizeof(uint32_t)));
+        CU(cudaMalloc(&w->pl_res_tile, 3 * tiles * sizeof(uint32_t))); // res_tile, w_tile, w_when
     }
     if(need <= w->pl_cap) return FSS_OK;
     size_t cap = std::max<size_t>(w->pl_cap ? (size_t)w->pl_cap * 2 : 4096, need);
@@ -703,21 +706,47 @@ static int particles_reserve(fss_world* w, size_t need) {
     CU(cudaMalloc(&next, cap * sizeof(fss_particle)));
     if(w->pl_n) CU(cudaMemcpyAsync(list, w->pl_list, (size_t)w->pl_n * sizeof(fss_particle), cudaMemcpyDeviceToDevice, w->stream));
     CU(cudaStreamSynchronize(w->stream));
-    void* old[] = {w->pl_list, w->pl_next, w->pl_decided, w->pl_keep, w->pl_sure, w->pl_act, w->pl_seen, w->pl_reach, w->pl_res_cell};
+    void* old[] = {w->pl_list, w->pl_next, w->pl_decided, w->pl_keep, w->pl_sure, w->pl_big, w->pl_ran, w->pl_listed, w->pl_act, w->pl_seen, w->pl_reach, w->pl_res_cell};
     for(void* p : old) cudaFree(p);
     w->pl_list = list;
     w->pl_next = next;
     CU(cudaMalloc(&w->pl_decided, cap));
     CU(cudaMalloc(&w->pl_keep, cap));
     CU(cudaMalloc(&w->pl_sure, cap));
+    CU(cudaMalloc(&w->pl_big, cap));
+    CU(cudaMalloc(&w->pl_ran, cap * sizeof(uint32_t)));
+    CU(cudaMalloc(&w->pl_listed, cap * sizeof(uint32_t)));
     CU(cudaMalloc(&w->pl_act, cap * sizeof(int4)));
     CU(cudaMalloc(&w->pl_seen, cap * sizeof(int4)));
     CU(cudaMalloc(&w->pl_reach, cap * sizeof(int4)));
-    size_t slots = 4096; // >= 8 slots per particle keeps chance collisions (which only delay a particle by a round) rare
-    while(slots < cap * 8) slots *= 2;
-    CU(cudaMalloc(&w->pl_res_cell, slots * sizeof(uint32_t)));
+    size_t slots = 4096; // >= 16 slots per particle keeps chance collisions (which only delay a particle by a round) rare
+    while(slots < cap * 16) slots *= 2;
+    CU(cudaMalloc(&w->pl_res_cell, 4 * slots * sizeof(uint32_t)));
     w->pl_res_mask = (uint32_t)(slots - 1);
     w->pl_cap = (uint32_t)cap;
+    return FSS_OK;
+}
+
+// the visiting order of the landing search, world.cpp:2256-2290 (`X = Y = 32`, x/y/dx/dy as there)
+static int particles_spiral_init() {
+    char2 h[FSS_PSPIRAL_N];
+    int X = 32, Y = 32, x = 0, y = 0, dx = 0, dy = -1, n = 0;
+    for(int j = 0; j < 32 * 32; j++) {
+        if((-X / 2 <= x) && (x <= X / 2) && (-Y / 2 <= y) && (y <= Y / 2)) {
+            h[n].x = (signed char)x;
+            h[n].y = (signed char)y;
+            n++;
+        }
+        if((x == y) || ((x < 0) && (x == -y)) || ((x > 0) && (x == 1 - y))) {
+            int t = dx;
+            dx = -dy;
+            dy = t;
+        }
+        x += dx;
+        y += dy;
+    }
+    if(n != FSS_PSPIRAL_N) return fail(FSS_ERR_STATE, "landing search visits %d cells, expected %d", n, FSS_PSPIRAL_N);
+    CU(cudaMemcpyToSymbol(c_spiral, h, sizeof h));
     return FSS_OK;
 }
 
@@ -816,7 +845,8 @@ int fss_particles_clear(fss_world* w) {
 
 int fss_particles_rounds(fss_world* w, uint64_t* rounds) {
     if(!w || !rounds) return fail(FSS_ERR_INVALID, "null argument");
-    *rounds = w->pl_rounds;
+    rounds[0] = w->pl_rounds;
+    rounds[1] = w->pl_passes;
     return FSS_OK;
 }
 
@@ -826,7 +856,7 @@ int fss_tick_particles(fss_world* w) {
     if(w->sharded) return fail(FSS_ERR_STATE, "device particles are not available on strip-sharded worlds");
     if(!w->zone_set || !w->mats_set) return fail(FSS_ERR_STATE, "fss_set_materials and fss_set_tick_zone first");
     if(int rc = particles_adopt(w)) return rc;
-    w->pl_rounds = 0;
+    w->pl_rounds = w->pl_passes = 0;
     const uint32_t n = w->pl_n;
     if(n == 0) return FSS_OK;
     if(int rc = particles_reserve(w, n)) return rc;
@@ -848,13 +878,23 @@ int fss_tick_particles(fss_world* w) {
     P.act = w->pl_act;
     P.seen = w->pl_seen;
     P.reach = w->pl_reach;
-    P.res_cell = w->pl_res_cell;
+    const size_t slots = (size_t)w->pl_res_mask + 1;
+    P.w_act = w->pl_res_cell;
+    P.r_act = w->pl_res_cell + slots;
+    P.w_pot = w->pl_res_cell + 2 * slots;
+    P.r_pot = w->pl_res_cell + 3 * slots;
     P.res_mask = w->pl_res_mask;
     P.res_tile = w->pl_res_tile;
+    P.big = w->pl_big;
     P.tiles_w = (int)((w->cfg.width + FSS_PTILE - 1) / FSS_PTILE);
     P.tiles_h = (int)((w->cfg.height + FSS_PTILE - 1) / FSS_PTILE);
+    P.w_tile = w->pl_res_tile + (size_t)P.tiles_w * P.tiles_h;
+    P.w_when = w->pl_res_tile + 2 * (size_t)P.tiles_w * P.tiles_h;
+    P.ran = w->pl_ran;
+    P.listed = w->pl_listed;
     P.ctl = w->pl_ctl;
     P.n = n;
+    P.pass = 0;
     P.q = (w->cfg.flags & FSS_NO_EARLY_OUT) ? nullptr : w->d_q;
     P.q_w = w->q_w;
     P.q_h = w->q_h;
@@ -862,17 +902,30 @@ int fss_tick_particles(fss_world* w) {
     const unsigned blocks = (n + 127) / 128;
     CU(cudaMemsetAsync(w->pl_decided, 0, n, w->stream));
     for(uint32_t left = n; left;) {
-        const uint32_t ctl0[2] = {0u, 0xFFFFFFFFu};
+        const uint32_t ctl0[4] = {0u, 0xFFFFFFFFu, 0u, 0u};
         CU(cudaMemcpyAsync(w->pl_ctl, ctl0, sizeof ctl0, cudaMemcpyHostToDevice, w->stream));
-        CU(cudaMemsetAsync(w->pl_res_cell, 0xFF, ((size_t)w->pl_res_mask + 1) * sizeof(uint32_t), w->stream));
-        CU(cudaMemsetAsync(w->pl_res_tile, 0xFF, (size_t)P.tiles_w * P.tiles_h * sizeof(uint32_t), w->stream));
+        CU(cudaMemsetAsync(w->pl_res_cell, 0xFF, 4 * slots * sizeof(uint32_t), w->stream));
+        CU(cudaMemsetAsync(w->pl_res_tile, 0xFF, 2 * (size_t)P.tiles_w * P.tiles_h * sizeof(uint32_t), w->stream));
+        CU(cudaMemsetAsync(P.w_when, 0, (size_t)P.tiles_w * P.tiles_h * sizeof(uint32_t), w->stream));
         k_particles_speculate<<<blocks, 128, 0, w->stream>>>(P);
-        k_particles_check_cells<<<blocks, 128, 0, w->stream>>>(P);
-        k_particles_check_tiles<false><<<blocks, 128, 0, w->stream>>>(P);
-        k_particles_check_tiles<true><<<blocks, 128, 0, w->stream>>>(P);
+        w->stats.kernel_launches++;
+        // "who is unsure" to its fixed point: a pass that changes nobody ends it
+        for(uint32_t last_change = 0; P.pass < FSS_PCASCADE_MAX;) {
+            for(int k = 0; k < FSS_PCASCADE_BATCH; k++) {
+                P.pass++;
+                k_particles_cascade<false><<<blocks, 128, 0, w->stream>>>(P);
+            }
+            w->stats.kernel_launches += FSS_PCASCADE_BATCH;
+            CU(cudaMemcpyAsync(&last_change, w->pl_ctl + 3, sizeof last_change, cudaMemcpyDeviceToHost, w->stream));
+            CU(cudaStreamSynchronize(w->stream));
+            w->pl_passes += FSS_PCASCADE_BATCH;
+            if(last_change < P.pass) break;
+        }
+        P.pass = 0;
+        k_particles_cascade<true><<<blocks, 128, 0, w->stream>>>(P);
         k_particles_commit<<<blocks, 128, 0, w->stream>>>(P);
         CU(cudaGetLastError());
-        w->stats.kernel_launches += 5;
+        w->stats.kernel_launches += 2;
         w->pl_rounds++;
         uint32_t now = 0;
         CU(cudaMemcpyAsync(&now, w->pl_ctl, sizeof now, cudaMemcpyDeviceToHost, w->stream));

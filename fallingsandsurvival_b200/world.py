@@ -60,7 +60,7 @@ def load():
         "fss_particles_count": [vp, C.POINTER(sz)],
         "fss_particles_download": [vp, vp, sz, C.POINTER(sz)],
         "fss_particles_clear": [vp],
-        "fss_particles_rounds": [vp, C.POINTER(C.c_uint64)],
+        "fss_particles_rounds": [vp, C.POINTER(C.c_uint64 * 2)],
         "fss_histogram": [vp, vp, i32],
         "fss_hash": [vp, C.POINTER(C.c_uint64)],
         "fss_fluid_totals": [vp, vp, i32],
@@ -232,9 +232,9 @@ class World:
         return out[: got.value]
 
     def particle_rounds(self):
-        r = C.c_uint64()
-        _check(self.L, self.L.fss_particles_rounds(self.h_, C.byref(r)))
-        return r.value
+        r = (C.c_uint64 * 2)()
+        _check(self.L, self.L.fss_particles_rounds(self.h_, r))
+        return int(r[0]), int(r[1])
 
     def clear_particles(self):
         _check(self.L, self.L.fss_particles_clear(self.h_))

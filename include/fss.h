@@ -269,8 +269,9 @@ int fss_particles_count(fss_world* w, size_t* n);
 /* the list in order, for World::renderParticles (world.cpp:2145-2169) */
 int fss_particles_download(fss_world* w, fss_particle* out, size_t cap, size_t* n_out);
 int fss_particles_clear(fss_world* w);
-/* how many retire rounds the last fss_tick_particles needed (1 when no particle depended on another) */
-int fss_particles_rounds(fss_world* w, uint64_t* rounds);
+/* rounds[0] = retire rounds of the last fss_tick_particles (1 when no particle depended on another), rounds[1] = cascade
+ * passes over all its rounds */
+int fss_particles_rounds(fss_world* w, uint64_t rounds[2]);
 /* per-material cell counts over the owned rows (movingTiles replacement, Game.cpp:2579-2589) */
 int fss_histogram(fss_world* w, uint64_t* counts, int n_materials);
 /* order-independent digest (sum of fss_cell_digest over owned rows); k-GPU digests add up */
