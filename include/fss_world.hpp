@@ -103,6 +103,11 @@ public:
     Rect tickZone;                     // world.hpp:132
     std::vector<fss_particle_spawn> spawned; // cells that left the grid during the last tick (world.cpp:1180, :1291, :1366)
     bool emitParticles = true;
+    // World::particles (world.hpp) kept on the device: tick() then leaves the spawn records where they are and
+    // tickParticles() turns them into particles and runs World::tickParticles (world.cpp:2171-2311) on the GPU;
+    // `particles` is the host copy of the list for World::renderParticles (world.cpp:2145-2169).
+    bool deviceParticles = false;
+    std::vector<fss_particle> particles;
 
     World() {}
     World(const World&) = delete;
@@ -198,6 +203,10 @@ public:
         tickCt++;
         // the tick writes at most 2 cells outside the zone (fire ignition, world.cpp:1198-1206)
         pull(tickZone.x - 2, tickZone.y - 2, tickZone.w + 4, tickZone.h + 4, true);
+        if(deviceParticles) {
+            spawned.clear();
+            return;
+        }
         size_t n = 0, total = 0;
         spawned.resize(1 << 16);
         int rc = fss_drain_particles(core_, spawned.data(), spawned.size(), &n, &total);
@@ -208,6 +217,21 @@ public:
             spawned.resize(n);
         }
     }
+
+    // World::tickParticles (world.cpp:2171-2311); needs deviceParticles.  Landed particles change tiles[] (dirty is set).
+    void tickParticles() {
+        flush();
+        applyZone();
+        check(fss_tick_particles(core_), "fss_tick_particles");
+        size_t n = 0;
+        check(fss_particles_count(core_, &n), "fss_particles_count");
+        particles.resize(n);
+        check(fss_particles_download(core_, particles.data(), n, &n), "fss_particles_download");
+        // a particle that starts inside the zone lands within its path and the 32 x 32 landing search around it
+        pull(tickZone.x - 48, tickZone.y - 48, tickZone.w + 96, tickZone.h + 96, true);
+    }
+    // particles.push_back(new Particle(...)) by game code
+    void addParticle(const fss_particle& p) { check(fss_particles_add(core_, &p, 1), "fss_particles_add"); }
 
     // World::tickTemperature (world.cpp:2043-2143)
     void tickTemperature() {

@@ -4,6 +4,7 @@
 // Writes the initial grid, the edits and the final tiles[] as fss_cell arrays so that tests/test_gpu_parity.py can replay
 // the same script on the oracle and compare bit for bit.
 #include <cstdio>
+#include <string>
 #include <vector>
 
 #include "fss_rng.h"
@@ -22,6 +23,7 @@ static void dump(const char* path, const World& w) {
 int main(int argc, char** argv) {
     if(argc < 2) return 2;
     const std::string dir = argv[1];
+    const bool deviceParticles = argc > 2 && std::string(argv[2]) == "particles"; // World::tickParticles on the GPU as well
     const int W = 328, H = 240, ticks = 12;
     try {
         // Materials.cpp:5-46 in miniature; ids are dense
@@ -54,6 +56,7 @@ int main(int argc, char** argv) {
         }
         dump((dir + "/initial.bin").c_str(), world);
         world.tickZone = Rect{16, 16, W - 32, H - 48};
+        world.deviceParticles = deviceParticles;
         for(int t = 0; t < ticks; t++) {
             if(t == 5) { // a brush stroke of sand written straight into tiles[], like Game.cpp:1147
                 for(int y = 40; y < 52; y++)
@@ -61,7 +64,21 @@ int main(int argc, char** argv) {
                 world.markDirty(100, 40, 40, 12);
             }
             world.tick();
+            if(deviceParticles) {
+                if(t == 3) { // game code throwing a grain of sand, like the tools in Game.cpp do with particles.push_back
+                    fss_particle p = {};
+                    p.x = 150.5f, p.y = 60.25f, p.vx = 1.5f, p.vy = -2.0f, p.ay = 0.1f, p.fade_time = 60;
+                    p.tile = World::toCell(MaterialInstance(&mats[2], 0x112233));
+                    world.addParticle(p);
+                }
+                world.tickParticles(); // Game.cpp:2459-2483
+            }
             if(t % 4 == 2) world.tickTemperature();
+        }
+        if(deviceParticles) {
+            FILE* f = std::fopen((dir + "/particles.bin").c_str(), "wb");
+            std::fwrite(world.particles.data(), sizeof(fss_particle), world.particles.size(), f);
+            std::fclose(f);
         }
         dump((dir + "/final.bin").c_str(), world);
         size_t ndirty = 0;

@@ -526,14 +526,16 @@ def test_tall_world_beyond_grid_dim_limits():
         w.close()
 
 
-def test_cpp_world_mirror_matches_oracle(tmp_path):
+@pytest.mark.parametrize("device_particles", [False, True])
+def test_cpp_world_mirror_matches_oracle(tmp_path, device_particles):
     """tests/cpp/world_shim_test.cpp plays a short game script against fss::World (include/fss_world.hpp); the oracle
-    replays the same script (same initial grid, same brush stroke) and must produce the same tiles[]"""
+    replays the same script (same initial grid, same brush stroke) and must produce the same tiles[].  With
+    device_particles the script also runs World::tickParticles every tick and throws one particle by hand."""
     import subprocess
 
     from test_abi import build_cpp_shim_test
     exe = build_cpp_shim_test(tmp_path)
-    r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True)
+    r = subprocess.run([str(exe), str(tmp_path)] + (["particles"] if device_particles else []), capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     W, H = 328, 240
     initial = np.fromfile(tmp_path / "initial.bin", dtype=abi.CELL_DTYPE).reshape(H, W)
@@ -554,11 +556,21 @@ def test_cpp_world_mirror_matches_oracle(tmp_path):
             patch["material"], patch["color"], patch["fluid_amount"] = 2, 0xABCDEF, 2.0
             o.view()[40:52, 100:140] = patch
         o.tick(t)
+        if device_particles:
+            if t == 3:
+                p = np.zeros(1, dtype=abi.LIVE_PARTICLE_DTYPE)
+                p["x"], p["y"], p["vx"], p["vy"], p["ay"], p["fade_time"] = 150.5, 60.25, 1.5, -2.0, 0.1, 60
+                p["tile"]["material"], p["tile"]["color"], p["tile"]["fluid_amount"] = 2, 0x112233, 2.0
+                o.add_particles(p)
+            o.tick_particles()
         if t % 4 == 2:
             o.tick_temperature()
     want = o.cells()
     assert final.tobytes() == want.tobytes(), diff_report(want, final)
     assert f"digest {oraclesim.hash_cells(want):016x}" in r.stdout
+    if device_particles:
+        got = np.fromfile(tmp_path / "particles.bin", dtype=abi.LIVE_PARTICLE_DTYPE)
+        assert got.tobytes() == o.particle_list().tobytes()
     o.close()
 
 
