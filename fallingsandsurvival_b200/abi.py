@@ -24,6 +24,7 @@ CREATE_FLAT, CREATE_RAND, CREATE_TEXTURE = 0, 1, 2
 PARTICLES_EMIT = 1
 NO_EARLY_OUT = 2
 TRACK_FLOW = 4
+TRACK_DIRTY = 8
 SITE_TILES = 10000
 
 ERRORS = {0: "FSS_OK", -1: "FSS_ERR_INVALID", -2: "FSS_ERR_ALIGN", -3: "FSS_ERR_CUDA", -4: "FSS_ERR_NO_DEVICE",
@@ -106,6 +107,10 @@ LIVE_PARTICLE_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("vx", "<f4"), ("vy"
                                 ("lifetime", "<i4"), ("fade_time", "<i4"), ("in_object_state", "<u2"),
                                 ("phase", "u1"), ("temporary", "u1"), ("tile", CELL_DTYPE)])
 assert LIVE_PARTICLE_DTYPE.itemsize == C.sizeof(Particle) == 68
+
+
+class RenderInfo(C.Structure):
+    _fields_ = [("had_dirty", C.c_uint32), ("had_fire", C.c_uint32), ("had_flow", C.c_uint32)]
 
 
 class FillSpec(C.Structure):

@@ -21,6 +21,7 @@
 
 #include "fss_kernels.cuh"
 #include "fss_particles.cuh"
+#include "fss_render.cuh"
 
 static thread_local std::string g_err;
 
@@ -138,6 +139,15 @@ struct fss_world {
     void* pl_tmp; // cub scratch
     size_t pl_tmp_bytes;
     uint64_t pl_rounds, pl_passes; // rounds / cascade passes of the last fss_tick_particles
+    // dirty -> pixels (fss_render.cuh): the four RGBA layers, the flow map's smoothing state, Material::alpha / emitColor
+    uint32_t* px[4];
+    float *prev_fx, *prev_fy;
+    uint8_t h_alpha[FSS_MAX_MATERIALS];
+    uint32_t h_emit[FSS_MAX_MATERIALS];
+    int32_t h_iterations[FSS_MAX_MATERIALS];
+    DLook* d_looks;
+    bool looks_stale;
+    unsigned long long* d_rinfo; // FSS_MAX_MATERIALS counters, then hadDirty / hadFire / hadFlow as uint32
     // strips
     void* comm;
     int rank, n_ranks;
@@ -305,6 +315,16 @@ int fss_create(const fss_config* cfg, fss_world** out) {
         CUX(cudaMemsetAsync(w->g.fx, 0, n * 4, w->stream));
         CUX(cudaMemsetAsync(w->g.fy, 0, n * 4, w->stream));
     }
+    if(cfg->flags & FSS_TRACK_DIRTY) {
+        if(w->k1_variant == 1) {
+            fss_destroy(w);
+            return fail(FSS_ERR_INVALID, "FSS_TRACK_DIRTY is not supported by the experimental FSS_K1=b kernel");
+        }
+        w->cfg.flags |= FSS_NO_EARLY_OUT; // a skipped chunk would lose the marks of its liquid cells (world.cpp:1814, :1823)
+        CUX(cudaMalloc(&w->g.dirty, n));
+        CUX(cudaMemsetAsync(w->g.dirty, 0, n, w->stream));
+    }
+    for(int m = 0; m < FSS_MAX_MATERIALS; m++) w->h_alpha[m] = 255;
     CUX(cudaMalloc(&w->d_mats, sizeof(DMat) * FSS_MAX_MATERIALS));
     CUX(cudaMalloc(&w->d_tex, sizeof(DTex) * FSS_MAX_TEXTURES));
     CUX(cudaMemsetAsync(w->d_tex, 0, sizeof(DTex) * FSS_MAX_TEXTURES, w->stream));
@@ -339,6 +359,12 @@ int fss_destroy(fss_world* w) {
     cudaFree(w->g.amt);
     cudaFree(w->g.dif);
     cudaFree(w->g.fx);
+    cudaFree(w->g.dirty);
+    for(int k = 0; k < 4; k++) cudaFree(w->px[k]);
+    cudaFree(w->prev_fx);
+    cudaFree(w->prev_fy);
+    cudaFree(w->d_looks);
+    cudaFree(w->d_rinfo);
     cudaFree(w->g.fy);
     cudaFree(w->d_mats);
     for(int i = 0; i < FSS_MAX_TEXTURES; i++) cudaFree((void*)w->h_tex[i].px);
@@ -418,6 +444,8 @@ int fss_set_materials(fss_world* w, const fss_material* t, int n) {
     }
     if(w->cfg.condense_material >= n) return fail(FSS_ERR_INVALID, "condense_material %d >= %d materials", w->cfg.condense_material, n);
     memcpy(w->h_mats, tmp, sizeof tmp);
+    for(int i = 0; i < n; i++) w->h_iterations[i] = t[i].iterations; // the flow map divides by the real count (Game.cpp:2636)
+    w->looks_stale = true;
     w->n_mat = n;
     w->fire_id = fire_id;
     w->nothing_mf = 0u | tmp[0].bits;
@@ -600,14 +628,20 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk) {
         static const bool no_spec = getenv("FSS_NO_SPECIALISE") != nullptr; // measurements: always the general kernel
         const int mode = no_spec ? K1_GENERAL : (iter >= w->liq_from_iter ? K1_LIQUID : (iter >= w->nogas_from_iter ? K1_NOGAS : K1_GENERAL));
         const bool flow = w->g.fx != nullptr;
-#define FSS_LAUNCH_K1(M, F) k_substep<M, F><<<grid, K1_THREADS, 0, w->stream>>>(p)
-        if(mode == K1_LIQUID) {
-            if(flow) FSS_LAUNCH_K1(K1_LIQUID, true); else FSS_LAUNCH_K1(K1_LIQUID, false);
-        } else if(mode == K1_NOGAS) {
-            if(flow) FSS_LAUNCH_K1(K1_NOGAS, true); else FSS_LAUNCH_K1(K1_NOGAS, false);
-        } else {
-            if(flow) FSS_LAUNCH_K1(K1_GENERAL, true); else FSS_LAUNCH_K1(K1_GENERAL, false);
-        }
+        const bool dirty = w->g.dirty != nullptr;
+#define FSS_LAUNCH_K1(M, F, D) k_substep<M, F, D><<<grid, K1_THREADS, 0, w->stream>>>(p)
+#define FSS_LAUNCH_K1_MODE(M)                                                                      \
+    do {                                                                                           \
+        if(dirty) {                                                                                \
+            if(flow) FSS_LAUNCH_K1(M, true, true); else FSS_LAUNCH_K1(M, false, true);             \
+        } else {                                                                                   \
+            if(flow) FSS_LAUNCH_K1(M, true, false); else FSS_LAUNCH_K1(M, false, false);           \
+        }                                                                                          \
+    } while(0)
+        if(mode == K1_LIQUID) FSS_LAUNCH_K1_MODE(K1_LIQUID);
+        else if(mode == K1_NOGAS) FSS_LAUNCH_K1_MODE(K1_NOGAS);
+        else FSS_LAUNCH_K1_MODE(K1_GENERAL);
+#undef FSS_LAUNCH_K1_MODE
 #undef FSS_LAUNCH_K1
     }
     w->stats.kernel_launches++;
@@ -942,6 +976,125 @@ int fss_tick_particles(fss_world* w) {
     CU(cudaMemcpyAsync(&kept, w->pl_ctl + 2, sizeof kept, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
     w->pl_n = kept;
+    return FSS_OK;
+}
+
+
+// ---- dirty -> pixels (fss_render.cuh; Game.cpp:2579-2650, :2751) ----------------------------------------------
+int fss_set_material_looks(fss_world* w, const uint8_t* alpha, const uint32_t* emit_color, int n) {
+    if(!w || !alpha || !emit_color) return fail(FSS_ERR_INVALID, "null argument");
+    if(n < 0 || n > FSS_MAX_MATERIALS) return fail(FSS_ERR_INVALID, "%d materials", n);
+    memcpy(w->h_alpha, alpha, (size_t)n);
+    memcpy(w->h_emit, emit_color, (size_t)n * 4);
+    w->looks_stale = true;
+    return FSS_OK;
+}
+
+static int dirty_ready(fss_world* w) {
+    if(!w) return fail(FSS_ERR_INVALID, "null world");
+    if(!w->g.dirty) return fail(FSS_ERR_STATE, "the world was created without FSS_TRACK_DIRTY");
+    if(w->sharded) return fail(FSS_ERR_STATE, "dirty -> pixels is not available on strip-sharded worlds");
+    return use_device(w);
+}
+
+int fss_mark_dirty(fss_world* w, int x, int y, int width, int height) {
+    if(int rc = dirty_ready(w)) return rc;
+    // like the reference's own writes, cells outside the world are skipped
+    const int x0 = std::max(x, 0), y0 = std::max(y, 0), x1 = std::min<long long>((long long)x + width, w->cfg.width), y1 = std::min<long long>((long long)y + height, w->cfg.height);
+    if(x1 <= x0 || y1 <= y0) return FSS_OK;
+    const long long cells = (long long)(x1 - x0) * (y1 - y0);
+    if(cells > 0x7FFFFFFFll) return fail(FSS_ERR_RANGE, "rectangle of %lld cells", cells);
+    k_mark_dirty<<<(unsigned)((cells + 255) / 256), 256, 0, w->stream>>>(w->g, x0, y0, x1 - x0, y1 - y0);
+    CU(cudaGetLastError());
+    w->stats.kernel_launches++;
+    return FSS_OK;
+}
+
+int fss_render_dirty(fss_world* w, uint64_t* moving_tiles, int n_materials, fss_render_info* info) {
+    if(int rc = dirty_ready(w)) return rc;
+    if(!w->mats_set) return fail(FSS_ERR_STATE, "fss_set_materials first");
+    if(n_materials < 0 || n_materials > FSS_MAX_MATERIALS) return fail(FSS_ERR_INVALID, "%d materials", n_materials);
+    const size_t cells = plane_cells(w), pixels = (size_t)w->cfg.width * w->cfg.height;
+    if(!w->px[0]) {
+        for(int k = 0; k < 4; k++) {
+            CU(cudaMalloc(&w->px[k], pixels * 4));
+            CU(cudaMemsetAsync(w->px[k], 0, pixels * 4, w->stream));
+        }
+        CU(cudaMalloc(&w->prev_fx, cells * 4));
+        CU(cudaMalloc(&w->prev_fy, cells * 4));
+        CU(cudaMemsetAsync(w->prev_fx, 0, cells * 4, w->stream)); // world.cpp:179-180
+        CU(cudaMemsetAsync(w->prev_fy, 0, cells * 4, w->stream));
+        CU(cudaMalloc(&w->d_looks, sizeof(DLook) * FSS_MAX_MATERIALS));
+        CU(cudaMalloc(&w->d_rinfo, 8 * FSS_MAX_MATERIALS + 16));
+        w->looks_stale = true;
+    }
+    if(w->looks_stale) {
+        DLook h[FSS_MAX_MATERIALS];
+        for(int m = 0; m < FSS_MAX_MATERIALS; m++) {
+            h[m].alpha = w->h_alpha[m];
+            h[m].emit_color = w->h_emit[m];
+            h[m].iterations = w->h_iterations[m];
+        }
+        CU(cudaMemcpyAsync(w->d_looks, h, sizeof h, cudaMemcpyHostToDevice, w->stream));
+        CU(cudaStreamSynchronize(w->stream)); // h is on the stack
+        w->looks_stale = false;
+    }
+    CU(cudaMemsetAsync(w->d_rinfo, 0, 8 * FSS_MAX_MATERIALS + 16, w->stream));
+    RenderParams p;
+    p.g = w->g;
+    p.looks = w->d_looks;
+    p.n_mat = w->n_mat;
+    p.width = (int)w->cfg.width;
+    for(int k = 0; k < 4; k++) p.px[k] = w->px[k];
+    p.prev_fx = w->prev_fx;
+    p.prev_fy = w->prev_fy;
+    p.moving = w->d_rinfo;
+    p.info = (uint32_t*)(w->d_rinfo + FSS_MAX_MATERIALS);
+    p.cells = cells;
+    k_render_dirty<<<(unsigned)((cells + 255) / 256), 256, 0, w->stream>>>(p);
+    CU(cudaGetLastError());
+    w->stats.kernel_launches++;
+    unsigned long long h[FSS_MAX_MATERIALS + 2];
+    CU(cudaMemcpyAsync(h, w->d_rinfo, sizeof h, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    if(moving_tiles)
+        for(int m = 0; m < n_materials; m++) moving_tiles[m] = h[m];
+    if(info) {
+        const uint32_t* f = (const uint32_t*)(h + FSS_MAX_MATERIALS);
+        info->had_dirty = f[0];
+        info->had_fire = f[1];
+        info->had_flow = f[2];
+    }
+    return FSS_OK;
+}
+
+int fss_download_pixels(fss_world* w, int layer, int x, int y, int width, int height, uint8_t* rgba, size_t pitch_bytes) {
+    if(int rc = dirty_ready(w)) return rc;
+    if(!rgba || layer < 0 || layer > 3) return fail(FSS_ERR_INVALID, "bad argument");
+    if(!w->px[0]) return fail(FSS_ERR_STATE, "fss_render_dirty first");
+    if(width <= 0 || height <= 0 || x < 0 || y < 0 || (uint32_t)(x + width) > w->cfg.width || (uint32_t)(y + height) > w->cfg.height)
+        return fail(FSS_ERR_RANGE, "rectangle (%d,%d,%d,%d) outside the %ux%u world", x, y, width, height, w->cfg.width, w->cfg.height);
+    if(pitch_bytes < (size_t)width * 4) return fail(FSS_ERR_INVALID, "pitch %zu < %d pixels", pitch_bytes, width);
+    CU(cudaMemcpy2DAsync(rgba, pitch_bytes, w->px[layer] + (size_t)y * w->cfg.width + x, (size_t)w->cfg.width * 4, (size_t)width * 4, (size_t)height,
+                         cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return FSS_OK;
+}
+
+int fss_download_dirty(fss_world* w, int x, int y, int width, int height, uint8_t* out, size_t pitch_bytes) {
+    if(int rc = dirty_ready(w)) return rc;
+    if(!out) return fail(FSS_ERR_INVALID, "null argument");
+    if(pitch_bytes < (size_t)width) return fail(FSS_ERR_INVALID, "pitch %zu < width %d", pitch_bytes, width);
+    size_t skip = 0;
+    if(int rc = rect_clip(w, x, y, width, height, skip)) return rc;
+    const int rows_per_pass = (int)std::max<size_t>(1, w->stage_bytes / (size_t)width);
+    for(int r0 = 0; r0 < height; r0 += rows_per_pass) {
+        const int nr = std::min(rows_per_pass, height - r0);
+        k_download_bytes<<<(unsigned)(((size_t)width * nr + 255) / 256), 256, 0, w->stream>>>(w->g.dirty, (uint8_t*)w->d_stage, w->g.pitch, w->g.sy0, x, y + r0, width, nr);
+        w->stats.kernel_launches++;
+        CU(cudaMemcpy2DAsync(out + (skip + r0) * pitch_bytes, pitch_bytes, w->d_stage, (size_t)width, (size_t)width, nr, cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+    }
     return FSS_OK;
 }
 

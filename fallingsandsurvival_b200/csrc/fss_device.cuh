@@ -98,6 +98,7 @@ struct Grid {
     float* dif;
     float* fx; // World::flowX / flowY, nullptr unless FSS_TRACK_FLOW
     float* fy;
+    uint8_t* dirty; // World::dirty, nullptr unless FSS_TRACK_DIRTY; same indexing as the other planes
     uint32_t pitch; // cells per stored row (multiple of 256)
     int sy0;        // global row of stored row 0
     int rows;       // stored rows

@@ -39,7 +39,7 @@ __global__ void k_code_pad(int* out) {
 #ifndef K1N_MIN_BLOCKS
 #define K1N_MIN_BLOCKS 7
 #endif
-template <int MODE, bool FLOW>
+template <int MODE, bool FLOW, bool DIRTY>
 __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS : (MODE == K1_NOGAS ? K1N_MIN_BLOCKS : K1_MIN_BLOCKS))
     k_substep(const __grid_constant__ SubstepParams p) {
     __shared__ float sden[FSS_MAX_MATERIALS];
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS
         if(*qown <= (uint8_t)p.iter) return; // verified settled: a warp whose 32 chunks are all settled ends here
     }
 #endif
-    ChunkWalk<MODE, FLOW> w(p, sden, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y,
+    ChunkWalk<MODE, FLOW, DIRTY> w(p, sden, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y,
                       __activemask());
     w.run(qown);
 }

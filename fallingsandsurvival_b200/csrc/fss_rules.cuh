@@ -143,8 +143,10 @@ __device__ __noinline__ unsigned long long rule_fire(const SubstepParams& p, int
     if(fss_rand(key, 1179, 0) % 10 == 0) {
         if(p.flags & FSS_PARTICLES_EMIT) emit_particle(p, x, y, 1180, key, tile);
     }
+    uint8_t* const dirty = p.g.dirty; // World::dirty, nullptr unless FSS_TRACK_DIRTY (a rare rule: tested at run time)
     if(fss_rand(key, 1191, 0) % 150 == 0) {
         st_cell(p.g, i, cell_nothing(p.nothing_mf));
+        if(dirty) dirty[i] = 1; // :1194
         return bit;
     }
     const bool found = solid_nb != 0u;
@@ -153,12 +155,14 @@ __device__ __noinline__ unsigned long long rule_fire(const SubstepParams& p, int
         if(fss_rand(key, 1202, k1202++) % 500 == 0) {
             const int q = __ffs(rest) - 1, xx = q / 5 - 2, yy = q % 5 - 2;
             st_cell(p.g, p.g.idx(x + xx, y + yy), create_cell(p, p.fire_id, x + xx, y + yy, key, kcreate++)); // Tiles::createFire()
+            if(dirty) dirty[p.g.idx(x + xx, y + yy)] = 1; // :1204
             const unsigned dx = (unsigned)(x + xx - cx), dy = (unsigned)(y + yy - cy);
             if(dx < (unsigned)FSS_CHUNK_W && dy < (unsigned)FSS_CHUNK_H) vis |= 1ull << (dy * FSS_CHUNK_W + dx);
         }
     }
     if(!found && fss_rand(key, 1210, 0) % 120 == 0) {
         st_cell(p.g, i, cell_nothing(p.nothing_mf));
+        if(dirty) dirty[i] = 1; // :1212
         vis |= bit;
     }
     return vis;
@@ -182,6 +186,7 @@ __device__ __noinline__ bool rule_sand_react(const SubstepParams& p, cidx_t i, i
             Cell c = create_cell(p, m.r_target[r], x, y, key, k);
             c.temp = temp;
             st_cell(p.g, i, c);
+            if(p.g.dirty) p.g.dirty[i] = 1; // :1259, :1267
             react = true;
         }
     }
@@ -199,7 +204,8 @@ __device__ __noinline__ void rule_soup_free_fall(const SubstepParams& p, cidx_t 
     int n = (int)(amt / 4);
     if(n < 1) n = 1;
     nt.amt = amt / n;
-    st_cell(p.g, i, cell_nothing(p.nothing_mf));
+    st_cell(p.g, i, cell_nothing(p.nothing_mf)); // :1353 setTile, which sets dirty (:1061)
+    if(p.g.dirty) p.g.dirty[i] = 1;
     for(int k = 0; k < n; k++) emit_particle(p, x, y, 1366, key, nt);
 }
 
@@ -215,7 +221,9 @@ __device__ __noinline__ void rule_soup_free_fall(const SubstepParams& p, cidx_t 
 #define K1_LIQUID 2
 // FLOW: also keep World::flowX / flowY (FSS_TRACK_FLOW); a compile-time switch because the four extra read-modify-writes
 // sit in the hottest rule and cost 10 % of the liquid kernel even when a run-time test skips them.
-template <int MODE, bool FLOW = false>
+// DIRTY: also keep World::dirty (FSS_TRACK_DIRTY): one byte store next to every store the reference accompanies with
+// `dirty[...] = true`; compile-time for the same reason.
+template <int MODE, bool FLOW = false, bool DIRTY = false>
 struct ChunkWalk {
     static constexpr bool LIQ = MODE == K1_LIQUID;
     static constexpr bool GASFIRE = MODE == K1_GENERAL;
@@ -253,6 +261,9 @@ struct ChunkWalk {
     }
 
     __device__ __forceinline__ cidx_t I(int x, int y) const { return p.g.idx(x, y); }
+    __device__ __forceinline__ void D(cidx_t i) const { // dirty[...] = true
+        if(DIRTY) p.g.dirty[i] = 1;
+    }
     __device__ __forceinline__ void mark(int x, int y) {
         unsigned dx = (unsigned)(x - cx), dy = (unsigned)(y - cy);
         if(dx < (unsigned)FSS_CHUNK_W && dy < (unsigned)FSS_CHUNK_H) vis |= 1ull << (dy * FSS_CHUNK_W + dx);
@@ -406,6 +417,7 @@ struct ChunkWalk {
             nmf = (mf & 0x00FFFFFFu) | (settle << MF_SETTLE_SHIFT);
             if(settle >= 10u) nmf |= MF_MOVED;
         } else {                 // :1529-1535: the by-value copies decide (a neighbour seeded above still counts as AIR)
+            D(i);                // :1530
             if(MF_IS(tmf, FSS_PHYS_SOUP) && (tmf & MF_MOVED)) g.mf[it] = tmf & ~MF_MOVED;
             if(MF_IS(bmf, FSS_PHYS_SOUP) && (bmf & MF_MOVED)) g.mf[ib] = bmf & ~MF_MOVED;
             if(MF_IS(lmf, FSS_PHYS_SOUP) && (lmf & MF_MOVED)) g.mf[il] = lmf & ~MF_MOVED;
@@ -442,12 +454,14 @@ struct ChunkWalk {
         if((can_l || can_r) && fss_rand(key, 1287, 0) % 20 == 0) return;
         if(GASFIRE && MF_IS(bmf, FSS_PHYS_GAS)) maybe_gas = true;
         st_cell(g, i, below); // :1289 / :1296
+        D(i);                 // :1289 setTile sets dirty (:1061); :1297
         if((p.flags & FSS_PARTICLES_EMIT) && MF_IS(bmf, FSS_PHYS_AIR) && MF_IS(g.mf[ib + g.pitch], FSS_PHYS_AIR) &&
            MF_IS(g.mf[ib + 2 * g.pitch], FSS_PHYS_AIR) && MF_IS(g.mf[ib + 3 * g.pitch], FSS_PHYS_AIR)) {
             emit_particle(p, x, y, 1291, key, tile); // :1288-1294 free fall: the cell leaves the grid
         } else {
             if(fss_rand(key, 1300, 0) % 2 == 0) tile.mf |= MF_MOVED;
             st_cell(g, ib, tile); // :1306
+            D(ib);                // :1307
             mark(x, y + 1);
         }
         if(fss_rand(key, 1313, 0) % 2 == 0) { // :1313-1335 transmit movement (x-1, x+1 are inside the world: zone margin)
@@ -538,6 +552,8 @@ struct ChunkWalk {
                 const bool open = MF_IS(almf, FSS_PHYS_AIR) || MF_IS(armf, FSS_PHYS_AIR);
                 if(!(open && fss_rand(fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y), 1654, 0) % 2 == 0)) {
                     swap_cells(i, ia);
+                    D(i); // :1656, :1659
+                    D(ia);
                     mark(x, y - 1);
                 }
             }
@@ -628,14 +644,17 @@ struct ChunkWalk {
         if(GASFIRE && MF_IS(diag.mf, FSS_PHYS_GAS)) maybe_gas = true;
         if(MF_IS(smf, FSS_PHYS_AIR)) {
             st_cell(g, iside, diag);
+            D(iside); // :1758 / :1782
             if(go_left) mark(x - 1, y);
             st_cell(g, i, cell_nothing(p.nothing_mf));
         } else {
             st_cell(g, i, diag);
             vis |= bit;
         }
+        D(i); // :1761, :1764 / :1784, :1787
         if(fss_rand(key, go_left ? 1768u : 1791u, 0) % (20u * slip) == 0) tile.mf &= ~MF_MOVED;
         st_cell(g, idiag, tile);
+        D(idiag); // :1775 / :1798
         mark(x + sx, y + 1);
     }
 
@@ -657,9 +676,13 @@ struct ChunkWalk {
             if(al || ar) busy = true;
             if(al && !(ar && fss_rand(fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y), 1884, 0) % 2 == 0)) {
                 swap_cells(i, ial);
+                D(i); // :1886, :1889
+                D(ial);
                 mark(x - 1, y - 1);
             } else if(ar) {
                 swap_cells(i, iar);
+                D(i); // :1893, :1896
+                D(iar);
                 mark(x + 1, y - 1);
             }
         }
@@ -698,6 +721,7 @@ struct ChunkWalk {
                 g.amt[rb + 32u * k] = amt;
                 g.dif[rb + 32u * k] = 0.0f;
             }
+            D(rb + 32u * k); // :1823: every liquid cell that scan 2 reaches, changed or not
             vis |= 1ull << (r * FSS_CHUNK_W + k);
         }
     }
@@ -713,6 +737,7 @@ struct ChunkWalk {
             g.amt[i] = amt;
             g.dif[i] = 0.0f;
         }
+        D(i); // :1814, :1823
         vis |= bit;
     }
 
@@ -730,12 +755,19 @@ struct ChunkWalk {
         if(l || r || ((sinfo[mf_mat(mf)] & HI_STEAM) && p.condense >= 0)) busy = true;
         if(l && !(r && fss_rand(key, 1950, 0) % 2 == 0)) { // :1944-1964
             swap_cells(i, il);
+            D(i); // :1952, :1955
+            D(il);
             mark(x - 1, y);
         } else if(r) {
             swap_cells(i, ir);
+            D(i); // :1959, :1962
+            D(ir);
             mark(x + 1, y);
         } else if((sinfo[mf_mat(mf)] & HI_STEAM) && p.condense >= 0) { // :1965-1969
-            if(fss_rand(key, 1966, 0) % 10 == 0) st_cell(g, i, create_cell(p, p.condense, x, y, key, 0)); // Tiles::createWater()
+            if(fss_rand(key, 1966, 0) % 10 == 0) {
+                st_cell(g, i, create_cell(p, p.condense, x, y, key, 0)); // Tiles::createWater()
+                D(i);                                                    // :1968
+            }
         }
     }
 

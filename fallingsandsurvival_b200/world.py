@@ -61,6 +61,11 @@ def load():
         "fss_particles_download": [vp, vp, sz, C.POINTER(sz)],
         "fss_particles_clear": [vp],
         "fss_particles_rounds": [vp, C.POINTER(C.c_uint64 * 2)],
+        "fss_set_material_looks": [vp, vp, vp, i32],
+        "fss_mark_dirty": [vp, i32, i32, i32, i32],
+        "fss_render_dirty": [vp, vp, i32, C.POINTER(abi.RenderInfo)],
+        "fss_download_pixels": [vp, i32, i32, i32, i32, i32, vp, sz],
+        "fss_download_dirty": [vp, i32, i32, i32, i32, vp, sz],
         "fss_histogram": [vp, vp, i32],
         "fss_hash": [vp, C.POINTER(C.c_uint64)],
         "fss_fluid_totals": [vp, vp, i32],
@@ -100,7 +105,8 @@ class World:
     """
 
     def __init__(self, cells=None, zone=None, defs=None, textures=None, seed=0xF55, particles=False,
-                 condense_material=M.WATER, device=0, size=None, strip=None, particle_capacity=0, early_out=True, track_flow=False):
+                 condense_material=M.WATER, device=0, size=None, strip=None, particle_capacity=0, early_out=True, track_flow=False,
+                 track_dirty=False):
         self.L = load()
         if cells is not None:
             h, w = cells.shape
@@ -112,7 +118,7 @@ class World:
         cfg = abi.Config()
         cfg.struct_size = C.sizeof(abi.Config)
         cfg.width, cfg.height, cfg.seed, cfg.device = w, h, seed, device
-        cfg.flags = (abi.PARTICLES_EMIT if particles else 0) | (0 if early_out else abi.NO_EARLY_OUT) | (abi.TRACK_FLOW if track_flow else 0)
+        cfg.flags = (abi.PARTICLES_EMIT if particles else 0) | (0 if early_out else abi.NO_EARLY_OUT) | (abi.TRACK_FLOW if track_flow else 0) | (abi.TRACK_DIRTY if track_dirty else 0)
         cfg.particle_capacity = particle_capacity
         cfg.strip_y0, cfg.strip_rows = strip if strip is not None else (0, 0)
         cfg.condense_material = condense_material
@@ -209,6 +215,37 @@ class World:
         n, total = C.c_size_t(), C.c_size_t()
         _check(self.L, self.L.fss_drain_particles(self.h_, out.ctypes.data, cap, C.byref(n), C.byref(total)))
         return out[: n.value]
+
+    # ---- World::dirty and the dirty -> pixels job of Game::tick (Game.cpp:2579-2650); needs track_dirty ----
+    def set_material_looks(self, alpha, emit_color):
+        alpha = np.ascontiguousarray(alpha, dtype=np.uint8)
+        emit_color = np.ascontiguousarray(emit_color, dtype=np.uint32)
+        _check(self.L, self.L.fss_set_material_looks(self.h_, alpha.ctypes.data, emit_color.ctypes.data, len(alpha)))
+
+    def mark_dirty(self, x, y, w, h):
+        _check(self.L, self.L.fss_mark_dirty(self.h_, x, y, w, h))
+
+    def render_dirty(self):
+        """(moving_tiles per material, (had_dirty, had_fire, had_flow)); the pixel layers stay on the device"""
+        moving = np.zeros(len(self.defs), dtype=np.uint64)
+        info = abi.RenderInfo()
+        _check(self.L, self.L.fss_render_dirty(self.h_, moving.ctypes.data, len(self.defs), C.byref(info)))
+        return moving, (info.had_dirty, info.had_fire, info.had_flow)
+
+    def pixels(self, layer, x=0, y=0, w=None, h=None):
+        """(h, w, 4) uint8, bytes r g b a, of layer 0 main / 1 fire / 2 emission / 3 flow"""
+        w = self.w - x if w is None else w
+        h = self.h - y if h is None else h
+        out = np.zeros((h, w, 4), dtype=np.uint8)
+        _check(self.L, self.L.fss_download_pixels(self.h_, layer, x, y, w, h, out.ctypes.data, w * 4))
+        return out
+
+    def dirty(self, x=0, y=0, w=None, h=None):
+        w = self.w - x if w is None else w
+        h = self.h - y if h is None else h
+        out = np.zeros((h, w), dtype=np.uint8)
+        _check(self.L, self.L.fss_download_dirty(self.h_, x, y, w, h, out.ctypes.data, w))
+        return out
 
     # ---- World::particles on the device (world.cpp:2171-2311) ----
     def tick_particles(self):

@@ -127,6 +127,12 @@ typedef struct fss_material {
                                  cell's entry (world.cpp:1405, :1447, :1477, :1509); the renderer reads and zeroes them
                                  (Game.cpp:2631-2646).  Two more 4-byte planes; off by default. */
 
+#define FSS_TRACK_DIRTY 8u    /* keep World::dirty (world.hpp:139) on the device: every site of World::tick / tickParticles that sets
+                                 it does (world.cpp:1061, :1194 ... :1968, :2269-2303), fss_mark_dirty for host edits, consumed by
+                                 fss_render_dirty.  One more byte per cell; a compile-time kernel variant, off by default.  Turns the
+                                 settled-chunk early-out off: the reference re-marks every liquid cell in every sub-step
+                                 (world.cpp:1814, :1823), so a chunk that is skipped would lose marks. */
+
 typedef struct fss_config {
     uint32_t struct_size; /* sizeof(fss_config), for ABI evolution */
     uint32_t width;       /* world width in cells (reference: uint16_t, world.hpp:106) */
@@ -212,6 +218,32 @@ int fss_tick_temperature(fss_world* w);
  * reset the consumer does after reading them (Game.cpp:2644-2645) */
 int fss_download_flow(fss_world* w, int x, int y, int width, int height, float* flow_x, float* flow_y, size_t pitch);
 int fss_clear_flow(fss_world* w);
+
+/* ---- dirty -> pixels: the `dirty` job of Game::tick, Game.cpp:2579-2650, and its memset (:2751) -------------
+ * Needs FSS_TRACK_DIRTY (and FSS_TRACK_FLOW for a meaningful flow layer).  For every dirty cell: count it in
+ * moving_tiles[material] (Game.cpp:2589; the reference's counters are uint16_t and wrap, these do not), then
+ *   AIR:   main, fire and emission pixels := 0, flow accumulators := 0;
+ *   else:  main := (r, g, b of MaterialInstance::color, Material::alpha); emission := Material::emitColor; fire layer := main
+ *          if the material is fire; liquids: prevFlow += (flow - prevFlow) * 0.25 (negative y halved), flow pixel =
+ *          clamp(prevFlow * (3.0 / iterations + 0.5) / 4.0 + 0.5, 0, 1) * 255 in double like the reference; flow := 0.
+ * The four RGBA layers (byte order r, g, b, a as the reference writes them) live on the device, row-major, and only change where
+ * cells were dirty; fss_download_pixels copies a rectangle of one layer to the host.  dirty is cleared afterwards. */
+typedef struct fss_render_info {
+    uint32_t had_dirty, had_fire, had_flow; /* Game.cpp:2588, :2626, :2639 */
+} fss_render_info;
+#define FSS_LAYER_MAIN 0
+#define FSS_LAYER_FIRE 1
+#define FSS_LAYER_EMISSION 2
+#define FSS_LAYER_FLOW 3
+/* Material::alpha (Material.hpp:34) and Material::emitColor (:38) per material id; defaults 255 and 0 */
+int fss_set_material_looks(fss_world* w, const uint8_t* alpha, const uint32_t* emit_color, int n);
+/* host code that writes tiles[] sets dirty itself (World::setTile world.cpp:1061, Game.cpp:1148, :2357 ...): after uploading the
+ * cells it marks the same rectangle here */
+int fss_mark_dirty(fss_world* w, int x, int y, int width, int height);
+int fss_render_dirty(fss_world* w, uint64_t* moving_tiles, int n_materials, fss_render_info* info);
+int fss_download_pixels(fss_world* w, int layer, int x, int y, int width, int height, uint8_t* rgba, size_t pitch_bytes);
+/* World::dirty of a rectangle, one byte per cell (tests) */
+int fss_download_dirty(fss_world* w, int x, int y, int width, int height, uint8_t* out, size_t pitch_bytes);
 
 /* ---- side outputs ---------------------------------------------------------------------------- */
 /* spawn records since the last drain in the order World::tick appends them to World::particles

@@ -13,7 +13,8 @@ path needs none of that.  Recipe:
   * FallingSandSurvival/world.cpp lines 1053-1062 (getTile/setTile), 1075-1088
     (CalculateVerticalFlowValue), 1091-2018 + 2027-2041 (World::tick minus the Box2D physicsCheck
     block), 2043-2143 (World::tickTemperature) and 2171-2338 (World::tickParticles) are extracted into
-    oracle/_ref/gen/tick_lines.inc behind #line directives (so __LINE__, our RNG site id, keeps the
+    oracle/_ref/gen/tick_lines.inc (and Game.cpp:2584-2650, the dirty -> pixels loop of Game::tick, into
+    oracle/_ref/gen/dirty_lines.inc) behind #line directives (so __LINE__, our RNG site id, keeps the
     reference's numbering) with three single-line instrumentation edits listed in PATCHES;
   * shims (oracle/ref_shim/): SDL typedefs, a cut-down `World` declaration, the C API.
 
@@ -36,6 +37,7 @@ F = os.path.join(REF, "FallingSandSurvival")
 OUT = os.path.join(HERE, "_ref")
 GEN = os.path.join(OUT, "gen")
 
+GAME_DIRTY_LOOP = (2584, 2650)
 RANGES = [(1053, 1062), (1075, 1088), (1091, 2018), (2027, 2041), (2043, 2143), (2171, 2338)]
 
 # (line number, exact text that must be present, replacement) -- all keep the line count
@@ -73,6 +75,15 @@ def generate():
         for ln in range(a, b + 1):
             out.append(patched.get(ln, lines[ln - 1]))
     with open(os.path.join(GEN, "tick_lines.inc"), "w") as f:
+        f.write("\n".join(out) + "\n")
+    # the `dirty` job of Game::tick (Game.cpp:2584-2650): the loop that turns dirty cells into pixels, as it stands
+    with open(os.path.join(F, "Game.cpp"), encoding="utf-8", errors="replace") as f:
+        glines = f.read().split("\n")
+    a, b = GAME_DIRTY_LOOP
+    if "world->dirty[i]" not in glines[a + 2] or "for(int i = 0; i < world->width * world->height; i++)" not in glines[a - 1]:
+        raise SystemExit("Game.cpp: the dirty loop is not where it was; reference changed?")
+    out = ["/* GENERATED from the reference by oracle/build_ref.py -- never commit */", f'#line {a} "Game.cpp"'] + glines[a - 1:b]
+    with open(os.path.join(GEN, "dirty_lines.inc"), "w") as f:
         f.write("\n".join(out) + "\n")
 
 

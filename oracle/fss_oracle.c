@@ -41,6 +41,10 @@ struct fsso_world {
     int condense_material;
     fss_cell* cells;
     float *flow_x, *flow_y; /* World::flowX / flowY (F/world.hpp:99-100) */
+    uint8_t* dirty;         /* World::dirty (F/world.hpp:139): set wherever the reference sets it, cleared by the render pass */
+    float *prev_flow_x, *prev_flow_y; /* World::prevFlowX / prevFlowY (F/world.hpp:101-102) */
+    uint8_t alpha[FSS_MAX_MATERIALS]; /* Material::alpha, Material::emitColor (F/Material.hpp:34, :38) */
+    uint32_t emit_color[FSS_MAX_MATERIALS];
     int32_t* new_temps;
     fss_material mat[FSS_MAX_MATERIALS];
     int max_stability[FSS_MAX_MATERIALS];
@@ -96,6 +100,7 @@ static inline int phys_get(fsso_world* w, int x, int y) {
     if(x < 0 || x >= w->width || y < 0 || y >= w->height) return FSS_PHYS_SOLID;
     return phys(w, at(w, x, y));
 }
+static inline void set_dirty(fsso_world* w, int x, int y) { w->dirty[(size_t)y * w->width + x] = 1; }
 static inline void mark(chunk_t* c, int x, int y) {
     int dx = x - c->cx, dy = y - c->cy;
     if(dx >= 0 && dx < CW && dy >= 0 && dy < CH) c->vis[dy][dx] = 1;
@@ -210,6 +215,7 @@ static void scan1_cell(chunk_t* c, int x, int y) {
         if(rnd(&r, 1179) % 10 == 0) emit(c, x, y, 1180, r.cellkey, &tile); /* spark, no grid effect */
         if(rnd(&r, 1191) % 150 == 0) {
             *self = nothing();
+            set_dirty(w, x, y);                             /* :1194 */
             c->vis[dy][dx] = 1;
         } else {
             int found = 0, xx, yy;
@@ -220,6 +226,7 @@ static void scan1_cell(chunk_t* c, int x, int y) {
                         found = 1;
                         if(rnd(&r, 1202) % 500 == 0) {
                             *n = create_cell(w, w->fire_id, x + xx, y + yy, &r); /* Tiles::createFire() */
+                            set_dirty(w, x + xx, y + yy);   /* :1204 */
                             mark(c, x + xx, y + yy);
                         }
                     }
@@ -227,6 +234,7 @@ static void scan1_cell(chunk_t* c, int x, int y) {
             }
             if(!found && rnd(&r, 1210) % 120 == 0) {
                 *self = nothing();
+                set_dirty(w, x, y);                         /* :1212 */
                 c->vis[dy][dx] = 1;
             }
         }
@@ -246,6 +254,7 @@ static void scan1_cell(chunk_t* c, int x, int y) {
                    (in->type == FSS_REACT_TEMPERATURE_ABOVE && tile.temperature > in->data1)) {
                     *self = create_cell(w, in->data2, x, y, &r);
                     self->temperature = tile.temperature;
+                    set_dirty(w, x, y);                     /* :1259, :1267 */
                     c->vis[dy][dx] = 1;
                     react = 1;
                 }
@@ -261,12 +270,15 @@ static void scan1_cell(chunk_t* c, int x, int y) {
         if(!((can_l || can_r) && rnd(&r, 1287) % 20 == 0)) { /* :1287 */
             if(particles && phys(w, &below) == FSS_PHYS_AIR && phys_get(w, x, y + 2) == FSS_PHYS_AIR &&
                phys_get(w, x, y + 3) == FSS_PHYS_AIR && phys_get(w, x, y + 4) == FSS_PHYS_AIR) {
-                *self = below;                              /* :1289 setTile(x, y, belowTile) */
+                *self = below;                              /* :1289 setTile(x, y, belowTile), which sets dirty (:1061) */
+                set_dirty(w, x, y);
                 emit(c, x, y, 1291, r.cellkey, &tile);
             } else {
                 *self = below;                              /* :1296 */
+                set_dirty(w, x, y);                         /* :1297 */
                 if(rnd(&r, 1300) % 2 == 0) tile.moved = 1;
                 *at(w, x, y + 1) = tile;                    /* :1306 */
+                set_dirty(w, x, y + 1);                     /* :1307 */
                 mark(c, x, y + 1);
             }
             if(rnd(&r, 1313) % 2 == 0) {                    /* :1313-1335 transmit movement */
@@ -292,7 +304,8 @@ static void scan1_cell(chunk_t* c, int x, int y) {
            phys_get(w, x, y + 2) == FSS_PHYS_AIR && phys_get(w, x, y + 3) == FSS_PHYS_AIR &&
            phys_get(w, x, y + 4) == FSS_PHYS_AIR) {         /* :1352-1374 */
             int n = (int)(tile.fluid_amount / 4), i;
-            *self = nothing();
+            *self = nothing();                              /* :1353 setTile: dirty */
+            set_dirty(w, x, y);
             if(n < 1) n = 1;
             for(i = 0; i < n; i++) {
                 fss_cell nt = liquid_seed(&tile);
@@ -402,6 +415,7 @@ static void scan1_cell(chunk_t* c, int x, int y) {
             tile.settle_count++;
             if(tile.settle_count >= 10) tile.moved = 1;
         } else {
+            set_dirty(w, x, y);                             /* :1530 */
             if(phys(w, &top) == FSS_PHYS_SOUP) at(w, x, y - 1)->moved = 0;
             if(phys(w, &bottom) == FSS_PHYS_SOUP) at(w, x, y + 1)->moved = 0;
             if(phys(w, &left) == FSS_PHYS_SOUP) at(w, x - 1, y)->moved = 0;
@@ -415,6 +429,8 @@ static void scan1_cell(chunk_t* c, int x, int y) {
         if(above == FSS_PHYS_AIR && !((above_l == FSS_PHYS_AIR || above_r == FSS_PHYS_AIR) && rnd(&r, 1654) % 2 == 0)) {
             *self = *at(w, x, y - 1);
             *at(w, x, y - 1) = tile;
+            set_dirty(w, x, y);                             /* :1656, :1659 */
+            set_dirty(w, x, y - 1);
             mark(c, x, y - 1);
         }
     }
@@ -470,25 +486,31 @@ static void scan2_cell(chunk_t* c, int x, int y) {
         if(should_move && can_l && (!can_r || rnd(&r, 1755) % 2 == 0)) { /* :1755-1777 */
             if(phys(w, at(w, x - 1, y)) == FSS_PHYS_AIR) {
                 *at(w, x - 1, y) = bl;
+                set_dirty(w, x - 1, y);                     /* :1758 */
                 mark(c, x - 1, y);
                 *self = nothing();
             } else {
                 *self = bl;
                 c->vis[dy][dx] = 1;
             }
+            set_dirty(w, x, y);                             /* :1761, :1764 */
             if(rnd(&r, 1768) % (uint32_t)(20 * slip) == 0) tile.moved = 0;
             *at(w, x - 1, y + 1) = tile;
+            set_dirty(w, x - 1, y + 1);                     /* :1775 */
             mark(c, x - 1, y + 1);
         } else if(should_move && can_r) {                   /* :1778-1800: (x+1, y) is NOT marked visited */
             if(phys(w, at(w, x + 1, y)) == FSS_PHYS_AIR) {
                 *at(w, x + 1, y) = br;
+                set_dirty(w, x + 1, y);                     /* :1782 */
                 *self = nothing();
             } else {
                 *self = br;
                 c->vis[dy][dx] = 1;
             }
+            set_dirty(w, x, y);                             /* :1784, :1787 */
             if(rnd(&r, 1791) % (uint32_t)(20 * slip) == 0) tile.moved = 0;
             *at(w, x + 1, y + 1) = tile;
+            set_dirty(w, x + 1, y + 1);                     /* :1798 */
             mark(c, x + 1, y + 1);
         } else {
             self->moved = 0;                                /* :1802 */
@@ -498,6 +520,7 @@ static void scan2_cell(chunk_t* c, int x, int y) {
         tile.fluid_amount_diff = 0.0f;
         if(tile.fluid_amount < FLUID_MinValue) *self = nothing();
         else *self = tile;
+        set_dirty(w, x, y);                                 /* :1814, :1823: every liquid cell that scan 2 reaches */
         c->vis[dy][dx] = 1;
     } else if(type == FSS_PHYS_GAS) {                       /* :1879-1899 */
         int above_l = phys(w, at(w, x - 1, y - 1));
@@ -505,10 +528,14 @@ static void scan2_cell(chunk_t* c, int x, int y) {
         if(above_l == FSS_PHYS_AIR && !(above_r == FSS_PHYS_AIR && rnd(&r, 1884) % 2 == 0)) {
             *self = *at(w, x - 1, y - 1);
             *at(w, x - 1, y - 1) = tile;
+            set_dirty(w, x, y);                             /* :1886, :1889 */
+            set_dirty(w, x - 1, y - 1);
             mark(c, x - 1, y - 1);
         } else if(above_r == FSS_PHYS_AIR) {
             *self = *at(w, x + 1, y - 1);
             *at(w, x + 1, y - 1) = tile;
+            set_dirty(w, x, y);                             /* :1893, :1896 */
+            set_dirty(w, x + 1, y - 1);
             mark(c, x + 1, y - 1);
         }
     }
@@ -531,13 +558,20 @@ static void scan3_cell(chunk_t* c, int x, int y) {
         if(l == FSS_PHYS_AIR && !(rr == FSS_PHYS_AIR && rnd(&r, 1950) % 2 == 0)) {
             *self = *at(w, x - 1, y);
             *at(w, x - 1, y) = tile;
+            set_dirty(w, x, y);                             /* :1952, :1955 */
+            set_dirty(w, x - 1, y);
             mark(c, x - 1, y);
         } else if(rr == FSS_PHYS_AIR) {
             *self = *at(w, x + 1, y);
             *at(w, x + 1, y) = tile;
+            set_dirty(w, x, y);                             /* :1959, :1962 */
+            set_dirty(w, x + 1, y);
             mark(c, x + 1, y);
         } else if((w->mat[tile.material].flags & FSS_MAT_IS_STEAM) && w->condense_material >= 0) {
-            if(rnd(&r, 1966) % 10 == 0) *self = create_cell(w, w->condense_material, x, y, &r); /* Tiles::createWater() */
+            if(rnd(&r, 1966) % 10 == 0) {
+                *self = create_cell(w, w->condense_material, x, y, &r); /* Tiles::createWater() */
+                set_dirty(w, x, y);                         /* :1968 */
+            }
         }
     }
 }
@@ -634,6 +668,10 @@ fsso_world* fsso_create(int width, int height, uint32_t seed, uint32_t flags, in
     w->new_temps = (int32_t*)calloc(n, sizeof(int32_t));
     w->flow_x = (float*)calloc(n, sizeof(float));
     w->flow_y = (float*)calloc(n, sizeof(float));
+    w->dirty = (uint8_t*)calloc(n, 1);
+    w->prev_flow_x = (float*)calloc(n, sizeof(float));
+    w->prev_flow_y = (float*)calloc(n, sizeof(float));
+    memset(w->alpha, 255, sizeof w->alpha);
     for(i = 0; i < n; i++) w->cells[i] = nothing();
     w->fire_id = -1;
     return w;
@@ -647,6 +685,9 @@ void fsso_destroy(fsso_world* w) {
     free(w->new_temps);
     free(w->flow_x);
     free(w->flow_y);
+    free(w->dirty);
+    free(w->prev_flow_x);
+    free(w->prev_flow_y);
     free(w->parts);
     free(w->plist);
     free(w);
@@ -692,6 +733,79 @@ int fsso_set_tick_zone(fsso_world* w, int x, int y, int zw, int zh) {
 fss_cell* fsso_cells(fsso_world* w) { return w->cells; }
 float* fsso_flow_x(fsso_world* w) { return w->flow_x; }
 float* fsso_flow_y(fsso_world* w) { return w->flow_y; }
+uint8_t* fsso_dirty(fsso_world* w) { return w->dirty; }
+
+int fsso_set_material_looks(fsso_world* w, const uint8_t* alpha, const uint32_t* emit_color, int n) {
+    if(n < 0 || n > FSS_MAX_MATERIALS) return FSS_ERR_INVALID;
+    memcpy(w->alpha, alpha, (size_t)n);
+    memcpy(w->emit_color, emit_color, (size_t)n * 4);
+    return FSS_OK;
+}
+
+/* The `dirty` job of Game::tick, F/Game.cpp:2579-2650, and the memset that follows it (:2751).  pixels[k] = row-major
+ * width * height * 4 bytes: 0 main layer, 1 fire, 2 emission, 3 flow.  moving[m] counts the dirty cells of material m
+ * (the reference's counters are uint16_t and wrap, F/Game.hpp:204; these do not). */
+void fsso_render_dirty(fsso_world* w, uint8_t* const pixels[4], uint64_t* moving, int n_materials, fss_render_info* info) {
+    size_t i, n = (size_t)w->width * w->height;
+    uint8_t *px = pixels[0], *fire = pixels[1], *emi = pixels[2], *flw = pixels[3];
+    int m;
+    memset(info, 0, sizeof *info);
+    for(m = 0; m < n_materials; m++) moving[m] = 0;
+    for(i = 0; i < n; i++) {
+        const size_t o = i * 4;
+        const fss_cell* t = &w->cells[i];
+        const fss_material* mat = &w->mat[t->material];
+        if(!w->dirty[i]) continue;
+        info->had_dirty = 1;
+        if(t->material < n_materials) moving[t->material]++;
+        if(mat->physics_type == FSS_PHYS_AIR) {                     /* :2590-2607 */
+            memset(px + o, 0, 4);
+            memset(fire + o, 0, 4);
+            memset(emi + o, 0, 4);
+            w->flow_y[i] = 0;
+            w->flow_x[i] = 0;
+        } else {
+            uint32_t color = t->color, emit = w->emit_color[t->material];
+            px[o + 2] = color & 0xff;                                /* :2611-2614 */
+            px[o + 1] = (color >> 8) & 0xff;
+            px[o + 0] = (color >> 16) & 0xff;
+            px[o + 3] = w->alpha[t->material];
+            emi[o + 2] = emit & 0xff;                                /* :2616-2619 */
+            emi[o + 1] = (emit >> 8) & 0xff;
+            emi[o + 0] = (emit >> 16) & 0xff;
+            emi[o + 3] = (emit >> 24) & 0xff;
+            if(mat->flags & FSS_MAT_IS_FIRE) {                       /* :2621-2627 */
+                fire[o + 2] = color & 0xff;
+                fire[o + 1] = (color >> 8) & 0xff;
+                fire[o + 0] = (color >> 16) & 0xff;
+                fire[o + 3] = w->alpha[t->material];
+                info->had_fire = 1;
+            }
+            if(mat->physics_type == FSS_PHYS_SOUP) {                 /* :2628-2643: double arithmetic, like the reference */
+                float newFlowX = w->prev_flow_x[i] + (w->flow_x[i] - w->prev_flow_x[i]) * 0.25;
+                float newFlowY = w->prev_flow_y[i] + (w->flow_y[i] - w->prev_flow_y[i]) * 0.25;
+                double gx, gy;
+                if(newFlowY < 0) newFlowY *= 0.5;
+                gy = newFlowY * (3.0 / mat->iterations + 0.5) / 4.0 + 0.5;
+                gx = newFlowX * (3.0 / mat->iterations + 0.5) / 4.0 + 0.5;
+                gy = gy < 0.0 ? 0.0 : gy; /* std::max(v, 0.0) = (v < 0.0) ? 0.0 : v */
+                gx = gx < 0.0 ? 0.0 : gx;
+                gy = 1.0 < gy ? 1.0 : gy; /* std::min(v, 1.0) = (1.0 < v) ? 1.0 : v */
+                gx = 1.0 < gx ? 1.0 : gx;
+                flw[o + 2] = 0;
+                flw[o + 1] = (uint8_t)(gy * 255);
+                flw[o + 0] = (uint8_t)(gx * 255);
+                flw[o + 3] = 0xff;
+                info->had_flow = 1;
+                w->prev_flow_x[i] = newFlowX;
+                w->prev_flow_y[i] = newFlowY;
+            }
+            w->flow_y[i] = 0;                                        /* :2642-2647 */
+            w->flow_x[i] = 0;
+        }
+    }
+    if(info->had_dirty) memset(w->dirty, 0, n);                      /* :2751 */
+}
 size_t fsso_num_particles(fsso_world* w) { return w->n_parts; }
 
 /* the order World::tick appends to World::particles, see fss_spawn_order_key (F/world.cpp:1140-1157, :1989-1994) */
@@ -836,10 +950,12 @@ static int particle_step(fsso_world* w, fss_particle* cur) {
                                 fss_cell* c = at(w, px, py);
                                 if(phys(w, c) == FSS_PHYS_AIR) {
                                     *c = cur->tile;
+                                    set_dirty(w, px, py);   /* :2269 */
                                     succeeded = 1;
                                     break;
                                 } else if(w->mat[cur->tile.material].physics_type == FSS_PHYS_SOUP && cur->tile.material == c->material) {
                                     c->fluid_amount += cur->tile.fluid_amount;
+                                    set_dirty(w, px, py);   /* :2275 */
                                     succeeded = 1;
                                     break;
                                 }
@@ -859,6 +975,7 @@ static int particle_step(fsso_world* w, fss_particle* cur) {
                     return 0;
                 } else {
                     *at(w, lx, ly) = cur->tile; /* :2301-2306 */
+                    set_dirty(w, lx, ly);
                     return 1;
                 }
             }

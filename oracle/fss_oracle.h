@@ -29,6 +29,10 @@ int fsso_set_tick_zone(fsso_world* w, int x, int y, int zw, int zh);
 fss_cell* fsso_cells(fsso_world* w); /* row-major width*height, owned by the world */
 float* fsso_flow_x(fsso_world* w);   /* World::flowX / flowY, row-major width*height: the caller zeroes them when it consumes them */
 float* fsso_flow_y(fsso_world* w);
+uint8_t* fsso_dirty(fsso_world* w);  /* World::dirty, row-major width*height */
+int fsso_set_material_looks(fsso_world* w, const uint8_t* alpha, const uint32_t* emit_color, int n);
+/* the `dirty` job of Game::tick (F/Game.cpp:2579-2650) + the memset of :2751; pixels[k]: width*height*4 bytes each */
+void fsso_render_dirty(fsso_world* w, uint8_t* const pixels[4], uint64_t* moving, int n_materials, fss_render_info* info);
 
 void fsso_tick(fsso_world* w, uint32_t tick_ct);
 /* one (iter, tk) sub-step restricted to micro-chunks whose first row lies in [cy_from, cy_to) */

@@ -51,6 +51,10 @@ def load():
     L.fsso_num_particles.argtypes = [C.c_void_p]
     L.fsso_drain_particles.restype = C.c_size_t
     L.fsso_drain_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.fsso_dirty.restype = C.c_void_p
+    L.fsso_dirty.argtypes = [C.c_void_p]
+    L.fsso_set_material_looks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.fsso_render_dirty.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.fsso_particles_add.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.fsso_particles.restype = C.c_void_p
     L.fsso_particles.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
@@ -131,6 +135,30 @@ class OracleWorld:
         out = np.zeros(max(n, 1), dtype=abi.PARTICLE_DTYPE)
         m = self.L.fsso_drain_particles(self.h_, out.ctypes.data, n)
         return out[:m]
+
+    # ---- World::dirty and the dirty -> pixels job of Game::tick (Game.cpp:2579-2650) ----
+    def dirty(self):
+        a = np.ctypeslib.as_array(C.cast(self.L.fsso_dirty(self.h_), C.POINTER(C.c_uint8)), shape=(self.h * self.w,))
+        return a.reshape(self.h, self.w).copy()
+
+    def mark_dirty(self, x, y, w, h):
+        a = np.ctypeslib.as_array(C.cast(self.L.fsso_dirty(self.h_), C.POINTER(C.c_uint8)), shape=(self.h * self.w,)).reshape(self.h, self.w)
+        a[max(y, 0):y + h, max(x, 0):x + w] = 1
+
+    def set_material_looks(self, alpha, emit_color):
+        alpha = np.ascontiguousarray(alpha, dtype=np.uint8)
+        emit_color = np.ascontiguousarray(emit_color, dtype=np.uint32)
+        assert self.L.fsso_set_material_looks(self.h_, alpha.ctypes.data, emit_color.ctypes.data, len(alpha)) == 0
+
+    def render_dirty(self):
+        """returns (moving_tiles, (had_dirty, had_fire, had_flow)); self.pixels[layer] is (H, W, 4) uint8 and persists"""
+        if not hasattr(self, "pixels"):
+            self.pixels = np.zeros((4, self.h, self.w, 4), dtype=np.uint8)
+        ptrs = (C.c_void_p * 4)(*[self.pixels[k].ctypes.data for k in range(4)])
+        moving = np.zeros(len(self.defs), dtype=np.uint64)
+        info = np.zeros(3, dtype=np.uint32)
+        self.L.fsso_render_dirty(self.h_, ptrs, moving.ctypes.data, len(self.defs), info.ctypes.data)
+        return moving, tuple(int(v) for v in info)
 
     def tick_particles(self):
         """World::tickParticles() after adopting the spawn records of the ticks since the last call"""

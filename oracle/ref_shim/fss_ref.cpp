@@ -86,6 +86,15 @@ int fss_ref_rand(int site) {
 using std::max; /* world.cpp:2258 `max(X, Y)` */
 #include "tick_lines.inc"
 
+/* ---- Game.cpp:2584-2650, the loop of the `dirty` job of Game::tick, with the names it uses bound to arguments ---- */
+#ifndef SDL_ALPHA_TRANSPARENT
+#define SDL_ALPHA_TRANSPARENT 0
+#endif
+static void ref_dirty_job(World* world, unsigned char* dpixels_ar, unsigned char* dpixelsFire_ar, unsigned char* dpixelsFlow_ar,
+                          unsigned char* dpixelsEmission_ar, uint16_t* movingTiles, bool& hadDirty, bool& hadFire, bool& hadFlow) {
+#include "dirty_lines.inc"
+}
+
 /* ---- C API ----------------------------------------------------------------------------------- */
 #define FSS_REF_N_TEX 16
 static SDL_Surface g_tex[FSS_REF_N_TEX];
@@ -214,6 +223,8 @@ void* fssref_world_create(int w, int h, int zx, int zy, int zw, int zh, int thre
     W.tiles = new MaterialInstance[n];
     W.flowX = new float[n]();
     W.flowY = new float[n]();
+    W.prevFlowX = new float[n]();
+    W.prevFlowY = new float[n]();
     W.tickVisited1 = new bool[n]();
     W.tickVisited2 = new bool[n]();
     W.dirty = new bool[n]();
@@ -234,6 +245,8 @@ void fssref_world_destroy(void* h) {
     delete[] W.tiles;
     delete[] W.flowX;
     delete[] W.flowY;
+    delete[] W.prevFlowX;
+    delete[] W.prevFlowY;
     delete[] W.tickVisited1;
     delete[] W.tickVisited2;
     delete[] W.dirty;
@@ -330,6 +343,47 @@ size_t fssref_drain_particles(void* h, float* xyv, fss_cell* cells, int32_t* tem
     }
     r->parts.clear();
     return n;
+}
+
+/* ---- World::dirty and the dirty -> pixels job (Game.cpp:2579-2650, :2751) -------------------------------- */
+int fssref_get_dirty(void* h, uint8_t* out) {
+    World& W = ((RefWorld*)h)->w;
+    size_t n = (size_t)W.width * W.height;
+    for(size_t i = 0; i < n; i++) out[i] = W.dirty[i] ? 1 : 0;
+    return 0;
+}
+
+int fssref_mark_dirty(void* h, int x, int y, int w, int hh) {
+    World& W = ((RefWorld*)h)->w;
+    for(int yy = y; yy < y + hh; yy++)
+        for(int xx = x; xx < x + w; xx++)
+            if(xx >= 0 && xx < W.width && yy >= 0 && yy < W.height) W.dirty[xx + (size_t)yy * W.width] = true;
+    return 0;
+}
+
+int fssref_get_material_looks(uint8_t* alpha, uint32_t* emit, int cap) {
+    int n = (int)Materials::MATERIALS.size() < cap ? (int)Materials::MATERIALS.size() : cap;
+    for(int i = 0; i < n; i++) {
+        alpha[i] = Materials::MATERIALS[i]->alpha;
+        emit[i] = Materials::MATERIALS[i]->emitColor;
+    }
+    return n;
+}
+
+/* pixels: 4 layers (main, fire, emission, flow) of width*height*4 bytes each, kept by the caller between calls;
+ * moving: one uint16_t per material like Game::movingTiles (Game.hpp:204); info = hadDirty, hadFire, hadFlow */
+double fssref_render_dirty(void* h, uint8_t* main_px, uint8_t* fire_px, uint8_t* emission_px, uint8_t* flow_px, uint16_t* moving, uint32_t* info) {
+    World& W = ((RefWorld*)h)->w;
+    bool hadDirty = false, hadFire = false, hadFlow = false;
+    auto t0 = std::chrono::steady_clock::now();
+    for(int i = 0; i < Materials::nMaterials; i++) moving[i] = 0;                                /* Game.cpp:2579 */
+    ref_dirty_job(&W, main_px, fire_px, flow_px, emission_px, moving, hadDirty, hadFire, hadFlow);
+    if(hadDirty) memset(W.dirty, false, (size_t)W.width * W.height);                             /* Game.cpp:2751 */
+    auto t1 = std::chrono::steady_clock::now();
+    info[0] = hadDirty;
+    info[1] = hadFire;
+    info[2] = hadFlow;
+    return std::chrono::duration<double>(t1 - t0).count();
 }
 
 /* ---- World::particles kept alive for World::tickParticles (world.cpp:2171-2338) ------------------------ */

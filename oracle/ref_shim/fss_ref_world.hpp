@@ -31,6 +31,8 @@ public:
     MaterialInstance* tiles = nullptr;
     float* flowX = nullptr;
     float* flowY = nullptr;
+    float* prevFlowX = nullptr;
+    float* prevFlowY = nullptr;
     std::vector<Particle*> particles;
     uint16_t width = 0;
     uint16_t height = 0;

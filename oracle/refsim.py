@@ -45,6 +45,11 @@ def load(variant="c4x16"):
     L.fssref_num_particles.argtypes = [C.c_void_p]
     L.fssref_drain_particles.restype = C.c_size_t
     L.fssref_drain_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.fssref_get_dirty.argtypes = [C.c_void_p, C.c_void_p]
+    L.fssref_mark_dirty.argtypes = [C.c_void_p] + [C.c_int] * 4
+    L.fssref_get_material_looks.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.fssref_render_dirty.restype = C.c_double
+    L.fssref_render_dirty.argtypes = [C.c_void_p] * 7
     L.fssref_keep_particles.argtypes = [C.c_void_p, C.c_int]
     L.fssref_tick_particles.restype = C.c_double
     L.fssref_tick_particles.argtypes = [C.c_void_p]
@@ -70,6 +75,16 @@ def materials(variant="c4x16"):
         inter = L.fssref_get_material(i, C.byref(m), name, 64)
         out.append((m, name.value.decode(), inter))
     return out
+
+
+def material_looks(variant="c4x16"):
+    """(alpha, emitColor) per material id, Material.hpp:34, :38"""
+    L = load(variant)
+    n = L.fssref_num_materials()
+    alpha = np.zeros(n, dtype=np.uint8)
+    emit = np.zeros(n, dtype=np.uint32)
+    L.fssref_get_material_looks(alpha.ctypes.data, emit.ctypes.data, n)
+    return alpha, emit
 
 
 def create(mat, x, y, seed, tick_ct, iter_, cx, cy, variant="c4x16"):
@@ -133,6 +148,25 @@ class RefWorld:
         temp = np.zeros(max(n, 1), dtype=np.int32)
         m = self.L.fssref_drain_particles(self.h_, xyv.ctypes.data, cells.ctypes.data, temp.ctypes.data, n)
         return xyv[:m], cells[:m], temp[:m]
+
+    def dirty(self):
+        out = np.zeros((self.h, self.w), dtype=np.uint8)
+        self.L.fssref_get_dirty(self.h_, out.ctypes.data)
+        return out
+
+    def mark_dirty(self, x, y, w, h):
+        self.L.fssref_mark_dirty(self.h_, x, y, w, h)
+
+    def render_dirty(self):
+        """the reference's own loop (Game.cpp:2584-2650); returns (moving_tiles as uint16, flags, seconds)"""
+        if not hasattr(self, "pixels"):
+            self.pixels = np.zeros((4, self.h, self.w, 4), dtype=np.uint8)
+        n = self.L.fssref_num_materials()
+        moving = np.zeros(n, dtype=np.uint16)
+        info = np.zeros(3, dtype=np.uint32)
+        dt = self.L.fssref_render_dirty(self.h_, self.pixels[0].ctypes.data, self.pixels[1].ctypes.data, self.pixels[2].ctypes.data,
+                                        self.pixels[3].ctypes.data, moving.ctypes.data, info.ctypes.data)
+        return moving, tuple(int(v) for v in info), dt
 
     def keep_particles(self, on=True):
         """leave World::particles in place after tick() so that tick_particles() can run on them"""

@@ -72,9 +72,36 @@ def main():
     with open(os.path.join(HERE, "tick_hashes.json"), "w") as f:
         json.dump(hashes, f, indent=1)
     particle_scene(helpers)
+    render_scene(helpers)
 
 
 PARTICLE_SCENE_TICKS = 16
+
+
+def render_scene(helpers):
+    """materials_looks.json (Material::alpha / emitColor) and render_scene.json: World::tick + World::tickParticles + the
+    dirty -> pixels job of Game::tick (Game.cpp:2584-2650) every third tick, all three being the reference's own lines"""
+    import hashlib
+    alpha, emit = refsim.material_looks()
+    with open(os.path.join(HERE, "materials_looks.json"), "w") as f:
+        json.dump(dict(alpha=[int(v) for v in alpha], emit_color=[int(v) for v in emit]), f)
+    cells, zone = helpers.make_world((264, 240), "c3", 4002)
+    r = refsim.RefWorld(cells, zone, particles=True, seed=0xF55)
+    r.keep_particles()
+    rows = []
+    for t in range(18):
+        r.tick(t)
+        r.tick_particles()
+        row = dict(tick=t, dirty=hashlib.sha256(r.dirty().tobytes()).hexdigest(), n_dirty=int(r.dirty().sum()))
+        if t % 3 == 1:
+            moving, info, _ = r.render_dirty()
+            row.update(info=list(info), moving=[int(v) for v in moving],
+                       layers=[hashlib.sha256(r.pixels[k].tobytes()).hexdigest() for k in range(4)])
+        rows.append(row)
+    r.close()
+    with open(os.path.join(HERE, "render_scene.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+    print("render_scene", rows[-1]["n_dirty"], rows[-2]["layers"][0][:16])
 
 
 def particle_scene(helpers):

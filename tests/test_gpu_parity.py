@@ -779,3 +779,70 @@ def test_device_particles_error_paths():
     g.tick_particles()  # empty list: nothing to do
     assert g.particles_count() == 0
     g.close()
+
+
+# ---- World::dirty on the device and the dirty -> pixels job of Game::tick ------------------------------
+def _looks():
+    """Material::alpha / emitColor of the 41 materials (tests/golden/materials_looks.json, exported from the reference build)"""
+    with open(os.path.join(GOLDEN, "materials_looks.json")) as f:
+        d = json.load(f)
+    return np.array(d["alpha"], dtype=np.uint8), np.array(d["emit_color"], dtype=np.uint32)
+
+
+@pytest.mark.parametrize("mix", ["c3", "sand", "liquids", "gas", "fire"])
+def test_device_dirty_and_pixels_match_oracle(mix):
+    """every site of World::tick / World::tickParticles that sets dirty[] sets it on the device; the render job gives the
+    same four RGBA layers, flags, per-material counts and consumes the flow accumulators the same way"""
+    cells, zone = make_world((264, 240), mix, seed=4000 + len(mix))
+    alpha, emit = _looks()
+    g = gpu_world(cells, zone, particles=True, track_dirty=True, track_flow=True)
+    o = oracle_world(cells, zone, particles=True)
+    g.set_material_looks(alpha, emit)
+    o.set_material_looks(alpha, emit)
+    for t in range(24):
+        g.tick(t)
+        o.tick(t)
+        g.tick_particles()
+        o.tick_particles()
+        if t == 5:  # a host edit: the game marks what it touched
+            g.mark_dirty(30, 30, 50, 20)
+            o.mark_dirty(30, 30, 50, 20)
+        if t % 4 == 2:
+            g.tick_temperature()
+            o.tick_temperature()
+        da, db = g.dirty(), o.dirty()
+        assert da.tobytes() == db.tobytes(), f"tick {t}: dirty differs in {int((da != db).sum())} cells, first {np.argwhere(da != db)[0]}"
+        if t % 3 == 1:
+            mg, ig = g.render_dirty()
+            mo, io = o.render_dirty()
+            assert ig == io and np.array_equal(mg, mo), f"tick {t}: {ig} vs {io}"
+            for layer in range(4):
+                a, b = g.pixels(layer), o.pixels[layer]
+                assert a.tobytes() == b.tobytes(), f"tick {t}: layer {layer} differs in {int((a != b).any(axis=2).sum())} pixels"
+            assert not g.dirty().any()
+            fa, fb = g.flow(), o.flow()
+            assert fa[0].tobytes() == fb[0].tobytes() and fa[1].tobytes() == fb[1].tobytes()
+        a, b = g.cells(), o.cells()
+        assert a.tobytes() == b.tobytes(), f"tick {t}: " + diff_report(a, b)
+    g.close()
+    o.close()
+
+
+def test_device_dirty_error_paths():
+    from fallingsandsurvival_b200 import world
+    cells, zone = make_world((264, 240), "c2", seed=1)
+    g = gpu_world(cells, zone)
+    with pytest.raises(world.FssError):
+        g.render_dirty()
+    with pytest.raises(world.FssError):
+        g.mark_dirty(0, 0, 8, 8)
+    g.close()
+    g = gpu_world(cells, zone, track_dirty=True)
+    with pytest.raises(world.FssError):
+        g.pixels(0)  # before the first render
+    g.mark_dirty(-5, -5, 20, 20)  # clipped like the reference's own bounds checks
+    assert int(g.dirty().sum()) == 15 * 15
+    moving, info = g.render_dirty()
+    assert info[0] == 1 and int(moving.sum()) == 15 * 15
+    assert g.pixels(0, 3, 3, 8, 8).shape == (8, 8, 4)
+    g.close()

@@ -117,6 +117,64 @@ def test_oracle_particle_tick_matches_reference_build(mix, have_ref):
     o.close()
 
 
+def _looks():
+    with open(os.path.join(GOLDEN, "materials_looks.json")) as f:
+        d = json.load(f)
+    return np.array(d["alpha"], dtype=np.uint8), np.array(d["emit_color"], dtype=np.uint32)
+
+
+def test_oracle_dirty_and_pixels_match_golden():
+    """World::dirty as World::tick / tickParticles set it, and the dirty -> pixels job of Game::tick (Game.cpp:2584-2650);
+    golden hashes minted from the reference's own lines (tests/golden/make_golden.py::render_scene)"""
+    import hashlib
+    with open(os.path.join(GOLDEN, "render_scene.json")) as f:
+        rows = json.load(f)
+    cells, zone = make_world((264, 240), "c3", 4002)
+    o = oraclesim.OracleWorld(cells, zone, defs=full_table(), particles=True)
+    o.set_material_looks(*_looks())
+    for row in rows:
+        o.tick(row["tick"])
+        o.tick_particles()
+        d = o.dirty()
+        assert int(d.sum()) == row["n_dirty"] and hashlib.sha256(d.tobytes()).hexdigest() == row["dirty"], f"tick {row['tick']}"
+        if "layers" in row:
+            moving, info = o.render_dirty()
+            assert list(info) == row["info"]
+            assert [int(v) & 0xFFFF for v in moving] == row["moving"]  # Game::movingTiles is uint16_t
+            assert [hashlib.sha256(o.pixels[k].tobytes()).hexdigest() for k in range(4)] == row["layers"], f"tick {row['tick']}"
+    o.close()
+
+
+@pytest.mark.parametrize("mix", ["c3", "sand", "liquids", "gas", "fire"])
+def test_oracle_dirty_and_pixels_match_reference_build(mix, have_ref):
+    if not have_ref:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from oracle import refsim
+    cells, zone = make_world((200, 176), mix, seed=77)
+    r = refsim.RefWorld(cells, zone, particles=True)
+    r.keep_particles()
+    o = oraclesim.OracleWorld(cells, zone, defs=full_table(), particles=True)
+    o.set_material_looks(*refsim.material_looks())
+    for t in range(20):
+        r.tick(t)
+        o.tick(t)
+        r.tick_particles()
+        o.tick_particles()
+        if t == 5:
+            r.mark_dirty(30, 30, 50, 20)
+            o.mark_dirty(30, 30, 50, 20)
+        assert r.dirty().tobytes() == o.dirty().tobytes(), f"tick {t}: dirty differs"
+        if t % 2 == 1:
+            mr, ir, _ = r.render_dirty()
+            mo, io = o.render_dirty()
+            assert ir == io and np.array_equal(mr.astype(np.uint64), mo[:len(mr)] & np.uint64(0xFFFF))
+            assert r.pixels.tobytes() == o.pixels.tobytes(), f"tick {t}: pixel layers differ"
+            fa, fb = r.flow(), o.flow()
+            assert fa[0].tobytes() == fb[0].tobytes() and fa[1].tobytes() == fb[1].tobytes()
+    r.close()
+    o.close()
+
+
 def test_reference_build_is_thread_count_independent(have_ref):
     """the 4x16 checkerboard is race-free: 1, 3 and 8 pool threads give the same grid"""
     if not have_ref:
