@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) k_render_dirty(const __grid_constant__ Re
     __syncthreads();
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     bool fire = false, flow = false, any = false;
+    uint32_t my_mat = 0xFFFFFFFFu; // material of this thread's dirty cell
     if(i < p.cells && p.g.dirty[i]) {
         const uint32_t row = (uint32_t)(i / p.g.pitch), x = fss_unperm((uint32_t)(i % p.g.pitch));
         if((int)x < p.width) {
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(256) k_render_dirty(const __grid_constant__ Re
             p.g.dirty[i] = 0; // Game.cpp:2751: the memset after the job, for the cells that were set
             const uint32_t mf = p.g.mf[i];
             const uint32_t mat = mf_mat(mf);
-            atomicAdd(&hist[mat], 1u); // :2589 movingTiles[mat->id]++
+            my_mat = mat;
             const size_t o = (size_t)(row + p.g.sy0) * p.width + x;
             if(MF_IS(mf, FSS_PHYS_AIR)) { // :2590-2607
                 p.px[0][o] = 0u;
@@ -79,6 +80,10 @@ __global__ void __launch_bounds__(256) k_render_dirty(const __grid_constant__ Re
                 p.g.fy[i] = 0.f;
             }
         }
+    }
+    { // :2589 movingTiles[mat->id]++: the lanes of a warp that hold the same material add once
+        const unsigned peers = __match_any_sync(0xffffffffu, my_mat);
+        if(my_mat != 0xFFFFFFFFu && (threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[my_mat], (unsigned)__popc(peers));
     }
     if(__syncthreads_or(any)) {
         if(threadIdx.x == 0) p.info[0] = 1u;
