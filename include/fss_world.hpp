@@ -55,6 +55,7 @@ struct Material {
     int id = 0;
     int physicsType = PhysicsType::AIR;
     std::uint8_t alpha = 255;
+    std::uint32_t emitColor = 0; // Material.hpp:38
     float density = 0;
     int iterations = 0;
     std::uint32_t color = 0;
@@ -108,6 +109,12 @@ public:
     // `particles` is the host copy of the list for World::renderParticles (world.cpp:2145-2169).
     bool deviceParticles = false;
     std::vector<fss_particle> particles;
+    // World::dirty kept on the device exactly as the reference sets it, and the dirty -> pixels job of Game::tick
+    // (Game.cpp:2579-2650) run there: set before init(); then renderDirty() replaces the job, and dirty[] stays unused.
+    bool deviceRender = false;
+    std::vector<unsigned char> pixels_ar, pixelsFire_ar, pixelsEmission_ar, pixelsFlow_ar; // Game.cpp:2452-2455, width * height * 4
+    std::vector<std::uint64_t> movingTiles;                                                // Game.hpp:204
+    bool hadDirty = false, hadFire = false, hadFlow = false;                               // Game.cpp:2443-2447
 
     World() {}
     World(const World&) = delete;
@@ -133,7 +140,7 @@ public:
         cfg.height = (std::uint32_t)h;
         cfg.seed = seed;
         cfg.device = device;
-        cfg.flags = emitParticles ? FSS_PARTICLES_EMIT : 0;
+        cfg.flags = (emitParticles ? FSS_PARTICLES_EMIT : 0u) | (deviceRender ? (FSS_TRACK_DIRTY | FSS_TRACK_FLOW) : 0u);
         cfg.condense_material = condenseMaterial;
         check(fss_create(&cfg, &core_), "fss_create");
         std::vector<fss_material> tbl(mats_.size());
@@ -162,6 +169,12 @@ public:
             d.create_temperature = m.createTemperature;
         }
         check(fss_set_materials(core_, tbl.data(), (int)tbl.size()), "fss_set_materials");
+        if(deviceRender) {
+            std::vector<std::uint8_t> alpha(mats_.size());
+            std::vector<std::uint32_t> emit(mats_.size());
+            for(size_t i = 0; i < mats_.size(); i++) alpha[i] = mats_[i].alpha, emit[i] = mats_[i].emitColor;
+            check(fss_set_material_looks(core_, alpha.data(), emit.data(), (int)mats_.size()), "fss_set_material_looks");
+        }
         markDirty(0, 0, w, h);
     }
 
@@ -184,6 +197,10 @@ public:
     }
     // after writing tiles[] directly (brush, rigid-body stamping, chunk merge ...): the rectangle goes to the GPU before the next tick
     void markDirty(int x, int y, int w, int h) {
+        if(deviceRender) { // World::setTile and the game's direct writes set dirty[] themselves
+            const bool covered = !marks_.empty() && x >= marks_[0].x && y >= marks_[0].y && x + w <= marks_[0].x + marks_[0].w && y + h <= marks_[0].y + marks_[0].h;
+            if(!covered) marks_.push_back(Rect{x, y, w, h});
+        }
         if(!pending_) {
             px0_ = x, py0_ = y, px1_ = x + w, py1_ = y + h;
             pending_ = true;
@@ -233,6 +250,28 @@ public:
     // particles.push_back(new Particle(...)) by game code
     void addParticle(const fss_particle& p) { check(fss_particles_add(core_, &p, 1), "fss_particles_add"); }
 
+    // The `dirty` job of Game::tick (Game.cpp:2579-2650) and the memset after it (:2751) on the device; the window
+    // (x, y, w, h) of the four layers is then copied into pixels*_ar (the rest of those arrays keeps its last content).
+    void renderDirty(int x, int y, int w, int h) {
+        flush();
+        fss_render_info info;
+        movingTiles.assign(mats_.size(), 0);
+        check(fss_render_dirty(core_, movingTiles.data(), (int)mats_.size(), &info), "fss_render_dirty");
+        hadDirty = info.had_dirty != 0;
+        hadFire = info.had_fire != 0;
+        hadFlow = info.had_flow != 0;
+        if(x < 0) w += x, x = 0;
+        if(y < 0) h += y, y = 0;
+        if(x + w > width) w = width - x;
+        if(y + h > height) h = height - y;
+        if(w <= 0 || h <= 0) return;
+        std::vector<unsigned char>* layers[4] = {&pixels_ar, &pixelsFire_ar, &pixelsEmission_ar, &pixelsFlow_ar};
+        for(int k = 0; k < 4; k++) {
+            layers[k]->resize((size_t)width * height * 4);
+            check(fss_download_pixels(core_, k, x, y, w, h, layers[k]->data() + ((size_t)y * width + x) * 4, (size_t)width * 4), "fss_download_pixels");
+        }
+    }
+
     // World::tickTemperature (world.cpp:2043-2143)
     void tickTemperature() {
         flush();
@@ -271,6 +310,7 @@ private:
     fss_world* core_ = nullptr;
     std::vector<Material> mats_;
     std::vector<fss_cell> stage_;
+    std::vector<Rect> marks_;
     bool pending_ = false;
     int px0_ = 0, py0_ = 0, px1_ = 0, py1_ = 0;
     Rect zoneSet_;
@@ -292,6 +332,8 @@ private:
         for(int r = 0; r < h; r++)
             for(int c = 0; c < w; c++) stage_[(size_t)r * w + c] = toCell(tiles[(x + c) + (size_t)(y + r) * width]);
         check(fss_upload_rect(core_, x, y, w, h, stage_.data(), (size_t)w), "fss_upload_rect");
+        for(const Rect& m : marks_) check(fss_mark_dirty(core_, m.x, m.y, m.w, m.h), "fss_mark_dirty");
+        marks_.clear();
     }
     void pull(int x, int y, int w, int h, bool setDirty) { // device -> tiles[]
         if(x < 0) w += x, x = 0;

@@ -23,7 +23,9 @@ static void dump(const char* path, const World& w) {
 int main(int argc, char** argv) {
     if(argc < 2) return 2;
     const std::string dir = argv[1];
-    const bool deviceParticles = argc > 2 && std::string(argv[2]) == "particles"; // World::tickParticles on the GPU as well
+    const std::string mode = argc > 2 ? argv[2] : "";
+    const bool deviceRender = mode == "render";                 // World::dirty + the dirty -> pixels job of Game::tick on the GPU as well
+    const bool deviceParticles = mode == "particles" || deviceRender; // World::tickParticles on the GPU as well
     const int W = 328, H = 240, ticks = 12;
     try {
         // Materials.cpp:5-46 in miniature; ids are dense
@@ -44,7 +46,13 @@ int main(int argc, char** argv) {
         mats.back().conductionOther = 0.7f;
         mats.back().createTemperature = 1024;
 
+        if(deviceRender) { // Materials.cpp: water is translucent, lava glows
+            mats[3].alpha = 0x80;
+            mats[5].alpha = 0xC0;
+            mats[5].emitColor = 0xC0FF7C00u;
+        }
         World world;
+        world.deviceRender = deviceRender;
         world.init(W, H, mats, 0xF55, 0, /*condense into*/ 3);
         for(int y = 0; y < H; y++) {
             for(int x = 0; x < W; x++) {
@@ -74,6 +82,18 @@ int main(int argc, char** argv) {
                 world.tickParticles(); // Game.cpp:2459-2483
             }
             if(t % 4 == 2) world.tickTemperature();
+            if(deviceRender && t % 3 == 2) world.renderDirty(0, 0, W, H); // Game.cpp:2579-2650
+        }
+        if(deviceRender) {
+            FILE* f = std::fopen((dir + "/layers.bin").c_str(), "wb");
+            std::fwrite(world.pixels_ar.data(), 1, world.pixels_ar.size(), f);
+            std::fwrite(world.pixelsFire_ar.data(), 1, world.pixelsFire_ar.size(), f);
+            std::fwrite(world.pixelsEmission_ar.data(), 1, world.pixelsEmission_ar.size(), f);
+            std::fwrite(world.pixelsFlow_ar.data(), 1, world.pixelsFlow_ar.size(), f);
+            std::fclose(f);
+            std::printf("moving");
+            for(std::uint64_t v : world.movingTiles) std::printf(" %llu", (unsigned long long)v);
+            std::printf(" had %d %d %d\n", (int)world.hadDirty, (int)world.hadFire, (int)world.hadFlow);
         }
         if(deviceParticles) {
             FILE* f = std::fopen((dir + "/particles.bin").c_str(), "wb");

@@ -526,7 +526,7 @@ def test_tall_world_beyond_grid_dim_limits():
         w.close()
 
 
-@pytest.mark.parametrize("device_particles", [False, True])
+@pytest.mark.parametrize("device_particles", [False, True, "render"])
 def test_cpp_world_mirror_matches_oracle(tmp_path, device_particles):
     """tests/cpp/world_shim_test.cpp plays a short game script against fss::World (include/fss_world.hpp); the oracle
     replays the same script (same initial grid, same brush stroke) and must produce the same tiles[].  With
@@ -535,7 +535,8 @@ def test_cpp_world_mirror_matches_oracle(tmp_path, device_particles):
 
     from test_abi import build_cpp_shim_test
     exe = build_cpp_shim_test(tmp_path)
-    r = subprocess.run([str(exe), str(tmp_path)] + (["particles"] if device_particles else []), capture_output=True, text=True)
+    render = device_particles == "render"  # + World::dirty and the dirty -> pixels job on the device
+    r = subprocess.run([str(exe), str(tmp_path)] + (["render"] if render else ["particles"] if device_particles else []), capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     W, H = 328, 240
     initial = np.fromfile(tmp_path / "initial.bin", dtype=abi.CELL_DTYPE).reshape(H, W)
@@ -550,11 +551,18 @@ def test_cpp_world_mirror_matches_oracle(tmp_path, device_particles):
             D(5, "Lava", LQ, 0, 255, 2.0, 1, color=0xFF7C00, add_temp=2, conduction_self=0.5, conduction_other=0.7, create_temperature=1024)]
     from oracle import oraclesim
     o = oraclesim.OracleWorld(initial, (16, 16, W - 32, H - 48), defs=defs, textures=[], particles=True, condense_material=3)
+    if render:
+        looks_a, looks_e = np.full(6, 255, dtype=np.uint8), np.zeros(6, dtype=np.uint32)
+        looks_a[3], looks_a[5], looks_e[5] = 0x80, 0xC0, 0xC0FF7C00
+        o.set_material_looks(looks_a, looks_e)
+        o.mark_dirty(0, 0, W, H)  # World::init painted every cell through setTile
     for t in range(12):
         if t == 5:
             patch = np.zeros((12, 40), dtype=abi.CELL_DTYPE)
             patch["material"], patch["color"], patch["fluid_amount"] = 2, 0xABCDEF, 2.0
             o.view()[40:52, 100:140] = patch
+            if render:
+                o.mark_dirty(100, 40, 40, 12)
         o.tick(t)
         if device_particles:
             if t == 3:
@@ -565,8 +573,15 @@ def test_cpp_world_mirror_matches_oracle(tmp_path, device_particles):
             o.tick_particles()
         if t % 4 == 2:
             o.tick_temperature()
+        if render and t % 3 == 2:
+            moving, info = o.render_dirty()
     want = o.cells()
     assert final.tobytes() == want.tobytes(), diff_report(want, final)
+    if render:
+        layers = np.fromfile(tmp_path / "layers.bin", dtype=np.uint8).reshape(4, H, W, 4)
+        for k in range(4):
+            assert layers[k].tobytes() == o.pixels[k].tobytes(), f"layer {k}: {int((layers[k] != o.pixels[k]).any(axis=2).sum())} pixels differ"
+        assert "moving " + " ".join(str(int(v)) for v in moving) + " had %d %d %d" % info in r.stdout
     assert f"digest {oraclesim.hash_cells(want):016x}" in r.stdout
     if device_particles:
         got = np.fromfile(tmp_path / "particles.bin", dtype=abi.LIVE_PARTICLE_DTYPE)
