@@ -116,6 +116,7 @@ struct fss_world {
     fss_stats stats;
     // settled-chunk flags (SubstepParams::q): (q_h x q_w) bytes, chunk (ci, cj) of the zone at [(cj - q_cj0 + 1) * q_w + ci + 1]
     uint8_t* d_q;
+    uint8_t* d_qskip; // FSS_TRACK_DIRTY: SubstepParams::qskip
     int q_w, q_h, q_cj0;
     // which materials can be in the grid (only ever grows): decides from which iter on the liquid-only kernel is exact
     bool present[FSS_MAX_MATERIALS];
@@ -320,7 +321,6 @@ int fss_create(const fss_config* cfg, fss_world** out) {
             fss_destroy(w);
             return fail(FSS_ERR_INVALID, "FSS_TRACK_DIRTY is not supported by the experimental FSS_K1=b kernel");
         }
-        w->cfg.flags |= FSS_NO_EARLY_OUT; // a skipped chunk would lose the marks of its liquid cells (world.cpp:1814, :1823)
         CUX(cudaMalloc(&w->g.dirty, n));
         CUX(cudaMemsetAsync(w->g.dirty, 0, n, w->stream));
     }
@@ -374,6 +374,7 @@ int fss_destroy(fss_world* w) {
     cudaFree(w->d_red);
     cudaFree(w->d_stage);
     cudaFree(w->d_q);
+    cudaFree(w->d_qskip);
     cudaFree(w->d_present);
     particles_free(w);
     if(w->own_stream) cudaStreamDestroy(w->own_stream);
@@ -475,6 +476,8 @@ int fss_set_texture(fss_world* w, int index, const uint32_t* argb, int tw, int t
     return FSS_OK;
 }
 
+static int skipped_marks(fss_world* w);
+
 int fss_set_tick_zone(fss_world* w, int x, int y, int zw, int zh) {
     if(!w) return fail(FSS_ERR_INVALID, "null world");
     if(x % FSS_ZONE_ALIGN_X || zw % FSS_ZONE_ALIGN_X || zh % FSS_ZONE_ALIGN_Y || zw <= 0 || zh <= 0)
@@ -490,6 +493,7 @@ int fss_set_tick_zone(fss_world* w, int x, int y, int zw, int zh) {
             return fail(FSS_ERR_ALIGN, "strip end %d is not zone.y + k*%d inside the zone", w->own_hi, FSS_ZONE_ALIGN_Y);
     }
     if(use_device(w)) return FSS_ERR_CUDA;
+    if(int rc = skipped_marks(w)) return rc; // notes taken under the old zone
     w->zx = x;
     w->zy = y;
     w->zw = zw;
@@ -498,6 +502,8 @@ int fss_set_tick_zone(fss_world* w, int x, int y, int zw, int zh) {
     CU(cudaStreamSynchronize(w->stream));
     cudaFree(w->d_q);
     w->d_q = nullptr;
+    cudaFree(w->d_qskip);
+    w->d_qskip = nullptr;
     if(!(w->cfg.flags & FSS_NO_EARLY_OUT)) {
         int j_lo, j_hi;
         owned_bands(w, j_lo, j_hi);
@@ -505,6 +511,10 @@ int fss_set_tick_zone(fss_world* w, int x, int y, int zw, int zh) {
         w->q_h = std::max(0, j_hi - j_lo) * 2 + 2;
         w->q_cj0 = j_lo * 2;
         CU(cudaMalloc(&w->d_q, (size_t)w->q_w * w->q_h));
+        if(w->g.dirty) {
+            CU(cudaMalloc(&w->d_qskip, (size_t)w->q_w * w->q_h));
+            CU(cudaMemsetAsync(w->d_qskip, 0xFF, (size_t)w->q_w * w->q_h, w->stream));
+        }
         if(dirty_chunks(w, 0, 0, -1, -1)) return FSS_ERR_CUDA;
     }
     return FSS_OK;
@@ -611,6 +621,7 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk) {
     p.part_count = w->d_part_count;
     p.part_cap = w->part_cap;
     p.q = w->d_q;
+    p.qskip = w->d_qskip;
     p.q_w = w->q_w;
     p.ofs_x = ofs_x;
     p.ofs_y = ofs_y;
@@ -990,6 +1001,26 @@ int fss_set_material_looks(fss_world* w, const uint8_t* alpha, const uint32_t* e
     return FSS_OK;
 }
 
+// the marks that skipped visits of settled chunks stand for (k_skipped_marks), before anybody looks at World::dirty
+static int skipped_marks(fss_world* w) {
+    if(!w->d_qskip || !w->d_q || !w->g.dirty) return FSS_OK;
+    SkippedMarks p;
+    p.g = w->g;
+    p.qskip = w->d_qskip;
+    p.q_w = w->q_w;
+    p.q_cj0 = w->q_cj0;
+    p.zx = w->zx;
+    p.zy = w->zy;
+    p.zw = w->zw;
+    p.zh = w->zh;
+    p.cells = plane_cells(w);
+    k_skipped_marks<<<(unsigned)((p.cells + 255) / 256), 256, 0, w->stream>>>(p);
+    CU(cudaGetLastError());
+    w->stats.kernel_launches++;
+    CU(cudaMemsetAsync(w->d_qskip, 0xFF, (size_t)w->q_w * w->q_h, w->stream));
+    return FSS_OK;
+}
+
 static int dirty_ready(fss_world* w) {
     if(!w) return fail(FSS_ERR_INVALID, "null world");
     if(!w->g.dirty) return fail(FSS_ERR_STATE, "the world was created without FSS_TRACK_DIRTY");
@@ -1014,6 +1045,7 @@ int fss_render_dirty(fss_world* w, uint64_t* moving_tiles, int n_materials, fss_
     if(int rc = dirty_ready(w)) return rc;
     if(!w->mats_set) return fail(FSS_ERR_STATE, "fss_set_materials first");
     if(n_materials < 0 || n_materials > FSS_MAX_MATERIALS) return fail(FSS_ERR_INVALID, "%d materials", n_materials);
+    if(int rc = skipped_marks(w)) return rc;
     const size_t cells = plane_cells(w), pixels = (size_t)w->cfg.width * w->cfg.height;
     if(!w->px[0]) {
         for(int k = 0; k < 4; k++) {
@@ -1085,6 +1117,7 @@ int fss_download_dirty(fss_world* w, int x, int y, int width, int height, uint8_
     if(int rc = dirty_ready(w)) return rc;
     if(!out) return fail(FSS_ERR_INVALID, "null argument");
     if(pitch_bytes < (size_t)width) return fail(FSS_ERR_INVALID, "pitch %zu < width %d", pitch_bytes, width);
+    if(int rc = skipped_marks(w)) return rc;
     size_t skip = 0;
     if(int rc = rect_clip(w, x, y, width, height, skip)) return rc;
     const int rows_per_pass = (int)std::max<size_t>(1, w->stage_bytes / (size_t)width);

@@ -58,7 +58,15 @@ __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS
 #ifndef K1_NO_EARLY
     if(p.q) {
         qown = p.q + (size_t)(2 * (int)blockIdx.y + p.ofs_y + 1) * p.q_w + (2 * gi + p.ofs_x + 1);
-        if(*qown <= (uint8_t)p.iter) return; // verified settled: a warp whose 32 chunks are all settled ends here
+        if(*qown <= (uint8_t)p.iter) { // verified settled: a warp whose 32 chunks are all settled ends here
+            if(DIRTY) {
+                // the visit that is skipped would have been the identity on the cells, but not on World::dirty: scan 2 marks
+                // every liquid cell it reaches (world.cpp:1823).  The render job adds those marks from this note.
+                uint8_t* s = p.qskip + (qown - p.q);
+                if(*s > (uint8_t)p.iter) *s = (uint8_t)p.iter;
+            }
+            return;
+        }
     }
 #endif
     ChunkWalk<MODE, FLOW, DIRTY> w(p, sden, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y,

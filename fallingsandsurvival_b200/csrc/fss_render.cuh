@@ -94,6 +94,27 @@ __global__ void __launch_bounds__(256) k_render_dirty(const __grid_constant__ Re
     if(flow) p.info[2] = 1u;
 }
 
+// The movement kernel skips the visits of chunks it has verified settled.  Such a visit is the identity on the cells but not
+// on World::dirty: scan 2 marks every liquid cell it reaches (world.cpp:1823), i.e. every liquid cell of the chunk that is
+// still active at that iter (the gate of world.cpp:1163-1166); nothing else in a settled chunk gets a mark.  The kernel notes
+// per chunk the lowest iter it skipped (SubstepParams::qskip); this turns the notes into the marks they stand for.
+struct SkippedMarks {
+    Grid g;
+    const uint8_t* qskip;
+    int q_w, q_cj0, zx, zy, zw, zh;
+    size_t cells;
+};
+__global__ void __launch_bounds__(256) k_skipped_marks(const __grid_constant__ SkippedMarks p) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if(i >= p.cells) return;
+    const int gx = (int)fss_unperm((uint32_t)(i % p.g.pitch)) - p.zx, gy = (int)(i / p.g.pitch) + p.g.sy0 - p.zy;
+    if(gx < 0 || gx >= p.zw || gy < 0 || gy >= p.zh) return;
+    const uint8_t k = p.qskip[(size_t)(gy / FSS_CHUNK_H - p.q_cj0 + 1) * p.q_w + gx / FSS_CHUNK_W + 1];
+    if(k == 0xFF) return;
+    const uint32_t mf = p.g.mf[i];
+    if(MF_IS(mf, FSS_PHYS_SOUP) && mf_iters(mf) > (int)k) p.g.dirty[i] = 1;
+}
+
 // dirty[...] = true over a rectangle (host code that edits tiles[] sets it itself: World::setTile world.cpp:1061, Game.cpp:1148 ...)
 __global__ void __launch_bounds__(256) k_mark_dirty(Grid g, int rx, int ry, int rw, int rh) {
     const int k = blockIdx.x * 256 + threadIdx.x;

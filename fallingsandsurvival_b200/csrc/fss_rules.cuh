@@ -43,6 +43,7 @@ struct SubstepParams {
     //   0xFF  must be processed;   v in 0..5  the chunk was verified at iter v to be left unchanged, without any
     //   RNG draw, by a sub-step: while its read window stays untouched, every sub-step with iter >= v skips it.
     uint8_t* q;   // nullptr = early-out disabled
+    uint8_t* qskip; // FSS_TRACK_DIRTY: per chunk the lowest iter whose visit was skipped since the last render (0xFF = none); same layout as q
     int q_w;      // flags per row of chunks (zone chunks + 2 guards)
     int ofs_x, ofs_y; // phase offsets in chunks: the chunk of thread (gi, by) is (2*gi + ofs_x, 2*by + ofs_y)
 };

@@ -129,9 +129,10 @@ typedef struct fss_material {
 
 #define FSS_TRACK_DIRTY 8u    /* keep World::dirty (world.hpp:139) on the device: every site of World::tick / tickParticles that sets
                                  it does (world.cpp:1061, :1194 ... :1968, :2269-2303), fss_mark_dirty for host edits, consumed by
-                                 fss_render_dirty.  One more byte per cell; a compile-time kernel variant, off by default.  Turns the
-                                 settled-chunk early-out off: the reference re-marks every liquid cell in every sub-step
-                                 (world.cpp:1814, :1823), so a chunk that is skipped would lose marks. */
+                                 fss_render_dirty.  One more byte per cell; a compile-time kernel variant, off by default.  Works with
+                                 the settled-chunk early-out: the reference re-marks every liquid cell in every sub-step
+                                 (world.cpp:1814, :1823), so for a chunk whose visit is skipped the kernel notes the iter and the
+                                 marks are added before World::dirty is next looked at. */
 
 typedef struct fss_config {
     uint32_t struct_size; /* sizeof(fss_config), for ABI evolution */

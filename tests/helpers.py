@@ -31,6 +31,7 @@ MIXES = {
     "fire": [(M.FIRE, 10), (M.SOFT_DIRT, 30), (M.CLOUD, 10), (M.TEST_SAND, 10)],
     "randmats": [(31 + i, 6) for i in range(10)] + [(M.STONE, 10)],
     "settled": [(M.COBBLE_STONE, 60), (M.TEST_SAND, 1)],
+    "pockets": [(M.COBBLE_STONE, 68), (M.WATER, 22), (M.LAVA, 4)],  # liquid trapped in stone: settles within a few ticks
 }
 
 

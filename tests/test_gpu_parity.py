@@ -804,13 +804,14 @@ def _looks():
     return np.array(d["alpha"], dtype=np.uint8), np.array(d["emit_color"], dtype=np.uint32)
 
 
-@pytest.mark.parametrize("mix", ["c3", "sand", "liquids", "gas", "fire"])
-def test_device_dirty_and_pixels_match_oracle(mix):
+@pytest.mark.parametrize("early_out", [True, False])
+@pytest.mark.parametrize("mix", ["c3", "sand", "liquids", "gas", "fire", "pockets"])
+def test_device_dirty_and_pixels_match_oracle(mix, early_out):
     """every site of World::tick / World::tickParticles that sets dirty[] sets it on the device; the render job gives the
     same four RGBA layers, flags, per-material counts and consumes the flow accumulators the same way"""
     cells, zone = make_world((264, 240), mix, seed=4000 + len(mix))
     alpha, emit = _looks()
-    g = gpu_world(cells, zone, particles=True, track_dirty=True, track_flow=True)
+    g = gpu_world(cells, zone, particles=True, track_dirty=True, track_flow=True, early_out=early_out)
     o = oracle_world(cells, zone, particles=True)
     g.set_material_looks(alpha, emit)
     o.set_material_looks(alpha, emit)
