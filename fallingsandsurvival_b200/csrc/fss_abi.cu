@@ -133,6 +133,8 @@ struct fss_world {
     uint32_t pl_n, pl_cap;
     uint32_t* pl_res_cell; // four hashed cell tables (W_act, R_act, W_pot, R_pot) of pl_res_mask + 1 entries each
     uint32_t pl_res_mask;
+    uint32_t* pl_small;    // the tables of the cooperative-launch path for short lists
+    int pl_coop_ctas;      // how many of its CTAs are resident at once
     uint32_t* pl_res_tile; // one entry per 16 x 16 tile of the world
     uint32_t* pl_ctl;      // [0] left undecided, [1] cutoff, [2] list length after compaction
     uint64_t *pl_key[2];   // spawn order keys / indices, `part_cap` long, for the sort
@@ -227,7 +229,7 @@ static int dirty_chunks(fss_world* w, int rx, int ry, int rw, int rh) {
 
 static void particles_free(fss_world* w) {
     void* ptrs[] = {w->pl_list, w->pl_next, w->pl_decided, w->pl_keep, w->pl_sure, w->pl_big, w->pl_ran, w->pl_listed, w->pl_act, w->pl_seen, w->pl_reach,
-                    w->pl_res_cell, w->pl_res_tile, w->pl_ctl, w->pl_key[0], w->pl_key[1], w->pl_idx[0], w->pl_idx[1], w->pl_tmp};
+                    w->pl_res_cell, w->pl_res_tile, w->pl_small, w->pl_ctl, w->pl_key[0], w->pl_key[1], w->pl_idx[0], w->pl_idx[1], w->pl_tmp};
     for(void* p : ptrs) cudaFree(p);
 }
 
@@ -933,8 +935,9 @@ int fss_tick_particles(fss_world* w) {
     P.big = w->pl_big;
     P.tiles_w = (int)((w->cfg.width + FSS_PTILE - 1) / FSS_PTILE);
     P.tiles_h = (int)((w->cfg.height + FSS_PTILE - 1) / FSS_PTILE);
-    P.w_tile = w->pl_res_tile + (size_t)P.tiles_w * P.tiles_h;
-    P.w_when = w->pl_res_tile + 2 * (size_t)P.tiles_w * P.tiles_h;
+    const size_t n_tiles = (size_t)P.tiles_w * P.tiles_h;
+    P.w_tile = w->pl_res_tile + n_tiles;
+    P.w_when = w->pl_res_tile + 2 * n_tiles;
     P.ran = w->pl_ran;
     P.listed = w->pl_listed;
     P.ctl = w->pl_ctl;
@@ -944,14 +947,53 @@ int fss_tick_particles(fss_world* w) {
     P.q_w = w->q_w;
     P.q_h = w->q_h;
     P.q_cj0 = w->q_cj0;
+    P.tile_mask = 0;
+    static const bool no_small = getenv("FSS_PARTICLES_NO_SMALL") != nullptr; // measurements: always the multi-kernel path
+    if(n <= FSS_PCOOP_MAX && !no_small) {
+        // a short list: rounds, passes and compaction inside one cooperative launch (k_particles_coop), on its own small tables
+        // table sizes follow the list (they are cleared every round): >= 64 cell slots and >= 8 tile slots per particle
+        uint32_t cslots = 4096, tslots = 1024;
+        while(cslots < 64 * n) cslots *= 2;
+        while(tslots < 8 * n) tslots *= 2;
+        if(!w->pl_small) {
+            CU(cudaMalloc(&w->pl_small, (4 * (64u * FSS_PCOOP_MAX) + 3 * (8u * FSS_PCOOP_MAX)) * sizeof(uint32_t)));
+            int per_sm = 0, sms = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_particles_coop, FSS_PCOOP_THREADS, 0));
+            CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device));
+            w->pl_coop_ctas = std::max(1, per_sm * sms);
+        }
+        SmallTables T;
+        T.words = w->pl_small;
+        T.n_ff = 4 * cslots + 2 * tslots;
+        T.n_zero = tslots;
+        P.w_act = w->pl_small;
+        P.r_act = w->pl_small + cslots;
+        P.w_pot = w->pl_small + 2 * cslots;
+        P.r_pot = w->pl_small + 3 * cslots;
+        P.res_mask = cslots - 1;
+        P.res_tile = w->pl_small + 4 * cslots;
+        P.w_tile = P.res_tile + tslots;
+        P.w_when = P.w_tile + tslots;
+        P.tile_mask = tslots - 1;
+        const unsigned ctas = (unsigned)std::min<size_t>((size_t)w->pl_coop_ctas, ((size_t)n * FSS_PCOOP_SPREAD + FSS_PCOOP_THREADS - 1) / FSS_PCOOP_THREADS);
+        void* args[] = {&P, &T};
+        CU(cudaLaunchCooperativeKernel((const void*)k_particles_coop, dim3(ctas), dim3(FSS_PCOOP_THREADS), args, 0, w->stream));
+        w->stats.kernel_launches++;
+        w->pl_rounds = w->pl_passes = 0; // not counted on this path
+        uint32_t kept = 0;
+        CU(cudaMemcpyAsync(&kept, w->pl_ctl + 2, sizeof kept, cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+        w->pl_n = kept;
+        return FSS_OK;
+    }
     const unsigned blocks = (n + 127) / 128;
     CU(cudaMemsetAsync(w->pl_decided, 0, n, w->stream));
     for(uint32_t left = n; left;) {
         const uint32_t ctl0[4] = {0u, 0xFFFFFFFFu, 0u, 0u};
         CU(cudaMemcpyAsync(w->pl_ctl, ctl0, sizeof ctl0, cudaMemcpyHostToDevice, w->stream));
         CU(cudaMemsetAsync(w->pl_res_cell, 0xFF, 4 * slots * sizeof(uint32_t), w->stream));
-        CU(cudaMemsetAsync(w->pl_res_tile, 0xFF, 2 * (size_t)P.tiles_w * P.tiles_h * sizeof(uint32_t), w->stream));
-        CU(cudaMemsetAsync(P.w_when, 0, (size_t)P.tiles_w * P.tiles_h * sizeof(uint32_t), w->stream));
+        CU(cudaMemsetAsync(w->pl_res_tile, 0xFF, 2 * n_tiles * sizeof(uint32_t), w->stream));
+        CU(cudaMemsetAsync(P.w_when, 0, n_tiles * sizeof(uint32_t), w->stream));
         k_particles_speculate<<<blocks, 128, 0, w->stream>>>(P);
         w->stats.kernel_launches++;
         // "who is unsure" to its fixed point: a pass that changes nobody ends it

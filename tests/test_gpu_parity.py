@@ -862,3 +862,26 @@ def test_device_dirty_error_paths():
     assert info[0] == 1 and int(moving.sum()) == 15 * 15
     assert g.pixels(0, 3, 3, 8, 8).shape == (8, 8, 4)
     g.close()
+
+
+def test_device_particles_short_list_path():
+    """lists of at most 1024 particles run their rounds inside one CTA (k_particles_small): the hand-made particles that
+    drive every branch, on a world that spawns none of its own, so the list stays short from the first tick on"""
+    from helpers import particle_scene
+    cells, zone, parts = particle_scene(seed=5)
+    parts = parts[:160]  # the hand-made ones, without the random crowd
+    g = gpu_world(cells, zone, particles=False)
+    o = oracle_world(cells, zone, particles=False)
+    g.add_particles(parts)
+    o.add_particles(parts)
+    for t in range(30):
+        g.tick(t)
+        o.tick(t)
+        g.tick_particles()
+        o.tick_particles()
+        _same_particles(t, g, o)
+        if t == 10:  # a second wave lands on what the first one built
+            g.add_particles(parts[:96])
+            o.add_particles(parts[:96])
+    g.close()
+    o.close()
