@@ -319,6 +319,10 @@ int fss_create(const fss_config* cfg, fss_world** out) {
         CUX(cudaMemsetAsync(w->g.fy, 0, n * 4, w->stream));
     }
     if(cfg->flags & FSS_TRACK_DIRTY) {
+        if(w->sharded) { // the marks a strip leaves in its ghost rows would have to travel with the halo exchange
+            fss_destroy(w);
+            return fail(FSS_ERR_INVALID, "FSS_TRACK_DIRTY is not available on strip-sharded worlds");
+        }
         if(w->k1_variant == 1) {
             fss_destroy(w);
             return fail(FSS_ERR_INVALID, "FSS_TRACK_DIRTY is not supported by the experimental FSS_K1=b kernel");

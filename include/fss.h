@@ -132,7 +132,7 @@ typedef struct fss_material {
                                  fss_render_dirty.  One more byte per cell; a compile-time kernel variant, off by default.  Works with
                                  the settled-chunk early-out: the reference re-marks every liquid cell in every sub-step
                                  (world.cpp:1814, :1823), so for a chunk whose visit is skipped the kernel notes the iter and the
-                                 marks are added before World::dirty is next looked at. */
+                                 marks are added before World::dirty is next looked at.  Not available on strip-sharded worlds. */
 
 typedef struct fss_config {
     uint32_t struct_size; /* sizeof(fss_config), for ABI evolution */

@@ -853,6 +853,8 @@ def test_device_dirty_error_paths():
     with pytest.raises(world.FssError):
         g.mark_dirty(0, 0, 8, 8)
     g.close()
+    with pytest.raises(world.FssError):
+        world.World(cells, zone, defs=full_table(), strip=(0, 128), track_dirty=True)  # no dirty plane on strips
     g = gpu_world(cells, zone, track_dirty=True)
     with pytest.raises(world.FssError):
         g.pixels(0)  # before the first render
