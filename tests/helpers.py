@@ -132,3 +132,31 @@ def _flat_cells(mat, shape, defs):
     c["color"] = defs[mat].color
     c["fluid_amount"] = 2.0
     return c
+
+
+def random_particles(seed, n, size):
+    """particles of every kind: fast ones (paths longer than the 64 cells that the device lists one by one), target forces,
+    `phase`, temporary ones, liquids of three materials, start cells anywhere (inside solids, outside the zone and the world)"""
+    rng = np.random.default_rng(seed)
+    parts = np.zeros(n, dtype=abi.LIVE_PARTICLE_DTYPE)
+    parts["x"] = rng.uniform(-4, size[0] + 4, n).astype(np.float32)
+    parts["y"] = rng.uniform(-4, size[1] + 4, n).astype(np.float32)
+    speed = np.where(rng.random(n) < 0.1, 100.0, 4.0)
+    parts["vx"] = (rng.uniform(-1, 1, n) * speed).astype(np.float32)
+    parts["vy"] = (rng.uniform(-1, 1, n) * speed).astype(np.float32)
+    parts["ay"] = np.float32(0.1)
+    parts["ax"] = (rng.uniform(-0.05, 0.05, n) * (rng.random(n) < 0.2)).astype(np.float32)
+    force = rng.random(n) < 0.1
+    parts["target_x"] = rng.uniform(0, size[0], n).astype(np.float32)
+    parts["target_y"] = rng.uniform(0, size[1], n).astype(np.float32)
+    parts["target_force"] = np.where(force, rng.uniform(0.1, 0.8, n), 0).astype(np.float32)
+    parts["phase"] = rng.random(n) < 0.05
+    parts["temporary"] = rng.random(n) < 0.15
+    parts["lifetime"] = rng.integers(0, 12, n)
+    parts["fade_time"] = 60
+    parts["in_object_state"] = rng.integers(0, 3, n)
+    parts["tile"]["material"] = rng.choice([M.TEST_SAND, M.WATER, M.LAVA, M.TEST_LIQUID, M.GOLD_ORE, M.FIRE, M.COBBLE_STONE], n)
+    parts["tile"]["color"] = rng.integers(0, 1 << 24, n)
+    parts["tile"]["fluid_amount"] = rng.uniform(0.01, 3.0, n).astype(np.float32)
+    parts["tile"]["temperature"] = rng.integers(-100, 100, n)
+    return parts

@@ -887,3 +887,30 @@ def test_device_particles_short_list_path():
             o.add_particles(parts[:96])
     g.close()
     o.close()
+
+
+@pytest.mark.parametrize("seed,n", [(1, 200), (2, 1500), (3, 6000)])
+def test_device_particles_fuzz(seed, n):
+    """random particles of every kind thrown into a busy world: fast ones (paths longer than the 64 cells that are listed
+    one by one), target forces, `phase`, temporary ones, liquids of three materials, start cells inside solids and
+    outside the zone; short-list path (n = 200), multi-kernel path, and the hand-over between them as the list shrinks"""
+    from helpers import random_particles
+    size = (392, 304)
+    cells, zone = make_world(size, "c3", seed=50 + seed)
+    parts = random_particles(seed, n, size)
+    g = gpu_world(cells, zone, particles=True, track_dirty=True)
+    o = oracle_world(cells, zone, particles=True)
+    g.add_particles(parts)
+    o.add_particles(parts)
+    for t in range(14):
+        g.tick(t)
+        o.tick(t)
+        g.tick_particles()
+        o.tick_particles()
+        _same_particles(t, g, o)
+        assert g.dirty().tobytes() == o.dirty().tobytes(), f"tick {t}: World::dirty differs"
+        if t == 6:  # a second batch while the first is still landing
+            g.add_particles(parts[: n // 2])
+            o.add_particles(parts[: n // 2])
+    g.close()
+    o.close()

@@ -117,6 +117,36 @@ def test_oracle_particle_tick_matches_reference_build(mix, have_ref):
     o.close()
 
 
+@pytest.mark.parametrize("seed,n", [(1, 200), (2, 1500)])
+def test_oracle_particle_tick_fuzz_matches_reference_build(seed, n, have_ref):
+    """random particles of every kind (helpers.random_particles) in a busy world: list, grid and dirty[] every tick"""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from helpers import random_particles
+    from oracle import refsim
+    size = (392, 304)
+    cells, zone = make_world(size, "c3", seed=50 + seed)
+    parts = random_particles(seed, n, size)
+    r = refsim.RefWorld(cells, zone, particles=True)
+    r.keep_particles()
+    o = oraclesim.OracleWorld(cells, zone, defs=full_table(), particles=True)
+    r.add_particles(parts)
+    o.add_particles(parts)
+    for t in range(14):
+        r.tick(t)
+        o.tick(t)
+        r.tick_particles()
+        o.tick_particles()
+        assert r.particle_list().tobytes() == o.particle_list().tobytes(), f"tick {t}"
+        assert r.cells().tobytes() == o.cells().tobytes(), f"tick {t}"
+        assert r.dirty().tobytes() == o.dirty().tobytes(), f"tick {t}"
+        if t == 6:
+            r.add_particles(parts[: n // 2])
+            o.add_particles(parts[: n // 2])
+    r.close()
+    o.close()
+
+
 def _looks():
     with open(os.path.join(GOLDEN, "materials_looks.json")) as f:
         d = json.load(f)
