@@ -141,6 +141,7 @@ struct fss_world {
     uint32_t *pl_idx[2];
     void* pl_tmp; // cub scratch
     size_t pl_tmp_bytes;
+    bool pl_used; // the caller keeps World::particles on the device (fss_tick_particles / fss_particles_add were called)
     uint64_t pl_rounds, pl_passes; // rounds / cascade passes of the last fss_tick_particles
     // dirty -> pixels (fss_render.cuh): the four RGBA layers, the flow map's smoothing state, Material::alpha / emitColor
     uint32_t* px[4];
@@ -858,6 +859,7 @@ int fss_particles_add(fss_world* w, const fss_particle* particles, size_t n) {
     for(size_t i = 0; i < n; i++)
         if(particles[i].tile.material >= w->n_mat) return fail(FSS_ERR_INVALID, "particle %zu: material %u of %d", i, particles[i].tile.material, w->n_mat);
     if(n == 0) return FSS_OK;
+    w->pl_used = true;
     if(int rc = particles_adopt(w)) return rc; // host pushes come after what the ticks so far pushed
     if(int rc = particles_reserve(w, (size_t)w->pl_n + n)) return rc;
     CU(cudaMemcpyAsync(w->pl_list + w->pl_n, particles, n * sizeof(fss_particle), cudaMemcpyHostToDevice, w->stream));
@@ -906,6 +908,7 @@ int fss_tick_particles(fss_world* w) {
     if(use_device(w)) return FSS_ERR_CUDA;
     if(w->sharded) return fail(FSS_ERR_STATE, "device particles are not available on strip-sharded worlds");
     if(!w->zone_set || !w->mats_set) return fail(FSS_ERR_STATE, "fss_set_materials and fss_set_tick_zone first");
+    w->pl_used = true;
     if(int rc = particles_adopt(w)) return rc;
     w->pl_rounds = w->pl_passes = 0;
     const uint32_t n = w->pl_n;
@@ -1352,6 +1355,14 @@ int fss_shift_grid(fss_world* w, int change_x, int change_y) {
     }
     w->temp2 = (int32_t*)spare;
     CU(cudaGetLastError());
+    if(w->pl_used) { // world.cpp:2729-2731: the particles move with the grid (what the ticks so far spawned is in the list by then)
+        if(int rc = particles_adopt(w)) return rc;
+        if(w->pl_n) {
+            k_particles_shift<<<(w->pl_n + 255) / 256, 256, 0, w->stream>>>(w->pl_list, w->pl_n, change_x, change_y);
+            CU(cudaGetLastError());
+            w->stats.kernel_launches++;
+        }
+    }
     return dirty_chunks(w, 0, 0, -1, -1);
 }
 

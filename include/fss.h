@@ -202,7 +202,8 @@ int fss_read_chunk_records(fss_world* w, int x0, int y0, int chunk_w, int chunk_
 
 /* World::tickChunks' grid shift when the camera moves (world.cpp:2617-2630): every cell moves by (change_x, change_y);
  * cells whose source would lie outside the grid keep their content, exactly like the reference's in-place loop.  The
- * caller then uploads the freshly loaded chunks into the vacated band.  Not available on strip-sharded worlds. */
+ * caller then uploads the freshly loaded chunks into the vacated band.  A device-resident particle list moves with the grid
+ * (world.cpp:2729-2731).  Not available on strip-sharded worlds. */
 int fss_shift_grid(fss_world* w, int change_x, int change_y);
 
 /* ---- the hot path ---------------------------------------------------------------------------- */

@@ -409,6 +409,18 @@ def test_shift_grid_matches_reference_loop(change):
     ok = (ox >= 0) & (ox < w) & (oy >= 0) & (oy < h)
     want[ok] = cells[oy[ok], ox[ok]]
     assert g.cells().tobytes() == want.tobytes()
+    # a device-resident particle list moves with the grid (world.cpp:2729-2731)
+    from helpers import random_particles
+    parts = random_particles(4, 300, (517, 301))
+    g2 = gpu_world(cells, zone)
+    g2.add_particles(parts)
+    g2.shift_grid(cx, cy)
+    want_p = parts.copy()
+    want_p["x"] = parts["x"] + np.float32(cx)
+    want_p["y"] = parts["y"] + np.float32(cy)
+    assert g2.particle_list().tobytes() == want_p.tobytes()
+    assert g2.cells().tobytes() == want.tobytes()
+    g2.close()
     # the world keeps ticking correctly afterwards (flags were reset): compare with the oracle on the shifted grid
     o = oracle_world(want, zone)
     for t in range(4):
