@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """World::tickParticles on the device (fss_tick_particles) next to the serial loop on the host.
 
-  python tune/bench_particles.py [--size 4096] [--ticks 12] [--cpu-size 1024]
+  python tests/perf/bench_particles.py [--size 4096] [--ticks 12] [--cpu-size 1024]
 
 Each step = World::tick (which feeds the list) + World::tickParticles.  The timed figure is the particle step alone (CUDA
 events around fss_tick_particles, which ends with a host read of the list length).  CPU: the reference's own lines
@@ -16,8 +16,8 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 
 
 def main():

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """The dirty -> pixels job of Game::tick (Game.cpp:2579-2650) on the device next to the reference's loop on the host.
 
-  python tune/bench_render.py [--size 8192] [--ticks 6] [--cpu-size 2048]
+  python tests/perf/bench_render.py [--size 8192] [--ticks 6] [--cpu-size 2048]
 
 Device: c3 fill, World::tick with FSS_TRACK_DIRTY | FSS_TRACK_FLOW (and without, for the cost of tracking), then
 fss_render_dirty timed with CUDA events (it ends with a host read of the counters).  CPU: the reference's own loop
@@ -12,8 +12,8 @@ import json
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 
 
 def main():
