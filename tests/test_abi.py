@@ -77,6 +77,8 @@ int main(void) {
   S(fss_reaction); S(fss_material); O(fss_material, reactions); O(fss_material, create_kind); O(fss_material, create_temperature);
   S(fss_config); O(fss_config, strip_y0); O(fss_config, condense_material);
   S(fss_particle_spawn); O(fss_particle_spawn, cell);
+  S(fss_particle); O(fss_particle, target_force); O(fss_particle, lifetime); O(fss_particle, in_object_state); O(fss_particle, phase); O(fss_particle, temporary); O(fss_particle, tile);
+  S(fss_render_info); O(fss_render_info, had_flow);
   S(fss_fill_spec); O(fss_fill_spec, cumulative_percent); O(fss_fill_spec, solid_from_row); O(fss_fill_spec, sparse_per_mille);
   S(fss_stats); O(fss_stats, storage_pitch);
   S(fss_tile_record); O(fss_tile_record, color); O(fss_tile_record, temperature);
@@ -90,7 +92,8 @@ int main(void) {
     out = dict(line.rsplit(" ", 1) for line in subprocess.check_output([str(exe)], text=True).splitlines() if not line.startswith("CHUNK"))
     out = {k: int(v) for k, v in out.items()}
     py = {"fss_cell": abi.CellStruct, "fss_reaction": abi.Reaction, "fss_material": abi.Material, "fss_config": abi.Config,
-          "fss_particle_spawn": abi.ParticleSpawn, "fss_fill_spec": abi.FillSpec, "fss_stats": abi.Stats}
+          "fss_particle_spawn": abi.ParticleSpawn, "fss_fill_spec": abi.FillSpec, "fss_stats": abi.Stats,
+          "fss_particle": abi.Particle, "fss_render_info": abi.RenderInfo}
     assert abi.RECORD_DTYPE.itemsize == out.pop("fss_tile_record") == 12
     assert abi.RECORD_DTYPE.fields["color"][1] == out.pop("fss_tile_record.color")
     assert abi.RECORD_DTYPE.fields["temperature"][1] == out.pop("fss_tile_record.temperature")
@@ -103,8 +106,43 @@ int main(void) {
     assert abi.CELL_DTYPE.itemsize == out["fss_cell"]
     assert abi.CELL_DTYPE.fields["fluid_amount_diff"][1] == out["fss_cell.fluid_amount_diff"]
     assert abi.PARTICLE_DTYPE.itemsize == out["fss_particle_spawn"]
+    assert abi.LIVE_PARTICLE_DTYPE.itemsize == out["fss_particle"] == 68
+    for f in ("target_force", "lifetime", "in_object_state", "phase", "temporary", "tile"):
+        assert abi.LIVE_PARTICLE_DTYPE.fields[f][1] == out["fss_particle." + f], f
     consts = subprocess.check_output([str(exe)], text=True).splitlines()[-1].split()[1:]
     assert [int(c) for c in consts] == [abi.FSS_CHUNK_W, abi.FSS_CHUNK_H, abi.FSS_ZONE_ALIGN_X, abi.FSS_ZONE_ALIGN_Y, abi.FSS_ZONE_MARGIN]
+
+
+def test_spawn_order_key_is_the_same_in_c_and_python(tmp_path):
+    """fss_spawn_order_key (fss.h) is what the device sorts by; abi.spawn_order is what the Python side merges strips with"""
+    rng = np.random.default_rng(5)
+    n = 4000
+    zone = (24, 40)
+    recs = np.zeros(n, dtype=abi.PARTICLE_DTYPE)
+    recs["tick_iter"] = rng.integers(0, 6, n) + 8 * rng.integers(0, 3, n)
+    recs["x"] = rng.integers(zone[0], zone[0] + 512, n)
+    recs["y"] = rng.integers(zone[1], zone[1] + 512, n)
+    prog = r'''
+#include <stdio.h>
+#include "fss.h"
+int main(void) {
+  unsigned t, x, y;
+  while(scanf("%u %u %u", &t, &x, &y) == 3) printf("%llu\n", (unsigned long long)fss_spawn_order_key(t, x, y, 24, 40));
+  return 0;
+}'''
+    src = tmp_path / "key.c"
+    src.write_text(prog)
+    exe = tmp_path / "key"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    text = "".join(f"{int(r['tick_iter'])} {int(r['x'])} {int(r['y'])}\n" for r in recs)
+    keys = np.array([int(v) for v in subprocess.check_output([str(exe)], input=text, text=True).split()], dtype=np.uint64)
+    assert len(keys) == n
+    order = abi.spawn_order(recs, zone)
+    assert np.array_equal(keys[order], np.sort(keys, kind="stable"))
+    # equal keys only for equal (tick_iter, x, y)
+    uniq = {}
+    for k, r in zip(keys, recs):
+        assert uniq.setdefault(int(k), (int(r["tick_iter"]), int(r["x"]), int(r["y"]))) == (int(r["tick_iter"]), int(r["x"]), int(r["y"]))
 
 
 def test_product_never_imports_the_oracle():
