@@ -451,6 +451,16 @@ int fss_set_materials(fss_world* w, const fss_material* t, int n) {
         if((m.flags & FSS_MAT_IS_FIRE) && fire_id < 0) fire_id = i;
     }
     if(w->cfg.condense_material >= n) return fail(FSS_ERR_INVALID, "condense_material %d >= %d materials", w->cfg.condense_material, n);
+    { // density ranks for `belowTile.mat->density < tile.mat->density` (world.cpp:1276-1285): equal densities, equal rank
+        std::vector<float> ds;
+        for(int i = 0; i < n; i++) ds.push_back(t[i].density);
+        std::sort(ds.begin(), ds.end());
+        ds.erase(std::unique(ds.begin(), ds.end()), ds.end());
+        for(int i = 0; i < n; i++) {
+            if(t[i].density != t[i].density) return fail(FSS_ERR_INVALID, "material %d: density is NaN", i);
+            tmp[i].bits |= (uint32_t)(std::lower_bound(ds.begin(), ds.end(), t[i].density) - ds.begin()) << MF_RANK_SHIFT;
+        }
+    }
     memcpy(w->h_mats, tmp, sizeof tmp);
     for(int i = 0; i < n; i++) w->h_iterations[i] = t[i].iterations; // the flow map divides by the real count (Game.cpp:2636)
     w->looks_stale = true;

@@ -1,7 +1,7 @@
 // fss_device.cuh -- device-side data layout of the world.
 //
 // HBM layout (DESIGN.md "data layout"): structure-of-arrays, five 4-byte planes
-//   mf    u32  material id | moved | cached physics type / iterations / is-fire | settleCount
+//   mf    u32  material id | cached density rank | moved | cached physics type / iterations / is-fire | settleCount
 //   color u32  MaterialInstance::color
 //   temp  i32  MaterialInstance::temperature   (two planes, ping-pong for the Jacobi stencil)
 //   amt   f32  MaterialInstance::fluidAmount
@@ -22,7 +22,9 @@
 #define FSS_HALO_ROWS 16 /* ghost rows stored above / below a strip */
 
 // ---- mf word -----------------------------------------------------------------------------------
-#define MF_MAT_MASK 0x0000FFFFu
+#define MF_MAT_MASK 0x000000FFu /* FSS_MAX_MATERIALS = 256 */
+#define MF_RANK_MASK 0x0000FF00u /* cached rank of the material's density among the table's distinct densities */
+#define MF_RANK_SHIFT 8
 #define MF_MOVED 0x00010000u
 #define MF_TYPE_SHIFT 17
 #define MF_TYPE_MASK 0x000E0000u
@@ -31,7 +33,7 @@
 #define MF_FIRE 0x00800000u
 #define MF_SETTLE_SHIFT 24
 #define MF_SETTLE_ONE 0x01000000u
-#define MF_DERIVED_MASK (MF_TYPE_MASK | MF_ITERS_MASK | MF_FIRE)
+#define MF_DERIVED_MASK (MF_RANK_MASK | MF_TYPE_MASK | MF_ITERS_MASK | MF_FIRE)
 
 __host__ __device__ __forceinline__ uint32_t fss_perm(uint32_t x) {
     return (x & ~255u) | ((x & 7u) << 5) | ((x >> 3) & 31u);

@@ -42,10 +42,8 @@ __global__ void k_code_pad(int* out) {
 template <int MODE, bool FLOW, bool DIRTY>
 __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS : (MODE == K1_NOGAS ? K1N_MIN_BLOCKS : K1_MIN_BLOCKS))
     k_substep(const __grid_constant__ SubstepParams p) {
-    __shared__ float sden[FSS_MAX_MATERIALS];
     __shared__ uint32_t sinfo[FSS_MAX_MATERIALS];
     for(int m = threadIdx.x; m < p.n_mat; m += K1_THREADS) {
-        sden[m] = p.mats[m].density;
         const DMat& d = p.mats[m];
         uint32_t stab = d.max_stability > 255 ? 255u : (uint32_t)d.max_stability;
         sinfo[m] = ((uint32_t)d.slip & 0xFFFFu) | (stab << 16) | (((uint32_t)d.n_react & 3u) << 24) |
@@ -69,7 +67,7 @@ __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS
         }
     }
 #endif
-    ChunkWalk<MODE, FLOW, DIRTY> w(p, sden, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y,
+    ChunkWalk<MODE, FLOW, DIRTY> w(p, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y,
                       __activemask());
     w.run(qown);
 }

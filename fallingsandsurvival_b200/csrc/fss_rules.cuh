@@ -229,7 +229,6 @@ struct ChunkWalk {
     static constexpr bool LIQ = MODE == K1_LIQUID;
     static constexpr bool GASFIRE = MODE == K1_GENERAL;
     const SubstepParams& p;
-    const float* sden;     // shared: density per material
     const uint32_t* sinfo; // shared: HI_* word per material
     int cx, cy;
     // storage offsets: own column dx is at pb + 32*dx (the four own columns share one 8-column group, so
@@ -244,8 +243,8 @@ struct ChunkWalk {
     unsigned long long vis; // tickVisited restricted to the chunk, bit dy*4+dx (flags set outside the chunk are
                             // never read back: the other buffer is cleared before reuse, world.cpp:1125-1131, :1998)
 
-    __device__ __forceinline__ ChunkWalk(const SubstepParams& p_, const float* sd, const uint32_t* si, int cx_, int cy_, unsigned wmask_)
-        : p(p_), sden(sd), sinfo(si), cx(cx_), cy(cy_), wmask(wmask_), busy(false), maybe_gas(false), vis(0ull) {
+    __device__ __forceinline__ ChunkWalk(const SubstepParams& p_, const uint32_t* si, int cx_, int cy_, unsigned wmask_)
+        : p(p_), sinfo(si), cx(cx_), cy(cy_), wmask(wmask_), busy(false), maybe_gas(false), vis(0ull) {
         pb = fss_perm((uint32_t)cx);
         pl = fss_perm((uint32_t)(cx - 1));
         pr = fss_perm((uint32_t)(cx + FSS_CHUNK_W));
@@ -269,11 +268,10 @@ struct ChunkWalk {
         unsigned dx = (unsigned)(x - cx), dy = (unsigned)(y - cy);
         if(dx < (unsigned)FSS_CHUNK_W && dy < (unsigned)FSS_CHUNK_H) vis |= 1ull << (dy * FSS_CHUNK_W + dx);
     }
-    __device__ __forceinline__ bool can_move_into(uint32_t dst_mf, float self_density) const {
-        // world.cpp:1276-1285: AIR, or not SOLID and lighter.  The density is looked up unconditionally (no branch in front
-        // of the shared-memory load), so the two or three tests of one visit have their lookups in flight together.
-        const float d = sden[mf_mat(dst_mf)];
-        return MF_IS(dst_mf, FSS_PHYS_AIR) || (!MF_IS(dst_mf, FSS_PHYS_SOLID) && d < self_density);
+    __device__ __forceinline__ bool can_move_into(uint32_t dst_mf, uint32_t self_mf) const {
+        // world.cpp:1276-1285: AIR, or not SOLID and lighter.  `density < density` is decided on the density RANKS cached in
+        // the two mf words (equal densities share a rank): no table lookup behind the neighbour's load.
+        return MF_IS(dst_mf, FSS_PHYS_AIR) || (!MF_IS(dst_mf, FSS_PHYS_SOLID) && (dst_mf & MF_RANK_MASK) < (self_mf & MF_RANK_MASK));
     }
     __device__ __forceinline__ void swap_cells(cidx_t a, cidx_t b) const {
         Cell ca = ld_cell(p.g, a), cb = ld_cell(p.g, b);
@@ -443,8 +441,7 @@ struct ChunkWalk {
         const cidx_t ib = i + g.pitch;
         const cidx_t ibl = il + p.g.pitch, ibr = ir + p.g.pitch;
         const uint32_t bmf = g.mf[ib], blmf = g.mf[ibl], brmf = g.mf[ibr]; // one batch of loads
-        const float dself = sden[mat];
-        const bool can_b = can_move_into(bmf, dself), can_l = can_move_into(blmf, dself), can_r = can_move_into(brmf, dself);
+        const bool can_b = can_move_into(bmf, mf), can_l = can_move_into(blmf, mf), can_r = can_move_into(brmf, mf);
         if(!can_b) return; // :1276, :1287
         busy = true;
         // the cell will move in 19 of 20 cases: its words and those of the cell below are requested now, so that the loads
@@ -579,8 +576,7 @@ struct ChunkWalk {
         }
         const cidx_t ibl = il + p.g.pitch, ibr = ir + p.g.pitch;
         const uint32_t blmf = g.mf[ibl], brmf = g.mf[ibr];
-        const float dself = sden[mat];
-        const bool can_l = can_move_into(blmf, dself), can_r = can_move_into(brmf, dself);
+        const bool can_l = can_move_into(blmf, mf), can_r = can_move_into(brmf, mf);
         if(!(can_l || can_r)) {
             // :1697-1734 with no open diagonal: whatever the pillar probe and its draw decide, `moved` ends up false
             if(mf & MF_MOVED) {
