@@ -228,6 +228,9 @@ template <int MODE, bool FLOW = false, bool DIRTY = false>
 struct ChunkWalk {
     static constexpr bool LIQ = MODE == K1_LIQUID;
     static constexpr bool GASFIRE = MODE == K1_GENERAL;
+    // K1_NOGAS: a SAND cell's first three loads are requested before the warp meets in the scan-1 prologue (measured on c2: 1 %
+    // off iters 0 / 1; not measured in the general kernel, which keeps them inside the rule)
+    static constexpr bool HOIST_SAND = MODE == K1_NOGAS;
     const SubstepParams& p;
     const uint32_t* sinfo; // shared: HI_* word per material
     int cx, cy;
@@ -427,7 +430,7 @@ struct ChunkWalk {
     }
 
     // ---- SAND, scan 1, world.cpp:1218-1337 -----------------------------------------------------------------
-    __device__ __forceinline__ void sand1(cidx_t i, int x, int y, uint32_t mf, unsigned long long bit) {
+    __device__ __forceinline__ void sand1(cidx_t i, int x, int y, uint32_t mf, unsigned long long bit, const uint32_t* pre = nullptr) {
         const Grid& g = p.g;
         const uint32_t mat = mf_mat(mf);
         // :1223-1249 interactions: `interact` is false for every material (Materials.cpp:128, :144)
@@ -440,7 +443,7 @@ struct ChunkWalk {
         }
         const cidx_t ib = i + g.pitch;
         const cidx_t ibl = il + p.g.pitch, ibr = ir + p.g.pitch;
-        const uint32_t bmf = g.mf[ib], blmf = g.mf[ibl], brmf = g.mf[ibr]; // one batch of loads
+        const uint32_t bmf = HOIST_SAND ? pre[0] : g.mf[ib], blmf = HOIST_SAND ? pre[1] : g.mf[ibl], brmf = HOIST_SAND ? pre[2] : g.mf[ibr];
         const bool can_b = can_move_into(bmf, mf), can_l = can_move_into(blmf, mf), can_r = can_move_into(brmf, mf);
         if(!can_b) return; // :1276, :1287
         busy = true;
@@ -501,6 +504,14 @@ struct ChunkWalk {
             const uint32_t mf = seen ? 0u : p.g.mf[i];
             const bool active = !seen && p.iter < mf_iters(mf);
             uint32_t solid_nb = 0u;
+            // the three cells a SAND cell looks at first, requested before the warp meets: every rule body that follows finds
+            // its first loads on the way instead of each divergent group exposing its own latency
+            uint32_t pre[3] = {0u, 0u, 0u};
+            if(HOIST_SAND && active && MF_IS(mf, FSS_PHYS_SAND)) {
+                pre[0] = p.g.mf[i + p.g.pitch];
+                pre[1] = p.g.mf[il + p.g.pitch];
+                pre[2] = p.g.mf[ir + p.g.pitch];
+            }
             if(GASFIRE) {
                 const unsigned fire_lanes = __ballot_sync(wmask, active && (mf & MF_FIRE));
                 if(fire_lanes) solid_nb = coop_fire_scan(fire_lanes, x, y);
@@ -510,6 +521,10 @@ struct ChunkWalk {
             if(seen) return;
             if(!active) { // :1163-1166
                 vis |= bit;
+                return;
+            }
+            if(HOIST_SAND && MF_IS(mf, FSS_PHYS_SAND)) {
+                sand1(i, x, y, mf, bit, pre);
                 return;
             }
             scan1_body(i, x, y, mf, bit, solid_nb);
