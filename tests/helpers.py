@@ -160,3 +160,21 @@ def random_particles(seed, n, size):
     parts["tile"]["fluid_amount"] = rng.uniform(0.01, 3.0, n).astype(np.float32)
     parts["tile"]["temperature"] = rng.integers(-100, 100, n)
     return parts
+
+
+def thin_liquid_world(seed=6, size=(200, 176)):
+    """liquids whose amounts sit around FLUID_MinValue (0.0005): the `amount < MinValue` exits of the SOUP rule
+    (world.cpp:1346-1350 and the four `remainingValue < FLUID_MinValue` exits, :1414 ... :1518) and the deletion in scan 2
+    (:1812-1815) all come into play, which a world of full cells (amount 2.0) never reaches"""
+    rng = np.random.default_rng(seed)
+    cells, zone = make_world(size, "liquids", seed=seed)
+    soup = np.isin(cells["material"], [M.WATER, M.LAVA, M.TEST_LIQUID, M.GOLD_MOLTEN])
+    r = rng.random(cells.shape)
+    amt = cells["fluid_amount"].copy()
+    amt[soup & (r < 0.15)] = 0.0
+    thin = soup & (r >= 0.15) & (r < 0.6)
+    amt[thin] = rng.uniform(0.0, 0.004, cells.shape).astype(np.float32)[thin]
+    mid = soup & (r >= 0.6) & (r < 0.8)
+    amt[mid] = rng.uniform(0.0, 0.6, cells.shape).astype(np.float32)[mid]
+    cells["fluid_amount"] = amt
+    return cells, zone

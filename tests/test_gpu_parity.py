@@ -926,3 +926,21 @@ def test_device_particles_fuzz(seed, n):
             o.add_particles(parts[: n // 2])
     g.close()
     o.close()
+
+
+def test_thin_liquids_match_oracle():
+    """amounts around FLUID_MinValue (helpers.thin_liquid_world): the early exits of the SOUP rule that full cells never reach"""
+    from helpers import thin_liquid_world
+    cells, zone = thin_liquid_world()
+    g = gpu_world(cells, zone, particles=True, track_dirty=True, track_flow=True)
+    o = oracle_world(cells, zone, particles=True)
+    for t in range(30):
+        g.tick(t)
+        o.tick(t)
+        a, b = g.cells(), o.cells()
+        assert a.tobytes() == b.tobytes(), f"tick {t}: " + diff_report(b, a)
+        assert g.dirty().tobytes() == o.dirty().tobytes(), f"tick {t}: dirty differs"
+    fa, fb = g.flow(), o.flow()
+    assert fa[0].tobytes() == fb[0].tobytes() and fa[1].tobytes() == fb[1].tobytes()
+    g.close()
+    o.close()

@@ -147,6 +147,25 @@ def test_oracle_particle_tick_fuzz_matches_reference_build(seed, n, have_ref):
     o.close()
 
 
+def test_oracle_thin_liquids_match_reference_build(have_ref):
+    """amounts around FLUID_MinValue: every early exit of the SOUP rule, every tick"""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from helpers import thin_liquid_world
+    from oracle import refsim
+    cells, zone = thin_liquid_world()
+    r = refsim.RefWorld(cells, zone, particles=True)
+    o = oraclesim.OracleWorld(cells, zone, defs=full_table(), particles=True)
+    for t in range(30):
+        r.tick(t)
+        o.tick(t)
+        a, b = r.cells(), o.cells()
+        assert a.tobytes() == b.tobytes(), f"tick {t}: " + diff_report(a, b)
+        assert r.dirty().tobytes() == o.dirty().tobytes(), f"tick {t}: dirty differs"
+    r.close()
+    o.close()
+
+
 def _looks():
     with open(os.path.join(GOLDEN, "materials_looks.json")) as f:
         d = json.load(f)
