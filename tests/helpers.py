@@ -178,3 +178,15 @@ def thin_liquid_world(seed=6, size=(200, 176)):
     amt[mid] = rng.uniform(0.0, 0.6, cells.shape).astype(np.float32)[mid]
     cells["fluid_amount"] = amt
     return cells, zone
+
+
+def fat_drops_world(seed=8, size=(200, 176)):
+    """liquid cells holding 8 to 20 units in open air: a falling cell then leaves the grid as n = amount / 4 particles of
+    amount / n each (world.cpp:1355-1371), which is the only way to get more than one spawn record per cell visit"""
+    rng = np.random.default_rng(seed)
+    cells, zone = make_world(size, [(M.WATER, 6), (M.LAVA, 2), (M.COBBLE_STONE, 6), (M.TEST_SAND, 4)], seed=seed)
+    soup = np.isin(cells["material"], [M.WATER, M.LAVA])
+    amt = cells["fluid_amount"].copy()
+    amt[soup] = rng.uniform(0.5, 20.0, cells.shape).astype(np.float32)[soup]
+    cells["fluid_amount"] = amt
+    return cells, zone

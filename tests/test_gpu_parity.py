@@ -944,3 +944,46 @@ def test_thin_liquids_match_oracle():
     assert fa[0].tobytes() == fb[0].tobytes() and fa[1].tobytes() == fb[1].tobytes()
     g.close()
     o.close()
+
+
+def test_fat_drops_match_oracle():
+    """several spawn records per cell visit (helpers.fat_drops_world): their order, the velocity draws 2j / 2j+1, landing"""
+    from helpers import fat_drops_world
+    cells, zone = fat_drops_world()
+    g = gpu_world(cells, zone, particles=True)
+    o = oracle_world(cells, zone, particles=True)
+    for t in range(16):
+        g.tick(t)
+        o.tick(t)
+        g.tick_particles()
+        o.tick_particles()
+        _same_particles(t, g, o)
+    g.close()
+    o.close()
+
+
+def test_sand_reaction_below_a_temperature():
+    """REACT_TEMPERATURE_BELOW on a SAND material (world.cpp:1255-1263): the shipped table only has the ABOVE kind on one"""
+    defs = full_table()
+    import copy
+    defs = [copy.copy(d) for d in defs]
+    defs[M.TEST_SAND].reactions = [(abi.REACT_TEMPERATURE_BELOW, -200, M.DIRT), (abi.REACT_TEMPERATURE_ABOVE, 300, M.GOLD_MOLTEN)]
+    cells, zone = make_world((264, 208), "c3", seed=12, defs=defs)
+    rng = np.random.default_rng(2)
+    sand = cells["material"] == M.TEST_SAND
+    cells["temperature"][sand] = rng.integers(-400, 500, cells.shape)[sand]
+    from fallingsandsurvival_b200 import world
+    from oracle import oraclesim
+    g = world.World(cells, zone, defs=defs, particles=True)
+    o = oraclesim.OracleWorld(cells, zone, defs=defs, particles=True)
+    for t in range(8):
+        g.tick(t)
+        o.tick(t)
+        if t % 4 == 2:
+            g.tick_temperature()
+            o.tick_temperature()
+        a, b = g.cells(), o.cells()
+        assert a.tobytes() == b.tobytes(), f"tick {t}: " + diff_report(b, a)
+    assert (b["material"] == M.DIRT).sum() > (cells["material"] == M.DIRT).sum()
+    g.close()
+    o.close()

@@ -166,6 +166,31 @@ def test_oracle_thin_liquids_match_reference_build(have_ref):
     o.close()
 
 
+def test_oracle_fat_drops_match_reference_build(have_ref):
+    """several particles per falling liquid cell (world.cpp:1355-1371): spawn order, the 2j / 2j+1 velocity draws, landing"""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from helpers import fat_drops_world
+    from oracle import refsim
+    cells, zone = fat_drops_world()
+    r = refsim.RefWorld(cells, zone, particles=True)
+    r.keep_particles()
+    o = oraclesim.OracleWorld(cells, zone, defs=full_table(), particles=True)
+    most = 0
+    for t in range(16):
+        r.tick(t)
+        o.tick(t)
+        r.tick_particles()
+        o.tick_particles()
+        a, b = r.particle_list(), o.particle_list()
+        assert a.tobytes() == b.tobytes(), f"tick {t}: particle lists differ ({len(a)} vs {len(b)})"
+        assert r.cells().tobytes() == o.cells().tobytes(), f"tick {t}"
+        most = max(most, len(b))
+    assert most > 100
+    r.close()
+    o.close()
+
+
 def _looks():
     with open(os.path.join(GOLDEN, "materials_looks.json")) as f:
         d = json.load(f)
