@@ -783,7 +783,13 @@ struct ChunkWalk {
         }
     }
 
-    static __device__ __forceinline__ void prefetch_l1(const void* q) { asm volatile("prefetch.global.L1 [%0];" ::"l"(q)); }
+    static __device__ __forceinline__ void prefetch_l1(const void* q) {
+#ifdef __CUDA_ARCH__
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+#else
+        (void)q; // tests/hostsim compiles these rules for the host
+#endif
+    }
 
     // first touch of a chunk row (dy may be -1 .. 15), issued ahead of the scan: own four columns of mf / amt / dif
     // plus the mf of the column either side
