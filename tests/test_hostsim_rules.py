@@ -18,10 +18,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GENERAL, NOGAS, LIQUID = 0, 1, 2
 
 
-@pytest.fixture(scope="module")
-def hostsim(tmp_path_factory):
-    so = tmp_path_factory.mktemp("hostsim") / "libhostsim.so"
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+def _build(tmp_path_factory, name, defines=()):
+    so = tmp_path_factory.mktemp(name) / "libhostsim.so"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", *defines,
                            "-I", os.path.join(ROOT, "tests", "hostsim", "shim"), "-I", os.path.join(ROOT, "fallingsandsurvival_b200", "csrc"),
                            "-o", str(so), os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")])
     L = C.CDLL(str(so))
@@ -37,6 +36,17 @@ def hostsim(tmp_path_factory):
     L.hs_drain.restype = C.c_size_t
     L.hs_drain.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     return L
+
+
+@pytest.fixture(scope="module")
+def hostsim(tmp_path_factory):
+    return _build(tmp_path_factory, "hostsim")
+
+
+@pytest.fixture(scope="module")
+def hostsim_decoupled(tmp_path_factory):
+    """the rules with the scan-2 experiment of fss_rules.cuh switched on (-DK1_DECOUPLED_SCAN2; off in the product build)"""
+    return _build(tmp_path_factory, "hostsim_dec", ["-DK1_DECOUPLED_SCAN2"])
 
 
 class HostSim:
@@ -128,3 +138,12 @@ def _compare(L, cells, zone, modes, flags, ticks, early_out=False):
             assert hs.drain().tobytes() == o.drain_particles().tobytes(), f"tick {t}: spawn records differ"
     hs.close()
     o.close()
+
+
+@pytest.mark.parametrize("mix", ["c2", "c3", "sand", "gas", "fire", "randmats"])
+def test_decoupled_scan2_experiment_matches_oracle(hostsim_decoupled, mix):
+    """the one-cursor-per-lane scan 2 (an experiment that is not in the product build): its order of operations inside a chunk"""
+    cells, zone = make_world((200, 176), mix, seed=800 + len(mix))
+    _compare(hostsim_decoupled, cells, zone, [GENERAL] * 6, abi.PARTICLES_EMIT | abi.TRACK_FLOW | abi.TRACK_DIRTY, ticks=10)
+    if mix in SPECIALISED:
+        _compare(hostsim_decoupled, cells, zone, SPECIALISED[mix], abi.PARTICLES_EMIT, ticks=10)
