@@ -25,7 +25,7 @@ struct int4 {
     int x, y, z, w;
 };
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
-static thread_local uint3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0};
+static thread_local uint3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, gridDim = {1, 1, 1};
 
 using std::max;
 using std::min;
@@ -52,6 +52,29 @@ static inline T __shfl_sync(unsigned, T v, int) { return v; }
 static inline unsigned __reduce_or_sync(unsigned, unsigned v) { return v; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
     unsigned long long old = *p;
+    *p = old + v;
+    return old;
+}
+
+/* ---- what csrc/fss_particles.cuh needs on top ---- */
+#define __constant__
+#define __shared__ static
+struct char2 {
+    signed char x, y;
+};
+static inline void __syncthreads() {}
+static inline unsigned atomicMin(unsigned* p, unsigned v) {
+    unsigned old = *p;
+    if(v < old) *p = v;
+    return old;
+}
+static inline unsigned atomicMax(unsigned* p, unsigned v) {
+    unsigned old = *p;
+    if(v > old) *p = v;
+    return old;
+}
+static inline unsigned atomicAdd(unsigned* p, unsigned v) {
+    unsigned old = *p;
     *p = old + v;
     return old;
 }
