@@ -4,6 +4,7 @@
 // inside every phase, so that the round scheme as written can be compared with the oracle without a GPU
 // (tests/test_hostsim_particles.py).  Restated here and therefore not covered: the host loop of fss_tick_particles, the
 // sort and the compaction (cub on the device), the cooperative-launch kernel.  Test infrastructure only.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <numeric>
@@ -243,11 +244,63 @@ int hp_tick(void* h, int slots_per_particle, int order) {
         for(uint32_t i : seq) particles_cascade_one<true>(P, i);
         uint32_t now = 0;
         std::vector<std::pair<uint32_t, int4>> go;
+        uint32_t why_unsure = 0, why_boxed = 0, why_reader_act = 0, why_reader_pot = 0;
         for(uint32_t i : seq) {
             if(decided[i]) continue;
             int4 a;
             if(particles_may_commit(P, i, a)) go.push_back({i, a});
-            else now++;
+            else {
+                now++;
+                if(getenv("HP_STATS")) { // why does it wait?
+                    if(!(sure[i] & PS_SURE)) ((sure[i] & PS_BOXED) ? why_boxed : why_unsure)++;
+                    else if(P.r_act[pcell_hash(act[i].y, act[i].z, P.res_mask)] < i) why_reader_act++;
+                    else why_reader_pot++;
+                }
+            }
+        }
+        if(getenv("HP_STATS"))
+            fprintf(stderr, "round %llu: %u undecided before, %zu act, wait: %u unsure, %u boxed, %u a lower particle looked at the target, %u may look; passes so far %llu\n",
+                    (unsigned long long)w->rounds + 1, left, go.size(), why_unsure, why_boxed, why_reader_act, why_reader_pot, (unsigned long long)w->passes);
+        if(getenv("HP_TWO_PHASE")) {
+            // EXPERIMENT (host only, to count rounds): a sure particle whose target was merely LOOKED AT by a lower particle need not
+            // wait if that particle acts in this very round (it looked before anybody wrote, which is its place in the serial
+            // order).  So: everybody who does not act publishes the cells it looked at (R_stay); a particle that would act but
+            // whose target is in R_stay of a lower one stays as well and publishes; repeat until nobody changes.
+            std::vector<uint32_t> r_stay(slots, 0xFFFFFFFFu);
+            std::vector<uint8_t> acts(n, 0);
+            auto publish_reads = [&](uint32_t i) {
+                fss_particle cur = P.in[i];
+                SeenPublish v{r_stay.data(), P.res_mask, i, 0x7fffffff, 0x7fffffff, -1, -1, 0};
+                int tx, ty, k0;
+                particle_walk(P, cur, v, tx, ty, k0);
+            };
+            go.clear();
+            now = 0;
+            for(uint32_t i : seq) {
+                if(decided[i]) continue;
+                const int4 a = act[i];
+                bool ok = (sure[i] & PS_SURE) && i < ctl[1];
+                if(ok && a.x >= PA_DEPOSIT) ok = !(P.r_pot[pcell_hash(a.y, a.z, P.res_mask)] < i || P.res_tile[ptile_of(P, a.y, a.z)] < i);
+                acts[i] = ok;
+                if(!ok) publish_reads(i);
+            }
+            for(bool changed = true; changed;) {
+                changed = false;
+                for(uint32_t i : seq) {
+                    if(decided[i] || !acts[i]) continue;
+                    const int4 a = act[i];
+                    if(a.x >= PA_DEPOSIT && r_stay[pcell_hash(a.y, a.z, P.res_mask)] < i) {
+                        acts[i] = 0;
+                        publish_reads(i);
+                        changed = true;
+                    }
+                }
+            }
+            for(uint32_t i : seq) {
+                if(decided[i]) continue;
+                if(acts[i]) go.push_back({i, act[i]});
+                else now++;
+            }
         }
         for(auto& it : go) particles_commit_one(P, it.first, it.second); // after every decision: like the kernel, decisions never see this round's writes
         w->rounds++;

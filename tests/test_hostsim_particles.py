@@ -113,3 +113,15 @@ def test_particle_kernels_dense_rain(hp):
     cells, zone = make_world((264, 240), [(M.TEST_SAND, 35), (M.WATER, 15), (M.COBBLE_STONE, 3)], seed=5)
     rounds = _run(hp, cells, zone, None, ticks=5, slots=16, order=2)
     assert rounds > 5
+
+
+def test_two_phase_commit_experiment(hp, monkeypatch):
+    """a round-count experiment that only exists in the host harness (HP_TWO_PHASE, tests/hostsim/hostsim_particles.cpp): a sure
+    particle does not wait for a lower particle that merely looked at its target if that one acts in the same round.  Must stay
+    exact to be worth building into the kernels (profiles/r01_tuning_log.md)."""
+    monkeypatch.setenv("HP_TWO_PHASE", "1")
+    cells, zone, parts = particle_scene()
+    _run(hp, cells, zone, parts, ticks=8, slots=16, order=2)
+    size = (392, 304)
+    cells, zone = make_world(size, "c3", seed=52)
+    _run(hp, cells, zone, random_particles(2, 1500, size), ticks=8, slots=1, order=0, second_wave_at=4)
