@@ -666,7 +666,8 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk) {
             if(flow) FSS_LAUNCH_K1(M, true, false); else FSS_LAUNCH_K1(M, false, false);           \
         }                                                                                          \
     } while(0)
-        if(mode == K1_LIQUID) FSS_LAUNCH_K1_MODE(K1_LIQUID);
+        if(liq_window_applies(mode, iter, w->cfg.flags, flow, dirty)) k_substep_liq<<<grid, K1_THREADS, 0, w->stream>>>(p);
+        else if(mode == K1_LIQUID) FSS_LAUNCH_K1_MODE(K1_LIQUID);
         else if(mode == K1_NOGAS) FSS_LAUNCH_K1_MODE(K1_NOGAS);
         else FSS_LAUNCH_K1_MODE(K1_GENERAL);
 #undef FSS_LAUNCH_K1_MODE

@@ -6,6 +6,7 @@
 //   k_rederive / k_hash / k_histogram / k_fluid_totals   bookkeeping
 #pragma once
 #include "fss_rules.cuh"
+#include "fss_rules_liq.cuh"
 #include "fss_rules_sm.cuh"
 
 #ifndef K1_THREADS
@@ -72,6 +73,25 @@ __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS
     w.run(qown);
 }
 
+// ---- K1w: liquid-only sub-step with the chunk rows in a register window (fss_rules_liq.cuh) ------------------------
+// Same grid and chunk ownership as k_substep; launched instead of k_substep<K1_LIQUID> where liq_window_applies().
+#ifndef K1W_MIN_BLOCKS
+#define K1W_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(K1_THREADS, K1W_MIN_BLOCKS) k_substep_liq(const __grid_constant__ SubstepParams p) {
+    const int gi = blockIdx.x * K1_THREADS + threadIdx.x;
+    if(gi >= p.nx) return;
+    uint8_t* qown = nullptr;
+#ifndef K1_NO_EARLY
+    if(p.q) {
+        qown = p.q + (size_t)(2 * (int)blockIdx.y + p.ofs_y + 1) * p.q_w + (2 * gi + p.ofs_x + 1);
+        if(*qown <= (uint8_t)p.iter) return; // verified settled
+    }
+#endif
+    LiqWalk w(p, nullptr, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y, 0u);
+    w.run(qown);
+}
+
 // ---- K1b: movement sub-step, window in shared memory, lanes decoupled (fss_rules_sm.cuh) ---------------------
 // One warp per CTA; grid = (ceil(nx / 32), ny); lane l of CTA bx owns the micro-chunk at column x_begin + 8*(32*bx + l).
 #ifndef K1B_MIN_BLOCKS
@@ -106,18 +126,24 @@ __global__ void __launch_bounds__(32, K1B_MIN_BLOCKS) k_substep_sm(const __grid_
 }
 
 // ---- K2: temperature stencil ---------------------------------------------------------------------------
-// One thread owns the 8 consecutive columns of one "group" (x >> 3) and walks TEMP_ROWS stored rows
-// top-down, keeping the conduction terms of rows y-1, y, y+1 (10 columns each: the group plus one column
-// either side) in registers.  Lanes of a warp own consecutive groups, so each of a thread's 8 (+2) loads per
-// row and plane is one fully used 128-byte line per warp.  The per-neighbour terms
+// World::tickTemperature, world.cpp:2043-2143.  One thread owns the 8 consecutive columns of one "group" (x >> 3) and
+// walks TEMP_ROWS stored rows top-down; lanes of a warp own consecutive groups, so each of a thread's loads is one fully
+// used 128-byte line per warp.  The per-neighbour terms
 //   factor = abs(T)/64.0f * conductionOther;  v += T*factor;  n += factor      (world.cpp:2072-2116)
-// depend only on the neighbour, so they are computed once per loaded cell; a cell with T == 0 contributes
-// (+0.0f, +0.0f), which leaves the fp32 running sums bit-identical to the reference's `if(T != 0)` skip.
+// depend only on the neighbour, so they are computed once per loaded cell and kept in registers for the three rows
+// they take part in; a cell with T == 0 contributes (+0.0f, +0.0f), which leaves the fp32 running sums bit-identical to
+// the reference's `if(T != 0)` skip.  The nine terms are added in the reference's order (x offset outer, y offset inner).
 // Output goes to the second temperature plane (Jacobi); cells outside tickZone are copied.
-#define TEMP_ROWS 32
+//
+// Round 2: the kernel was latency-bound at 10 warps per SM -- every row iteration issued its 20 loads and
+// waited for them.  Now the raw words of row y+2 are requested BEFORE row y is computed (software pipelining: a full row
+// of arithmetic, ~400 instructions, covers the DRAM latency), row pointers are carried instead of recomputed, the
+// per-material terms (1 - conductionSelf, float(addTemp)) come from shared-memory tables, and the row loop is unrolled
+// by three so that the three-row register window rotates by renaming.
+#define TEMP_ROWS 64
 #define TEMP_THREADS 128
 #ifndef K2_MIN_BLOCKS
-#define K2_MIN_BLOCKS 1
+#define K2_MIN_BLOCKS 3
 #endif
 
 struct TempParams {
@@ -129,38 +155,92 @@ struct TempParams {
     int own_lo, own_hi; // global rows this world computes (owned rows); other stored rows are copied
 };
 
-struct TempRow {
+struct TempRaw { // one stored row as loaded: columns x0-1 .. x0+8
+    int32_t t[10];
+    uint32_t m[10];
+};
+struct TempRow { // the conduction terms of one row, plus what the row needs when it is the centre row
     float f[10], tf[10];
+    int32_t t[8];
+    uint32_t mlo, mhi; // material ids of the 8 own columns, one byte each
 };
 
-__device__ __forceinline__ void temp_load_row(const TempParams& p, const float* s_co, size_t rowbase, const uint32_t* col_ofs,
-                                              TempRow& r, int32_t* tc, uint32_t* mc) {
+struct TempCols {
+    const int32_t* t;   // column x0 of the current stored row (temperature plane)
+    const uint32_t* mf; // same cell, mf plane
+    int lofs, rofs;     // word offsets of columns x0-1 and x0+8 relative to column x0
+};
+
+__device__ __forceinline__ void temp_request(const TempCols& c, size_t row_ofs, TempRaw& r) {
+    const int32_t* t = c.t + row_ofs;
+    const uint32_t* m = c.mf + row_ofs;
+    r.t[0] = t[c.lofs];
+    r.m[0] = m[c.lofs];
+#pragma unroll
+    for(int k = 0; k < 8; k++) {
+        r.t[k + 1] = t[32 * k];
+        r.m[k + 1] = m[32 * k];
+    }
+    r.t[9] = t[c.rofs];
+    r.m[9] = m[c.rofs];
+}
+
+__device__ __forceinline__ void temp_terms(const float* s_co, const TempRaw& r, TempRow& o) {
+    uint32_t lo = 0, hi = 0;
 #pragma unroll
     for(int c = 0; c < 10; c++) {
-        const size_t i = rowbase + col_ofs[c];
-        const int32_t t = p.g.temp[i];
-        const uint32_t m = mf_mat(p.g.mf[i]);
-        float f = 0.0f, tf = 0.0f;
-        if(t != 0) {
-            f = abs(t) / 64.0f * s_co[m];
-            tf = t * f;
+        const int32_t t = r.t[c];
+        const uint32_t m = mf_mat(r.m[c]);
+        // `if(T != 0) { factor = abs(T) / 64.0f * conductionOther; v += T * factor; n += factor; }` as selects
+        const float fa = abs(t) / 64.0f * s_co[m];
+        const float ta = t * fa;
+        o.f[c] = t != 0 ? fa : 0.0f;
+        o.tf[c] = t != 0 ? ta : 0.0f;
+        if(c >= 1 && c <= 4) lo |= m << (8 * (c - 1));
+        if(c >= 5 && c <= 8) hi |= m << (8 * (c - 5));
+        if(c >= 1 && c <= 8) o.t[c - 1] = t;
+    }
+    o.mlo = lo;
+    o.mhi = hi;
+}
+
+// the eight outputs of the row whose terms are in B (A = the row above, C = the row below)
+// s_self[m] = {conductionSelf, 1 - conductionSelf, float(addTemp), addTemp bits}
+__device__ __forceinline__ void temp_outputs(const float4* s_self, const TempRow& A, const TempRow& B, const TempRow& C, int32_t* out) {
+#pragma unroll
+    for(int r = 0; r < 8; r++) {
+        // neighbour order of world.cpp:2072-2116: x offset -1, 0, +1 outer; y offset -1, 0, +1 inner
+        float n = 0.01f, v = 0.0f;
+#pragma unroll
+        for(int c = r; c < r + 3; c++) {
+            v += A.tf[c];
+            n += A.f[c];
+            v += B.tf[c];
+            n += B.f[c];
+            v += C.tf[c];
+            n += C.f[c];
         }
-        r.f[c] = f;
-        r.tf[c] = tf;
-        if(c >= 1 && c <= 8) {
-            tc[c - 1] = t;
-            mc[c - 1] = m;
+        const uint32_t m = ((r < 4 ? B.mlo : B.mhi) >> (8 * (r & 3))) & 0xFFu;
+        const float4 self = s_self[m];
+        int32_t o;
+        if(v != 0) { // :2128-2132; addTemp is Uint32 (Material.hpp:40): `addTemp + float` converts it to float
+            o = (int32_t)(self.z + (v / n * self.x) + (B.t[r] * self.y));
+        } else {
+            o = (int32_t)(__float_as_uint(self.w) + (uint32_t)B.t[r]);
         }
+        out[32 * r] = o;
     }
 }
 
 __global__ void __launch_bounds__(TEMP_THREADS, K2_MIN_BLOCKS) k_temperature(const __grid_constant__ TempParams p) {
-    __shared__ float s_co[FSS_MAX_MATERIALS], s_cs[FSS_MAX_MATERIALS];
-    __shared__ uint32_t s_add[FSS_MAX_MATERIALS];
-    for(int m = threadIdx.x; m < p.n_mat; m += TEMP_THREADS) {
-        s_co[m] = p.mats[m].cond_other;
-        s_cs[m] = p.mats[m].cond_self;
-        s_add[m] = p.mats[m].add_temp;
+    __shared__ float s_co[FSS_MAX_MATERIALS];
+    __shared__ float4 s_self[FSS_MAX_MATERIALS];
+    for(int m = threadIdx.x; m < FSS_MAX_MATERIALS; m += TEMP_THREADS) {
+        const bool in = m < p.n_mat;
+        const float cs = in ? p.mats[m].cond_self : 1.0f;
+        const uint32_t add = in ? p.mats[m].add_temp : 0u;
+        s_co[m] = in ? p.mats[m].cond_other : 0.0f;
+        s_self[m] = make_float4(cs, 1 - cs, (float)add, __uint_as_float(add));
     }
     __syncthreads();
     const uint32_t grp = blockIdx.x * TEMP_THREADS + threadIdx.x;
@@ -171,62 +251,45 @@ __global__ void __launch_bounds__(TEMP_THREADS, K2_MIN_BLOCKS) k_temperature(con
     const size_t pitch = p.g.pitch;
     const uint32_t base = (grp >> 5) * 256u + (grp & 31u);
     const bool in_zone_x = x0 >= p.zx && x0 + 8 <= p.zx + p.zw;
+    // stored rows [c0, c1) of this band are computed, the others copied
     const int y_lo = max(p.zy, p.own_lo), y_hi = min(p.zy + p.zh, p.own_hi);
-
-    uint32_t col_ofs[10];
-#pragma unroll
-    for(int c = 0; c < 10; c++) col_ofs[c] = fss_perm((uint32_t)(x0 - 1 + c));
-
-    TempRow A, B, C;
-    int32_t tb[8], tcn[8];
-    uint32_t mb[8], mcn[8];
-    bool window = false; // A, B (and tb, mb) hold rows y-1, y
-#pragma unroll 1
+    int c0 = max(sr0, y_lo - p.g.sy0), c1 = min(sr1, y_hi - p.g.sy0);
+    if(!in_zone_x || c0 >= c1) c0 = c1 = sr1;
     for(int sr = sr0; sr < sr1; sr++) {
-        const int y = p.g.sy0 + sr;
-        const size_t rowbase = (size_t)sr * pitch;
-        if(!(in_zone_x && y >= y_lo && y < y_hi)) {
+        if(sr >= c0 && sr < c1) continue;
+        const size_t rb = (size_t)sr * pitch + base;
 #pragma unroll
-            for(int r = 0; r < 8; r++) p.out[rowbase + base + r * 32] = p.g.temp[rowbase + base + r * 32];
-            window = false;
-            continue;
-        }
-        if(!window) {
-            temp_load_row(p, s_co, rowbase - pitch, col_ofs, A, tcn, mcn);
-            temp_load_row(p, s_co, rowbase, col_ofs, B, tb, mb);
-            window = true;
-        }
-        temp_load_row(p, s_co, rowbase + pitch, col_ofs, C, tcn, mcn);
-#pragma unroll
-        for(int r = 0; r < 8; r++) {
-            // neighbour order of world.cpp:2072-2116: x offset -1, 0, +1 outer; y offset -1, 0, +1 inner
-            float n = 0.01f, v = 0.0f;
-#pragma unroll
-            for(int c = r; c < r + 3; c++) {
-                v += A.tf[c];
-                n += A.f[c];
-                v += B.tf[c];
-                n += B.f[c];
-                v += C.tf[c];
-                n += C.f[c];
-            }
-            const float cs = s_cs[mb[r]];
-            const uint32_t add = s_add[mb[r]];
-            int32_t o;
-            if(v != 0) { // :2128-2132; addTemp is Uint32 (Material.hpp:40)
-                o = (int32_t)(add + (v / n * cs) + (tb[r] * (1 - cs)));
-            } else {
-                o = (int32_t)(add + (uint32_t)tb[r]);
-            }
-            p.out[rowbase + base + r * 32] = o;
-        }
+        for(int r = 0; r < 8; r++) p.out[rb + r * 32] = p.g.temp[rb + r * 32];
+    }
+    if(c0 >= c1) return;
+
+    TempCols cols;
+    cols.t = p.g.temp + (size_t)c0 * pitch + base;
+    cols.mf = p.g.mf + (size_t)c0 * pitch + base;
+    cols.lofs = (int)fss_perm((uint32_t)(x0 - 1)) - (int)base;
+    cols.rofs = (int)fss_perm((uint32_t)(x0 + 8)) - (int)base;
+    int32_t* out = p.out + (size_t)c0 * pitch + base;
+
+    // rows c0-1 and c1 exist: the zone lies FSS_ZONE_MARGIN rows inside the world and a strip stores FSS_HALO_ROWS ghost rows
+    TempRow A, B, C;
+    TempRaw raw;
+    temp_request(cols, (size_t)0 - pitch, raw);
+    temp_terms(s_co, raw, A);
+    temp_request(cols, 0, raw);
+    temp_terms(s_co, raw, B);
+    temp_request(cols, pitch, raw);
+    // invariant at the top of an iteration for stored row sr: A, B = terms of rows sr-1, sr; `raw` = the words of row sr+1,
+    // requested while the previous row's outputs were computed
+#pragma unroll 3
+    for(int sr = c0; sr < c1; sr++) {
+        temp_terms(s_co, raw, C);
+        if(sr + 1 < c1) temp_request(cols, 2 * pitch, raw); // row sr+2, used by the next iteration: in flight during the outputs below
+        temp_outputs(s_self, A, B, C, out);
         A = B;
         B = C;
-#pragma unroll
-        for(int r = 0; r < 8; r++) {
-            tb[r] = tcn[r];
-            mb[r] = mcn[r];
-        }
+        cols.t += pitch;
+        cols.mf += pitch;
+        out += pitch;
     }
 }
 

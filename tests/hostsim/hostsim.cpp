@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "fss_rules.cuh"
+#include "fss_rules_liq.cuh"
 
 struct HostWorld {
     int width, height;
@@ -41,8 +42,14 @@ static void run_launch(HostWorld* w, const SubstepParams& p) {
                 qown = p.q + (size_t)(2 * by + p.ofs_y + 1) * p.q_w + (2 * gi + p.ofs_x + 1);
                 if(*qown <= (uint8_t)p.iter) continue;
             }
-            ChunkWalk<MODE, FLOW, DIRTY> walk(p, w->sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * by, 1u);
-            walk.run(qown);
+            const int cx = p.x_begin + 2 * FSS_CHUNK_W * gi, cy = p.y_begin + 2 * FSS_CHUNK_H * by;
+            if(liq_window_applies(MODE, p.iter, p.flags, FLOW, DIRTY)) { // launch_substep's choice (csrc/fss_abi.cu)
+                LiqWalk walk(p, w->sinfo, cx, cy, 1u);
+                walk.run(qown);
+            } else {
+                ChunkWalk<MODE, FLOW, DIRTY> walk(p, w->sinfo, cx, cy, 1u);
+                walk.run(qown);
+            }
         }
     }
 }

@@ -111,6 +111,15 @@ def test_rule_code_matches_oracle_specialised_kernels(hostsim, mix, flags):
     _compare(hostsim, cells, zone, SPECIALISED[mix], flags, ticks=12)
 
 
+@pytest.mark.parametrize("mix", sorted(SPECIALISED))
+def test_register_window_liquid_path_matches_oracle(hostsim, mix):
+    """csrc/fss_rules_liq.cuh (LiqWalk: the liquid-only sub-steps with the chunk rows in registers, scan 2 fused in) takes over
+    from ChunkWalk<K1_LIQUID> where liq_window_applies(): iter >= 1, particles off, no flow / dirty planes"""
+    cells, zone = make_world((200, 176), mix, seed=900 + len(mix))
+    _compare(hostsim, cells, zone, SPECIALISED[mix], 0, ticks=16)
+    _compare(hostsim, cells, zone, SPECIALISED[mix], 0, ticks=30, early_out=True)
+
+
 def test_rule_code_with_early_out(hostsim):
     """the settled-chunk flags as the rules maintain them (ChunkWalk::run): skipping must not change anything"""
     cells, zone = make_world((264, 208), "pockets", seed=9)
