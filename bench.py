@@ -160,80 +160,78 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    workload = args.workload
-    r = cpu_tick_throughput(workload, args.steps, args.warmup, workload == "c3")
+    workload = default_workload(args)
+    r = cpu_tick_throughput("c2" if workload == "c4" else workload, args.steps, args.warmup, workload == "c3")
+    zw, zh = main_zone(workload, args.size, args.gpus)
+    cfg = workload_config(workload, args.gpus, (zw, zh), early_out=not args.no_early_out)
+    cfg["timed_zone_cells"] = list(CPU_SAMPLE_ZONE)  # what this arm's steps actually cover: a bounded sample of the workload
     line = {
         "impl": "reference", "metric": "cell-updates/sec", "value": r["value"], "unit": "cell-updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic",
-        "config": workload_config(workload, args.gpus, args.size),
+        "scaling": "strong" if workload == "c4" else "weak", "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic",
+        "config": cfg,
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(workload, n, size, zone_wh=None):
-    zone_wh = zone_wh or (size, size * n)
+FILLS = {
+    "c2": "25% TEST_SAND / 20% WATER / 10% COBBLE_STONE, rest AIR (hash(seed, x, y) % 100)",
+    "c3": "c2 fill + 3% LAVA 2% FIRE 3% GOLD_ORE 3% STEAM 5% SOFT_DIRT",
+    "c4": "25% TEST_SAND / 20% WATER / 10% COBBLE_STONE, rest AIR (hash(seed, x, y) % 100)",
+    "c5": "rows below 90% height COBBLE_STONE; above: 0.1% TEST_SAND scattered + 64 boxes of 256 x 256 cells with the c2 fill",
+}
+
+
+def workload_config(workload, n, zone_wh, early_out=True):
     return {"workload": {"c4": "BASELINE.json configs[3]: 65536 x 65536 world strip-sharded with per-sub-step halo exchange over NVLink (NCCL)",
                          "c2": "BASELINE.json configs[1]: synthetic random sand/water/stone world, movement-only tick",
                          "c3": "BASELINE.json configs[2]: configs[1] + lava/fire/gold ore/steam/soft dirt, tickTemperature every 4th tick",
                          "c5": "BASELINE.json configs[4]: mostly settled world with sparse active boxes"}[workload],
             "zone_cells": list(zone_wh), "zone_cells_per_gpu": [zone_wh[0], zone_wh[1] // n], "strips": n,
-            "fill": "25% TEST_SAND / 20% WATER / 10% COBBLE_STONE" + (" + 3% LAVA 2% FIRE 3% GOLD_ORE 3% STEAM 5% SOFT_DIRT" if workload == "c3" else ""),
-            "particles": "off", "early_out": "on (chunks verified settled are skipped; results identical)", "l2": "working set (5 planes x 4 B x cells) is far larger than the 126 MB L2; no flush needed"}
+            "fill": FILLS[workload], "particles": "off",
+            "early_out": "on (chunks verified settled are skipped; results identical)" if early_out else "off (FSS_NO_EARLY_OUT: every micro-chunk visited in every sub-step)",
+            "l2": "working set (5 planes x 4 B x cells) is far larger than the 126 MB L2; no flush needed"}
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
-                    help="c4 = BASELINE configs[3]: ONE 65536 x 65536 zone cut into --gpus strips (strong scaling; needs >= 2 GPUs)")
-    ap.add_argument("--size", type=int, default=ZONE_PER_GPU, help="zone cells per GPU along each axis (multiple of 32)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-early-out", action="store_true", help="visit every micro-chunk in every sub-step (FSS_NO_EARLY_OUT)")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
+def default_workload(args):
+    """N = 1: c2 (BASELINE configs[1]); N > 1: c4 (configs[3], ONE 65536 x 65536 world cut into N strips: strong scaling)"""
+    if args.workload:
+        return args.workload
+    return "c2" if args.gpus == 1 else "c4"
 
+
+def main_zone(workload, size, n):
+    if workload == "c4":
+        s = size or 65536
+        return s, s
+    s = size or (32768 if workload == "c5" else ZONE_PER_GPU)
+    return s, s * n
+
+
+def measure(args, workload, size, steps, warmup, early_out=True, e2e_steps=0, per_launch=True, rank=0, n=1, local=0):
+    """Build the workload's world on the device(s), time `steps` ticks after `warmup`, return a dict of raw measurements."""
     import torch
     import torch.distributed as dist
 
     from fallingsandsurvival_b200 import materials as M
-    from fallingsandsurvival_b200 import strips, world
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fallingsandsurvival_b200 import strips
     import helpers
 
-    rank = int(os.environ.get("RANK", "0"))
-    n = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert n == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={n}: launch with torchrun --nproc-per-node {args.gpus}"
-    torch.cuda.set_device(local)
-    if n > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    S = args.size
-    ZW, ZH = S, S * n
-    if args.workload == "c4":
-        ZW = ZH = 65536 if args.size == ZONE_PER_GPU else args.size
+    ZW, ZH = main_zone(workload, size, n)
     W, H = ZW + 2 * BORDER, ZH + 2 * BORDER
     zone = (BORDER, BORDER, ZW, ZH)
     defs = helpers.full_table()
-    workload = args.workload
     temperature = workload == "c3"
-
-    rw = strips.RankWorld((W, H), zone, rank, n, local, defs=defs, early_out=not args.no_early_out)
+    rw = strips.RankWorld((W, H), zone, rank, n, local, defs=defs, early_out=early_out)
     g = rw.world
     stream = torch.cuda.Stream()  # a real stream: handle 0 would mean "the world's own stream" to fss_set_stream
     torch.cuda.set_stream(stream)
     g.set_stream(stream.cuda_stream)
     fill = dict(seed=0xF55, border=BORDER)
     if workload == "c5":
-        fill.update(solid_from_row=int(H * 0.9), n_boxes=64 if S >= 4096 else 4, box_size=256, sparse_material=M.TEST_SAND, sparse_per_mille=1)
+        fill.update(solid_from_row=int(H * 0.9), n_boxes=64 if ZW >= 4096 else 4, box_size=256, sparse_material=M.TEST_SAND, sparse_per_mille=1)
     g.fill_synthetic(mixes()[workload], **fill)
     g.sync()
 
@@ -242,6 +240,13 @@ def main():
         if n > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if n == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     tick_ct = 0
 
@@ -252,7 +257,7 @@ def main():
             g.tick_temperature()
         tick_ct += 1
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     barrier()
     sampler = ClockSampler(local)
@@ -262,18 +267,27 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     ev1.record(stream)
     barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = g.stats().kernel_launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    out = {"zone": (ZW, ZH), "ms": max_over_ranks(ev0.elapsed_time(ev1)), "launches": g.stats().kernel_launches - launches0,
+           "clocks": sampler.stop() if rank == 0 else None, "stored_cells": (g.stored[1] - g.stored[0]) * g.stats().storage_pitch}
+
+    # the grid after warmup + steps ticks, as one number: fss_hash per strip, summed (mod 2^64) over the ranks.  The same
+    # world at a different GPU count must give the same digest: the driver-visible proof that the strips are bit-exact.
+    digest = g.hash()
+    if n > 1:
+        t = torch.tensor([digest - (1 << 64) if digest >= (1 << 63) else digest], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)  # two's complement wrap-around = addition mod 2^64
+        digest = int(t.item()) & 0xFFFFFFFFFFFFFFFF
+    out["digest"] = f"{digest:016x}"
+    out["digest_after_ticks"] = tick_ct
 
     # K1 alone, per launch, for the roofline: one more tick with an event pair around every sub-step launch
-    k1_ms = []
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(SUBSTEPS + 1)]
-    if n == 1:
+    out["k1_ms"] = []
+    if n == 1 and per_launch:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(SUBSTEPS + 1)]
         evs[0].record(stream)
         k = 0
         for it in range(6):
@@ -283,40 +297,39 @@ def main():
                 evs[k].record(stream)
         tick_ct += 1
         torch.cuda.synchronize()
-        k1_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(SUBSTEPS)]
+        out["k1_ms"] = [evs[i].elapsed_time(evs[i + 1]) for i in range(SUBSTEPS)]
 
-    k2_ms = None
+    out["k2_ms"] = None
     if temperature and n == 1:
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g.tick_temperature()
         torch.cuda.synchronize()
         t0e.record(stream)
-        for _ in range(3):
+        for _ in range(5):
             g.tick_temperature()
         t1e.record(stream)
         torch.cuda.synchronize()
-        k2_ms = t0e.elapsed_time(t1e) / 3
+        out["k2_ms"] = t0e.elapsed_time(t1e) / 5
 
     # ---- e2e: host buffers through the C ABI --------------------------------------------------------------
     y0, y1 = g.stored
     rows = y1 - y0
-    e2e_ms = e2e_win_ms = None
-    ww = wh = 0
-    if args.e2e_steps > 0:
+    out["e2e"] = None
+    if e2e_steps > 0:
         host = torch.empty((rows, W, 20), dtype=torch.uint8, pin_memory=True).numpy().view(helpers.abi.CELL_DTYPE).reshape(rows, W)
         g.download(0, y0, W, rows, out=host)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
+        for _ in range(e2e_steps):
             g.upload(0, y0, host)
             step()
             g.download(0, y0, W, rows, out=host)
         e1.record(stream)
         barrier()
         e2e_wall = time.perf_counter() - t0
-        e2e_ms = max(e0.elapsed_time(e1), e2e_wall * 1e3)
+        e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), e2e_wall * 1e3))
 
         # the same loop with the rectangle the reference game itself keeps loaded (1024 x 768 cells, Game.cpp:450-452)
         # instead of the whole grid: what a shim that tracks its edits pays per tick
@@ -326,73 +339,137 @@ def main():
         barrier()
         w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0.record(stream)
-        for _ in range(args.e2e_steps):
+        for _ in range(e2e_steps):
             g.upload(wx, wy, win)
             step()
             g.download(wx, wy, ww, wh, out=win)
         w1.record(stream)
         barrier()
-        e2e_win_ms = w0.elapsed_time(w1)
+        e2e_win_ms = max_over_ranks(w0.elapsed_time(w1))
+        cells = ZW * ZH
+        out["e2e"] = {"value": cells * e2e_steps / (e2e_ms / 1e3), "unit": "cell-updates/s",
+                      "h2d_bytes_per_step": int(rows * W * 20), "d2h_bytes_per_step": int(rows * W * 20), "steps": e2e_steps,
+                      "ms_per_step": e2e_ms / e2e_steps,
+                      "what": "per step: fss_upload_rect(whole stored grid of the rank, pinned host) + fss_tick + fss_download_rect(whole stored grid)"}
+        out["e2e_window"] = {"value": cells * e2e_steps / (e2e_win_ms / 1e3), "unit": "cell-updates/s", "ms_per_step": e2e_win_ms / e2e_steps,
+                             "h2d_bytes_per_step": int(ww * wh * 20), "d2h_bytes_per_step": int(ww * wh * 20),
+                             "what": "same, but only a 1024 x 768 rectangle (the reference game's loaded window) crosses PCIe each step"}
+        del host, win
+    g.close()
+    torch.cuda.empty_cache()
+    return out
 
-    def max_over_ranks(v):
-        if n == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
 
-    ms = max_over_ranks(ms)
-    if e2e_ms is not None:
-        e2e_ms = max_over_ranks(e2e_ms)
-        e2e_win_ms = max_over_ranks(e2e_win_ms)
+def k1_roofline(k1_ms, zone_cells, workload, size):
+    peak, peak_src = measured_peak()
+    avg = float(np.mean(k1_ms))
+    algo = ALGO_BYTES_PER_CELL_UPDATE * zone_cells / SUBSTEPS  # bytes per k_substep launch
+    sweep = 2.0 * CELL_BYTES_PLANES * zone_cells / 4            # active micro-chunks read + written once, all planes
+    traffic, traffic_src = ncu_traffic(workload, size)
+    return {
+        "kernel": "k_substep (K1: k_substep<NOGAS> iters 0-1, k_substep_liq iters 2-5 on the c2 fill)", "bound": "hbm",
+        "achieved": algo / (avg / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+        "frac": algo / (avg / 1e3) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
+        "dram_achieved": (traffic / (avg / 1e3) / 1e9) if traffic else None,
+        "dram_frac": (traffic / (avg / 1e3) / 1e9 / peak) if traffic else None, "peak_source": peak_src,
+        "launch_ms_avg": avg, "launch_ms_by_iter": [float(np.sum(k1_ms[4 * i:4 * i + 4])) for i in range(6)],
+        "algorithmic_bytes_per_launch": algo,
+        "note": "algorithmic = 32 B per cell-update (whole tick) x zone cells / 24 launches per tick; the shipped schedule "
+                "sweeps the active quarter of the grid once per launch: see sweep_*",
+        "sweep_bytes_per_launch": sweep, "sweep_achieved": sweep / (avg / 1e3) / 1e9, "sweep_frac": sweep / (avg / 1e3) / 1e9 / peak,
+    }
+
+
+def k2_roofline(k2_ms, stored_cells):
+    peak, _ = measured_peak()
+    return {"kernel": "k_temperature", "bound": "hbm", "launch_ms": k2_ms, "unit": "GB/s",
+            "achieved": 12.0 * stored_cells / (k2_ms / 1e3) / 1e9, "peak": peak,
+            "frac": 12.0 * stored_cells / (k2_ms / 1e3) / 1e9 / peak,
+            "note": "12 B per cell-temperature-update (read temp + mf, write temp) x stored cells"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=["c2", "c3", "c4", "c5"],
+                    help="default: c2 at --gpus 1, c4 (BASELINE configs[3]: ONE 65536 x 65536 zone cut into --gpus strips, strong scaling) above")
+    ap.add_argument("--size", type=int, default=None, help="zone cells per GPU along each axis (multiple of 32); c4: the whole zone")
+    ap.add_argument("--e2e-steps", type=int, default=None, help="default 5 (3 for c4, whose strips are tens of GB per rank)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra.c3 / extra.c5 records of the default N = 1 line")
+    ap.add_argument("--no-early-out", action="store_true", help="visit every micro-chunk in every sub-step (FSS_NO_EARLY_OUT)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+    rank = int(os.environ.get("RANK", "0"))
+    n = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert n == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={n}: launch with torchrun --nproc-per-node {args.gpus}"
+    torch.cuda.set_device(local)
+    if n > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    workload = default_workload(args)
+    explicit = args.workload is not None or args.size is not None
+    e2e_steps = args.e2e_steps if args.e2e_steps is not None else (3 if workload == "c4" else 5)
+    m = measure(args, workload, args.size, args.steps, args.warmup, early_out=not args.no_early_out, e2e_steps=e2e_steps,
+                rank=rank, n=n, local=local)
+    ZW, ZH = m["zone"]
     zone_cells = ZW * ZH
-    value = zone_cells * args.steps / (ms / 1e3)
+    line = None
     if rank == 0:
-        peak, peak_src = measured_peak()
         line = {
-            "metric": "cell-updates/sec", "value": value, "unit": "cell-updates/s", "n_gpus": n, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if workload == "c4" else "weak",
-            "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic", "config": workload_config(workload, n, S, (ZW, ZH)),
-            "gpu_launches": int(launches), "clocks": clocks,
+            "metric": "cell-updates/sec", "value": zone_cells * args.steps / (m["ms"] / 1e3), "unit": "cell-updates/s", "n_gpus": n, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps, "higher_is_better": True, "scaling": "strong" if workload == "c4" else "weak",
+            "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic", "config": workload_config(workload, n, (ZW, ZH), early_out=not args.no_early_out),
+            "gpu_launches": int(m["launches"]), "clocks": m["clocks"],
+            "digest": m["digest"], "digest_what": f"fss_hash of the whole grid (sum over ranks mod 2^64) after {m['digest_after_ticks']} ticks; "
+                                                  "identical for every --gpus N on the same workload",
         }
-        if e2e_ms is not None:
-            line["e2e"] = {"value": zone_cells * args.e2e_steps / (e2e_ms / 1e3), "unit": "cell-updates/s",
-                    "h2d_bytes_per_step": int(rows * W * 20), "d2h_bytes_per_step": int(rows * W * 20), "steps": args.e2e_steps,
-                    "ms_per_step": e2e_ms / args.e2e_steps,
-                    "what": "per step: fss_upload_rect(whole stored grid, pinned host) + fss_tick + fss_download_rect(whole stored grid)"}
-            line["e2e_window"] = {"value": zone_cells * args.e2e_steps / (e2e_win_ms / 1e3), "unit": "cell-updates/s", "ms_per_step": e2e_win_ms / args.e2e_steps,
-                           "h2d_bytes_per_step": int(ww * wh * 20), "d2h_bytes_per_step": int(ww * wh * 20),
-                           "what": "same, but only a 1024 x 768 rectangle (the reference game's loaded window) crosses PCIe each step"}
-        if k1_ms:
-            avg = float(np.mean(k1_ms))
-            algo = ALGO_BYTES_PER_CELL_UPDATE * zone_cells / SUBSTEPS  # bytes per k_substep launch
-            sweep = 2.0 * CELL_BYTES_PLANES * zone_cells / 4            # active micro-chunks read + written once, all planes
-            traffic, traffic_src = ncu_traffic(workload, S)
-            line["roofline"] = {
-                "kernel": "k_substep", "bound": "hbm", "achieved": algo / (avg / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": algo / (avg / 1e3) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "dram_achieved": (traffic / (avg / 1e3) / 1e9) if traffic else None,
-                "dram_frac": (traffic / (avg / 1e3) / 1e9 / peak) if traffic else None, "peak_source": peak_src,
-                "launch_ms_avg": avg, "launch_ms_by_iter": [float(np.sum(k1_ms[4 * i:4 * i + 4])) for i in range(6)],
-                "algorithmic_bytes_per_launch": algo,
-                "note": "algorithmic = 32 B per cell-update (whole tick) x zone cells / 24 launches per tick; the shipped schedule "
-                        "sweeps the active quarter of the grid once per launch: see sweep_*",
-                "sweep_bytes_per_launch": sweep, "sweep_achieved": sweep / (avg / 1e3) / 1e9, "sweep_frac": sweep / (avg / 1e3) / 1e9 / peak,
-            }
-        if k2_ms is not None:
-            stored_cells = (y1 - y0) * g.stats().storage_pitch
-            line["roofline_k2"] = {"kernel": "k_temperature", "bound": "hbm", "launch_ms": k2_ms, "unit": "GB/s",
-                                   "achieved": 12.0 * stored_cells / (k2_ms / 1e3) / 1e9, "peak": peak,
-                                   "frac": 12.0 * stored_cells / (k2_ms / 1e3) / 1e9 / peak,
-                                   "note": "12 B per cell-temperature-update (read temp + mf, write temp) x stored cells"}
+        if m["e2e"]:
+            line["e2e"] = m["e2e"]
+            line["e2e_window"] = m["e2e_window"]
+        if m["k1_ms"]:
+            line["roofline"] = k1_roofline(m["k1_ms"], zone_cells, workload, ZW)
+        if m["k2_ms"] is not None:
+            line["roofline_k2"] = k2_roofline(m["k2_ms"], m["stored_cells"])
+
+    # ---- the other single-GPU BASELINE configs, a few ticks each (default N = 1 run only) -------------------------
+    if n == 1 and not explicit and not args.no_extras:
+        extra = {}
+        c3 = measure(args, "c3", None, 8, 4, e2e_steps=0)
+        extra["c3"] = {"config": workload_config("c3", 1, c3["zone"]), "steps": 8, "warmup": 4, "ms_per_step": c3["ms"] / 8,
+                       "value": c3["zone"][0] * c3["zone"][1] * 8 / (c3["ms"] / 1e3), "unit": "cell-updates/s", "digest": c3["digest"],
+                       "launch_ms_by_iter": [float(np.sum(c3["k1_ms"][4 * i:4 * i + 4])) for i in range(6)],
+                       "roofline_k2": k2_roofline(c3["k2_ms"], c3["stored_cells"]),
+                       "note": "tickTemperature runs in the timed region every 4th tick (Game.cpp:2759); roofline_k2 = k_temperature alone, 5 launches"}
+        line["roofline_k2"] = extra["c3"]["roofline_k2"]
+        on = measure(args, "c5", None, 8, 6, early_out=True, e2e_steps=0, per_launch=False)
+        off = measure(args, "c5", None, 4, 2, early_out=False, e2e_steps=0, per_launch=False)
+        cells5 = on["zone"][0] * on["zone"][1]
+        extra["c5"] = {"config": workload_config("c5", 1, on["zone"]), "steps": 8, "warmup": 6,
+                       "ms_per_step": on["ms"] / 8, "value": cells5 * 8 / (on["ms"] / 1e3), "unit": "cell-updates/s", "digest": on["digest"],
+                       "early_out_off": {"steps": 4, "warmup": 2, "ms_per_step": off["ms"] / 4, "value": cells5 * 4 / (off["ms"] / 1e3), "digest": off["digest"]},
+                       "early_out_speedup": (off["ms"] / 4) / (on["ms"] / 8),
+                       "note": "effective cell-updates/s (zone cells per tick, skipped or not); the two digests are taken after different tick counts"}
+        line["extra"] = extra
+
+    if rank == 0:
         if n == 1 and not args.no_cpu:
             try:
-                c = cpu_tick_throughput(workload, 10, 2, temperature, variants=True)
+                c = cpu_tick_throughput(workload, 10, 2, workload == "c3", variants=True)
                 line["cpu_baseline"] = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample", "variants") if k in c}
             except Exception as e:  # the checker libraries are optional on a box without them
                 line["cpu_baseline"] = {"value": None, "unit": "cell-updates/s", "cores": os.cpu_count(), "kind": "port", "sample": f"unavailable: {e}"}
         print(json.dumps(line), flush=True)
-    g.close()
     if n > 1:
         dist.destroy_process_group()
 

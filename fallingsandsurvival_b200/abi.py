@@ -4,7 +4,7 @@ import ctypes as C
 
 import numpy as np
 
-FSS_ABI_VERSION = 1
+FSS_ABI_VERSION = 2
 
 FSS_CHUNK_W = 4
 FSS_CHUNK_H = 16
@@ -125,7 +125,8 @@ class FillSpec(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("substeps", C.c_uint64), ("storage_bytes", C.c_uint64),
-                ("storage_pitch", C.c_uint32), ("storage_rows", C.c_uint32), ("storage_y0", C.c_uint32)]
+                ("storage_pitch", C.c_uint32), ("storage_rows", C.c_uint32), ("storage_y0", C.c_uint32), ("reserved", C.c_uint32),
+                ("spawns_refused", C.c_uint64)]
 
 
 # fss_tile_record == MaterialInstanceData (Chunk.hpp:27-31): 12 bytes, 2 bytes of padding after `index`

@@ -124,7 +124,7 @@ struct fss_world {
     uint8_t* d_present;
     int liq_from_iter;    // from this iter on only liquids can act
     int nogas_from_iter;  // from this iter on no GAS / fire can act
-    int k1_variant; // 0 = K1a lock-step (k_substep), 1 = K1b shared-memory decoupled (k_substep_sm)
+    bool sand_reacts;     // a SAND material with reactions can be present (world.cpp:1251-1274): no register-window kernel
     // World::particles (fss_particles.cuh): the list, its scratch copy and the per-particle round state, all `pl_cap` long
     fss_particle *pl_list, *pl_next;
     uint8_t *pl_decided, *pl_keep, *pl_sure, *pl_big;
@@ -191,8 +191,10 @@ static void recompute_liq(fss_world* w) {
     }
     int from = 0;
     bool gas_or_fire = false;
+    w->sand_reacts = false;
     for(int m = 0; m < w->n_mat; m++) {
         if(!pres[m]) continue;
+        if(mf_type(w->h_mats[m].bits) == FSS_PHYS_SAND && w->h_mats[m].n_react > 0) w->sand_reacts = true;
         const int type = mf_type(w->h_mats[m].bits), iters = std::min(mf_iters(w->h_mats[m].bits), 6);
         const bool gf = type == FSS_PHYS_GAS || (w->h_mats[m].bits & MF_FIRE);
         gas_or_fire = gas_or_fire || gf;
@@ -275,10 +277,6 @@ int fss_create(const fss_config* cfg, fss_world** out) {
     w->g.sy0 = s_lo;
     w->g.rows = s_hi - s_lo;
     w->part_cap = cfg->particle_capacity ? cfg->particle_capacity : (1u << 20);
-    {
-        const char* v = getenv("FSS_K1"); // kernel selection for A/B measurements: "a" lock-step, "b" shared-memory
-        w->k1_variant = (v && (v[0] == 'b' || v[0] == 'B')) ? 1 : 0; // K1b is 3x slower (profiles/r01_tuning_log.md)
-    }
     if(sizeof(cidx_t) == 4 && (unsigned long long)w->g.rows * w->g.pitch >= (1ull << 32)) {
         delete w;
         return fail(FSS_ERR_INVALID, "%d stored rows x pitch %u is 2^32 cells or more: shard the world into more strips", s_hi - s_lo, (cfg->width + FSS_BLOCK_COLS - 1) / FSS_BLOCK_COLS * FSS_BLOCK_COLS);
@@ -310,10 +308,6 @@ int fss_create(const fss_config* cfg, fss_world** out) {
     CUX(cudaMemsetAsync(w->g.amt, 0, n * 4, w->stream));
     CUX(cudaMemsetAsync(w->g.dif, 0, n * 4, w->stream));
     if(cfg->flags & FSS_TRACK_FLOW) {
-        if(w->k1_variant == 1) {
-            fss_destroy(w);
-            return fail(FSS_ERR_INVALID, "FSS_TRACK_FLOW is not supported by the experimental FSS_K1=b kernel");
-        }
         CUX(cudaMalloc(&w->g.fx, n * 4));
         CUX(cudaMalloc(&w->g.fy, n * 4));
         CUX(cudaMemsetAsync(w->g.fx, 0, n * 4, w->stream));
@@ -324,10 +318,6 @@ int fss_create(const fss_config* cfg, fss_world** out) {
             fss_destroy(w);
             return fail(FSS_ERR_INVALID, "FSS_TRACK_DIRTY is not available on strip-sharded worlds");
         }
-        if(w->k1_variant == 1) {
-            fss_destroy(w);
-            return fail(FSS_ERR_INVALID, "FSS_TRACK_DIRTY is not supported by the experimental FSS_K1=b kernel");
-        }
         CUX(cudaMalloc(&w->g.dirty, n));
         CUX(cudaMemsetAsync(w->g.dirty, 0, n, w->stream));
     }
@@ -336,8 +326,8 @@ int fss_create(const fss_config* cfg, fss_world** out) {
     CUX(cudaMalloc(&w->d_tex, sizeof(DTex) * FSS_MAX_TEXTURES));
     CUX(cudaMemsetAsync(w->d_tex, 0, sizeof(DTex) * FSS_MAX_TEXTURES, w->stream));
     CUX(cudaMalloc(&w->d_parts, sizeof(fss_particle_spawn) * (size_t)w->part_cap));
-    CUX(cudaMalloc(&w->d_part_count, 8));
-    CUX(cudaMemsetAsync(w->d_part_count, 0, 8, w->stream));
+    CUX(cudaMalloc(&w->d_part_count, 16)); // [0] records written, [1] spawns refused because the buffer was full
+    CUX(cudaMemsetAsync(w->d_part_count, 0, 16, w->stream));
     CUX(cudaMalloc(&w->d_red, FSS_MAX_MATERIALS * 16));
     CUX(cudaMalloc(&w->d_present, FSS_MAX_MATERIALS));
     CUX(cudaMemsetAsync(w->d_present, 0, FSS_MAX_MATERIALS, w->stream));
@@ -482,14 +472,25 @@ int fss_set_texture(fss_world* w, int index, const uint32_t* argb, int tw, int t
     if(index < 0 || index >= FSS_MAX_TEXTURES || tw < 1 || th < 1) return fail(FSS_ERR_INVALID, "texture %d (%dx%d)", index, tw, th);
     if(use_device(w)) return FSS_ERR_CUDA;
     CU(cudaStreamSynchronize(w->stream));
-    cudaFree((void*)w->h_tex[index].px);
+    // the replacement is complete on the device before the table entry changes; the old pixels are freed last
     uint32_t* d = nullptr;
     CU(cudaMalloc(&d, (size_t)tw * th * 4));
-    CU(cudaMemcpy(d, argb, (size_t)tw * th * 4, cudaMemcpyHostToDevice));
+    cudaError_t e = cudaMemcpy(d, argb, (size_t)tw * th * 4, cudaMemcpyHostToDevice);
+    if(e != cudaSuccess) {
+        cudaFree(d);
+        return fail(FSS_ERR_CUDA, "texture upload: %s", cudaGetErrorString(e));
+    }
+    const DTex old = w->h_tex[index];
     w->h_tex[index].px = d;
     w->h_tex[index].w = tw;
     w->h_tex[index].h = th;
-    CU(cudaMemcpy(w->d_tex, w->h_tex, sizeof(DTex) * FSS_MAX_TEXTURES, cudaMemcpyHostToDevice));
+    e = cudaMemcpy(w->d_tex, w->h_tex, sizeof(DTex) * FSS_MAX_TEXTURES, cudaMemcpyHostToDevice);
+    if(e != cudaSuccess) { // the device table still names the old pixels: keep them
+        w->h_tex[index] = old;
+        cudaFree(d);
+        return fail(FSS_ERR_CUDA, "texture table upload: %s", cudaGetErrorString(e));
+    }
+    cudaFree((void*)old.px);
     return FSS_OK;
 }
 
@@ -644,14 +645,7 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk) {
     p.ofs_y = ofs_y;
     w->stats.substeps++;
     if(p.ny <= 0 || p.nx <= 0) return FSS_OK;
-    if(w->k1_variant == 1) {
-        static bool carveout_set = false;
-        if(!carveout_set) {
-            cudaFuncSetAttribute(k_substep_sm, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            carveout_set = true;
-        }
-        k_substep_sm<<<dim3((p.nx + 31) / 32, p.ny), 32, 0, w->stream>>>(p);
-    } else {
+    {
         const dim3 grid((p.nx + K1_THREADS - 1) / K1_THREADS, p.ny);
         static const bool no_spec = getenv("FSS_NO_SPECIALISE") != nullptr; // measurements: always the general kernel
         const int mode = no_spec ? K1_GENERAL : (iter >= w->liq_from_iter ? K1_LIQUID : (iter >= w->nogas_from_iter ? K1_NOGAS : K1_GENERAL));
@@ -666,8 +660,10 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk) {
             if(flow) FSS_LAUNCH_K1(M, true, false); else FSS_LAUNCH_K1(M, false, false);           \
         }                                                                                          \
     } while(0)
-        if(liq_window_applies(mode, iter, w->cfg.flags, flow, dirty)) k_substep_liq<<<grid, K1_THREADS, 0, w->stream>>>(p);
-        else if(mode == K1_LIQUID) FSS_LAUNCH_K1_MODE(K1_LIQUID);
+        if(liq_window_applies(mode, iter, w->cfg.flags, flow, dirty, w->sand_reacts)) {
+            if(mode == K1_LIQUID) k_substep_win<false><<<grid, K1_THREADS, 0, w->stream>>>(p);
+            else k_substep_win<true><<<grid, K1_THREADS, 0, w->stream>>>(p);
+        } else if(mode == K1_LIQUID) FSS_LAUNCH_K1_MODE(K1_LIQUID);
         else if(mode == K1_NOGAS) FSS_LAUNCH_K1_MODE(K1_NOGAS);
         else FSS_LAUNCH_K1_MODE(K1_GENERAL);
 #undef FSS_LAUNCH_K1_MODE
@@ -729,25 +725,40 @@ int fss_tick_temperature(fss_world* w) {
 }
 
 // ---- side outputs -------------------------------------------------------------------------------------------
+// the two counters of the spawn buffer; refusals (SubstepParams::part_count[1]) are moved into the statistics
+static int spawn_counters(fss_world* w, unsigned long long& total) {
+    unsigned long long c[2] = {0, 0};
+    CU(cudaMemcpyAsync(c, w->d_part_count, 16, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    total = c[0];
+    if(c[1]) {
+        w->stats.spawns_refused += c[1];
+        CU(cudaMemsetAsync(w->d_part_count + 1, 0, 8, w->stream));
+    }
+    return FSS_OK;
+}
+
 int fss_drain_particles(fss_world* w, fss_particle_spawn* out, size_t cap, size_t* n_out, size_t* n_total) {
     if(!w || (!out && cap)) return fail(FSS_ERR_INVALID, "null argument");
     if(use_device(w)) return FSS_ERR_CUDA;
     unsigned long long total = 0;
-    CU(cudaMemcpyAsync(&total, w->d_part_count, 8, cudaMemcpyDeviceToHost, w->stream));
-    CU(cudaStreamSynchronize(w->stream));
-    const size_t kept = (size_t)std::min<unsigned long long>(total, w->part_cap);
-    std::vector<fss_particle_spawn> v(kept);
-    if(kept) CU(cudaMemcpy(v.data(), w->d_parts, kept * sizeof(fss_particle_spawn), cudaMemcpyDeviceToHost));
+    if(int rc = spawn_counters(w, total)) return rc;
+    if(n_out) *n_out = 0;
+    if(n_total) *n_total = (size_t)total;
+    if(total > cap) { // nothing is consumed: the caller comes back with room for *n_total records (cap == 0: a plain query)
+        if(cap == 0) return FSS_OK;
+        return fail(FSS_ERR_RANGE, "%llu spawn records waiting, room for %zu: nothing was drained", total, cap);
+    }
+    const size_t n = (size_t)total; // (the kernels never write more than part_cap records: reserve_spawns, fss_rules.cuh)
+    std::vector<fss_particle_spawn> v(n);
+    if(n) CU(cudaMemcpy(v.data(), w->d_parts, n * sizeof(fss_particle_spawn), cudaMemcpyDeviceToHost));
     CU(cudaMemsetAsync(w->d_part_count, 0, 8, w->stream));
     const int zx = w->zx, zy = w->zy; // the order World::tick pushes them (fss_spawn_order_key); equal keys are identical records
     std::stable_sort(v.begin(), v.end(), [zx, zy](const fss_particle_spawn& a, const fss_particle_spawn& b) {
         return fss_spawn_order_key(a.tick_iter, a.x, a.y, zx, zy) < fss_spawn_order_key(b.tick_iter, b.x, b.y, zx, zy);
     });
-    const size_t n = std::min(kept, cap);
     if(n) memcpy(out, v.data(), n * sizeof(fss_particle_spawn));
     if(n_out) *n_out = n;
-    if(n_total) *n_total = (size_t)total;
-    if(total > kept || kept > cap) return fail(FSS_ERR_RANGE, "%llu spawn records produced, %zu kept, %zu returned", total, kept, n);
     return FSS_OK;
 }
 
@@ -827,11 +838,9 @@ static int cub_scratch(fss_world* w, size_t bytes) {
 // since the last call: the spawn records, in push order, become Particles at the end of the list
 static int particles_adopt(fss_world* w) {
     unsigned long long total = 0;
-    CU(cudaMemcpyAsync(&total, w->d_part_count, 8, cudaMemcpyDeviceToHost, w->stream));
-    CU(cudaStreamSynchronize(w->stream));
+    if(int rc = spawn_counters(w, total)) return rc;
     if(total == 0) return FSS_OK;
-    if(total > w->part_cap) return fail(FSS_ERR_RANGE, "%llu spawn records produced, capacity %u (fss_config.particle_capacity)", total, w->part_cap);
-    const uint32_t n = (uint32_t)total;
+    const uint32_t n = (uint32_t)std::min<unsigned long long>(total, w->part_cap); // (never more than part_cap: reserve_spawns)
     if(int rc = particles_reserve(w, (size_t)w->pl_n + n)) return rc;
     if(!w->pl_key[0]) {
         for(int k = 0; k < 2; k++) {
@@ -1098,6 +1107,32 @@ int fss_mark_dirty(fss_world* w, int x, int y, int width, int height) {
     k_mark_dirty<<<(unsigned)((cells + 255) / 256), 256, 0, w->stream>>>(w->g, x0, y0, x1 - x0, y1 - y0);
     CU(cudaGetLastError());
     w->stats.kernel_launches++;
+    return FSS_OK;
+}
+
+int fss_mark_dirty_list(fss_world* w, const fss_rect* rects, size_t n) {
+    if(int rc = dirty_ready(w)) return rc;
+    if(!rects && n) return fail(FSS_ERR_INVALID, "null argument");
+    // clipped like fss_mark_dirty; one launch per 65535 rectangles (gridDim.y), the list goes through the staging buffer
+    std::vector<int4> v;
+    long long biggest = 0;
+    for(size_t i = 0; i < n; i++) {
+        const int x0 = std::max(rects[i].x, 0), y0 = std::max(rects[i].y, 0);
+        const int x1 = (int)std::min<long long>((long long)rects[i].x + rects[i].w, w->cfg.width), y1 = (int)std::min<long long>((long long)rects[i].y + rects[i].h, w->cfg.height);
+        if(x1 <= x0 || y1 <= y0) continue;
+        v.push_back(make_int4(x0, y0, x1 - x0, y1 - y0));
+        biggest = std::max(biggest, (long long)(x1 - x0) * (y1 - y0));
+    }
+    const size_t per_pass = std::min<size_t>(65535, w->stage_bytes / sizeof(int4));
+    for(size_t k = 0; k < v.size(); k += per_pass) {
+        const size_t m = std::min(per_pass, v.size() - k);
+        CU(cudaMemcpyAsync(w->d_stage, v.data() + k, m * sizeof(int4), cudaMemcpyHostToDevice, w->stream));
+        const unsigned bx = (unsigned)std::min<long long>(1024, (biggest + 255) / 256);
+        k_mark_dirty_list<<<dim3(bx, (unsigned)m), 256, 0, w->stream>>>(w->g, (const int4*)w->d_stage);
+        CU(cudaGetLastError());
+        w->stats.kernel_launches++;
+        CU(cudaStreamSynchronize(w->stream)); // `v` and the staging buffer are reused
+    }
     return FSS_OK;
 }
 
@@ -1496,7 +1531,12 @@ int fss_exchange_halo(fss_world* w, int tk) {
         if(has_upper) rc = nccl_rows(w, true, w->rank - 1, w->own_lo + UP_LO, w->own_lo + UP_HI, false);
         if(!rc && has_lower) rc = nccl_rows(w, false, w->rank + 1, w->own_hi + UP_LO, w->own_hi + UP_HI, false);
     }
-    NC(g_nccl.group_end());
+    // the group is always closed, also after a failed send / recv: an open group would leave the communicator unusable and the
+    // neighbour blocked.  A communicator error is fatal for the world (the strips are out of step): destroy and re-create it.
+    const std::string first_error = rc ? g_err : std::string();
+    const int end = g_nccl.group_end();
+    if(rc) return fail(rc, "%s", first_error.c_str());
+    if(end != 0) return fail(FSS_ERR_COMM, "ncclGroupEnd: %s", g_nccl.err_string ? g_nccl.err_string(end) : "nccl error");
     w->stats.kernel_launches++; // one fused NCCL send/recv kernel per group
     if(!rc) { // received rows replace cells that settled chunks may have looked at
         if(tk == 1 && has_upper) rc = dirty_chunks(w, 0, w->own_lo + DOWN_LO, (int)w->cfg.width, DOWN_HI - DOWN_LO);
@@ -1520,7 +1560,10 @@ int fss_exchange_halo_temperature(fss_world* w) {
         rc = nccl_rows(w, true, w->rank - 1, w->own_lo, w->own_lo + FSS_HALO_ROWS, true);
         if(!rc) rc = nccl_rows(w, false, w->rank - 1, w->own_lo - FSS_HALO_ROWS, w->own_lo, true);
     }
-    NC(g_nccl.group_end());
+    const std::string first_error = rc ? g_err : std::string(); // (the group is always closed: see fss_exchange_halo)
+    const int end = g_nccl.group_end();
+    if(rc) return fail(rc, "%s", first_error.c_str());
+    if(end != 0) return fail(FSS_ERR_COMM, "ncclGroupEnd: %s", g_nccl.err_string ? g_nccl.err_string(end) : "nccl error");
     w->stats.kernel_launches++;
     return rc;
 }

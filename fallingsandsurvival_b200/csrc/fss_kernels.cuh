@@ -7,7 +7,6 @@
 #pragma once
 #include "fss_rules.cuh"
 #include "fss_rules_liq.cuh"
-#include "fss_rules_sm.cuh"
 
 #ifndef K1_THREADS
 #define K1_THREADS 128
@@ -73,12 +72,27 @@ __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS
     w.run(qown);
 }
 
-// ---- K1w: liquid-only sub-step with the chunk rows in a register window (fss_rules_liq.cuh) ------------------------
-// Same grid and chunk ownership as k_substep; launched instead of k_substep<K1_LIQUID> where liq_window_applies().
+// ---- K1w: sub-step with the chunk rows in a register window (fss_rules_liq.cuh) -------------------------------------
+// Same grid and chunk ownership as k_substep; launched instead of k_substep<K1_LIQUID> (SAND = false) or k_substep<K1_NOGAS>
+// (SAND = true) where liq_window_applies().
 #ifndef K1W_MIN_BLOCKS
-#define K1W_MIN_BLOCKS 4
+#define K1W_MIN_BLOCKS 5
 #endif
-__global__ void __launch_bounds__(K1_THREADS, K1W_MIN_BLOCKS) k_substep_liq(const __grid_constant__ SubstepParams p) {
+#ifndef K1WS_MIN_BLOCKS
+#define K1WS_MIN_BLOCKS 4
+#endif
+template <bool SAND>
+__global__ void __launch_bounds__(K1_THREADS, SAND ? K1WS_MIN_BLOCKS : K1W_MIN_BLOCKS) k_substep_win(const __grid_constant__ SubstepParams p) {
+    __shared__ uint32_t sinfo[SAND ? FSS_MAX_MATERIALS : 1];
+    if(SAND) {
+        for(int m = threadIdx.x; m < p.n_mat; m += K1_THREADS) {
+            const DMat& d = p.mats[m];
+            uint32_t stab = d.max_stability > 255 ? 255u : (uint32_t)d.max_stability;
+            sinfo[m] = ((uint32_t)d.slip & 0xFFFFu) | (stab << 16) | (((uint32_t)d.n_react & 3u) << 24) |
+                       ((d.flags & FSS_MAT_IS_STEAM) ? HI_STEAM : 0u);
+        }
+        __syncthreads();
+    }
     const int gi = blockIdx.x * K1_THREADS + threadIdx.x;
     if(gi >= p.nx) return;
     uint8_t* qown = nullptr;
@@ -88,41 +102,8 @@ __global__ void __launch_bounds__(K1_THREADS, K1W_MIN_BLOCKS) k_substep_liq(cons
         if(*qown <= (uint8_t)p.iter) return; // verified settled
     }
 #endif
-    LiqWalk w(p, nullptr, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y, 0u);
+    WinWalk<SAND> w(p, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y, __activemask());
     w.run(qown);
-}
-
-// ---- K1b: movement sub-step, window in shared memory, lanes decoupled (fss_rules_sm.cuh) ---------------------
-// One warp per CTA; grid = (ceil(nx / 32), ny); lane l of CTA bx owns the micro-chunk at column x_begin + 8*(32*bx + l).
-#ifndef K1B_MIN_BLOCKS
-#define K1B_MIN_BLOCKS 5
-#endif
-__global__ void __launch_bounds__(32, K1B_MIN_BLOCKS) k_substep_sm(const __grid_constant__ SubstepParams p) {
-    __shared__ uint32_t s_mf[SW_CELLS * 32];
-    __shared__ float s_amt[SW_CELLS * 32];
-    __shared__ float s_dif[SW_CELLS * 32];
-    __shared__ float sden[FSS_MAX_MATERIALS];
-    __shared__ uint32_t sinfo[FSS_MAX_MATERIALS];
-    const int lane = threadIdx.x;
-    for(int m = lane; m < p.n_mat; m += 32) {
-        const DMat& d = p.mats[m];
-        sden[m] = d.density;
-        uint32_t stab = d.max_stability > 255 ? 255u : (uint32_t)d.max_stability;
-        sinfo[m] = ((uint32_t)d.slip & 0xFFFFu) | (stab << 16) | (((uint32_t)d.n_react & 3u) << 24) |
-                   ((d.flags & FSS_MAT_IS_STEAM) ? HI_STEAM : 0u);
-    }
-    __syncwarp();
-    const int gi = blockIdx.x * 32 + lane;
-    if(gi >= p.nx) return;
-    uint8_t* qown = nullptr;
-    if(p.q) {
-        qown = p.q + (size_t)(2 * (int)blockIdx.y + p.ofs_y + 1) * p.q_w + (2 * gi + p.ofs_x + 1);
-        if(*qown <= (uint8_t)p.iter) return; // verified settled
-    }
-    const unsigned mask = __activemask();
-    ChunkWalkS w(p, sden, sinfo, s_mf + lane, s_amt + lane, s_dif + lane, p.x_begin + 2 * FSS_CHUNK_W * gi,
-                 p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y);
-    w.run(qown, mask);
 }
 
 // ---- K2: temperature stencil ---------------------------------------------------------------------------

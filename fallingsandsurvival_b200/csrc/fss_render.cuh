@@ -122,6 +122,14 @@ __global__ void __launch_bounds__(256) k_mark_dirty(Grid g, int rx, int ry, int 
     g.dirty[g.idx(rx + k % rw, ry + k / rw)] = 1;
 }
 
+// the same for a list of rectangles (already clipped to the world) in one launch: blockIdx.y = rectangle
+__global__ void __launch_bounds__(256) k_mark_dirty_list(Grid g, const int4* __restrict__ rects) {
+    const int4 r = rects[blockIdx.y]; // x, y, w, h
+    const long long n = (long long)r.z * r.w;
+    for(long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < n; k += (long long)gridDim.x * 256)
+        g.dirty[g.idx(r.x + (int)(k % r.z), r.y + (int)(k / r.z))] = 1;
+}
+
 // one byte plane of a rectangle, permuted storage -> row-major staging
 __global__ void __launch_bounds__(256) k_download_bytes(const uint8_t* __restrict__ plane, uint8_t* __restrict__ out, uint32_t pitch, int sy0,
                                                         int rx, int ry, int rw, int rh) {

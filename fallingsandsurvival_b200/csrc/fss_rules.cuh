@@ -22,6 +22,18 @@
 #define FLUID_MaxFlow 8.0f
 #define FLUID_FlowSpeed 1.0f
 
+// host-only path counters (tests/hostsim with -DK1_STATS): how often each branch of the SAND rules is taken
+#if defined(K1_STATS) && !defined(__CUDA_ARCH__)
+extern unsigned long long g_k1_stats[32];
+#define K1_STAT(k) (g_k1_stats[k]++)
+#define g_k1_add(k, v) (g_k1_stats[k] += (unsigned long long)(v))
+#define __popcll_host(v) __builtin_popcountll(v)
+#else
+#define K1_STAT(k) ((void)0)
+#define g_k1_add(k, v) ((void)0)
+#define __popcll_host(v) 0
+#endif
+
 struct SubstepParams {
     Grid g;
     const DMat* mats;
@@ -109,10 +121,19 @@ __device__ __noinline__ Cell create_cell(const SubstepParams& p, int m, int x, i
     return c;
 }
 
+// Room for n spawn records (world.cpp:1180, :1291, :1366).  false = the buffer (fss_config.particle_capacity) is full: nothing is
+// reserved, the refusal is counted in part_count[1] and the caller must leave the cell in the grid (it takes the branch the
+// reference takes when the free-fall test fails), so that no matter is lost; fss_drain_particles / fss_get_stats report it.
+__device__ __forceinline__ bool reserve_spawns(const SubstepParams& p, unsigned n, unsigned long long& slot) {
+    slot = atomicAdd(p.part_count, (unsigned long long)n);
+    if(slot + n <= (unsigned long long)p.part_cap) return true;
+    atomicAdd(p.part_count, 0ull - (unsigned long long)n); // hand them back: part_count[0] ends up as the number of records written
+    atomicAdd(p.part_count + 1, 1ull);
+    return false;
+}
+
 // Particle spawn record (world.cpp:1180, :1291, :1366): the cell leaves the grid for the host
-__device__ __noinline__ void emit_particle(const SubstepParams& p, int x, int y, uint32_t site, uint32_t key, Cell c) {
-    unsigned long long slot = atomicAdd(p.part_count, 1ull);
-    if(slot >= p.part_cap) return;
+__device__ __noinline__ void emit_particle(const SubstepParams& p, unsigned long long slot, int x, int y, uint32_t site, uint32_t key, Cell c) {
     fss_particle_spawn* r = &p.parts[slot];
     r->x = (uint32_t)x;
     r->y = (uint32_t)y;
@@ -142,7 +163,8 @@ __device__ __noinline__ unsigned long long rule_fire(const SubstepParams& p, int
         tile.col = (((255u << 8) + 100 + fss_rand(key, 1174, 0) % 50) << 8) + 50;
     }
     if(fss_rand(key, 1179, 0) % 10 == 0) {
-        if(p.flags & FSS_PARTICLES_EMIT) emit_particle(p, x, y, 1180, key, tile);
+        unsigned long long slot; // a temporary, purely visual particle: dropped when the buffer is full
+        if((p.flags & FSS_PARTICLES_EMIT) && reserve_spawns(p, 1, slot)) emit_particle(p, slot, x, y, 1180, key, tile);
     }
     uint8_t* const dirty = p.g.dirty; // World::dirty, nullptr unless FSS_TRACK_DIRTY (a rare rule: tested at run time)
     if(fss_rand(key, 1191, 0) % 150 == 0) {
@@ -194,8 +216,8 @@ __device__ __noinline__ bool rule_sand_react(const SubstepParams& p, cidx_t i, i
     return react;
 }
 
-// ---- falling liquid leaves the grid as particles, world.cpp:1352-1374 ---------------------------------
-__device__ __noinline__ void rule_soup_free_fall(const SubstepParams& p, cidx_t i, int x, int y, uint32_t mf, float amt) {
+// ---- falling liquid leaves the grid as particles, world.cpp:1352-1374; false = no room for the records: the cell stays --
+__device__ __noinline__ bool rule_soup_free_fall(const SubstepParams& p, cidx_t i, int x, int y, uint32_t mf, float amt) {
     const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
     Cell nt;
     nt.mf = mf & (MF_MAT_MASK | MF_DERIVED_MASK);
@@ -205,9 +227,12 @@ __device__ __noinline__ void rule_soup_free_fall(const SubstepParams& p, cidx_t 
     int n = (int)(amt / 4);
     if(n < 1) n = 1;
     nt.amt = amt / n;
+    unsigned long long slot;
+    if(!reserve_spawns(p, (unsigned)n, slot)) return false;
     st_cell(p.g, i, cell_nothing(p.nothing_mf)); // :1353 setTile, which sets dirty (:1061)
     if(p.g.dirty) p.g.dirty[i] = 1;
-    for(int k = 0; k < n; k++) emit_particle(p, x, y, 1366, key, nt);
+    for(int k = 0; k < n; k++) emit_particle(p, slot + k, x, y, 1366, key, nt);
+    return true;
 }
 
 // per-thread state of one micro-chunk visit.
@@ -312,9 +337,10 @@ struct ChunkWalk {
         if((p.flags & FSS_PARTICLES_EMIT) && (double)amt > 0.005 && MF_IS(g.mf[i + pitch], FSS_PHYS_AIR) &&
            MF_IS(g.mf[i + 2 * pitch], FSS_PHYS_AIR) && MF_IS(g.mf[i + 3 * pitch], FSS_PHYS_AIR) &&
            MF_IS(g.mf[i + 4 * pitch], FSS_PHYS_AIR)) {
-            busy = true;
-            rule_soup_free_fall(p, i, x, y, mf, amt);
-            return;
+            if(rule_soup_free_fall(p, i, x, y, mf, amt)) {
+                busy = true;
+                return;
+            }
         }
         if(mf & MF_MOVED) return;    // :1376 (moved == settled for liquids)
         busy = true; // an unsettled liquid cell always changes: it flows, or its settle counter advances
@@ -445,7 +471,9 @@ struct ChunkWalk {
         const cidx_t ibl = il + p.g.pitch, ibr = ir + p.g.pitch;
         const uint32_t bmf = HOIST_SAND ? pre[0] : g.mf[ib], blmf = HOIST_SAND ? pre[1] : g.mf[ibl], brmf = HOIST_SAND ? pre[2] : g.mf[ibr];
         const bool can_b = can_move_into(bmf, mf), can_l = can_move_into(blmf, mf), can_r = can_move_into(brmf, mf);
+        K1_STAT(10); // sand1 visits
         if(!can_b) return; // :1276, :1287
+        K1_STAT(11); // can move below
         busy = true;
         // the cell will move in 19 of 20 cases: its words and those of the cell below are requested now, so that the loads
         // are in flight while the draw is computed
@@ -454,11 +482,14 @@ struct ChunkWalk {
         const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
         if((can_l || can_r) && fss_rand(key, 1287, 0) % 20 == 0) return;
         if(GASFIRE && MF_IS(bmf, FSS_PHYS_GAS)) maybe_gas = true;
+        unsigned long long slot = 0;
+        const bool free_fall = (p.flags & FSS_PARTICLES_EMIT) && MF_IS(bmf, FSS_PHYS_AIR) && MF_IS(g.mf[ib + g.pitch], FSS_PHYS_AIR) &&
+                               MF_IS(g.mf[ib + 2 * g.pitch], FSS_PHYS_AIR) && MF_IS(g.mf[ib + 3 * g.pitch], FSS_PHYS_AIR) &&
+                               reserve_spawns(p, 1, slot); // (no room for the record: the cell keeps falling in the grid)
         st_cell(g, i, below); // :1289 / :1296
         D(i);                 // :1289 setTile sets dirty (:1061); :1297
-        if((p.flags & FSS_PARTICLES_EMIT) && MF_IS(bmf, FSS_PHYS_AIR) && MF_IS(g.mf[ib + g.pitch], FSS_PHYS_AIR) &&
-           MF_IS(g.mf[ib + 2 * g.pitch], FSS_PHYS_AIR) && MF_IS(g.mf[ib + 3 * g.pitch], FSS_PHYS_AIR)) {
-            emit_particle(p, x, y, 1291, key, tile); // :1288-1294 free fall: the cell leaves the grid
+        if(free_fall) {
+            emit_particle(p, slot, x, y, 1291, key, tile); // :1288-1294 free fall: the cell leaves the grid
         } else {
             if(fss_rand(key, 1300, 0) % 2 == 0) tile.mf |= MF_MOVED;
             st_cell(g, ib, tile); // :1306
@@ -579,6 +610,8 @@ struct ChunkWalk {
         const cidx_t pitch = g.pitch;
         const uint32_t mat = mf_mat(mf);
         const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
+        K1_STAT(0); // sand2 visits
+        if(!(mf & MF_MOVED)) K1_STAT(1); // ... of stopped cells
         // A stopped cell (moved == false) only changes if its pillar draw hits: `rand() % chance == 0`, chance = 1000 / unstable,
         // unstable in 2..10 (:1710-1716); with no open diagonal it stays as it is as well.  So when the visit is already known
         // not to be idle (busy), the draw is looked at first: if it is not a multiple of ANY of the nine possible chances the
@@ -588,11 +621,13 @@ struct ChunkWalk {
         if(!(mf & MF_MOVED) && busy) {
             const uint32_t r = fss_rand(key, 1715, 0);
             if(r % 500u && r % 333u && r % 250u && r % 200u && r % 166u && r % 142u && r % 125u && r % 111u && r % 100u) return;
+            K1_STAT(2); // stopped, the draw could hit
         }
         const cidx_t ibl = il + p.g.pitch, ibr = ir + p.g.pitch;
         const uint32_t blmf = g.mf[ibl], brmf = g.mf[ibr];
         const bool can_l = can_move_into(blmf, mf), can_r = can_move_into(brmf, mf);
         if(!(can_l || can_r)) {
+            K1_STAT(3); // no open diagonal
             // :1697-1734 with no open diagonal: whatever the pillar probe and its draw decide, `moved` ends up false
             if(mf & MF_MOVED) {
                 busy = true;
@@ -626,6 +661,7 @@ struct ChunkWalk {
             if(stopped) return; // :1727-1734, moved is already false
         }
         busy = true;
+        K1_STAT(4); // moving cell with an open diagonal (or un-stuck)
         Cell tile; // requested before the draws below: the cell moves unless `should_move` fails (1 in 2*slip)
         tile.mf = mf;
         tile.col = g.col[i];
@@ -633,6 +669,7 @@ struct ChunkWalk {
         tile.amt = g.amt[i];
         tile.dif = g.dif[i];
         const bool should_move = fss_rand(key, 1736, 0) % (2u * slip) != 0;
+        if(should_move) K1_STAT(5); // slides
         if(!should_move) { // :1802 `tiles[index].moved = false`
             if(mf & MF_MOVED) g.mf[i] = mf & ~MF_MOVED;
             return;
@@ -679,7 +716,9 @@ struct ChunkWalk {
         const cidx_t i = locate(dx, dy);
         const uint32_t mf = g.mf[i];
         if(MF_IS(mf, FSS_PHYS_SAND)) {
+#ifndef EXP_SKIP_SAND2 /* timing experiment only: wrong results */
             sand2(i, x, y, mf, bit);
+#endif
         } else if(MF_IS(mf, FSS_PHYS_SOUP)) { // :1808-1825
             soup_apply(i, g.amt[i], g.dif[i], bit);
         } else if(GASFIRE && MF_IS(mf, FSS_PHYS_GAS)) { // :1879-1899
@@ -893,8 +932,39 @@ struct ChunkWalk {
             if(!GASFIRE && dy < FSS_CHUNK_H - 1) early_apply_row(dy + 1);
         }
         if(!GASFIRE) early_apply_row(0);
+        scan2_rest();
+    }
+
+    // Scan 2 driven by the tickVisited bits instead of by position (K1_NOGAS only, entered from WinWalk<true>::run with the
+    // bits its register-window scan 1 and fused liquid update left): scan 2 only acts on unvisited cells, and after scan 1 a
+    // chunk has about five of them (resting SAND; liquid cells whose update deletes them), so every lane steps through ITS OWN
+    // unvisited positions in the reference's order (rows bottom-up, columns left to right) and the rule bodies run with all
+    // lanes that still have one -- instead of all 64 positions in lock step with one or two lanes inside the SAND rule.
+    // The order inside a chunk is per lane anyway; a visit never clears a bit, and the bits it sets lie at positions the
+    // order has already passed (or its own), so the set of positions to visit only shrinks as the reference's does.
+    __device__ __forceinline__ void scan2_sparse() {
+        unsigned long long todo = ~vis;
+        while(__any_sync(wmask, todo != 0ull)) {
+            if(todo != 0ull) {
+                const int top = 63 - __clzll((long long)todo);          // highest row with an unvisited position
+                const int dy = top >> 2;
+                const unsigned nib = (unsigned)(todo >> (dy * FSS_CHUNK_W)) & 0xFu;
+                const int dx = __ffs((int)nib) - 1;                     // its leftmost unvisited column
+                todo &= ~(1ull << (dy * FSS_CHUNK_W + dx));
+                scan2_cell(dx, dy);
+            }
+        }
+    }
+
+    // scans 2 and 3 (also entered from WinWalk<true>::run, fss_rules_liq.cuh, after its register-window scan 1)
+    __device__ __forceinline__ void scan2_rest() {
+#ifdef EXP_SKIP_SCAN2 /* timing experiment only: wrong results */
+        return;
+#endif
         // scan 2 and scan 3 only act on cells that are not marked visited: when every lane's chunk is fully
         // visited (iter >= iterations everywhere: AIR, SOLID, spent SAND) the warp skips them
+        K1_STAT(8);                                   // chunk visits entering scan 2
+        g_k1_add(9, 64 - __popcll_host(vis));          // unvisited positions
         if(__all_sync(__activemask(), vis == ~0ull)) return;
 #ifndef K1_PF2
 #define K1_PF2 1 /* scan 2 is short per cell: its prefetch runs this many rows ahead */

@@ -1,10 +1,9 @@
-// fss_rules_liq.cuh -- the liquid-only sub-step of World::tick with the chunk rows held in REGISTERS (round 2).
+// fss_rules_liq.cuh -- sub-steps of World::tick with the chunk rows held in REGISTERS (round 2).
 //
-// Which sub-steps: the ones k_substep<K1_LIQUID> serves (only SOUP cells can act: no SAND / GAS / fire material with
-// `iterations > iter` can be present), further restricted to iter >= 1 (no SOUP-SOUP swaps, world.cpp:1406-1412 and
-// :1510-1516, which draw random numbers and move whole cells), no FSS_PARTICLES_EMIT (the free-fall test of
-// world.cpp:1352-1374 looks four rows down), no flow / dirty planes.  liq_window_applies() is the one definition of that
-// condition; everything else keeps running ChunkWalk<K1_LIQUID> (fss_rules.cuh).
+// Which sub-steps: the ones k_substep<K1_LIQUID> serves (only SOUP cells can act) and the ones k_substep<K1_NOGAS> serves
+// (SAND and SOUP act, no GAS / fire material present), without FSS_PARTICLES_EMIT (the free-fall tests of world.cpp:1288
+// and :1352 look four rows down) and without flow / dirty planes.  liq_window_applies() is the one definition of that
+// condition; everything else keeps running ChunkWalk (fss_rules.cuh).
 //
 // Why: ChunkWalk walks its 64 cells through L1: every liquid cell visit re-loads the mf / amt / dif words of its four
 // neighbours (13 loads), each behind 64-bit index arithmetic, and scan 2 walks the chunk a second time.  ncu (round 1):
@@ -29,11 +28,21 @@
 #include "fss_rules.cuh"
 
 // the one place that decides which sub-steps take the register-window path (kernel launch and tests/hostsim)
-__host__ __device__ __forceinline__ bool liq_window_applies(int mode, int iter, uint32_t cfg_flags, bool flow, bool dirty) {
+//   K1_LIQUID sub-steps: WinWalk<false>, scans 1 and 2 fused completely;
+//   K1_NOGAS sub-steps (SAND + SOUP act): WinWalk<true> runs scan 1 (SAND falling straight, world.cpp:1276-1335, and the
+//   liquid rule) and the liquid half of scan 2 on the window, then ChunkWalk<K1_NOGAS>::scan2_rest() runs scan 2's SAND rule
+//   through L1 as before.  `sand_reacts`: a SAND material with reactions (world.cpp:1251-1274: reads the temperature plane and
+//   re-creates the cell) can be present -- those worlds stay on ChunkWalk.
+__host__ __device__ __forceinline__ bool liq_window_applies(int mode, int iter, uint32_t cfg_flags, bool flow, bool dirty, bool sand_reacts = false) {
 #ifdef K1_NO_LIQ_WINDOW
     return false;
 #else
-    return mode == K1_LIQUID && iter >= 1 && !(cfg_flags & FSS_PARTICLES_EMIT) && !flow && !dirty;
+    if((cfg_flags & FSS_PARTICLES_EMIT) || flow || dirty) return false;
+#ifdef K1_NO_SAND_WINDOW
+    return mode == K1_LIQUID;
+#else
+    return mode == K1_LIQUID || (mode == K1_NOGAS && !sand_reacts);
+#endif
 #endif
 }
 
@@ -62,6 +71,7 @@ struct LRow { // one grid row of the chunk's four columns
 #define LF_MF 0x1u
 #define LF_DIF 0x10u
 #define LF_AMT 0x100u
+#define LF_ALL 0x111u
 #define LF_VIS 0x10000u
 
 struct LSide { // the cell left / right of the row being scanned (outside the chunk)
@@ -69,17 +79,26 @@ struct LSide { // the cell left / right of the row being scanned (outside the ch
     float amt, dif;
 };
 
-struct LiqWalk {
+// SAND = false: liquid-only sub-steps, scans 1 and 2 fused completely.
+// SAND = true:  SAND acts too: its scan-1 rule (falling straight down, world.cpp:1276-1335) runs on the window as well;
+//               cells that scan 2's liquid step would delete are left to scan 2 proper (they change type, which a SAND
+//               cell to their left tests first: ChunkWalk::early_apply_row), and `vis` is handed to ChunkWalk::scan2_rest().
+template <bool SAND>
+struct WinWalk {
     const SubstepParams& p;
+    const uint32_t* sinfo;
     int cx, cy;
     // word offsets relative to the chunk's column 0: the own columns are at +32*k (one 8-column group), the outside columns at
     // lofs / rofs (fss_device.cuh, permuted layout)
     int lofs, rofs;
     cidx_t c0; // index of (cx, cy) in the planes
-    bool busy; // this visit stored to the grid (else it was the identity); see SubstepParams::q
+    bool busy; // this visit stored to the grid or drew a random number (else it was the identity); see SubstepParams::q
+    unsigned long long vis; // SAND: tickVisited of the chunk as scan 2 finds it
+    uint32_t lb_mf, rb_mf;  // SAND: mf of the outside cells of the row BELOW the one being scanned (a SAND cell's diagonals)
+    unsigned wmask;
 
-    __device__ __forceinline__ LiqWalk(const SubstepParams& p_, const uint32_t*, int cx_, int cy_, unsigned)
-        : p(p_), cx(cx_), cy(cy_), busy(false) {
+    __device__ __forceinline__ WinWalk(const SubstepParams& p_, const uint32_t* si, int cx_, int cy_, unsigned wmask_)
+        : p(p_), sinfo(si), cx(cx_), cy(cy_), busy(false), vis(0ull), lb_mf(0u), rb_mf(0u), wmask(wmask_) {
         const uint32_t pb = fss_perm((uint32_t)cx);
         lofs = (int)fss_perm((uint32_t)(cx - 1)) - (int)pb;
         rofs = (int)fss_perm((uint32_t)(cx + FSS_CHUNK_W)) - (int)pb;
@@ -98,6 +117,19 @@ struct LiqWalk {
         }
         R.fl = 0u;
     }
+    // the colour / temperature words travel with a moving cell but are not part of the window: their lines are requested
+    // into L1 two rows ahead, so that exchange() does not wait for HBM in the middle of a row (SAND only: liquids do not move)
+    __device__ __forceinline__ void prefetch_payload(cidx_t i) const {
+#if !defined(K1W_NO_PF_PAYLOAD) && defined(__CUDA_ARCH__)
+#pragma unroll
+        for(int k = 0; k < FSS_CHUNK_W; k++) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.g.col + i + 32 * k));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.g.temp + i + 32 * k));
+        }
+#else
+        (void)i;
+#endif
+    }
     __device__ __forceinline__ void load_side(LSide& S, cidx_t i) const {
         S.mf = p.g.mf[i];
         S.amt = p.g.amt[i];
@@ -112,7 +144,7 @@ struct LiqWalk {
             X.mf[J] = self_mf & (MF_MAT_MASK | MF_DERIVED_MASK);
             X.amt[J] = 0.0f;
             X.dif[J] = 0.0f + flow;
-            X.fl |= (LF_MF | LF_DIF | LF_AMT) << J;
+            X.fl |= LF_ALL << J;
             p.g.col[in] = p.g.col[is];
             p.g.temp[in] = p.g.temp[is];
         } else {
@@ -134,15 +166,84 @@ struct LiqWalk {
         }
     }
 
-    // ---- SOUP, scan 1, world.cpp:1338-1537, on the window: A / C / B = rows r-1 / r / r+1, L / R = the outside cells of row r
+    // two vertically adjacent cells of column K change places (X over Y in the window; ix / iy their indices); the colour and
+    // temperature words, which the window does not hold, change places in memory.  xmf / xdif: what the cell that was in X
+    // carries into Y (SAND: `moved` may be set on the way, :1300; SOUP :1511: its running fluidAmountDiff)
     template <int K>
-    __device__ __forceinline__ void cell(LRow& A, LRow& C, LRow& B, LSide& L, LSide& R, cidx_t irow) {
+    __device__ __forceinline__ void exchange(LRow& X, LRow& Y, cidx_t ix, cidx_t iy, uint32_t xmf, float xdif) const {
+        const uint32_t cx_ = p.g.col[ix], cy_ = p.g.col[iy];
+        const int32_t tx = p.g.temp[ix], ty = p.g.temp[iy];
+        const float xamt = X.amt[K];
+        X.mf[K] = Y.mf[K];
+        X.amt[K] = Y.amt[K];
+        X.dif[K] = Y.dif[K];
+        Y.mf[K] = xmf;
+        Y.amt[K] = xamt;
+        Y.dif[K] = xdif;
+        X.fl |= LF_ALL << K;
+        Y.fl |= LF_ALL << K;
+        p.g.col[ix] = cy_;
+        p.g.col[iy] = cx_;
+        p.g.temp[ix] = ty;
+        p.g.temp[iy] = tx;
+    }
+
+    __device__ __forceinline__ bool can_move_into(uint32_t dst_mf, uint32_t self_mf) const { // world.cpp:1276-1285, on the density ranks
+        return MF_IS(dst_mf, FSS_PHYS_AIR) || (!MF_IS(dst_mf, FSS_PHYS_SOLID) && (dst_mf & MF_RANK_MASK) < (self_mf & MF_RANK_MASK));
+    }
+
+    // ---- SAND, scan 1, world.cpp:1218-1337 (no reactions: liq_window_applies; no free fall: particles are off) ------------
+    template <int K>
+    __device__ __forceinline__ void sand1(LRow& C, LRow& B, cidx_t irow, int r, uint32_t mf) {
+        const uint32_t bmf = B.mf[K];
+        const uint32_t blmf = K > 0 ? B.mf[K > 0 ? K - 1 : 0] : lb_mf;
+        const uint32_t brmf = K < FSS_CHUNK_W - 1 ? B.mf[K < FSS_CHUNK_W - 1 ? K + 1 : 0] : rb_mf;
+        const bool can_b = can_move_into(bmf, mf), can_l = can_move_into(blmf, mf), can_r = can_move_into(brmf, mf);
+        if(!can_b) return; // :1276, :1287
+        busy = true;
+        const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)(cx + K), (uint32_t)(cy + r));
+        if((can_l || can_r) && fss_rand(key, 1287, 0) % 20 == 0) return;
+        const cidx_t i = irow + 32 * K, ib = i + p.g.pitch;
+        uint32_t tile_mf = mf;
+        if(fss_rand(key, 1300, 0) % 2 == 0) tile_mf |= MF_MOVED;
+        exchange<K>(C, B, i, ib, tile_mf, C.dif[K]); // :1296-1306
+        B.fl |= LF_VIS << K;                         // :1308 tickVisited[x + (y + 1) * width]; row 16 is outside the chunk (ignored)
+        if(fss_rand(key, 1313, 0) % 2 == 0) { // :1313-1335 transmit movement
+            if(MF_IS(blmf, FSS_PHYS_SAND) && fss_rand(key, 1316, 0) % 2 == 0 && !(blmf & MF_MOVED)) {
+                if(K > 0) {
+                    B.mf[K > 0 ? K - 1 : 0] = blmf | MF_MOVED;
+                    B.fl |= LF_MF << (K > 0 ? K - 1 : 0);
+                } else {
+                    lb_mf = blmf | MF_MOVED;
+                    p.g.mf[irow + p.g.pitch + lofs] = lb_mf;
+                }
+            }
+            if(MF_IS(brmf, FSS_PHYS_SAND) && fss_rand(key, 1327, 0) % 2 == 0 && !(brmf & MF_MOVED)) {
+                if(K < FSS_CHUNK_W - 1) {
+                    B.mf[K < FSS_CHUNK_W - 1 ? K + 1 : 0] = brmf | MF_MOVED;
+                    B.fl |= LF_MF << (K < FSS_CHUNK_W - 1 ? K + 1 : 0);
+                } else {
+                    rb_mf = brmf | MF_MOVED;
+                    p.g.mf[irow + p.g.pitch + rofs] = rb_mf;
+                }
+            }
+        }
+    }
+
+    // ---- scan 1 of one cell, world.cpp:1154-1665, on the window: A / C / B = rows r-1 / r / r+1, L / R = the outside cells of row r
+    template <int K>
+    __device__ __forceinline__ void cell(LRow& A, LRow& C, LRow& B, LSide& L, LSide& R, cidx_t irow, int r) {
         const uint32_t mf = C.mf[K];
         if(p.iter >= mf_iters(mf)) { // :1163-1166
             C.fl |= LF_VIS << K;
             return;
         }
+        if(SAND && MF_IS(mf, FSS_PHYS_SAND)) {
+            sand1<K>(C, B, irow, r, mf);
+            return;
+        }
         if(!MF_IS(mf, FSS_PHYS_SOUP)) return;
+        // ---- SOUP, world.cpp:1338-1537
         const float amt = C.amt[K];
         if(amt == 0.0f) return;    // :1344
         if(amt < FLUID_MinValue) { // :1346-1350
@@ -177,6 +278,12 @@ struct LiqWalk {
                 tdif -= flow;
                 give<K>(B, flow, mf, i, i + pitch);
             }
+        } else if(p.iter == 0 && MF_IS(bmf, FSS_PHYS_SOUP)) { // :1406-1412 (a different liquid below)
+            const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)(cx + K), (uint32_t)(cy + r));
+            if(fss_rand(key, 1407, 0) % 10 == 0) {
+                exchange<K>(C, B, i, i + pitch, mf, C.dif[K]);
+                return;
+            }
         }
         bool done = remaining < FLUID_MinValue; // :1414-1418
         if(!done) {
@@ -208,17 +315,25 @@ struct LiqWalk {
                 }
                 done = remaining < FLUID_MinValue;
             }
-            // :1486-1516 (the swap of :1510-1516 needs iter == 0)
-            if(!done && (MF_IS(tmf, FSS_PHYS_AIR) || mf_mat(tmf) == mat)) {
-                const float dst = MF_IS(tmf, FSS_PHYS_SOUP) ? A.amt[K] : 0.0f;
-                float flow = remaining - vertical_flow_fast(remaining, dst);
-                flow = clamp_flow(flow, remaining);
-                if(flow != 0) {
-                    remaining -= flow;
-                    tdif -= flow;
-                    give<K>(A, flow, mf, i, i - pitch);
+            // :1486-1516
+            if(!done) {
+                if(MF_IS(tmf, FSS_PHYS_AIR) || mf_mat(tmf) == mat) {
+                    const float dst = MF_IS(tmf, FSS_PHYS_SOUP) ? A.amt[K] : 0.0f;
+                    float flow = remaining - vertical_flow_fast(remaining, dst);
+                    flow = clamp_flow(flow, remaining);
+                    if(flow != 0) {
+                        remaining -= flow;
+                        tdif -= flow;
+                        give<K>(A, flow, mf, i, i - pitch);
+                    }
+                    done = remaining < FLUID_MinValue;
+                } else if(p.iter == 0 && MF_IS(tmf, FSS_PHYS_SOUP)) { // :1510-1516
+                    const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)(cx + K), (uint32_t)(cy + r));
+                    if(fss_rand(key, 1511, 0) % 10 == 0) {
+                        exchange<K>(C, A, i, i - pitch, mf, tdif);
+                        return;
+                    }
                 }
-                done = remaining < FLUID_MinValue;
             }
         }
         if(done) { // :1414-1418, :1450-1454, :1480-1484, :1518-1522
@@ -267,27 +382,30 @@ struct LiqWalk {
         return sum <= FLUID_MaxValue ? FLUID_MaxValue : value;
     }
 
-    // A row leaves the window.  A chunk row (inside = true) first gets scan 2's SOUP step (world.cpp:1808-1825:
+    // A row leaves the window.  A chunk row (inside = true, r = 0 .. 15) first gets scan 2's SOUP step (world.cpp:1808-1825:
     // `fluidAmount += fluidAmountDiff; fluidAmountDiff = 0`, below FLUID_MinValue -> Tiles::NOTHING) on its unvisited SOUP cells;
     // then whatever differs from memory is stored.
-    __device__ __forceinline__ void retire(const LRow& X, cidx_t irow, bool inside) {
+    __device__ __forceinline__ void retire(const LRow& X, cidx_t irow, int r, bool inside) {
 #pragma unroll
         for(int k = 0; k < FSS_CHUNK_W; k++) {
             const cidx_t i = irow + 32 * k;
             const uint32_t mf = X.mf[k];
             const float a = X.amt[k], d = X.dif[k];
-            const bool soup = inside && !(X.fl & (LF_VIS << k)) && MF_IS(mf, FSS_PHYS_SOUP);
+            const bool visited = (X.fl & (LF_VIS << k)) != 0u;
+            const bool soup = inside && !visited && MF_IS(mf, FSS_PHYS_SOUP);
             const float s = a + d;
-            if(soup && s < FLUID_MinValue) {
+            const bool gone = soup && s < FLUID_MinValue;
+            if(!SAND && gone) {
                 busy = true;
                 st_cell(p.g, i, cell_nothing(p.nothing_mf));
                 continue;
             }
-            const bool apply = soup && __float_as_uint(d) != 0u; // else the stores would rewrite the same bits
+            const bool apply = soup && !gone && __float_as_uint(d) != 0u; // else the stores would rewrite the same bits
             if(apply) busy = true;
             if(X.fl & (LF_MF << k)) p.g.mf[i] = mf;
             if(apply || (X.fl & (LF_AMT << k))) p.g.amt[i] = apply ? s : a;
             if(apply || (X.fl & (LF_DIF << k))) p.g.dif[i] = apply ? 0.0f : d;
+            if(SAND && inside && (visited || (soup && !gone))) vis |= 1ull << (r * FSS_CHUNK_W + k);
         }
     }
 
@@ -301,6 +419,13 @@ struct LiqWalk {
         load_row(N, ir - pitch);
         load_side(L, ir + lofs);
         load_side(R, ir + rofs);
+        if(SAND) {
+            lb_mf = p.g.mf[ir + pitch + lofs];
+            rb_mf = p.g.mf[ir + pitch + rofs];
+            prefetch_payload(ir + pitch);
+            prefetch_payload(ir);
+            prefetch_payload(ir - pitch);
+        }
         Ln = L;
         Rn = R;
 #pragma unroll 1
@@ -308,28 +433,44 @@ struct LiqWalk {
             A = N;
             if(r >= 1) { // requested a whole row of arithmetic ahead of their use
                 load_row(N, ir - 2 * pitch);
+                if(SAND) prefetch_payload(ir - 2 * pitch);
                 load_side(Ln, ir - pitch + lofs);
                 load_side(Rn, ir - pitch + rofs);
             }
-            cell<0>(A, C, B, L, R, ir);
-            cell<1>(A, C, B, L, R, ir);
-            cell<2>(A, C, B, L, R, ir);
-            cell<3>(A, C, B, L, R, ir);
-            retire(B, ir + pitch, r < FSS_CHUNK_H - 1);
+            cell<0>(A, C, B, L, R, ir, r);
+            cell<1>(A, C, B, L, R, ir, r);
+            cell<2>(A, C, B, L, R, ir, r);
+            cell<3>(A, C, B, L, R, ir, r);
+            retire(B, ir + pitch, r + 1, r < FSS_CHUNK_H - 1);
             B = C;
             C = A;
+            if(SAND) {
+                lb_mf = L.mf;
+                rb_mf = R.mf;
+            }
             L = Ln;
             R = Rn;
             ir -= pitch;
         }
         // ir = column 0 of row -1; B = row 0, C = row -1
-        retire(B, ir + pitch, true);
-        retire(C, ir, false);
+        retire(B, ir + pitch, 0, true);
+        retire(C, ir, -1, false);
     }
 
     // early-out bookkeeping after the scans (same contract as ChunkWalk::run)
     __device__ __forceinline__ void run(uint8_t* qown) {
         scans();
+        if(SAND) { // scan 2's SAND rule (and the liquid cells its order matters for), through L1
+            ChunkWalk<K1_NOGAS, false, false> w(p, sinfo, cx, cy, wmask);
+            w.vis = vis;
+            w.busy = busy;
+#ifdef K1_SCAN2_LOCKSTEP
+            w.scan2_rest();
+#else
+            w.scan2_sparse();
+#endif
+            busy = w.busy;
+        }
         if(!qown) return;
         if(!busy) {
             *qown = (uint8_t)p.iter;
@@ -341,3 +482,4 @@ struct LiqWalk {
         }
     }
 };
+typedef WinWalk<false> LiqWalk;

@@ -63,6 +63,7 @@ def load():
         "fss_particles_rounds": [vp, C.POINTER(C.c_uint64 * 2)],
         "fss_set_material_looks": [vp, vp, vp, i32],
         "fss_mark_dirty": [vp, i32, i32, i32, i32],
+        "fss_mark_dirty_list": [vp, vp, sz],
         "fss_render_dirty": [vp, vp, i32, C.POINTER(abi.RenderInfo)],
         "fss_download_pixels": [vp, i32, i32, i32, i32, i32, vp, sz],
         "fss_download_dirty": [vp, i32, i32, i32, i32, vp, sz],
@@ -210,10 +211,12 @@ class World:
         _check(self.L, self.L.fss_set_stream(self.h_, C.c_void_p(cuda_stream)))
 
     # ---- side outputs ----
-    def drain_particles(self, cap=1 << 20):
-        out = np.zeros(max(cap, 1), dtype=abi.PARTICLE_DTYPE)
+    def drain_particles(self, cap=None):
+        """the spawn records since the last drain, in World::tick's push order (cap: ignored, the buffer is sized by a query)"""
         n, total = C.c_size_t(), C.c_size_t()
-        _check(self.L, self.L.fss_drain_particles(self.h_, out.ctypes.data, cap, C.byref(n), C.byref(total)))
+        _check(self.L, self.L.fss_drain_particles(self.h_, None, 0, C.byref(n), C.byref(total)))
+        out = np.zeros(max(total.value, 1), dtype=abi.PARTICLE_DTYPE)
+        _check(self.L, self.L.fss_drain_particles(self.h_, out.ctypes.data, total.value, C.byref(n), C.byref(total)))
         return out[: n.value]
 
     # ---- World::dirty and the dirty -> pixels job of Game::tick (Game.cpp:2579-2650); needs track_dirty ----
@@ -224,6 +227,11 @@ class World:
 
     def mark_dirty(self, x, y, w, h):
         _check(self.L, self.L.fss_mark_dirty(self.h_, x, y, w, h))
+
+    def mark_dirty_list(self, rects):
+        """rects: (n, 4) int32 array of x, y, w, h -- one kernel launch for all of them"""
+        rects = np.ascontiguousarray(rects, dtype=np.int32).reshape(-1, 4)
+        _check(self.L, self.L.fss_mark_dirty_list(self.h_, rects.ctypes.data, len(rects)))
 
     def render_dirty(self):
         """(moving_tiles per material, (had_dirty, had_fire, had_flow)); the pixel layers stay on the device"""

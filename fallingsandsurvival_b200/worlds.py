@@ -100,3 +100,45 @@ def default_zone(width: int, height: int, border: int = 16):
 
 MIX_C2 = [(M.TEST_SAND, 25), (M.WATER, 20), (M.COBBLE_STONE, 10)]
 MIX_C3 = MIX_C2 + [(M.LAVA, 3), (M.FIRE, 2), (M.GOLD_ORE, 3), (M.STEAM, 3), (M.SOFT_DIRT, 5)]
+
+
+C1_SIZE = (1984, 1152)
+C1_ZONE = (32, 32, 1920, 1088)
+
+
+def material_test_world(defs, textures=None):
+    """BASELINE.json configs[0] at full size: a 1984 x 1152 world, tick zone 1920 x 1088, laid out like
+    MaterialTestGenerator::generateChunk (MaterialTestGenerator.cpp:32-48, CHUNK_W = CHUNK_H = 128): the cobblestone band
+    at rows 401..450, four walled containers in chunks (1..4, 1) each filled with one random `Mat_N` that is SAND or SOUP,
+    the two cobblestone ramps in chunk columns 1 and 4 -- plus painted 200 x 200 blobs of TEST_SAND, WATER and STEAM, a
+    FIRE strip on a SOFT_DIRT block and a hot GOLD_ORE strip, so that every rule family runs.  Returns (cells, zone)."""
+    w, h = C1_SIZE
+    textures = textures if textures is not None else [M.synthetic_texture(i) for i in range(M.N_TEXTURES)]
+    key = cell_key_grid(1, w, h)
+    py, px = np.mgrid[0:h, 0:w]
+    chx, chy, x, y = px // 128, py // 128, px % 128, py % 128
+    mat = np.zeros((h, w), dtype=np.uint16)
+    # the generator draws `rand() % MATERIALS.size()` per chunk until it hits a Mat_N of type SAND or SOUP: here the first four
+    fillers = [d.id for d in defs if d.id >= 31 and d.physics_type in (abi.PHYS_SAND, abi.PHYS_SOUP)][:4]
+    assert len(fillers) == 4, "the material table needs four Mat_N of type SAND / SOUP (helpers.full_table())"
+    box = (chy == 1) & (chx >= 1) & (chx <= 4)
+    wall = box & ((x < 8) | (y < 8) | (x >= 120) | ((y >= 120) & ((x < 60) | (x >= 68))))
+    mat[wall] = M.COBBLE_DIRT
+    for k, m in enumerate(fillers):
+        mat[box & ~wall & (y > 96) & (chx == 1 + k)] = m
+    ramp = (py <= 400) & (py > 300) & (((chx == 1) & (x < py - 300)) | ((chx == 4) & (128 - x < py - 300)))
+    mat[ramp & ~box] = M.COBBLE_STONE
+    mat[(py > 400) & (py <= 450)] = M.COBBLE_STONE
+    mat[100:300, 700:900] = M.TEST_SAND
+    mat[100:300, 1000:1200] = M.WATER
+    mat[100:300, 1300:1500] = M.STEAM
+    mat[250:300, 1600:1800] = M.SOFT_DIRT
+    mat[246:250, 1610:1790] = M.FIRE
+    mat[60:66, 700:900] = M.GOLD_ORE
+    mat[600:800, 300:500] = M.WATER  # below the band: falls to the world floor
+    mat[600:800, 900:1100] = M.TEST_SAND
+    mat[:16, :] = mat[-16:, :] = M.SOLID
+    mat[:, :16] = mat[:, -16:] = M.SOLID
+    cells = cells_of_material(defs, textures, mat, key)
+    cells["temperature"][mat == M.GOLD_ORE] = 700
+    return cells, C1_ZONE

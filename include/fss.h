@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FSS_ABI_VERSION 1
+#define FSS_ABI_VERSION 2
 
 /* error codes */
 #define FSS_OK 0
@@ -242,6 +242,11 @@ int fss_set_material_looks(fss_world* w, const uint8_t* alpha, const uint32_t* e
 /* host code that writes tiles[] sets dirty itself (World::setTile world.cpp:1061, Game.cpp:1148, :2357 ...): after uploading the
  * cells it marks the same rectangle here */
 int fss_mark_dirty(fss_world* w, int x, int y, int width, int height);
+/* the same for many rectangles with one kernel launch (a brush stroke or a rigid-body stamp is hundreds of small edits) */
+typedef struct fss_rect {
+    int32_t x, y, w, h;
+} fss_rect;
+int fss_mark_dirty_list(fss_world* w, const fss_rect* rects, size_t n);
 int fss_render_dirty(fss_world* w, uint64_t* moving_tiles, int n_materials, fss_render_info* info);
 int fss_download_pixels(fss_world* w, int layer, int x, int y, int width, int height, uint8_t* rgba, size_t pitch_bytes);
 /* World::dirty of a rectangle, one byte per cell (tests) */
@@ -249,8 +254,10 @@ int fss_download_dirty(fss_world* w, int x, int y, int width, int height, uint8_
 
 /* ---- side outputs ---------------------------------------------------------------------------- */
 /* spawn records since the last drain in the order World::tick appends them to World::particles
- * (fss_spawn_order_key below); *n_total = records produced (may exceed cap / capacity: then the surplus
- * was dropped and the call returns FSS_ERR_RANGE). */
+ * (fss_spawn_order_key below).  *n_total = records waiting.  If they do not fit into `cap`, NOTHING is drained and the
+ * call returns FSS_ERR_RANGE (cap == 0: FSS_OK, a plain query): come back with room for *n_total.  The device buffer holds
+ * fss_config.particle_capacity records; a spawn site that finds it full leaves its cell in the grid (it keeps falling
+ * there) and is counted in fss_stats.spawns_refused. */
 int fss_drain_particles(fss_world* w, fss_particle_spawn* out, size_t cap, size_t* n_out, size_t* n_total);
 
 /* The order of World::particles after a tick: per sub-step (iter, tk) the chunk futures are collected in launch order
@@ -361,6 +368,10 @@ typedef struct fss_stats {
     uint32_t storage_pitch;     /* cells per stored row */
     uint32_t storage_rows;
     uint32_t storage_y0;        /* global row of the first stored row */
+    uint32_t reserved;
+    uint64_t spawns_refused;    /* spawn sites that found the record buffer (fss_config.particle_capacity) full: their cells stayed
+                                 * in the grid (no matter is lost) instead of leaving as particles; counted when the host next
+                                 * looks at the buffer (fss_drain_particles, fss_tick_particles) */
 } fss_stats;
 int fss_get_stats(fss_world* w, fss_stats* out);
 

@@ -20,6 +20,7 @@
 #ifndef FSS_WORLD_HPP
 #define FSS_WORLD_HPP
 
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <stdexcept>
@@ -197,10 +198,7 @@ public:
     }
     // after writing tiles[] directly (brush, rigid-body stamping, chunk merge ...): the rectangle goes to the GPU before the next tick
     void markDirty(int x, int y, int w, int h) {
-        if(deviceRender) { // World::setTile and the game's direct writes set dirty[] themselves
-            const bool covered = !marks_.empty() && x >= marks_[0].x && y >= marks_[0].y && x + w <= marks_[0].x + marks_[0].w && y + h <= marks_[0].y + marks_[0].h;
-            if(!covered) marks_.push_back(Rect{x, y, w, h});
-        }
+        if(deviceRender) addMark(x, y, w, h); // World::setTile and the game's direct writes set dirty[] themselves
         if(!pending_) {
             px0_ = x, py0_ = y, px1_ = x + w, py1_ = y + h;
             pending_ = true;
@@ -224,15 +222,14 @@ public:
             spawned.clear();
             return;
         }
+        // every record the tick produced: the cells they stand for have left the grid, so none may be dropped.  A query
+        // (cap 0) tells how many wait; a spawn site that found the device buffer full left its cell in the grid instead
+        // (fss_stats.spawns_refused), so nothing is lost there either.
         size_t n = 0, total = 0;
-        spawned.resize(1 << 16);
-        int rc = fss_drain_particles(core_, spawned.data(), spawned.size(), &n, &total);
-        if(rc == FSS_ERR_RANGE && total > spawned.size()) { // more than fit: the C ABI kept what its own buffer holds
-            spawned.resize(n);
-        } else {
-            check(rc, "fss_drain_particles");
-            spawned.resize(n);
-        }
+        check(fss_drain_particles(core_, nullptr, 0, &n, &total), "fss_drain_particles");
+        spawned.resize(total);
+        if(total) check(fss_drain_particles(core_, spawned.data(), spawned.size(), &n, &total), "fss_drain_particles");
+        spawned.resize(n);
     }
 
     // World::tickParticles (world.cpp:2171-2311); needs deviceParticles.  Landed particles change tiles[] (dirty is set).
@@ -316,6 +313,30 @@ private:
     Rect zoneSet_;
     std::uint32_t nextId_ = 1;
 
+    // World::dirty marks of host edits, kept exact (no cell is marked that the game did not mark) and short: a new rectangle
+    // that an existing one contains is dropped, one that extends an existing one to a larger rectangle (same rows and adjacent
+    // or overlapping columns, or the other way round: a brush stroke, a stamped scan line) is merged into it
+    void addMark(int x, int y, int w, int h) {
+        if(w <= 0 || h <= 0) return;
+        for(size_t k = marks_.size(); k-- > 0 && marks_.size() - k <= 64;) { // the recent ones: edits come in runs
+            Rect& m = marks_[k];
+            if(x >= m.x && y >= m.y && x + w <= m.x + m.w && y + h <= m.y + m.h) return;
+            if(y == m.y && h == m.h && x <= m.x + m.w && x + w >= m.x) {
+                const int x1 = std::max(m.x + m.w, x + w);
+                m.x = std::min(m.x, x);
+                m.w = x1 - m.x;
+                return;
+            }
+            if(x == m.x && w == m.w && y <= m.y + m.h && y + h >= m.y) {
+                const int y1 = std::max(m.y + m.h, y + h);
+                m.y = std::min(m.y, y);
+                m.h = y1 - m.y;
+                return;
+            }
+        }
+        marks_.push_back(Rect{x, y, w, h});
+    }
+
     void applyZone() {
         if(zoneSet_.x != tickZone.x || zoneSet_.y != tickZone.y || zoneSet_.w != tickZone.w || zoneSet_.h != tickZone.h) {
             check(fss_set_tick_zone(core_, tickZone.x, tickZone.y, tickZone.w, tickZone.h), "fss_set_tick_zone");
@@ -332,8 +353,11 @@ private:
         for(int r = 0; r < h; r++)
             for(int c = 0; c < w; c++) stage_[(size_t)r * w + c] = toCell(tiles[(x + c) + (size_t)(y + r) * width]);
         check(fss_upload_rect(core_, x, y, w, h, stage_.data(), (size_t)w), "fss_upload_rect");
-        for(const Rect& m : marks_) check(fss_mark_dirty(core_, m.x, m.y, m.w, m.h), "fss_mark_dirty");
-        marks_.clear();
+        if(!marks_.empty()) { // all marks of the frame in one kernel launch
+            static_assert(sizeof(Rect) == sizeof(fss_rect), "Rect and fss_rect are both four ints");
+            check(fss_mark_dirty_list(core_, reinterpret_cast<const fss_rect*>(marks_.data()), marks_.size()), "fss_mark_dirty_list");
+            marks_.clear();
+        }
     }
     void pull(int x, int y, int w, int h, bool setDirty) { // device -> tiles[]
         if(x < 0) w += x, x = 0;

@@ -73,9 +73,36 @@ def main():
         json.dump(hashes, f, indent=1)
     particle_scene(helpers)
     render_scene(helpers)
+    c1_full_size(helpers)
 
 
 PARTICLE_SCENE_TICKS = 16
+C1_CHECKPOINTS = (100, 500, 1000)
+
+
+def c1_full_size(helpers):
+    """c1_material_test_1984x1152.json: BASELINE.json configs[0] at its stated size (worlds.material_test_world: the
+    MaterialTestGenerator layout, 1920 x 1088 tick zone), World::tick with tickTemperature every 4th tick as Game::tick runs
+    them (Game.cpp:2759), particles emitted, 1000 ticks on the reference's own lines (about 20 minutes on 8 cores)."""
+    from fallingsandsurvival_b200 import worlds
+    cells, zone = worlds.material_test_world(helpers.full_table())
+    r = refsim.RefWorld(cells, zone, particles=True, seed=0xF55)
+    out = dict(size=list(worlds.C1_SIZE), zone=list(zone), checkpoints={})
+    spawned = 0
+    for t in range(max(C1_CHECKPOINTS)):
+        r.tick(t)
+        if t % 4 == 2:
+            r.tick_temperature()
+        if t + 1 in C1_CHECKPOINTS:
+            spawned += len(r.drain_particles()[1])
+            c = r.cells()
+            out["checkpoints"][str(t + 1)] = dict(
+                digest=f"{oraclesim.hash_cells(c):016x}", spawn_records=spawned,
+                histogram={str(k): int(v) for k, v in zip(*np.unique(c['material'], return_counts=True))})
+            print("c1", t + 1, out["checkpoints"][str(t + 1)]["digest"], flush=True)
+    r.close()
+    with open(os.path.join(HERE, "c1_material_test_1984x1152.json"), "w") as f:
+        json.dump(out, f, indent=1)
 
 
 def render_scene(helpers):
@@ -125,4 +152,8 @@ def particle_scene(helpers):
 
 
 if __name__ == "__main__":
-    main()
+    if "--c1" in sys.argv:  # only the full-size configs[0] record (the slow one)
+        import helpers
+        c1_full_size(helpers)
+    else:
+        main()

@@ -12,6 +12,14 @@
 #include "fss_rules.cuh"
 #include "fss_rules_liq.cuh"
 
+#ifdef K1_STATS
+unsigned long long g_k1_stats[32];
+extern "C" void hs_stats(unsigned long long* out, int reset) {
+    memcpy(out, g_k1_stats, sizeof g_k1_stats);
+    if(reset) memset(g_k1_stats, 0, sizeof g_k1_stats);
+}
+#endif
+
 struct HostWorld {
     int width, height;
     Grid g;
@@ -28,13 +36,18 @@ struct HostWorld {
     int condense;
     int zx, zy, zw, zh;
     std::vector<fss_particle_spawn> parts;
-    unsigned long long part_count = 0;
+    unsigned long long part_count[2] = {0, 0};
     std::vector<uint8_t> q;
     int q_w = 0, q_h = 0;
 };
 
 template <int MODE, bool FLOW, bool DIRTY>
 static void run_launch(HostWorld* w, const SubstepParams& p) {
+    // fss_abi.cu keeps track of which materials can be present; here the grid itself is asked: is there a SAND cell whose
+    // material has reactions (world.cpp:1251-1274)?  Without one no reaction can create one during the launch.
+    bool sand_reacts = false;
+    for(size_t i = 0; i < w->mf.size() && !sand_reacts; i++)
+        sand_reacts = MF_IS(w->mf[i], FSS_PHYS_SAND) && w->mats[mf_mat(w->mf[i])].n_react > 0;
     for(int by = 0; by < p.ny; by++) {
         for(int gi = 0; gi < p.nx; gi++) {
             uint8_t* qown = nullptr;
@@ -43,8 +56,8 @@ static void run_launch(HostWorld* w, const SubstepParams& p) {
                 if(*qown <= (uint8_t)p.iter) continue;
             }
             const int cx = p.x_begin + 2 * FSS_CHUNK_W * gi, cy = p.y_begin + 2 * FSS_CHUNK_H * by;
-            if(liq_window_applies(MODE, p.iter, p.flags, FLOW, DIRTY)) { // launch_substep's choice (csrc/fss_abi.cu)
-                LiqWalk walk(p, w->sinfo, cx, cy, 1u);
+            if(liq_window_applies(MODE, p.iter, p.flags, FLOW, DIRTY, sand_reacts)) { // launch_substep's choice (csrc/fss_abi.cu)
+                WinWalk<MODE == K1_NOGAS> walk(p, w->sinfo, cx, cy, 1u);
                 walk.run(qown);
             } else {
                 ChunkWalk<MODE, FLOW, DIRTY> walk(p, w->sinfo, cx, cy, 1u);
@@ -223,7 +236,7 @@ int hs_substep(void* h, uint32_t tick_ct, int iter, int tk, int mode) {
     p.fire_id = w->fire_id;
     p.nothing_mf = 0u | w->mats[0].bits;
     p.parts = w->parts.data();
-    p.part_count = &w->part_count;
+    p.part_count = w->part_count;
     p.part_cap = (uint32_t)w->parts.size();
     p.q = w->q.empty() ? nullptr : w->q.data();
     p.qskip = nullptr;
@@ -250,9 +263,9 @@ int hs_substep(void* h, uint32_t tick_ct, int iter, int tk, int mode) {
 
 size_t hs_drain(void* h, fss_particle_spawn* out, size_t cap) {
     HostWorld* w = (HostWorld*)h;
-    size_t n = (size_t)std::min<unsigned long long>(w->part_count, cap);
+    size_t n = (size_t)std::min<unsigned long long>(w->part_count[0], cap);
     memcpy(out, w->parts.data(), n * sizeof(fss_particle_spawn));
-    w->part_count = 0;
+    w->part_count[0] = 0;
     return n;
 }
 

@@ -42,6 +42,7 @@ static inline float __uint_as_float(unsigned u) {
 }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
 static inline unsigned __activemask() { return 1u; }
 static inline unsigned __ballot_sync(unsigned, int pred) { return pred ? 1u : 0u; }
 static inline int __any_sync(unsigned, int pred) { return pred != 0; }

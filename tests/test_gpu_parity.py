@@ -351,6 +351,33 @@ def test_thousand_ticks_bit_exact():
     o.close()
 
 
+def test_c1_full_size_thousand_ticks_against_the_reference_build():
+    """BASELINE.json configs[0] at its stated size: the MaterialTestGenerator world (worlds.material_test_world, 1984 x 1152,
+    tick zone 1920 x 1088), 1000 ticks with tickTemperature every 4th, particles emitted -- against the digests, spawn-record
+    counts and material histograms the reference's OWN lines (oracle/_ref) produced offline
+    (tests/golden/c1_material_test_1984x1152.json, minted by tests/golden/make_golden.py --c1)."""
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_material_test_1984x1152.json")) as f:
+        gold = json.load(f)
+    cells, zone = worlds.material_test_world(full_table())
+    assert list(cells.shape[::-1]) == gold["size"] and list(zone) == gold["zone"]
+    g = gpu_world(cells, zone, particles=True, particle_capacity=1 << 22)
+    spawned = 0
+    for t in range(1000):
+        g.tick(t)
+        if t % 4 == 2:
+            g.tick_temperature()
+        if t % 20 == 19:
+            spawned += len(g.drain_particles(cap=1 << 22))
+        if str(t + 1) in gold["checkpoints"]:
+            want = gold["checkpoints"][str(t + 1)]
+            assert f"{g.hash():016x}" == want["digest"], f"tick {t + 1}: digest differs from the reference build's"
+            assert spawned == want["spawn_records"], f"tick {t + 1}: {spawned} spawn records, the reference build pushed {want['spawn_records']}"
+            hist = g.histogram()
+            assert {str(m): int(c) for m, c in enumerate(hist) if c} == want["histogram"]
+    g.close()
+
+
 def test_full_size_properties():
     """at BASELINE's 16384 x 16384 the oracle is out of reach; check what does not need it: the digest of a 2-strip
     run equals the undivided run, early-out on equals off, and SAND / SOLID counts are conserved"""
@@ -987,3 +1014,42 @@ def test_sand_reaction_below_a_temperature():
     assert (b["material"] == M.DIRT).sum() > (cells["material"] == M.DIRT).sum()
     g.close()
     o.close()
+
+
+def test_full_spawn_buffer_loses_no_matter():
+    """a spawn site that finds the record buffer (fss_config.particle_capacity) full must leave its cell in
+    the grid instead of dropping the record of a cell that already left it.  SAND cells in the grid + SAND records handed
+    out stays constant; the refusals are counted; a drain that does not fit consumes nothing."""
+    import ctypes as C
+    cells, zone = make_world((264, 208), "sand", seed=31)
+    g = gpu_world(cells, zone, particles=True, particle_capacity=64)
+    sand_ids = [d.id for d in full_table() if d.physics_type == abi.PHYS_SAND]
+    before = int(np.isin(cells["material"], sand_ids).sum())
+    handed_out = 0
+    for t in range(6):
+        g.tick(t)
+        n, total = C.c_size_t(), C.c_size_t()
+        small = np.zeros(4, dtype=abi.PARTICLE_DTYPE)
+        rc = g.L.fss_drain_particles(g.h_, small.ctypes.data, 4, C.byref(n), C.byref(total))
+        if total.value > 4:
+            assert rc == abi.FSS_ERR_RANGE and n.value == 0  # nothing consumed
+        recs = g.drain_particles()
+        assert len(recs) <= 64 and (total.value <= 4 or len(recs) == total.value)
+        handed_out += int(np.isin(recs["cell"]["material"], sand_ids).sum())
+        now = int(np.isin(g.cells()["material"], sand_ids).sum())
+        assert now + handed_out == before, f"tick {t}: {before - now - handed_out} SAND cells vanished"
+    assert g.stats().spawns_refused > 0
+    g.close()
+
+
+def test_mark_dirty_list_equals_single_marks():
+    cells, zone = make_world((264, 208), "c3", seed=32)
+    rects = np.array([[20, 20, 5, 1], [25, 20, 9, 1], [40, 60, 3, 7], [-4, 100, 10, 10], [200, 190, 100, 100], [50, 50, 0, 4]], dtype=np.int32)
+    a = gpu_world(cells, zone, track_dirty=True)
+    b = gpu_world(cells, zone, track_dirty=True)
+    for x, y, w, h in rects:
+        a.mark_dirty(int(x), int(y), int(w), int(h))
+    b.mark_dirty_list(rects)
+    assert a.dirty().tobytes() == b.dirty().tobytes() and int(a.dirty().sum()) > 0
+    a.close()
+    b.close()

@@ -297,3 +297,21 @@ def test_oracle_flow_matches_reference_build(mix, have_ref):
     assert rx.tobytes() == ox.tobytes() and ry.tobytes() == oy.tobytes()
     r.close()
     o.close()
+
+
+def test_oracle_matches_c1_full_size_golden():
+    """BASELINE.json configs[0] at its stated size (1984 x 1152 MaterialTestGenerator world, worlds.material_test_world): the
+    plain-C restatement against what the reference's own lines produced offline (tests/golden/make_golden.py --c1), at the
+    first checkpoint (100 ticks; the GPU test runs all 1000)."""
+    from fallingsandsurvival_b200 import worlds
+    with open(os.path.join(GOLDEN, "c1_material_test_1984x1152.json")) as f:
+        gold = json.load(f)
+    cells, zone = worlds.material_test_world(full_table())
+    o = oraclesim.OracleWorld(cells, zone, defs=full_table(), particles=True)
+    run_ticks(o, 100)
+    want = gold["checkpoints"]["100"]
+    c = o.cells()
+    assert f"{oraclesim.hash_cells(c):016x}" == want["digest"]
+    assert len(o.drain_particles()) == want["spawn_records"]
+    assert {str(k): int(v) for k, v in zip(*np.unique(c["material"], return_counts=True))} == want["histogram"]
+    o.close()
