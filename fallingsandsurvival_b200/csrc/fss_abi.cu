@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
+#include <cmath>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -112,6 +113,10 @@ struct fss_world {
     uint32_t part_cap;
     void* d_stage;
     size_t stage_bytes;
+    // fss_tick_host: its own staging buffer for the way back, the two copy streams, one event pair per band
+    void* d_stage_down;
+    cudaStream_t up_stream, down_stream;
+    cudaEvent_t ev_up[32], ev_wave[32], ev_stage_free;
     unsigned long long* d_red; // FSS_MAX_MATERIALS u64 + FSS_MAX_MATERIALS f64
     fss_stats stats;
     // settled-chunk flags (SubstepParams::q): (q_h x q_w) bytes, chunk (ci, cj) of the zone at [(cj - q_cj0 + 1) * q_w + ci + 1]
@@ -370,6 +375,14 @@ int fss_destroy(fss_world* w) {
     cudaFree(w->d_part_count);
     cudaFree(w->d_red);
     cudaFree(w->d_stage);
+    cudaFree(w->d_stage_down);
+    if(w->up_stream) cudaStreamDestroy(w->up_stream);
+    if(w->down_stream) cudaStreamDestroy(w->down_stream);
+    for(int k = 0; k < 32; k++) {
+        if(w->ev_up[k]) cudaEventDestroy(w->ev_up[k]);
+        if(w->ev_wave[k]) cudaEventDestroy(w->ev_wave[k]);
+    }
+    if(w->ev_stage_free) cudaEventDestroy(w->ev_stage_free);
     cudaFree(w->d_q);
     cudaFree(w->d_qskip);
     cudaFree(w->d_present);
@@ -413,6 +426,8 @@ int fss_set_materials(fss_world* w, const fss_material* t, int n) {
             return fail(FSS_ERR_INVALID, "material %d: the fire material must be PASSABLE like Materials::FIRE (Materials.cpp:42)", i);
         if(m.n_reactions < 0 || m.n_reactions > FSS_MAX_REACTIONS) return fail(FSS_ERR_INVALID, "material %d: %d reactions", i, m.n_reactions);
         if(m.create_kind == FSS_CREATE_RAND && m.create_rand_mod == 0) return fail(FSS_ERR_INVALID, "material %d: create_rand_mod == 0", i);
+        if(!std::isfinite(m.conduction_other) || !std::isfinite(m.conduction_self))
+            return fail(FSS_ERR_INVALID, "material %d: conductionSelf / conductionOther must be finite (world.cpp:2072-2132)", i);
         if(m.create_kind == FSS_CREATE_TEXTURE && m.create_texture >= FSS_MAX_TEXTURES) return fail(FSS_ERR_INVALID, "material %d: texture %d", i, m.create_texture);
         d.density = m.density;
         const int iters = m.iterations < 0 ? 0 : (m.iterations > 7 ? 7 : m.iterations); // iter < 6 always: clamping is exact
@@ -613,12 +628,18 @@ static int ready(fss_world* w) {
     return use_device(w);
 }
 
-static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk) {
+// jr_lo / jr_hi >= 0: only the 32-row bands [jr_lo, jr_hi) of the zone (fss_tick_host's waves), else all the owned ones
+static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int jr_lo = -1, int jr_hi = -1) {
     // world.cpp:1115-1141: phase tk activates chunks at zone + (tk%2, 1 - tk/2) * chunk + 2*chunk*(i, j)
     const int ofs_x = tk % 2, ofs_y = 1 - tk / 2;
     // rows of active chunks owned by this strip (boundaries are multiples of 2*CHUNK_H from zone.y)
     int j_lo, j_hi;
     owned_bands(w, j_lo, j_hi);
+    const int own_j_lo = j_lo;
+    if(jr_lo >= 0) {
+        j_lo = std::max(j_lo, jr_lo);
+        j_hi = std::min(j_hi, jr_hi);
+    }
     SubstepParams p;
     p.g = w->g;
     p.mats = w->d_mats;
@@ -638,12 +659,14 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk) {
     p.parts = w->d_parts;
     p.part_count = w->d_part_count;
     p.part_cap = w->part_cap;
-    p.q = w->d_q;
-    p.qskip = w->d_qskip;
+    // (the kernels index the flags by blockIdx.y: start them at this launch's first band)
+    const size_t q_ofs = (size_t)std::max(0, 2 * (j_lo - own_j_lo)) * (size_t)w->q_w;
+    p.q = w->d_q ? w->d_q + q_ofs : nullptr;
+    p.qskip = w->d_qskip ? w->d_qskip + q_ofs : nullptr;
     p.q_w = w->q_w;
     p.ofs_x = ofs_x;
     p.ofs_y = ofs_y;
-    w->stats.substeps++;
+    if(jr_lo < 0) w->stats.substeps++;
     if(p.ny <= 0 || p.nx <= 0) return FSS_OK;
     {
         const dim3 grid((p.nx + K1_THREADS - 1) / K1_THREADS, p.ny);
@@ -661,8 +684,13 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk) {
         }                                                                                          \
     } while(0)
         if(liq_window_applies(mode, iter, w->cfg.flags, flow, dirty, w->sand_reacts)) {
-            if(mode == K1_LIQUID) k_substep_win<false><<<grid, K1_THREADS, 0, w->stream>>>(p);
-            else k_substep_win<true><<<grid, K1_THREADS, 0, w->stream>>>(p);
+            if(mode == K1_LIQUID) {
+                if(iter == 0) k_substep_win<false, true><<<grid, K1_THREADS, 0, w->stream>>>(p);
+                else k_substep_win<false, false><<<grid, K1_THREADS, 0, w->stream>>>(p);
+            } else {
+                if(iter == 0) k_substep_win<true, true><<<grid, K1_THREADS, 0, w->stream>>>(p);
+                else k_substep_win<true, false><<<grid, K1_THREADS, 0, w->stream>>>(p);
+            }
         } else if(mode == K1_LIQUID) FSS_LAUNCH_K1_MODE(K1_LIQUID);
         else if(mode == K1_NOGAS) FSS_LAUNCH_K1_MODE(K1_NOGAS);
         else FSS_LAUNCH_K1_MODE(K1_GENERAL);
@@ -698,6 +726,122 @@ int fss_tick(fss_world* w, uint32_t tick_ct) {
         }
     }
     CU(cudaGetLastError());
+    return FSS_OK;
+}
+
+// ---- fss_tick_host: upload | 24 sub-steps | download, pipelined in row bands ----------------------------------------------
+// Band b = stored rows [R_b, R_b+1), interior boundaries at zone.y + 32 * K_b.  After band b has arrived, "wave b" runs the 24
+// sub-steps s = 0 .. 23 on the 32-row bands [F_b-1(s), F_b(s)) of the zone, F_b(s) = K_b - (s + 1) (last band: all the rest):
+// a chunk visit reads at most 10 rows below its chunk and writes at most 2, so everything sub-step s reads inside
+// [.., F_b(s)) was brought to the state after sub-step s-1 by this or an earlier wave and lies above row zone.y + 32 * K_b,
+// i.e. in the bands that have arrived; and the chunks a later wave adds to sub-step s are, as in every sub-step, independent
+// of the ones that already ran it (the checkerboard phase is race-free in any order).  Rows above F_b(23) - 1 are final
+// after wave b and go back to the host while the next band is still on its way in.
+#ifndef FSS_HOST_BAND_ROWS
+#define FSS_HOST_BAND_ROWS 1024
+#endif
+static int host_copy_rows(fss_world* w, cudaStream_t st, void* stage, int y, int nrows, fss_cell* cells, size_t pitch_cells, bool upload) {
+    const int width = (int)w->cfg.width;
+    const int rows_per_pass = (int)std::min<size_t>(65535, std::max<size_t>(1, w->stage_bytes / ((size_t)width * sizeof(fss_cell))));
+    const int nblk = ((width - 1) >> 8) + 1;
+    for(int r0 = 0; r0 < nrows; r0 += rows_per_pass) {
+        const int nr = std::min(rows_per_pass, nrows - r0);
+        RectParams p;
+        p.g = w->g;
+        p.mats = w->d_mats;
+        p.n_mat = w->n_mat;
+        p.aos = (uint32_t*)stage;
+        p.present = w->d_present;
+        p.rx = 0;
+        p.ry = y + r0;
+        p.rw = width;
+        p.rh = nr;
+        fss_cell* h = cells + (size_t)(y + r0 - w->g.sy0) * pitch_cells;
+        const size_t row_bytes = (size_t)width * sizeof(fss_cell);
+        if(upload) {
+            if(pitch_cells == (size_t)width) CU(cudaMemcpyAsync(stage, h, row_bytes * nr, cudaMemcpyHostToDevice, st));
+            else CU(cudaMemcpy2DAsync(stage, row_bytes, h, pitch_cells * sizeof(fss_cell), row_bytes, nr, cudaMemcpyHostToDevice, st));
+            k_upload<<<dim3(nblk, nr), 256, 0, st>>>(p);
+        } else {
+            k_download<<<dim3(nblk, nr), 256, 0, st>>>(p);
+            if(pitch_cells == (size_t)width) CU(cudaMemcpyAsync(h, stage, row_bytes * nr, cudaMemcpyDeviceToHost, st));
+            else CU(cudaMemcpy2DAsync(h, pitch_cells * sizeof(fss_cell), stage, row_bytes, row_bytes, nr, cudaMemcpyDeviceToHost, st));
+        }
+        w->stats.kernel_launches++;
+        CU(cudaGetLastError());
+    }
+    return FSS_OK;
+}
+
+int fss_tick_host(fss_world* w, uint32_t tick_ct, fss_cell* cells, size_t pitch_cells) {
+    int rc = ready(w);
+    if(rc) return rc;
+    if(!cells) return fail(FSS_ERR_INVALID, "null argument");
+    if(pitch_cells < (size_t)w->cfg.width) return fail(FSS_ERR_INVALID, "pitch %zu < width %u", pitch_cells, w->cfg.width);
+    const int y0 = w->g.sy0, rows = w->g.rows, width = (int)w->cfg.width;
+    static const int band_rows = getenv("FSS_HOST_BAND_ROWS") ? std::max(32 * 26, atoi(getenv("FSS_HOST_BAND_ROWS")) / 32 * 32) : FSS_HOST_BAND_ROWS;
+    int n_bands = std::min(32, w->zh / band_rows);
+    if(w->sharded || n_bands < 2) { // nothing to overlap (or halo exchanges in between): the plain sequence
+        if((rc = fss_upload_rect(w, 0, y0, width, rows, cells, pitch_cells))) return rc;
+        if((rc = fss_tick(w, tick_ct))) return rc;
+        return fss_download_rect(w, 0, y0, width, rows, cells, pitch_cells);
+    }
+    if(!w->up_stream) {
+        CU(cudaStreamCreateWithFlags(&w->up_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&w->down_stream, cudaStreamNonBlocking));
+        CU(cudaMalloc(&w->d_stage_down, w->stage_bytes));
+        for(int k = 0; k < 32; k++) {
+            CU(cudaEventCreateWithFlags(&w->ev_up[k], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&w->ev_wave[k], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&w->ev_stage_free, cudaEventDisableTiming));
+    }
+    // whatever the world's stream still has queued comes first
+    CU(cudaEventRecord(w->ev_stage_free, w->stream));
+    CU(cudaStreamWaitEvent(w->up_stream, w->ev_stage_free, 0));
+    CU(cudaStreamWaitEvent(w->down_stream, w->ev_stage_free, 0));
+    const int zbands = w->zh / FSS_ZONE_ALIGN_Y; // 32-row bands of the zone
+    auto K = [&](int b) { return b >= n_bands ? zbands : (int)((long long)zbands * b / n_bands); };   // band b ends before 32-row band K(b+1)
+    auto row_end = [&](int b) { return b + 1 >= n_bands ? y0 + rows : w->zy + K(b + 1) * FSS_ZONE_ALIGN_Y; }; // first stored row after band b
+    auto front = [&](int b, int s) { return b < 0 ? 0 : (b + 1 >= n_bands ? zbands : std::max(0, K(b + 1) - (s + 1))); };
+    std::vector<uint8_t> seen(FSS_MAX_MATERIALS * (size_t)n_bands);
+    auto upload_band = [&](int b) -> int {
+        const int lo = b == 0 ? y0 : row_end(b - 1), hi = row_end(b);
+        if(int r = host_copy_rows(w, w->up_stream, w->d_stage, lo, hi - lo, cells, pitch_cells, true)) return r;
+        CU(cudaMemcpyAsync(seen.data() + (size_t)b * FSS_MAX_MATERIALS, w->d_present, FSS_MAX_MATERIALS, cudaMemcpyDeviceToHost, w->up_stream));
+        CU(cudaEventRecord(w->ev_up[b], w->up_stream));
+        return FSS_OK;
+    };
+    if((rc = upload_band(0))) return rc;
+    int down_lo = y0; // next row to go back to the host
+    for(int b = 0; b < n_bands; b++) {
+        if(b + 1 < n_bands && (rc = upload_band(b + 1))) return rc; // keep the bus busy while the host waits below
+        // which materials the bands so far hold decides which kernel specialisation is exact for this wave: everything wave b
+        // computes is a function of the bands 0 .. b only (see above)
+        CU(cudaEventSynchronize(w->ev_up[b]));
+        for(int m = 0; m < FSS_MAX_MATERIALS; m++) w->present[m] = w->present[m] || seen[(size_t)b * FSS_MAX_MATERIALS + m];
+        recompute_liq(w);
+        const int lo = b == 0 ? y0 : row_end(b - 1), hi = row_end(b);
+        CU(cudaStreamWaitEvent(w->stream, w->ev_up[b], 0));
+        if(dirty_chunks(w, 0, lo, width, hi - lo)) return FSS_ERR_CUDA;
+        for(int s = 0; s < 24; s++) {
+            const int j0 = front(b - 1, s), j1 = front(b, s);
+            if(j1 > j0 && (rc = launch_substep(w, tick_ct, s / 4, s % 4, j0, j1))) return rc;
+        }
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(w->ev_wave[b], w->stream));
+        // rows that no later wave touches: above the last sub-step's front, less one chunk pair (a visit writes 2 rows up)
+        const int final_hi = b + 1 >= n_bands ? y0 + rows : std::max(down_lo, w->zy + (front(b, 23) - 1) * FSS_ZONE_ALIGN_Y);
+        if(final_hi > down_lo) {
+            CU(cudaStreamWaitEvent(w->down_stream, w->ev_wave[b], 0));
+            if((rc = host_copy_rows(w, w->down_stream, w->d_stage_down, down_lo, final_hi - down_lo, cells, pitch_cells, false))) return rc;
+            down_lo = final_hi;
+        }
+    }
+    w->stats.substeps += 24;
+    CU(cudaStreamSynchronize(w->down_stream));
+    CU(cudaStreamSynchronize(w->up_stream));
+    CU(cudaStreamSynchronize(w->stream));
     return FSS_OK;
 }
 

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS
 #ifndef K1WS_MIN_BLOCKS
 #define K1WS_MIN_BLOCKS 4
 #endif
-template <bool SAND>
+template <bool SAND, bool ITER0>
 __global__ void __launch_bounds__(K1_THREADS, SAND ? K1WS_MIN_BLOCKS : K1W_MIN_BLOCKS) k_substep_win(const __grid_constant__ SubstepParams p) {
     __shared__ uint32_t sinfo[SAND ? FSS_MAX_MATERIALS : 1];
     if(SAND) {
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(K1_THREADS, SAND ? K1WS_MIN_BLOCKS : K1W_MIN_B
         if(*qown <= (uint8_t)p.iter) return; // verified settled
     }
 #endif
-    WinWalk<SAND> w(p, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y, __activemask());
+    WinWalk<SAND, ITER0> w(p, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y, __activemask());
     w.run(qown);
 }
 
@@ -172,11 +172,15 @@ __device__ __forceinline__ void temp_terms(const float* s_co, const TempRaw& r, 
     for(int c = 0; c < 10; c++) {
         const int32_t t = r.t[c];
         const uint32_t m = mf_mat(r.m[c]);
-        // `if(T != 0) { factor = abs(T) / 64.0f * conductionOther; v += T * factor; n += factor; }` as selects
-        const float fa = abs(t) / 64.0f * s_co[m];
-        const float ta = t * fa;
-        o.f[c] = t != 0 ? fa : 0.0f;
-        o.tf[c] = t != 0 ? ta : 0.0f;
+        // `if(T != 0) { factor = abs(T) / 64.0f * conductionOther; v += T * factor; n += factor; }` without the test: for
+        // T == 0 the two terms come out as zeros (conductionOther is finite: fss_set_materials), and adding a zero of either
+        // sign leaves the running sums as the skipped statement does (v and n are never -0: n starts at 0.01, v at +0 and
+        // x + (-x) rounds to +0).  float(abs(T)) == fabsf(float(T)): the conversion rounds symmetrically.
+        const float ft = (float)t;
+        const float fa = fabsf(ft) / 64.0f * s_co[m];
+        const float ta = ft * fa;
+        o.f[c] = fa;
+        o.tf[c] = ta;
         if(c >= 1 && c <= 4) lo |= m << (8 * (c - 1));
         if(c >= 5 && c <= 8) hi |= m << (8 * (c - 5));
         if(c >= 1 && c <= 8) o.t[c - 1] = t;

@@ -83,7 +83,10 @@ struct LSide { // the cell left / right of the row being scanned (outside the ch
 // SAND = true:  SAND acts too: its scan-1 rule (falling straight down, world.cpp:1276-1335) runs on the window as well;
 //               cells that scan 2's liquid step would delete are left to scan 2 proper (they change type, which a SAND
 //               cell to their left tests first: ChunkWalk::early_apply_row), and `vis` is handed to ChunkWalk::scan2_rest().
-template <bool SAND>
+// ITER0: the sub-step is an iter-0 one: only then can two different liquids change places (world.cpp:1406-1412, :1510-1516);
+//        compiled out of the other five iters' kernels (their code is a tenth shorter: instruction-cache misses are a
+//        measurable part of this kernel's stalls)
+template <bool SAND, bool ITER0 = true>
 struct WinWalk {
     const SubstepParams& p;
     const uint32_t* sinfo;
@@ -278,7 +281,7 @@ struct WinWalk {
                 tdif -= flow;
                 give<K>(B, flow, mf, i, i + pitch);
             }
-        } else if(p.iter == 0 && MF_IS(bmf, FSS_PHYS_SOUP)) { // :1406-1412 (a different liquid below)
+        } else if(ITER0 && p.iter == 0 && MF_IS(bmf, FSS_PHYS_SOUP)) { // :1406-1412 (a different liquid below)
             const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)(cx + K), (uint32_t)(cy + r));
             if(fss_rand(key, 1407, 0) % 10 == 0) {
                 exchange<K>(C, B, i, i + pitch, mf, C.dif[K]);
@@ -327,7 +330,7 @@ struct WinWalk {
                         give<K>(A, flow, mf, i, i - pitch);
                     }
                     done = remaining < FLUID_MinValue;
-                } else if(p.iter == 0 && MF_IS(tmf, FSS_PHYS_SOUP)) { // :1510-1516
+                } else if(ITER0 && p.iter == 0 && MF_IS(tmf, FSS_PHYS_SOUP)) { // :1510-1516
                     const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)(cx + K), (uint32_t)(cy + r));
                     if(fss_rand(key, 1511, 0) % 10 == 0) {
                         exchange<K>(C, A, i, i - pitch, mf, tdif);
@@ -482,4 +485,3 @@ struct WinWalk {
         }
     }
 };
-typedef WinWalk<false> LiqWalk;

@@ -52,6 +52,7 @@ def load():
         "fss_merge_chunk_records": [vp, i32, i32, i32, i32, vp],
         "fss_read_chunk_records": [vp, i32, i32, i32, i32, vp],
         "fss_tick": [vp, u32],
+        "fss_tick_host": [vp, u32, vp, sz],
         "fss_substep": [vp, u32, i32, i32],
         "fss_tick_temperature": [vp],
         "fss_drain_particles": [vp, vp, sz, C.POINTER(sz), C.POINTER(sz)],
@@ -196,6 +197,15 @@ class World:
         if tick_ct is None:
             tick_ct = self.tick_ct
         _check(self.L, self.L.fss_tick(self.h_, tick_ct))
+        self.tick_ct = tick_ct + 1
+
+    def tick_host(self, cells, tick_ct=None):
+        """World::tick() for a grid kept on the host: `cells` = the stored rows (rows, W) of abi.CELL_DTYPE, updated in place;
+        upload, the 24 sub-steps and download overlap band by band (fss_tick_host); pin the array for the overlap to happen"""
+        if tick_ct is None:
+            tick_ct = self.tick_ct
+        assert cells.dtype == abi.CELL_DTYPE and cells.flags["C_CONTIGUOUS"] and cells.shape == (self.stored[1] - self.stored[0], self.w)
+        _check(self.L, self.L.fss_tick_host(self.h_, tick_ct, cells.ctypes.data, self.w))
         self.tick_ct = tick_ct + 1
 
     def substep(self, tick_ct, iter_, tk):

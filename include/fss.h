@@ -211,6 +211,16 @@ int fss_shift_grid(fss_world* w, int change_x, int change_y);
  * `tick_ct` is World::tickCt (world.cpp:2017), the RNG key.  Asynchronous.  For a strip-sharded
  * world with a communicator attached this also performs the per-sub-step halo exchange. */
 int fss_tick(fss_world* w, uint32_t tick_ct);
+/* One World::tick() for a caller that keeps `tiles[]` on the host (the shim's worst case: the whole grid crosses PCIe both
+ * ways every tick).  Same result as
+ *     fss_upload_rect(w, 0, y0, width, rows, cells, pitch); fss_tick(w, tick_ct); fss_download_rect(w, 0, y0, width, rows, cells, pitch);
+ * for the stored rows [y0, y0 + rows) of the world (all rows unless strip-sharded; `cells` points at row y0), but pipelined in
+ * row bands on three streams: while band b+1 is still being uploaded, the 24 sub-steps already run on the rows that can no
+ * longer see it (a sub-step reaches 26 rows down, so the band's lower edge recedes by one 32-row chunk pair per sub-step), and
+ * the rows that are final go back to the host meanwhile -- both PCIe directions and the kernels overlap.  Synchronous: the
+ * caller owns `cells` again on return.  `cells` should be page-locked (cudaHostAlloc / cudaHostRegister) for the overlap to
+ * happen.  Strip-sharded worlds run the plain sequence above. */
+int fss_tick_host(fss_world* w, uint32_t tick_ct, fss_cell* cells, size_t pitch_cells);
 /* one sub-step (iter, tk) of the above without halo exchange */
 int fss_substep(fss_world* w, uint32_t tick_ct, int iter, int tk);
 /* one World::tickTemperature() (world.cpp:2043-2143).  Asynchronous. */

@@ -57,8 +57,13 @@ static void run_launch(HostWorld* w, const SubstepParams& p) {
             }
             const int cx = p.x_begin + 2 * FSS_CHUNK_W * gi, cy = p.y_begin + 2 * FSS_CHUNK_H * by;
             if(liq_window_applies(MODE, p.iter, p.flags, FLOW, DIRTY, sand_reacts)) { // launch_substep's choice (csrc/fss_abi.cu)
-                WinWalk<MODE == K1_NOGAS> walk(p, w->sinfo, cx, cy, 1u);
-                walk.run(qown);
+                if(p.iter == 0) {
+                    WinWalk<MODE == K1_NOGAS, true> walk(p, w->sinfo, cx, cy, 1u);
+                    walk.run(qown);
+                } else {
+                    WinWalk<MODE == K1_NOGAS, false> walk(p, w->sinfo, cx, cy, 1u);
+                    walk.run(qown);
+                }
             } else {
                 ChunkWalk<MODE, FLOW, DIRTY> walk(p, w->sinfo, cx, cy, 1u);
                 walk.run(qown);
