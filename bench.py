@@ -180,7 +180,7 @@ FILLS = {
     "c2": "25% TEST_SAND / 20% WATER / 10% COBBLE_STONE, rest AIR (hash(seed, x, y) % 100)",
     "c3": "c2 fill + 3% LAVA 2% FIRE 3% GOLD_ORE 3% STEAM 5% SOFT_DIRT",
     "c4": "25% TEST_SAND / 20% WATER / 10% COBBLE_STONE, rest AIR (hash(seed, x, y) % 100)",
-    "c5": "rows below 90% height COBBLE_STONE; above: 0.1% TEST_SAND scattered + 64 boxes of 256 x 256 cells with the c2 fill",
+    "c5": "the lower 90% of the rows COBBLE_STONE; 0.1% TEST_SAND scattered in the air above; 64 boxes of 256 x 256 cells with the c2 fill (pockets in the stone)",
 }
 
 
@@ -231,7 +231,9 @@ def measure(args, workload, size, steps, warmup, early_out=True, e2e_steps=0, pe
     g.set_stream(stream.cuda_stream)
     fill = dict(seed=0xF55, border=BORDER)
     if workload == "c5":
-        fill.update(solid_from_row=int(H * 0.9), n_boxes=64 if ZW >= 4096 else 4, box_size=256, sparse_material=M.TEST_SAND, sparse_per_mille=1)
+        # "rows below 90 % height COBBLE_STONE" = the lower nine tenths of the world are stone (mostly settled);
+        # the active boxes are pockets of the c2 mix inside it, the sparse sand falls through the air above
+        fill.update(solid_from_row=int(H * 0.1), n_boxes=64 if ZW >= 4096 else 4, box_size=256, sparse_material=M.TEST_SAND, sparse_per_mille=1)
     g.fill_synthetic(mixes()[workload], **fill)
     g.sync()
 

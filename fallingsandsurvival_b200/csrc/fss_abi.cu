@@ -157,6 +157,13 @@ struct fss_world {
     DLook* d_looks;
     bool looks_stale;
     unsigned long long* d_rinfo; // FSS_MAX_MATERIALS counters, then hadDirty / hadFire / hadFlow as uint32
+    // compacted worklist of not-settled tiles (mostly settled worlds): SubstepParams::work
+    uint32_t* d_work;
+    uint32_t* d_work_n;
+    volatile uint32_t* h_work_n; // pinned: the latest count the device has reported (read without synchronising: a hint only)
+    size_t work_cap;
+    uint32_t work_tiles;         // tiles of the launch that count belongs to
+    bool work_mode;              // launches go through the worklist
     // strips
     void* comm;
     int rank, n_ranks;
@@ -386,6 +393,9 @@ int fss_destroy(fss_world* w) {
     cudaFree(w->d_q);
     cudaFree(w->d_qskip);
     cudaFree(w->d_present);
+    cudaFree(w->d_work);
+    cudaFree(w->d_work_n);
+    if(w->h_work_n) cudaFreeHost((void*)w->h_work_n);
     particles_free(w);
     if(w->own_stream) cudaStreamDestroy(w->own_stream);
     delete w;
@@ -669,7 +679,45 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
     if(jr_lo < 0) w->stats.substeps++;
     if(p.ny <= 0 || p.nx <= 0) return FSS_OK;
     {
-        const dim3 grid((p.nx + K1_THREADS - 1) / K1_THREADS, p.ny);
+        dim3 grid((p.nx + K1_THREADS - 1) / K1_THREADS, p.ny);
+        p.work = nullptr;
+        p.work_n = nullptr;
+        // Mostly settled worlds: a small kernel lists the tiles that still hold a not-settled chunk and a fixed grid strides over
+        // that list, so settled regions cost neither CTAs nor flag loads.  Whether a launch goes through the list is decided from
+        // the last count the device reported (a hint read without synchronising: both ways give the same cells); while launches are
+        // plain, the count is refreshed once per tick.  (FSS_TRACK_DIRTY needs a note per skipped chunk: plain launches only.)
+        static const bool no_worklist = getenv("FSS_NO_WORKLIST") != nullptr;
+        static const bool always_worklist = getenv("FSS_WORKLIST_ALWAYS") != nullptr; // tests: every launch through the list
+        if(w->d_q && !w->d_qskip && !no_worklist && grid.x <= 0xFFFu && grid.y <= 0xFFFFFu) {
+            const uint32_t tiles = grid.x * grid.y;
+            if(tiles > w->work_cap) {
+                CU(cudaStreamSynchronize(w->stream));
+                cudaFree(w->d_work);
+                w->d_work = nullptr;
+                w->work_cap = 0;
+                CU(cudaMalloc(&w->d_work, (size_t)tiles * sizeof(uint32_t)));
+                w->work_cap = tiles;
+                if(!w->d_work_n) {
+                    CU(cudaMalloc(&w->d_work_n, sizeof(uint32_t)));
+                    CU(cudaHostAlloc((void**)&w->h_work_n, sizeof(uint32_t), cudaHostAllocDefault));
+                    *w->h_work_n = 0xFFFFFFFFu;
+                }
+            }
+            if(w->work_tiles && *w->h_work_n != 0xFFFFFFFFu) w->work_mode = (double)*w->h_work_n < 0.5 * (double)w->work_tiles;
+            if(always_worklist) w->work_mode = true;
+            if(w->work_mode || (iter == 0 && tk == 0)) {
+                CU(cudaMemsetAsync(w->d_work_n, 0, sizeof(uint32_t), w->stream));
+                k_worklist<<<(tiles * 32 + 127) / 128, 128, 0, w->stream>>>(p.q, p.q_w, ofs_x, ofs_y, iter, p.nx, (int)grid.x, p.ny, w->d_work, w->d_work_n);
+                CU(cudaMemcpyAsync((void*)w->h_work_n, w->d_work_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+                w->work_tiles = tiles;
+                w->stats.kernel_launches++;
+                if(w->work_mode) {
+                    p.work = w->d_work;
+                    p.work_n = w->d_work_n;
+                    grid = dim3(std::min<uint32_t>(tiles, 148u * 8u), 1);
+                }
+            }
+        }
         static const bool no_spec = getenv("FSS_NO_SPECIALISE") != nullptr; // measurements: always the general kernel
         const int mode = no_spec ? K1_GENERAL : (iter >= w->liq_from_iter ? K1_LIQUID : (iter >= w->nogas_from_iter ? K1_NOGAS : K1_GENERAL));
         const bool flow = w->g.fx != nullptr;

@@ -39,6 +39,25 @@ __global__ void k_code_pad(int* out) {
 #ifndef K1N_MIN_BLOCKS
 #define K1N_MIN_BLOCKS 7
 #endif
+// The tiles one CTA works on: its own (blockIdx) in a plain launch, or every gridDim.x-th entry of the worklist.
+struct TileLoop {
+    uint32_t t, n, stride;
+    const uint32_t* work;
+    __device__ __forceinline__ TileLoop(const SubstepParams& p) : work(p.work) {
+        t = work ? blockIdx.x : 0u;
+        n = work ? *p.work_n : 1u;
+        stride = gridDim.x;
+    }
+    __device__ __forceinline__ bool next(int& bx, int& by) {
+        if(t >= n) return false;
+        const uint32_t e = work ? work[t] : ((uint32_t)blockIdx.y << 12 | blockIdx.x);
+        bx = (int)(e & 0xFFFu);
+        by = (int)(e >> 12);
+        t += work ? stride : 1u;
+        return true;
+    }
+};
+
 template <int MODE, bool FLOW, bool DIRTY>
 __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS : (MODE == K1_NOGAS ? K1N_MIN_BLOCKS : K1_MIN_BLOCKS))
     k_substep(const __grid_constant__ SubstepParams p) {
@@ -50,26 +69,31 @@ __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS
                    ((d.flags & FSS_MAT_IS_STEAM) ? HI_STEAM : 0u);
     }
     __syncthreads();
-    const int gi = blockIdx.x * K1_THREADS + threadIdx.x;
-    if(gi >= p.nx) return;
-    uint8_t* qown = nullptr;
+    TileLoop tiles(p);
+    int bx, by;
+    while(tiles.next(bx, by)) {
+        const int gi = bx * K1_THREADS + threadIdx.x;
+        bool live = gi < p.nx;
+        uint8_t* qown = nullptr;
 #ifndef K1_NO_EARLY
-    if(p.q) {
-        qown = p.q + (size_t)(2 * (int)blockIdx.y + p.ofs_y + 1) * p.q_w + (2 * gi + p.ofs_x + 1);
-        if(*qown <= (uint8_t)p.iter) { // verified settled: a warp whose 32 chunks are all settled ends here
-            if(DIRTY) {
-                // the visit that is skipped would have been the identity on the cells, but not on World::dirty: scan 2 marks
-                // every liquid cell it reaches (world.cpp:1823).  The render job adds those marks from this note.
-                uint8_t* s = p.qskip + (qown - p.q);
-                if(*s > (uint8_t)p.iter) *s = (uint8_t)p.iter;
+        if(live && p.q) {
+            qown = p.q + (size_t)(2 * by + p.ofs_y + 1) * p.q_w + (2 * gi + p.ofs_x + 1);
+            if(*qown <= (uint8_t)p.iter) { // verified settled: a warp whose 32 chunks are all settled has nothing to do
+                if(DIRTY) {
+                    // the visit that is skipped would have been the identity on the cells, but not on World::dirty: scan 2 marks
+                    // every liquid cell it reaches (world.cpp:1823).  The render job adds those marks from this note.
+                    uint8_t* s = p.qskip + (qown - p.q);
+                    if(*s > (uint8_t)p.iter) *s = (uint8_t)p.iter;
+                }
+                live = false;
             }
-            return;
+        }
+#endif
+        if(live) {
+            ChunkWalk<MODE, FLOW, DIRTY> w(p, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * by, __activemask());
+            w.run(qown);
         }
     }
-#endif
-    ChunkWalk<MODE, FLOW, DIRTY> w(p, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y,
-                      __activemask());
-    w.run(qown);
 }
 
 // ---- K1w: sub-step with the chunk rows in a register window (fss_rules_liq.cuh) -------------------------------------
@@ -93,17 +117,40 @@ __global__ void __launch_bounds__(K1_THREADS, SAND ? K1WS_MIN_BLOCKS : K1W_MIN_B
         }
         __syncthreads();
     }
-    const int gi = blockIdx.x * K1_THREADS + threadIdx.x;
-    if(gi >= p.nx) return;
-    uint8_t* qown = nullptr;
+    TileLoop tiles(p);
+    int bx, by;
+    while(tiles.next(bx, by)) {
+        const int gi = bx * K1_THREADS + threadIdx.x;
+        bool live = gi < p.nx;
+        uint8_t* qown = nullptr;
 #ifndef K1_NO_EARLY
-    if(p.q) {
-        qown = p.q + (size_t)(2 * (int)blockIdx.y + p.ofs_y + 1) * p.q_w + (2 * gi + p.ofs_x + 1);
-        if(*qown <= (uint8_t)p.iter) return; // verified settled
-    }
+        if(live && p.q) {
+            qown = p.q + (size_t)(2 * by + p.ofs_y + 1) * p.q_w + (2 * gi + p.ofs_x + 1);
+            if(*qown <= (uint8_t)p.iter) live = false; // verified settled
+        }
 #endif
-    WinWalk<SAND, ITER0> w(p, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * (int)blockIdx.y, __activemask());
-    w.run(qown);
+        if(live) {
+            WinWalk<SAND, ITER0> w(p, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * by, __activemask());
+            w.run(qown);
+        }
+    }
+}
+
+// ---- the worklist of a sub-step: which tiles (K1_THREADS chunks of one active chunk row) hold a chunk that is not settled ----
+// One warp per tile; lane l looks at the flags of the tile's chunks 4l .. 4l+3.
+__global__ void __launch_bounds__(128) k_worklist(const uint8_t* __restrict__ q, int q_w, int ofs_x, int ofs_y, int iter, int nx, int tiles_x, int ny,
+                                                  uint32_t* __restrict__ work, uint32_t* __restrict__ work_n) {
+    const int tile = (int)((blockIdx.x * 128u + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if(tile >= tiles_x * ny) return;
+    const int bx = tile % tiles_x, by = tile / tiles_x;
+    const uint8_t* row = q + (size_t)(2 * by + ofs_y + 1) * q_w + (ofs_x + 1);
+    bool active = false;
+#pragma unroll
+    for(int k = 0; k < K1_THREADS / 32; k++) {
+        const int gi = bx * K1_THREADS + lane * (K1_THREADS / 32) + k;
+        if(gi < nx && row[2 * gi] > (uint8_t)iter) active = true;
+    }
+    if(__any_sync(0xFFFFFFFFu, active) && lane == 0) work[atomicAdd(work_n, 1u)] = ((uint32_t)by << 12) | (uint32_t)bx;
 }
 
 // ---- K2: temperature stencil ---------------------------------------------------------------------------
@@ -379,13 +426,14 @@ __global__ void __launch_bounds__(256) k_fill(const __grid_constant__ FillParams
     int mat = 0;
     const uint32_t key = fss_rng_cell_key(s.seed, x, y);
     if(x < p.width) {
+        const bool boxed = s.n_boxes != 0 && fill_in_box(s, p.width, p.height, x, y);
         if(x < s.border || y < s.border || x >= p.width - s.border || y >= p.height - s.border) {
             mat = s.border_material;
-        } else if(s.solid_from_row && y >= s.solid_from_row) {
+        } else if(s.solid_from_row && y >= s.solid_from_row && !boxed) { // (a box inside the solid region is a pocket of the mix)
             mat = s.solid_material;
         } else {
             const uint32_t r = key % 100u;
-            if(s.n_boxes == 0 || fill_in_box(s, p.width, p.height, x, y)) {
+            if(s.n_boxes == 0 || boxed) {
                 for(int e = 0; e < s.n_entries; e++) {
                     if(r < (uint32_t)s.cumulative_percent[e]) {
                         mat = s.material[e];

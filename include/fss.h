@@ -343,7 +343,7 @@ typedef struct fss_fill_spec {
     int32_t n_entries;
     int32_t material[16];
     int32_t cumulative_percent[16];
-    /* optional: rows >= solid_from_row are all `solid_material` (config 5, mostly settled) */
+    /* optional: rows >= solid_from_row are all `solid_material` (config 5, mostly settled), except inside the boxes below */
     uint32_t solid_from_row; /* 0 = off */
     int32_t solid_material;
     /* optional: entries apply only inside boxes; outside, sparse_material with probability

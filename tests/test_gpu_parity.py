@@ -290,7 +290,7 @@ def test_early_out_sparse_world_long_run():
     ws = []
     for eo in (True, False):
         g = world.World(None, zone, defs=full_table(), size=size, early_out=eo)
-        g.fill_synthetic(worlds.MIX_C2, seed=3, solid_from_row=int(size[1] * 0.8), n_boxes=3, box_size=128,
+        g.fill_synthetic(worlds.MIX_C2, seed=3, solid_from_row=int(size[1] * 0.3), n_boxes=3, box_size=128,
                          sparse_material=M.TEST_SAND, sparse_per_mille=2)
         ws.append(g)
     assert ws[0].hash() == ws[1].hash()
@@ -1084,3 +1084,38 @@ def test_tick_host_pipeline_equals_upload_tick_download(mix, monkeypatch):
         assert a.cells().tobytes() == host.tobytes()
     for w in (a, b, o):
         w.close()
+
+
+def test_worklist_launches_equal_plain_launches():
+    """mostly settled worlds go through a compacted list of the tiles that still hold a not-settled chunk (k_worklist); the
+    same ticks with the list forced on for every launch, with plain launches only, and with the early-out off must agree --
+    on the sparse world and on a dense one, through fss_tick and through the banded fss_tick_host"""
+    import subprocess, sys
+    code = r"""
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import numpy as np, torch
+from helpers import full_table
+from fallingsandsurvival_b200 import world, worlds, abi, materials as M
+size = (1056, 16 + 2 * 832 + 32 + 16)
+zone = worlds.default_zone(*size)
+out = []
+for sparse in (True, False):
+    g = world.World(None, zone, defs=full_table(), size=size, early_out=os.environ.get("EO", "1") == "1")
+    kw = dict(solid_from_row=int(size[1] * 0.3), n_boxes=3, box_size=128, sparse_material=M.TEST_SAND, sparse_per_mille=2) if sparse else {}
+    g.fill_synthetic(worlds.MIX_C2, seed=3, **kw)
+    for t in range(40):
+        g.tick(t)
+    host = torch.empty((size[1], size[0], 20), dtype=torch.uint8, pin_memory=True).numpy().view(abi.CELL_DTYPE).reshape(size[1], size[0])
+    host[...] = g.cells()
+    for t in range(40, 44):
+        g.tick_host(host, t)
+    out.append("%%016x" %% g.hash())
+    g.close()
+print(" ".join(out))
+""" % ((os.path.dirname(os.path.dirname(os.path.abspath(__file__))),) * 2)
+    res = {}
+    for name, env in (("list", {"FSS_WORKLIST_ALWAYS": "1"}), ("plain", {"FSS_NO_WORKLIST": "1"}), ("auto", {}), ("no early-out", {"EO": "0"})):
+        e = dict(os.environ, FSS_HOST_BAND_ROWS="832", **env)
+        res[name] = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, check=True).stdout.strip()
+    assert len(set(res.values())) == 1, res
