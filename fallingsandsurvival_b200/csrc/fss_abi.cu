@@ -164,7 +164,10 @@ struct fss_world {
     size_t work_cap;
     uint32_t work_tiles;         // tiles of the launch that count belongs to
     bool work_mode;              // launches go through the worklist
+    bool edge_launch;            // fss_tick is launching a strip's edge band on the exchange stream
     // strips
+    cudaStream_t comm_stream; // the halo exchange of fss_tick runs here, beside the interior bands
+    cudaEvent_t ev_edge, ev_halo;
     void* comm;
     int rank, n_ranks;
 };
@@ -360,7 +363,11 @@ int fss_destroy(fss_world* w) {
     if(!w) return FSS_OK;
     cudaSetDevice(w->device);
     if(w->own_stream) cudaStreamSynchronize(w->own_stream);
+    if(w->comm_stream) cudaStreamSynchronize(w->comm_stream);
     if(w->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(w->comm);
+    if(w->comm_stream) cudaStreamDestroy(w->comm_stream);
+    if(w->ev_edge) cudaEventDestroy(w->ev_edge);
+    if(w->ev_halo) cudaEventDestroy(w->ev_halo);
     cudaFree(w->g.mf);
     cudaFree(w->g.col);
     cudaFree(w->g.temp);
@@ -520,6 +527,8 @@ int fss_set_texture(fss_world* w, int index, const uint32_t* argb, int tw, int t
 }
 
 static int skipped_marks(fss_world* w);
+static int exchange_halo_on(fss_world* w, int tk, cudaStream_t st);
+static int halo_received(fss_world* w, int tk);
 
 int fss_set_tick_zone(fss_world* w, int x, int y, int zw, int zh) {
     if(!w) return fail(FSS_ERR_INVALID, "null world");
@@ -688,7 +697,7 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
         // plain, the count is refreshed once per tick.  (FSS_TRACK_DIRTY needs a note per skipped chunk: plain launches only.)
         static const bool no_worklist = getenv("FSS_NO_WORKLIST") != nullptr;
         static const bool always_worklist = getenv("FSS_WORKLIST_ALWAYS") != nullptr; // tests: every launch through the list
-        if(w->d_q && !w->d_qskip && !no_worklist && grid.x <= 0xFFFu && grid.y <= 0xFFFFFu) {
+        if(w->d_q && !w->d_qskip && !no_worklist && !w->edge_launch && grid.x <= 0xFFFu && grid.y <= 0xFFFFFu) {
             const uint32_t tiles = grid.x * grid.y;
             if(tiles > w->work_cap) {
                 CU(cudaStreamSynchronize(w->stream));
@@ -763,14 +772,50 @@ int fss_tick(fss_world* w, uint32_t tick_ct) {
     int rc = ready(w);
     if(rc) return rc;
     if(w->sharded && !w->comm) return fail(FSS_ERR_STATE, "strip-sharded world without communicator: attach one, or drive fss_substep + fss_exchange_halo_peer");
+    static const bool serial_halo = getenv("FSS_SERIAL_HALO") != nullptr; // measurements: exchange on the compute stream
+    if(w->comm && !w->comm_stream) {
+        int prio_lo = 0, prio_hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CU(cudaStreamCreateWithPriority(&w->comm_stream, cudaStreamNonBlocking, prio_hi));
+        CU(cudaEventCreateWithFlags(&w->ev_edge, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&w->ev_halo, cudaEventDisableTiming));
+    }
+    int j_lo, j_hi;
+    owned_bands(w, j_lo, j_hi);
     for(int iter = 0; iter < 6; iter++) {
         for(int tk = 0; tk < 4; tk++) {
-            rc = launch_substep(w, tick_ct, iter, tk);
-            if(rc) return rc;
-            if(w->comm && (tk == 1 || tk == 3)) {
-                rc = fss_exchange_halo(w, tk);
+            const bool exchange = w->comm && (tk == 1 || tk == 3);
+            if(!exchange || serial_halo || j_hi - j_lo < 3) {
+                rc = launch_substep(w, tick_ct, iter, tk);
                 if(rc) return rc;
+                if(exchange && (rc = fss_exchange_halo(w, tk))) return rc;
+                continue;
             }
+            // The rows that cross a strip boundary after this sub-step are written by ONE 32-row band: the strip's last band
+            // after tk 1 (its lower chunk row ran in tk 0 / 1: rows [B-2, B+2) go down), its first band after tk 3 (rows
+            // [B-2, B+10) go up).  That band runs first; while the other bands run, the ncclSend / ncclRecv group is on its own
+            // stream.  What is received lands in rows this sub-step does not touch (tk 1: the ghost rows and the first two
+            // rows of the strip, which only the upper chunk rows of tk 2 / 3 look at; tk 3: the ghost rows below, ten of which
+            // the last band's tk 0 / 1 chunks read): the next sub-step waits for it.
+            // (a launch lasts as long as one chunk visit however few chunks it has, so the edge band does not go in front of
+            // the others on the world's stream: it runs beside them on the high-priority exchange stream, followed there by
+            // the NCCL group)
+            const int edge = tk == 1 ? j_hi - 1 : j_lo;
+            cudaStream_t main_stream = w->stream;
+            CU(cudaEventRecord(w->ev_edge, main_stream)); // the sub-steps so far
+            CU(cudaStreamWaitEvent(w->comm_stream, w->ev_edge, 0));
+            w->stream = w->comm_stream;
+            w->edge_launch = true; // (one band, beside the launch that may be using the worklist buffers: a plain launch)
+            rc = launch_substep(w, tick_ct, iter, tk, edge, edge + 1);
+            w->edge_launch = false;
+            w->stream = main_stream;
+            if(rc) return rc;
+            if((rc = exchange_halo_on(w, tk, w->comm_stream))) return rc;
+            CU(cudaEventRecord(w->ev_halo, w->comm_stream));
+            if((rc = tk == 1 ? launch_substep(w, tick_ct, iter, tk, j_lo, edge) : launch_substep(w, tick_ct, iter, tk, edge + 1, j_hi))) return rc;
+            CU(cudaStreamWaitEvent(main_stream, w->ev_halo, 0));
+            if((rc = halo_received(w, tk))) return rc;
+            w->stats.substeps++;
         }
     }
     CU(cudaGetLastError());
@@ -1695,33 +1740,49 @@ int fss_comm_attach(fss_world* w, const void* id128, int rank, int n_ranks) {
     return FSS_OK;
 }
 
-static int nccl_rows(fss_world* w, bool send, int peer, int lo, int hi, bool temp_only) {
+static int nccl_rows(fss_world* w, bool send, int peer, int lo, int hi, bool temp_only, cudaStream_t st) {
     void* ptr[5];
     plane_ptrs(w, ptr);
     const size_t count = (size_t)(hi - lo) * w->g.pitch;
     for(int k = 0; k < 5; k++) {
         if(temp_only && k != 2) continue;
         char* a = (char*)ptr[k] + (size_t)(lo - w->g.sy0) * w->g.pitch * 4;
-        if(send) NC(g_nccl.send(a, count, NCCL_UINT32, peer, w->comm, w->stream));
-        else NC(g_nccl.recv(a, count, NCCL_UINT32, peer, w->comm, w->stream));
+        if(send) NC(g_nccl.send(a, count, NCCL_UINT32, peer, w->comm, st));
+        else NC(g_nccl.recv(a, count, NCCL_UINT32, peer, w->comm, st));
     }
     return FSS_OK;
 }
+
+static int exchange_halo_on(fss_world* w, int tk, cudaStream_t st);
+static int halo_received(fss_world* w, int tk);
 
 int fss_exchange_halo(fss_world* w, int tk) {
     if(!w) return fail(FSS_ERR_INVALID, "null world");
     if(!w->comm) return fail(FSS_ERR_STATE, "no communicator attached");
     if(tk != 1 && tk != 3) return FSS_OK;
     if(use_device(w)) return FSS_ERR_CUDA;
+    if(int rc = exchange_halo_on(w, tk, w->stream)) return rc;
+    return halo_received(w, tk);
+}
+
+// received rows replace cells that settled chunks may have looked at (on the world's stream: after the exchange has been joined)
+static int halo_received(fss_world* w, int tk) {
+    const bool has_upper = w->rank > 0, has_lower = w->rank + 1 < w->n_ranks;
+    if(tk == 1 && has_upper) return dirty_chunks(w, 0, w->own_lo + DOWN_LO, (int)w->cfg.width, DOWN_HI - DOWN_LO);
+    if(tk == 3 && has_lower) return dirty_chunks(w, 0, w->own_hi + UP_LO, (int)w->cfg.width, UP_HI - UP_LO);
+    return FSS_OK;
+}
+
+static int exchange_halo_on(fss_world* w, int tk, cudaStream_t st) {
     const bool has_upper = w->rank > 0, has_lower = w->rank + 1 < w->n_ranks;
     int rc = FSS_OK;
     NC(g_nccl.group_start());
     if(tk == 1) { // data flows down
-        if(has_lower) rc = nccl_rows(w, true, w->rank + 1, w->own_hi + DOWN_LO, w->own_hi + DOWN_HI, false);
-        if(!rc && has_upper) rc = nccl_rows(w, false, w->rank - 1, w->own_lo + DOWN_LO, w->own_lo + DOWN_HI, false);
+        if(has_lower) rc = nccl_rows(w, true, w->rank + 1, w->own_hi + DOWN_LO, w->own_hi + DOWN_HI, false, st);
+        if(!rc && has_upper) rc = nccl_rows(w, false, w->rank - 1, w->own_lo + DOWN_LO, w->own_lo + DOWN_HI, false, st);
     } else { // data flows up
-        if(has_upper) rc = nccl_rows(w, true, w->rank - 1, w->own_lo + UP_LO, w->own_lo + UP_HI, false);
-        if(!rc && has_lower) rc = nccl_rows(w, false, w->rank + 1, w->own_hi + UP_LO, w->own_hi + UP_HI, false);
+        if(has_upper) rc = nccl_rows(w, true, w->rank - 1, w->own_lo + UP_LO, w->own_lo + UP_HI, false, st);
+        if(!rc && has_lower) rc = nccl_rows(w, false, w->rank + 1, w->own_hi + UP_LO, w->own_hi + UP_HI, false, st);
     }
     // the group is always closed, also after a failed send / recv: an open group would leave the communicator unusable and the
     // neighbour blocked.  A communicator error is fatal for the world (the strips are out of step): destroy and re-create it.
@@ -1730,10 +1791,6 @@ int fss_exchange_halo(fss_world* w, int tk) {
     if(rc) return fail(rc, "%s", first_error.c_str());
     if(end != 0) return fail(FSS_ERR_COMM, "ncclGroupEnd: %s", g_nccl.err_string ? g_nccl.err_string(end) : "nccl error");
     w->stats.kernel_launches++; // one fused NCCL send/recv kernel per group
-    if(!rc) { // received rows replace cells that settled chunks may have looked at
-        if(tk == 1 && has_upper) rc = dirty_chunks(w, 0, w->own_lo + DOWN_LO, (int)w->cfg.width, DOWN_HI - DOWN_LO);
-        if(tk == 3 && has_lower) rc = dirty_chunks(w, 0, w->own_hi + UP_LO, (int)w->cfg.width, UP_HI - UP_LO);
-    }
     return rc;
 }
 
@@ -1745,12 +1802,12 @@ int fss_exchange_halo_temperature(fss_world* w) {
     int rc = FSS_OK;
     NC(g_nccl.group_start());
     if(has_lower) {
-        rc = nccl_rows(w, true, w->rank + 1, w->own_hi - FSS_HALO_ROWS, w->own_hi, true);
-        if(!rc) rc = nccl_rows(w, false, w->rank + 1, w->own_hi, w->own_hi + FSS_HALO_ROWS, true);
+        rc = nccl_rows(w, true, w->rank + 1, w->own_hi - FSS_HALO_ROWS, w->own_hi, true, w->stream);
+        if(!rc) rc = nccl_rows(w, false, w->rank + 1, w->own_hi, w->own_hi + FSS_HALO_ROWS, true, w->stream);
     }
     if(!rc && has_upper) {
-        rc = nccl_rows(w, true, w->rank - 1, w->own_lo, w->own_lo + FSS_HALO_ROWS, true);
-        if(!rc) rc = nccl_rows(w, false, w->rank - 1, w->own_lo - FSS_HALO_ROWS, w->own_lo, true);
+        rc = nccl_rows(w, true, w->rank - 1, w->own_lo, w->own_lo + FSS_HALO_ROWS, true, w->stream);
+        if(!rc) rc = nccl_rows(w, false, w->rank - 1, w->own_lo - FSS_HALO_ROWS, w->own_lo, true, w->stream);
     }
     const std::string first_error = rc ? g_err : std::string(); // (the group is always closed: see fss_exchange_halo)
     const int end = g_nccl.group_end();
