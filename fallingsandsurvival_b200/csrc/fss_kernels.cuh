@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS
 template <bool SAND, bool ITER0>
 __global__ void __launch_bounds__(K1_THREADS, SAND ? K1WS_MIN_BLOCKS : K1W_MIN_BLOCKS) k_substep_win(const __grid_constant__ SubstepParams p) {
     __shared__ uint32_t sinfo[SAND ? FSS_MAX_MATERIALS : 1];
+    __shared__ uint32_t spay[SAND ? WIN_PAY_WORDS * K1_THREADS : 1]; // WinWalk::pay: colour / temperature of the window rows
     if(SAND) {
         for(int m = threadIdx.x; m < p.n_mat; m += K1_THREADS) {
             const DMat& d = p.mats[m];
@@ -130,7 +131,8 @@ __global__ void __launch_bounds__(K1_THREADS, SAND ? K1WS_MIN_BLOCKS : K1W_MIN_B
         }
 #endif
         if(live) {
-            WinWalk<SAND, ITER0> w(p, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * by, __activemask());
+            WinWalk<SAND, ITER0> w(p, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * by, __activemask(), spay + threadIdx.x,
+                                   K1_THREADS);
             w.run(qown);
         }
     }

@@ -940,6 +940,95 @@ struct ChunkWalk {
         scan2_rest();
     }
 
+    // SAND in scan 2 for scan2_sparse(): the same rule as sand2(), with everything it can need requested in ONE batch of
+    // independent loads behind the cell's own mf word (the two diagonals with all their planes, the two side cells and the
+    // cell below: none of them is stored to by this visit before the rule looks at it) instead of four dependent round
+    // trips.  In the lock-step scan those chains hit lines the row prefetch has brought into L1; here every lane is at its
+    // own position, most of them miss L1, and a lane's round is as long as its longest chain.
+    __device__ __forceinline__ void sand2_sparse(cidx_t i, int x, int y, uint32_t mf, unsigned long long bit) {
+        const Grid& g = p.g;
+        const cidx_t pitch = g.pitch;
+        const uint32_t mat = mf_mat(mf);
+        const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
+        if(!(mf & MF_MOVED) && busy) { // see sand2(): the draw cannot un-stick the cell whatever the probe counts
+            const uint32_t r = fss_rand(key, 1715, 0);
+            if(r % 500u && r % 333u && r % 250u && r % 200u && r % 166u && r % 142u && r % 125u && r % 111u && r % 100u) return;
+        }
+        const cidx_t ibl = il + pitch, ibr = ir + pitch, ib = i + pitch;
+        const uint32_t blmf = g.mf[ibl], brmf = g.mf[ibr], bmf = g.mf[ib], lmf = g.mf[il], rmf = g.mf[ir];
+        Cell tile, dl, dr;
+        tile.mf = mf;
+        tile.col = g.col[i];
+        tile.temp = g.temp[i];
+        tile.amt = g.amt[i];
+        tile.dif = g.dif[i];
+        dl.mf = blmf;
+        dl.col = g.col[ibl];
+        dl.temp = g.temp[ibl];
+        dl.amt = g.amt[ibl];
+        dl.dif = g.dif[ibl];
+        dr.mf = brmf;
+        dr.col = g.col[ibr];
+        dr.temp = g.temp[ibr];
+        dr.amt = g.amt[ibr];
+        dr.dif = g.dif[ibr];
+        const bool can_l = can_move_into(blmf, mf), can_r = can_move_into(brmf, mf);
+        if(!(can_l || can_r)) { // :1697-1734 with no open diagonal: `moved` ends up false
+            if(mf & MF_MOVED) {
+                busy = true;
+                g.mf[i] = mf & ~MF_MOVED;
+            }
+            return;
+        }
+        const uint32_t info = sinfo[mat];
+        const uint32_t slip = HI_SLIP(info);
+        bool stopped = !(mf & MF_MOVED);
+        if(stopped) { // :1697-1725
+            int drop = (MF_IS(blmf, FSS_PHYS_AIR) || MF_IS(brmf, FSS_PHYS_AIR)) ? 1 : 0;
+            uint32_t pl[9], pr[9];
+#pragma unroll
+            for(int pil = 1; pil < 10; pil++) {
+                pl[pil - 1] = g.mf[ibl + (cidx_t)pil * pitch];
+                pr[pil - 1] = g.mf[ibr + (cidx_t)pil * pitch];
+            }
+#pragma unroll
+            for(int pil = 0; pil < 9; pil++) drop += (MF_IS(pl[pil], FSS_PHYS_AIR) || MF_IS(pr[pil], FSS_PHYS_AIR)) ? 1 : 0;
+            const int unstable = drop + 1 - (int)HI_STAB(info);
+            if(unstable > 0) {
+                const int chance = 1000 / unstable;
+                if(chance < 1000) busy = true; // a draw decides
+                if(chance < 1000 && fss_rand(key, 1715, 0) % (uint32_t)chance == 0) stopped = false;
+            }
+            if(stopped) return; // :1727-1734, moved is already false
+        }
+        busy = true;
+        const bool should_move = fss_rand(key, 1736, 0) % (2u * slip) != 0;
+        if(!should_move) { // :1802 `tiles[index].moved = false`
+            if(mf & MF_MOVED) g.mf[i] = mf & ~MF_MOVED;
+            return;
+        }
+        if(fss_rand(key, 1741, 0) % 2 == 0) { // :1738-1753
+            if(MF_IS(bmf, FSS_PHYS_SAND) && fss_rand(key, 1744, 0) % 2 == 0 && !(bmf & MF_MOVED)) g.mf[ib] = bmf | MF_MOVED;
+        }
+        // :1755-1800 (the left / right asymmetry of the visited marks as in sand2())
+        const bool go_left = can_l && (!can_r || fss_rand(key, 1755, 0) % 2 == 0);
+        const int sx = go_left ? -1 : 1;
+        const cidx_t idiag = go_left ? ibl : ibr, iside = go_left ? il : ir;
+        const Cell diag = go_left ? dl : dr;
+        const uint32_t smf = go_left ? lmf : rmf;
+        if(MF_IS(smf, FSS_PHYS_AIR)) {
+            st_cell(g, iside, diag);
+            if(go_left) mark(x - 1, y);
+            st_cell(g, i, cell_nothing(p.nothing_mf));
+        } else {
+            st_cell(g, i, diag);
+            vis |= bit;
+        }
+        if(fss_rand(key, go_left ? 1768u : 1791u, 0) % (20u * slip) == 0) tile.mf &= ~MF_MOVED;
+        st_cell(g, idiag, tile);
+        mark(x + sx, y + 1);
+    }
+
     // Scan 2 driven by the tickVisited bits instead of by position (K1_NOGAS only, entered from WinWalk<true>::run with the
     // bits its register-window scan 1 and fused liquid update left): scan 2 only acts on unvisited cells, and after scan 1 a
     // chunk has about five of them (resting SAND; liquid cells whose update deletes them), so every lane steps through ITS OWN
@@ -955,8 +1044,14 @@ struct ChunkWalk {
                 const int dy = top >> 2;
                 const unsigned nib = (unsigned)(todo >> (dy * FSS_CHUNK_W)) & 0xFu;
                 const int dx = __ffs((int)nib) - 1;                     // its leftmost unvisited column
-                todo &= ~(1ull << (dy * FSS_CHUNK_W + dx));
-                scan2_cell(dx, dy);
+                const unsigned long long bit = 1ull << (dy * FSS_CHUNK_W + dx);
+                todo &= ~bit;
+                if(!(vis & bit)) { // :1676 (a visit earlier in this scan may have marked it)
+                    const cidx_t i = locate(dx, dy);
+                    const uint32_t mf = p.g.mf[i];
+                    if(MF_IS(mf, FSS_PHYS_SAND)) sand2_sparse(i, cx + dx, cy + dy, mf, bit);
+                    else if(MF_IS(mf, FSS_PHYS_SOUP)) soup_apply(i, p.g.amt[i], p.g.dif[i], bit); // :1808-1825
+                }
             }
         }
     }

@@ -26,6 +26,9 @@
 // columns (one cell either side of the row being scanned) and the outside rows (-1 and 16) are written through.
 #pragma once
 #include "fss_rules.cuh"
+#ifdef __CUDACC__
+#include <cuda_pipeline.h>
+#endif
 
 // the one place that decides which sub-steps take the register-window path (kernel launch and tests/hostsim)
 //   K1_LIQUID sub-steps: WinWalk<false>, scans 1 and 2 fused completely;
@@ -72,7 +75,9 @@ struct LRow { // one grid row of the chunk's four columns
 #define LF_DIF 0x10u
 #define LF_AMT 0x100u
 #define LF_ALL 0x111u
+#define LF_PAY 0x1000u /* bits 12-15: the colour / temperature words in shared memory differ from memory (SAND) */
 #define LF_VIS 0x10000u
+#define WIN_PAY_WORDS (3 * 2 * FSS_CHUNK_W) /* per thread: 3 window rows x {colour, temperature} x 4 columns */
 
 struct LSide { // the cell left / right of the row being scanned (outside the chunk)
     uint32_t mf;
@@ -99,9 +104,17 @@ struct WinWalk {
     unsigned long long vis; // SAND: tickVisited of the chunk as scan 2 finds it
     uint32_t lb_mf, rb_mf;  // SAND: mf of the outside cells of the row BELOW the one being scanned (a SAND cell's diagonals)
     unsigned wmask;
+    // SAND: cells move, and their colour / temperature words move with them.  Those two planes of the three window rows live in
+    // SHARED memory (requested with cp.async one row ahead, no registers, no global round trip in the middle of a row):
+    // word (slot, plane, column) of this thread at pay[((slot * 2 + plane) * 4 + column) * pstride].  sA / sC / sB = the slots of
+    // rows r-1 / r / r+1.  (Liquid-only sub-steps copy the two words through global memory in the rare cases they need them.)
+    uint32_t* pay;
+    int pstride;
+    int sA, sC, sB;
 
-    __device__ __forceinline__ WinWalk(const SubstepParams& p_, const uint32_t* si, int cx_, int cy_, unsigned wmask_)
-        : p(p_), sinfo(si), cx(cx_), cy(cy_), busy(false), vis(0ull), lb_mf(0u), rb_mf(0u), wmask(wmask_) {
+    __device__ __forceinline__ WinWalk(const SubstepParams& p_, const uint32_t* si, int cx_, int cy_, unsigned wmask_, uint32_t* pay_ = nullptr,
+                                       int pstride_ = 1)
+        : p(p_), sinfo(si), cx(cx_), cy(cy_), busy(false), vis(0ull), lb_mf(0u), rb_mf(0u), wmask(wmask_), pay(pay_), pstride(pstride_), sA(0), sC(1), sB(2) {
         const uint32_t pb = fss_perm((uint32_t)cx);
         lofs = (int)fss_perm((uint32_t)(cx - 1)) - (int)pb;
         rofs = (int)fss_perm((uint32_t)(cx + FSS_CHUNK_W)) - (int)pb;
@@ -120,17 +133,26 @@ struct WinWalk {
         }
         R.fl = 0u;
     }
-    // the colour / temperature words travel with a moving cell but are not part of the window: their lines are requested
-    // into L1 two rows ahead, so that exchange() does not wait for HBM in the middle of a row (SAND only: liquids do not move)
-    __device__ __forceinline__ void prefetch_payload(cidx_t i) const {
-#if !defined(K1W_NO_PF_PAYLOAD) && defined(__CUDA_ARCH__)
+    __device__ __forceinline__ uint32_t& P(int slot, int plane, int k) const { return pay[((slot * 2 + plane) * FSS_CHUNK_W + k) * pstride]; }
+    // colour / temperature of one grid row (column 0 at index i) into a slot: asynchronous on the device
+    __device__ __forceinline__ void fetch_payload(int slot, cidx_t i) const {
 #pragma unroll
         for(int k = 0; k < FSS_CHUNK_W; k++) {
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.g.col + i + 32 * k));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.g.temp + i + 32 * k));
-        }
+#ifdef __CUDA_ARCH__
+            __pipeline_memcpy_async(&P(slot, 0, k), p.g.col + i + 32 * k, 4);
+            __pipeline_memcpy_async(&P(slot, 1, k), p.g.temp + i + 32 * k, 4);
 #else
-        (void)i;
+            P(slot, 0, k) = p.g.col[i + 32 * k];
+            P(slot, 1, k) = (uint32_t)p.g.temp[i + 32 * k];
+#endif
+        }
+#ifdef __CUDA_ARCH__
+        __pipeline_commit();
+#endif
+    }
+    static __device__ __forceinline__ void wait_payload() {
+#ifdef __CUDA_ARCH__
+        __pipeline_wait_prior(0);
 #endif
     }
     __device__ __forceinline__ void load_side(LSide& S, cidx_t i) const {
@@ -141,27 +163,36 @@ struct WinWalk {
 
     // `neighbour created (copy of mat/colour/temperature, amount 0) if AIR; neighbour.diff += flow`
     // (world.cpp:1399-1403, :1441-1445, :1471-1475, :1503-1507), into a window cell; is = own cell, in = the neighbour
-    template <int J>
-    __device__ __forceinline__ void give(LRow& X, float flow, uint32_t self_mf, cidx_t is, cidx_t in) const {
+    // (K = the giver's column in row slot sC; sx = the slot of row X)
+    template <int J, int K>
+    __device__ __forceinline__ void give(LRow& X, float flow, uint32_t self_mf, cidx_t is, cidx_t in, int sx) const {
         if(MF_IS(X.mf[J], FSS_PHYS_AIR)) {
             X.mf[J] = self_mf & (MF_MAT_MASK | MF_DERIVED_MASK);
             X.amt[J] = 0.0f;
             X.dif[J] = 0.0f + flow;
             X.fl |= LF_ALL << J;
-            p.g.col[in] = p.g.col[is];
-            p.g.temp[in] = p.g.temp[is];
+            if(SAND) {
+                wait_payload(); // (row r-1's words may still be on their way in)
+                P(sx, 0, J) = P(sC, 0, K);
+                P(sx, 1, J) = P(sC, 1, K);
+                X.fl |= LF_PAY << J;
+            } else {
+                p.g.col[in] = p.g.col[is];
+                p.g.temp[in] = p.g.temp[is];
+            }
         } else {
             X.dif[J] = X.dif[J] + flow;
             X.fl |= LF_DIF << J;
         }
     }
     // the same into an outside column: written through
+    template <int K>
     __device__ __forceinline__ void give_side(LSide& S, float flow, uint32_t self_mf, cidx_t is, cidx_t in) const {
         if(MF_IS(S.mf, FSS_PHYS_AIR)) {
             S.mf = self_mf & (MF_MAT_MASK | MF_DERIVED_MASK);
             p.g.mf[in] = S.mf;
-            p.g.col[in] = p.g.col[is];
-            p.g.temp[in] = p.g.temp[is];
+            p.g.col[in] = SAND ? P(sC, 0, K) : p.g.col[is];
+            p.g.temp[in] = SAND ? (int32_t)P(sC, 1, K) : p.g.temp[is];
             p.g.amt[in] = 0.0f;
             p.g.dif[in] = 0.0f + flow;
         } else {
@@ -173,9 +204,18 @@ struct WinWalk {
     // temperature words, which the window does not hold, change places in memory.  xmf / xdif: what the cell that was in X
     // carries into Y (SAND: `moved` may be set on the way, :1300; SOUP :1511: its running fluidAmountDiff)
     template <int K>
-    __device__ __forceinline__ void exchange(LRow& X, LRow& Y, cidx_t ix, cidx_t iy, uint32_t xmf, float xdif) const {
-        const uint32_t cx_ = p.g.col[ix], cy_ = p.g.col[iy];
-        const int32_t tx = p.g.temp[ix], ty = p.g.temp[iy];
+    __device__ __forceinline__ void exchange(LRow& X, LRow& Y, cidx_t ix, cidx_t iy, int sx, int sy, uint32_t xmf, float xdif) const {
+        if(SAND) {
+            const uint32_t c = P(sx, 0, K), t = P(sx, 1, K);
+            P(sx, 0, K) = P(sy, 0, K);
+            P(sx, 1, K) = P(sy, 1, K);
+            P(sy, 0, K) = c;
+            P(sy, 1, K) = t;
+            X.fl |= LF_PAY << K;
+            Y.fl |= LF_PAY << K;
+        }
+        const uint32_t cx_ = SAND ? 0u : p.g.col[ix], cy_ = SAND ? 0u : p.g.col[iy];
+        const int32_t tx = SAND ? 0 : p.g.temp[ix], ty = SAND ? 0 : p.g.temp[iy];
         const float xamt = X.amt[K];
         X.mf[K] = Y.mf[K];
         X.amt[K] = Y.amt[K];
@@ -185,10 +225,12 @@ struct WinWalk {
         Y.dif[K] = xdif;
         X.fl |= LF_ALL << K;
         Y.fl |= LF_ALL << K;
-        p.g.col[ix] = cy_;
-        p.g.col[iy] = cx_;
-        p.g.temp[ix] = ty;
-        p.g.temp[iy] = tx;
+        if(!SAND) {
+            p.g.col[ix] = cy_;
+            p.g.col[iy] = cx_;
+            p.g.temp[ix] = ty;
+            p.g.temp[iy] = tx;
+        }
     }
 
     __device__ __forceinline__ bool can_move_into(uint32_t dst_mf, uint32_t self_mf) const { // world.cpp:1276-1285, on the density ranks
@@ -209,7 +251,7 @@ struct WinWalk {
         const cidx_t i = irow + 32 * K, ib = i + p.g.pitch;
         uint32_t tile_mf = mf;
         if(fss_rand(key, 1300, 0) % 2 == 0) tile_mf |= MF_MOVED;
-        exchange<K>(C, B, i, ib, tile_mf, C.dif[K]); // :1296-1306
+        exchange<K>(C, B, i, ib, sC, sB, tile_mf, C.dif[K]); // :1296-1306
         B.fl |= LF_VIS << K;                         // :1308 tickVisited[x + (y + 1) * width]; row 16 is outside the chunk (ignored)
         if(fss_rand(key, 1313, 0) % 2 == 0) { // :1313-1335 transmit movement
             if(MF_IS(blmf, FSS_PHYS_SAND) && fss_rand(key, 1316, 0) % 2 == 0 && !(blmf & MF_MOVED)) {
@@ -279,12 +321,12 @@ struct WinWalk {
             if(flow != 0) {
                 remaining -= flow;
                 tdif -= flow;
-                give<K>(B, flow, mf, i, i + pitch);
+                give<K, K>(B, flow, mf, i, i + pitch, sB);
             }
         } else if(ITER0 && p.iter == 0 && MF_IS(bmf, FSS_PHYS_SOUP)) { // :1406-1412 (a different liquid below)
             const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)(cx + K), (uint32_t)(cy + r));
             if(fss_rand(key, 1407, 0) % 10 == 0) {
-                exchange<K>(C, B, i, i + pitch, mf, C.dif[K]);
+                exchange<K>(C, B, i, i + pitch, sC, sB, mf, C.dif[K]);
                 return;
             }
         }
@@ -301,8 +343,8 @@ struct WinWalk {
                 if(flow != 0) {
                     remaining -= flow;
                     tdif -= flow;
-                    if(K > 0) give<(K > 0 ? K - 1 : 0)>(C, flow, mf, i, i - 32);
-                    else give_side(L, flow, mf, i, irow + lofs);
+                    if(K > 0) give<(K > 0 ? K - 1 : 0), K>(C, flow, mf, i, i - 32, sC);
+                    else give_side<K>(L, flow, mf, i, irow + lofs);
                 }
             }
             done = remaining < FLUID_MinValue;
@@ -313,8 +355,8 @@ struct WinWalk {
                 if(flow != 0) {
                     remaining -= flow;
                     tdif -= flow;
-                    if(K < FSS_CHUNK_W - 1) give<(K < FSS_CHUNK_W - 1 ? K + 1 : 0)>(C, flow, mf, i, i + 32);
-                    else give_side(R, flow, mf, i, irow + rofs);
+                    if(K < FSS_CHUNK_W - 1) give<(K < FSS_CHUNK_W - 1 ? K + 1 : 0), K>(C, flow, mf, i, i + 32, sC);
+                    else give_side<K>(R, flow, mf, i, irow + rofs);
                 }
                 done = remaining < FLUID_MinValue;
             }
@@ -327,13 +369,14 @@ struct WinWalk {
                     if(flow != 0) {
                         remaining -= flow;
                         tdif -= flow;
-                        give<K>(A, flow, mf, i, i - pitch);
+                        give<K, K>(A, flow, mf, i, i - pitch, sA);
                     }
                     done = remaining < FLUID_MinValue;
                 } else if(ITER0 && p.iter == 0 && MF_IS(tmf, FSS_PHYS_SOUP)) { // :1510-1516
                     const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)(cx + K), (uint32_t)(cy + r));
                     if(fss_rand(key, 1511, 0) % 10 == 0) {
-                        exchange<K>(C, A, i, i - pitch, mf, tdif);
+                        if(SAND) wait_payload(); // (row r-1's words may still be on their way in)
+                        exchange<K>(C, A, i, i - pitch, sC, sA, mf, tdif);
                         return;
                     }
                 }
@@ -388,7 +431,7 @@ struct WinWalk {
     // A row leaves the window.  A chunk row (inside = true, r = 0 .. 15) first gets scan 2's SOUP step (world.cpp:1808-1825:
     // `fluidAmount += fluidAmountDiff; fluidAmountDiff = 0`, below FLUID_MinValue -> Tiles::NOTHING) on its unvisited SOUP cells;
     // then whatever differs from memory is stored.
-    __device__ __forceinline__ void retire(const LRow& X, cidx_t irow, int r, bool inside) {
+    __device__ __forceinline__ void retire(const LRow& X, cidx_t irow, int r, bool inside, int slot) {
 #pragma unroll
         for(int k = 0; k < FSS_CHUNK_W; k++) {
             const cidx_t i = irow + 32 * k;
@@ -405,6 +448,10 @@ struct WinWalk {
             }
             const bool apply = soup && !gone && __float_as_uint(d) != 0u; // else the stores would rewrite the same bits
             if(apply) busy = true;
+            if(SAND && (X.fl & (LF_PAY << k))) {
+                p.g.col[i] = P(slot, 0, k);
+                p.g.temp[i] = (int32_t)P(slot, 1, k);
+            }
             if(X.fl & (LF_MF << k)) p.g.mf[i] = mf;
             if(apply || (X.fl & (LF_AMT << k))) p.g.amt[i] = apply ? s : a;
             if(apply || (X.fl & (LF_DIF << k))) p.g.dif[i] = apply ? 0.0f : d;
@@ -425,18 +472,20 @@ struct WinWalk {
         if(SAND) {
             lb_mf = p.g.mf[ir + pitch + lofs];
             rb_mf = p.g.mf[ir + pitch + rofs];
-            prefetch_payload(ir + pitch);
-            prefetch_payload(ir);
-            prefetch_payload(ir - pitch);
+            fetch_payload(sB, ir + pitch);
+            fetch_payload(sC, ir);
         }
         Ln = L;
         Rn = R;
 #pragma unroll 1
         for(int r = FSS_CHUNK_H - 1; r >= 0; r--) {
             A = N;
+            if(SAND) { // rows r and r+1 have arrived (requested an iteration ago); row r-1 is needed from the next iteration on
+                wait_payload();
+                fetch_payload(sA, ir - pitch);
+            }
             if(r >= 1) { // requested a whole row of arithmetic ahead of their use
                 load_row(N, ir - 2 * pitch);
-                if(SAND) prefetch_payload(ir - 2 * pitch);
                 load_side(Ln, ir - pitch + lofs);
                 load_side(Rn, ir - pitch + rofs);
             }
@@ -444,9 +493,15 @@ struct WinWalk {
             cell<1>(A, C, B, L, R, ir, r);
             cell<2>(A, C, B, L, R, ir, r);
             cell<3>(A, C, B, L, R, ir, r);
-            retire(B, ir + pitch, r + 1, r < FSS_CHUNK_H - 1);
+            retire(B, ir + pitch, r + 1, r < FSS_CHUNK_H - 1, sB);
             B = C;
             C = A;
+            {
+                const int freed = sB;
+                sB = sC;
+                sC = sA;
+                sA = freed;
+            }
             if(SAND) {
                 lb_mf = L.mf;
                 rb_mf = R.mf;
@@ -456,8 +511,9 @@ struct WinWalk {
             ir -= pitch;
         }
         // ir = column 0 of row -1; B = row 0, C = row -1
-        retire(B, ir + pitch, 0, true);
-        retire(C, ir, -1, false);
+        if(SAND) wait_payload();
+        retire(B, ir + pitch, 0, true, sB);
+        retire(C, ir, -1, false, sC);
     }
 
     // early-out bookkeeping after the scans (same contract as ChunkWalk::run)

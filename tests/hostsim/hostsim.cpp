@@ -57,11 +57,12 @@ static void run_launch(HostWorld* w, const SubstepParams& p) {
             }
             const int cx = p.x_begin + 2 * FSS_CHUNK_W * gi, cy = p.y_begin + 2 * FSS_CHUNK_H * by;
             if(liq_window_applies(MODE, p.iter, p.flags, FLOW, DIRTY, sand_reacts)) { // launch_substep's choice (csrc/fss_abi.cu)
+                uint32_t pay[WIN_PAY_WORDS]; // the kernel's shared-memory slice of this thread
                 if(p.iter == 0) {
-                    WinWalk<MODE == K1_NOGAS, true> walk(p, w->sinfo, cx, cy, 1u);
+                    WinWalk<MODE == K1_NOGAS, true> walk(p, w->sinfo, cx, cy, 1u, pay, 1);
                     walk.run(qown);
                 } else {
-                    WinWalk<MODE == K1_NOGAS, false> walk(p, w->sinfo, cx, cy, 1u);
+                    WinWalk<MODE == K1_NOGAS, false> walk(p, w->sinfo, cx, cy, 1u, pay, 1);
                     walk.run(qown);
                 }
             } else {
