@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfss_b200.so")
 SOURCES = [os.path.join(CSRC, "fss_abi.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("fss_device.cuh", "fss_rules.cuh", "fss_rules_liq.cuh", "fss_kernels.cuh", "fss_particles.cuh", "fss_render.cuh")] + [
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("fss_device.cuh", "fss_chunkio.h", "fss_rules.cuh", "fss_rules_liq.cuh", "fss_kernels.cuh", "fss_particles.cuh", "fss_render.cuh")] + [
     os.path.join(HERE, "..", "include", f) for f in ("fss.h", "fss_rng.h")]
 
 NVCC_FLAGS = [

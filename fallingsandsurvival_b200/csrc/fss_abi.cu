@@ -20,6 +20,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 
+#include "fss_chunkio.h"
 #include "fss_kernels.cuh"
 #include "fss_particles.cuh"
 #include "fss_render.cuh"
@@ -1589,6 +1590,74 @@ int fss_merge_chunk_records(fss_world* w, int x0, int y0, int chunk_w, int chunk
 }
 int fss_read_chunk_records(fss_world* w, int x0, int y0, int chunk_w, int chunk_h, fss_tile_record* records) {
     return chunk_records(w, x0, y0, chunk_w, chunk_h, records, false);
+}
+
+// ---- the chunk file of Chunk::read / Chunk::write (Chunk.cpp:47-281): host code, no world needed ---------------------------
+#define FSS_FILE_CELLS ((size_t)FSS_CHUNK_FILE_W * FSS_CHUNK_FILE_H)
+
+int fss_lz4_compress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_size) {
+    if((!src && n) || !dst || !out_size) return fail(FSS_ERR_INVALID, "null argument");
+    if(cap < fss_lz4::compress_bound(n)) return fail(FSS_ERR_RANGE, "LZ4 output buffer of %zu bytes, %zu needed in the worst case", cap, fss_lz4::compress_bound(n));
+    *out_size = fss_lz4::compress(src, n, dst, cap);
+    return FSS_OK;
+}
+
+int fss_lz4_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_size) {
+    if(!src || (!dst && cap) || !out_size) return fail(FSS_ERR_INVALID, "null argument");
+    const long got = fss_lz4::decompress(src, n, dst, cap);
+    if(got < 0) return fail(FSS_ERR_INVALID, "malformed LZ4 block (or the output does not fit %zu bytes)", cap);
+    *out_size = (size_t)got;
+    return FSS_OK;
+}
+
+size_t fss_chunk_file_bound(void) {
+    return 1 + 4 * sizeof(int32_t) + fss_lz4::compress_bound(FSS_FILE_CELLS * 2 * sizeof(fss_tile_record)) + fss_lz4::compress_bound(FSS_FILE_CELLS * sizeof(uint32_t));
+}
+
+int fss_chunk_file_encode(int8_t generation_phase, const fss_tile_record* tiles, const fss_tile_record* layer2, const uint32_t* background, uint8_t* out,
+                          size_t cap, size_t* size) {
+    if(!tiles || !layer2 || !background || !out || !size) return fail(FSS_ERR_INVALID, "null argument");
+    if(cap < fss_chunk_file_bound()) return fail(FSS_ERR_RANGE, "chunk file buffer of %zu bytes, fss_chunk_file_bound() = %zu", cap, fss_chunk_file_bound());
+    // Chunk::write, Chunk.cpp:208-212: the tiles layer then layer2 in one buffer of MaterialInstanceData
+    std::vector<fss_tile_record> buf(FSS_FILE_CELLS * 2);
+    memcpy(buf.data(), tiles, FSS_FILE_CELLS * sizeof(fss_tile_record));
+    memcpy(buf.data() + FSS_FILE_CELLS, layer2, FSS_FILE_CELLS * sizeof(fss_tile_record));
+    const int32_t src_size = (int32_t)(FSS_FILE_CELLS * 2 * sizeof(fss_tile_record)), src_size2 = (int32_t)(FSS_FILE_CELLS * sizeof(uint32_t));
+    uint8_t* body = out + 1 + 4 * sizeof(int32_t);
+    const int32_t c1 = (int32_t)fss_lz4::compress((const uint8_t*)buf.data(), (size_t)src_size, body, fss_lz4::compress_bound((size_t)src_size));
+    const int32_t c2 = (int32_t)fss_lz4::compress((const uint8_t*)background, (size_t)src_size2, body + c1, fss_lz4::compress_bound((size_t)src_size2));
+    out[0] = (uint8_t)generation_phase; // :262-270
+    memcpy(out + 1, &src_size, 4);
+    memcpy(out + 5, &c1, 4);
+    memcpy(out + 9, &src_size2, 4);
+    memcpy(out + 13, &c2, 4);
+    *size = 17 + (size_t)c1 + (size_t)c2;
+    return FSS_OK;
+}
+
+int fss_chunk_file_decode(const uint8_t* file, size_t size, int8_t* generation_phase, fss_tile_record* tiles, fss_tile_record* layer2, uint32_t* background) {
+    if(!file || !tiles || !layer2 || !background) return fail(FSS_ERR_INVALID, "null argument");
+    if(size < 17) return fail(FSS_ERR_INVALID, "chunk file of %zu bytes: shorter than its header", size);
+    int32_t src_size, c1, src_size2, c2;
+    memcpy(&src_size, file + 1, 4);
+    memcpy(&c1, file + 5, 4);
+    memcpy(&src_size2, file + 9, 4);
+    memcpy(&c2, file + 13, 4);
+    // Chunk::read throws on these two (Chunk.cpp:99, :109)
+    if(src_size != (int32_t)(FSS_FILE_CELLS * 2 * sizeof(fss_tile_record)))
+        return fail(FSS_ERR_INVALID, "Chunk src_size was different from expected: %d vs %zu", src_size, FSS_FILE_CELLS * 2 * sizeof(fss_tile_record));
+    if(src_size2 != (int32_t)(FSS_FILE_CELLS * sizeof(uint32_t)))
+        return fail(FSS_ERR_INVALID, "Chunk src_size2 was different from expected: %d vs %zu", src_size2, FSS_FILE_CELLS * sizeof(uint32_t));
+    if(c1 < 0 || c2 < 0 || (size_t)c1 + (size_t)c2 > size - 17) return fail(FSS_ERR_INVALID, "chunk file of %zu bytes is shorter than its two blocks (%d + %d)", size, c1, c2);
+    std::vector<fss_tile_record> buf(FSS_FILE_CELLS * 2);
+    // (the reference logs these two and carries on with whatever was decoded, :129-133, :172-176; here the caller is told)
+    if(fss_lz4::decompress(file + 17, (size_t)c1, (uint8_t*)buf.data(), (size_t)src_size) != src_size) return fail(FSS_ERR_INVALID, "Decompressed chunk tile data is corrupt");
+    if(fss_lz4::decompress(file + 17 + c1, (size_t)c2, (uint8_t*)background, (size_t)src_size2) != src_size2)
+        return fail(FSS_ERR_INVALID, "Decompressed chunk background data is corrupt");
+    memcpy(tiles, buf.data(), FSS_FILE_CELLS * sizeof(fss_tile_record));
+    memcpy(layer2, buf.data() + FSS_FILE_CELLS, FSS_FILE_CELLS * sizeof(fss_tile_record));
+    if(generation_phase) *generation_phase = (int8_t)file[0];
+    return FSS_OK;
 }
 
 int fss_download_flow(fss_world* w, int x, int y, int width, int height, float* flow_x, float* flow_y, size_t pitch) {

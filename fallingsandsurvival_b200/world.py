@@ -51,6 +51,10 @@ def load():
         "fss_clear_flow": [vp],
         "fss_merge_chunk_records": [vp, i32, i32, i32, i32, vp],
         "fss_read_chunk_records": [vp, i32, i32, i32, i32, vp],
+        "fss_chunk_file_encode": [C.c_int8, vp, vp, vp, vp, sz, C.POINTER(sz)],
+        "fss_chunk_file_decode": [vp, sz, C.POINTER(C.c_int8), vp, vp, vp],
+        "fss_lz4_compress": [vp, sz, vp, sz, C.POINTER(sz)],
+        "fss_lz4_decompress": [vp, sz, vp, sz, C.POINTER(sz)],
         "fss_tick": [vp, u32],
         "fss_tick_host": [vp, u32, vp, sz],
         "fss_substep": [vp, u32, i32, i32],
@@ -85,6 +89,8 @@ def load():
         f = getattr(L, name)
         f.argtypes = args
         f.restype = C.c_int
+    L.fss_chunk_file_bound.restype = C.c_size_t
+    L.fss_chunk_file_bound.argtypes = []
     L.fss_last_error.restype = C.c_char_p
     L.fss_last_error.argtypes = []
     if L.fss_abi_version() != abi.FSS_ABI_VERSION:
@@ -404,3 +410,52 @@ class StripWorld:
     def close(self):
         for p in self.parts:
             p.close()
+
+
+# ---- the reference's chunk files (Chunk::read / Chunk::write, Chunk.cpp:47-281): host code, no world, no GPU ----
+FILE_CELLS = 128 * 128
+
+
+def chunk_file_encode(generation_phase, tiles, layer2, background) -> bytes:
+    """tiles, layer2: (128, 128) arrays of abi.RECORD_DTYPE; background: (128, 128) uint32"""
+    L = load()
+    tiles = np.ascontiguousarray(tiles, dtype=abi.RECORD_DTYPE)
+    layer2 = np.ascontiguousarray(layer2, dtype=abi.RECORD_DTYPE)
+    background = np.ascontiguousarray(background, dtype=np.uint32)
+    assert tiles.size == layer2.size == background.size == FILE_CELLS
+    cap = L.fss_chunk_file_bound()
+    out = np.zeros(cap, dtype=np.uint8)
+    n = C.c_size_t()
+    _check(L, L.fss_chunk_file_encode(generation_phase, tiles.ctypes.data, layer2.ctypes.data, background.ctypes.data, out.ctypes.data, cap, C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def chunk_file_decode(data: bytes):
+    """-> (generation_phase, tiles, layer2, background)"""
+    L = load()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    tiles = np.zeros((128, 128), dtype=abi.RECORD_DTYPE)
+    layer2 = np.zeros((128, 128), dtype=abi.RECORD_DTYPE)
+    background = np.zeros((128, 128), dtype=np.uint32)
+    phase = C.c_int8()
+    _check(L, L.fss_chunk_file_decode(buf.ctypes.data, len(buf), C.byref(phase), tiles.ctypes.data, layer2.ctypes.data, background.ctypes.data))
+    return phase.value, tiles, layer2, background
+
+
+def lz4_compress(data: bytes) -> bytes:
+    L = load()
+    src = np.frombuffer(data, dtype=np.uint8)
+    cap = len(src) + len(src) // 255 + 16
+    out = np.zeros(cap, dtype=np.uint8)
+    n = C.c_size_t()
+    _check(L, L.fss_lz4_compress(src.ctypes.data if len(src) else None, len(src), out.ctypes.data, cap, C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def lz4_decompress(data: bytes, size: int) -> bytes:
+    L = load()
+    src = np.frombuffer(data, dtype=np.uint8)
+    out = np.zeros(max(size, 1), dtype=np.uint8)
+    n = C.c_size_t()
+    _check(L, L.fss_lz4_decompress(src.ctypes.data, len(src), out.ctypes.data, size, C.byref(n)))
+    return out[: n.value].tobytes()

@@ -200,6 +200,25 @@ typedef struct fss_tile_record {
 int fss_merge_chunk_records(fss_world* w, int x0, int y0, int chunk_w, int chunk_h, const fss_tile_record* records);
 int fss_read_chunk_records(fss_world* w, int x0, int y0, int chunk_w, int chunk_h, fss_tile_record* records);
 
+/* The chunk FILE around those records: Chunk::write / Chunk::read (Chunk.cpp:189-281, :47-187).  Layout: int8 generationPhase;
+ * int32 src_size, compressed_size, src_size2, compressed_size2; an LZ4 block holding the 128 x 128 records of the `tiles`
+ * layer followed by those of `layer2` (MaterialInstanceData, Chunk.hpp:27-31); an LZ4 block holding the 128 x 128 Uint32 of
+ * `background`.  Host code only (no GPU, no world): together with fss_read_chunk_records / fss_merge_chunk_records a save
+ * round-trips between the device planes and the reference's files without the 40-byte host mirror.  The LZ4 block format is
+ * implemented in the library (the reference links liblz4, which this build does not); blocks written here are read by any
+ * LZ4 decoder and the other way round.  layer2 and background are not part of the tick path: the caller keeps them. */
+#define FSS_CHUNK_FILE_W 128 /* CHUNK_W, CHUNK_H of the reference (Chunk.hpp:18-19): the unit of its files, not the micro-chunk */
+#define FSS_CHUNK_FILE_H 128
+size_t fss_chunk_file_bound(void); /* buffer size fss_chunk_file_encode needs */
+int fss_chunk_file_encode(int8_t generation_phase, const fss_tile_record* tiles, const fss_tile_record* layer2, const uint32_t* background,
+                          uint8_t* out, size_t cap, size_t* size);
+int fss_chunk_file_decode(const uint8_t* file, size_t size, int8_t* generation_phase, fss_tile_record* tiles, fss_tile_record* layer2,
+                          uint32_t* background);
+/* the two halves of the codec on their own (LZ4_compress_fast / LZ4_decompress_safe of Chunk.cpp:226, :127); cap of
+ * fss_lz4_compress must be at least n + n/255 + 16 */
+int fss_lz4_compress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_size);
+int fss_lz4_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_size);
+
 /* World::tickChunks' grid shift when the camera moves (world.cpp:2617-2630): every cell moves by (change_x, change_y);
  * cells whose source would lie outside the grid keep their content, exactly like the reference's in-place loop.  The
  * caller then uploads the freshly loaded chunks into the vacated band.  A device-resident particle list moves with the grid

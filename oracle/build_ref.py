@@ -18,6 +18,9 @@ path needs none of that.  Recipe:
     reference's numbering) with three single-line instrumentation edits listed in PATCHES;
   * shims (oracle/ref_shim/): SDL typedefs, a cut-down `World` declaration, the C API.
 
+libfss_ref_chunk.so (separate, because it needs the system's liblz4): Chunk.cpp lines 47-187 (Chunk::read) and 189-281
+(Chunk::write) behind a cut-down `Chunk` declaration (oracle/ref_shim/fss_ref_chunk.cpp), for tests/test_chunkio.py.
+
 No reference SOURCE is written into the repository: the generated file and the libraries live in
 oracle/_ref/, which is git-ignored (but travels to the GPU box with gpurun).
 
@@ -87,6 +90,35 @@ def generate():
         f.write("\n".join(out) + "\n")
 
 
+CHUNK_RANGES = [(47, 187), (189, 281)]  # Chunk::read, Chunk::write
+
+
+def generate_chunk():
+    with open(os.path.join(F, "Chunk.cpp"), encoding="utf-8", errors="replace") as f:
+        lines = f.read().split("\n")
+    if not lines[46].startswith("void Chunk::read()") or not lines[188].startswith("void Chunk::write("):
+        raise SystemExit("Chunk.cpp: Chunk::read / Chunk::write are not where they were; reference changed?")
+    out = ["/* GENERATED from the reference by oracle/build_ref.py -- never commit */"]
+    for a, b in CHUNK_RANGES:
+        out.append(f'#line {a} "Chunk.cpp"')
+        out += lines[a - 1:b]
+    with open(os.path.join(GEN, "chunk_lines.inc"), "w") as f:
+        f.write("\n".join(out) + "\n")
+
+
+def build_chunk(objs):
+    """libfss_ref_chunk.so: the reference's Chunk::read / Chunk::write lines + the system liblz4 (skipped where that is missing)"""
+    lz4 = next((p for p in ("/usr/lib/x86_64-linux-gnu/liblz4.so.1", "/usr/lib64/liblz4.so.1", "/usr/lib/liblz4.so.1") if os.path.exists(p)), None)
+    if lz4 is None:
+        print("liblz4.so.1 not found: libfss_ref_chunk.so not built", file=sys.stderr)
+        return
+    shim = os.path.join(HERE, "ref_shim")
+    so = os.path.join(OUT, "libfss_ref_chunk.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-w", "-shared", "-I", shim, "-I", F, "-I", GEN, "-include", "vector", "-include", "cstdio",
+                           "-o", so, os.path.join(shim, "fss_ref_chunk.cpp")] + [o for o in objs if not o.endswith("Particle.o")] + [lz4])
+    print("built", so)
+
+
 def build(variants):
     shim = os.path.join(HERE, "ref_shim")
     common = ["g++", "-O2", "-std=c++17", "-pthread", "-fPIC", "-ffp-contract=off", "-w",
@@ -110,6 +142,7 @@ def build(variants):
         so = os.path.join(OUT, f"libfss_ref_{v}.so")
         subprocess.check_call(["g++", "-shared", "-pthread", "-o", so, api_o, tiles_o] + objs)
         print("built", so)
+    build_chunk(objs)
 
 
 def main():
@@ -118,6 +151,7 @@ def main():
         return 0
     variants = sys.argv[1:] or list(VARIANTS)
     generate()
+    generate_chunk()
     build(variants)
     return 0
 

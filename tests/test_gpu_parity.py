@@ -1119,3 +1119,27 @@ print(" ".join(out))
         e = dict(os.environ, FSS_HOST_BAND_ROWS="832", **env)
         res[name] = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, check=True).stdout.strip()
     assert len(set(res.values())) == 1, res
+
+
+def test_chunk_file_from_device_planes_and_back():
+    """Chunk::write / Chunk::read through the ABI: device planes -> 12-byte records (fss_read_chunk_records) -> the reference's
+    file (fss_chunk_file_encode: LZ4) -> records (fss_chunk_file_decode) -> another world's planes (fss_merge_chunk_records)"""
+    from fallingsandsurvival_b200 import world
+    cells, zone = make_world((264, 208), "c3", seed=41)
+    a = gpu_world(cells, zone)
+    for t in range(3):
+        a.tick(t)
+    recs = a.read_chunk_records(40, 30, 128, 128)
+    layer2 = np.zeros((128, 128), dtype=abi.RECORD_DTYPE)
+    bg = np.arange(128 * 128, dtype=np.uint32).reshape(128, 128)
+    data = world.chunk_file_encode(2, recs, layer2, bg)
+    phase, r2, l2, b2 = world.chunk_file_decode(data)
+    assert phase == 2 and np.array_equal(b2, bg)
+    b = gpu_world(make_world((264, 208), "sand", seed=42)[0], zone)
+    b.merge_chunk_records(40, 30, r2)
+    ca, cb = a.cells()[30:158, 40:168], b.cells()[30:158, 40:168]
+    for f in ("material", "color", "temperature"):
+        assert np.array_equal(ca[f], cb[f]), f
+    assert (cb["fluid_amount"] == 2.0).all() and (cb["moved"] == 0).all()  # the fields the file does not store (MaterialInstance.hpp:21)
+    a.close()
+    b.close()
