@@ -172,8 +172,11 @@ __global__ void __launch_bounds__(128) k_worklist(const uint8_t* __restrict__ q,
 // by three so that the three-row register window rotates by renaming.
 #define TEMP_ROWS 64
 #define TEMP_THREADS 128
+#ifndef K2_COLS
+#define K2_COLS 4 /* columns per thread: 8 (a whole group) or 4 (half a group: half the registers, twice the warps) */
+#endif
 #ifndef K2_MIN_BLOCKS
-#define K2_MIN_BLOCKS 3
+#define K2_MIN_BLOCKS (K2_COLS == 4 ? 5 : 3)
 #endif
 
 struct TempParams {
@@ -185,20 +188,20 @@ struct TempParams {
     int own_lo, own_hi; // global rows this world computes (owned rows); other stored rows are copied
 };
 
-struct TempRaw { // one stored row as loaded: columns x0-1 .. x0+8
-    int32_t t[10];
-    uint32_t m[10];
+struct TempRaw { // one stored row as loaded: the thread's columns plus one either side
+    int32_t t[K2_COLS + 2];
+    uint32_t m[K2_COLS + 2];
 };
 struct TempRow { // the conduction terms of one row, plus what the row needs when it is the centre row
-    float f[10], tf[10];
-    int32_t t[8];
-    uint32_t mlo, mhi; // material ids of the 8 own columns, one byte each
+    float f[K2_COLS + 2], tf[K2_COLS + 2];
+    int32_t t[K2_COLS];
+    uint32_t mpk[K2_COLS / 4]; // material ids of the own columns, one byte each
 };
 
 struct TempCols {
-    const int32_t* t;   // column x0 of the current stored row (temperature plane)
+    const int32_t* t;   // the thread's first column in the current stored row (temperature plane)
     const uint32_t* mf; // same cell, mf plane
-    int lofs, rofs;     // word offsets of columns x0-1 and x0+8 relative to column x0
+    int lofs, rofs;     // word offsets of the columns left / right of the thread's columns, relative to its first column
 };
 
 __device__ __forceinline__ void temp_request(const TempCols& c, size_t row_ofs, TempRaw& r) {
@@ -207,18 +210,19 @@ __device__ __forceinline__ void temp_request(const TempCols& c, size_t row_ofs, 
     r.t[0] = t[c.lofs];
     r.m[0] = m[c.lofs];
 #pragma unroll
-    for(int k = 0; k < 8; k++) {
+    for(int k = 0; k < K2_COLS; k++) {
         r.t[k + 1] = t[32 * k];
         r.m[k + 1] = m[32 * k];
     }
-    r.t[9] = t[c.rofs];
-    r.m[9] = m[c.rofs];
+    r.t[K2_COLS + 1] = t[c.rofs];
+    r.m[K2_COLS + 1] = m[c.rofs];
 }
 
 __device__ __forceinline__ void temp_terms(const float* s_co, const TempRaw& r, TempRow& o) {
-    uint32_t lo = 0, hi = 0;
 #pragma unroll
-    for(int c = 0; c < 10; c++) {
+    for(int q = 0; q < K2_COLS / 4; q++) o.mpk[q] = 0u;
+#pragma unroll
+    for(int c = 0; c < K2_COLS + 2; c++) {
         const int32_t t = r.t[c];
         const uint32_t m = mf_mat(r.m[c]);
         // `if(T != 0) { factor = abs(T) / 64.0f * conductionOther; v += T * factor; n += factor; }` without the test: for
@@ -230,39 +234,45 @@ __device__ __forceinline__ void temp_terms(const float* s_co, const TempRaw& r, 
         const float ta = ft * fa;
         o.f[c] = fa;
         o.tf[c] = ta;
-        if(c >= 1 && c <= 4) lo |= m << (8 * (c - 1));
-        if(c >= 5 && c <= 8) hi |= m << (8 * (c - 5));
-        if(c >= 1 && c <= 8) o.t[c - 1] = t;
+        if(c >= 1 && c <= K2_COLS) {
+            o.mpk[(c - 1) / 4] |= m << (8 * ((c - 1) & 3));
+            o.t[c - 1] = t;
+        }
     }
-    o.mlo = lo;
-    o.mhi = hi;
 }
 
-// the eight outputs of the row whose terms are in B (A = the row above, C = the row below)
+// the outputs of the row whose terms are in B (A = the row above, C = the row below)
 // s_self[m] = {conductionSelf, 1 - conductionSelf, float(addTemp), addTemp bits}
 __device__ __forceinline__ void temp_outputs(const float4* s_self, const TempRow& A, const TempRow& B, const TempRow& C, int32_t* out) {
+    // The two running sums of every cell are chains of nine dependent adds each (the reference's order is part of the result):
+    // all the chains of the row are written out first, without a branch between them, so that they can be issued
+    // interleaved instead of each waiting four cycles for its predecessor.
+    float v[K2_COLS], n[K2_COLS];
 #pragma unroll
-    for(int r = 0; r < 8; r++) {
+    for(int r = 0; r < K2_COLS; r++) {
         // neighbour order of world.cpp:2072-2116: x offset -1, 0, +1 outer; y offset -1, 0, +1 inner
-        float n = 0.01f, v = 0.0f;
+        float nn = 0.01f, vv = 0.0f;
 #pragma unroll
         for(int c = r; c < r + 3; c++) {
-            v += A.tf[c];
-            n += A.f[c];
-            v += B.tf[c];
-            n += B.f[c];
-            v += C.tf[c];
-            n += C.f[c];
+            vv += A.tf[c];
+            nn += A.f[c];
+            vv += B.tf[c];
+            nn += B.f[c];
+            vv += C.tf[c];
+            nn += C.f[c];
         }
-        const uint32_t m = ((r < 4 ? B.mlo : B.mhi) >> (8 * (r & 3))) & 0xFFu;
+        v[r] = vv;
+        n[r] = nn;
+    }
+#pragma unroll
+    for(int r = 0; r < K2_COLS; r++) {
+        const uint32_t m = (B.mpk[r / 4] >> (8 * (r & 3))) & 0xFFu;
         const float4 self = s_self[m];
-        int32_t o;
-        if(v != 0) { // :2128-2132; addTemp is Uint32 (Material.hpp:40): `addTemp + float` converts it to float
-            o = (int32_t)(self.z + (v / n * self.x) + (B.t[r] * self.y));
-        } else {
-            o = (int32_t)(__float_as_uint(self.w) + (uint32_t)B.t[r]);
-        }
-        out[32 * r] = o;
+        // :2128-2132; addTemp is Uint32 (Material.hpp:40): `addTemp + float` converts it to float.  Both forms are computed and
+        // one is selected (no branch: v != 0 almost everywhere a temperature is not zero)
+        const int32_t warm = (int32_t)(self.z + (v[r] / n[r] * self.x) + (B.t[r] * self.y));
+        const int32_t cold = (int32_t)(__float_as_uint(self.w) + (uint32_t)B.t[r]);
+        out[32 * r] = v[r] != 0 ? warm : cold;
     }
 }
 
@@ -277,14 +287,19 @@ __global__ void __launch_bounds__(TEMP_THREADS, K2_MIN_BLOCKS) k_temperature(con
         s_self[m] = make_float4(cs, 1 - cs, (float)add, __uint_as_float(add));
     }
     __syncthreads();
-    const uint32_t grp = blockIdx.x * TEMP_THREADS + threadIdx.x;
+    // thread -> (group of 8 columns, part of the group): the 32 lanes of a warp own 32 consecutive groups (one 128-byte line per
+    // column), the warps of a CTA alternate over the parts
+    constexpr int PARTS = 8 / K2_COLS;
+    const uint32_t slot = blockIdx.x * TEMP_THREADS + threadIdx.x;
+    const uint32_t grp = (slot / (32 * PARTS)) * 32 + (slot & 31u);
+    const int part = (int)((slot >> 5) % PARTS);
     if(grp >= p.g.pitch / 8) return;
-    const int x0 = (int)grp * 8;
+    const int x0 = (int)grp * 8 + part * K2_COLS;
     const int sr0 = blockIdx.y * TEMP_ROWS;
     const int sr1 = min(sr0 + TEMP_ROWS, p.g.rows);
     const size_t pitch = p.g.pitch;
-    const uint32_t base = (grp >> 5) * 256u + (grp & 31u);
-    const bool in_zone_x = x0 >= p.zx && x0 + 8 <= p.zx + p.zw;
+    const uint32_t base = fss_perm((uint32_t)x0);
+    const bool in_zone_x = x0 >= p.zx && x0 + K2_COLS <= p.zx + p.zw;
     // stored rows [c0, c1) of this band are computed, the others copied
     const int y_lo = max(p.zy, p.own_lo), y_hi = min(p.zy + p.zh, p.own_hi);
     int c0 = max(sr0, y_lo - p.g.sy0), c1 = min(sr1, y_hi - p.g.sy0);
@@ -293,7 +308,7 @@ __global__ void __launch_bounds__(TEMP_THREADS, K2_MIN_BLOCKS) k_temperature(con
         if(sr >= c0 && sr < c1) continue;
         const size_t rb = (size_t)sr * pitch + base;
 #pragma unroll
-        for(int r = 0; r < 8; r++) p.out[rb + r * 32] = p.g.temp[rb + r * 32];
+        for(int r = 0; r < K2_COLS; r++) p.out[rb + r * 32] = p.g.temp[rb + r * 32];
     }
     if(c0 >= c1) return;
 
@@ -301,7 +316,7 @@ __global__ void __launch_bounds__(TEMP_THREADS, K2_MIN_BLOCKS) k_temperature(con
     cols.t = p.g.temp + (size_t)c0 * pitch + base;
     cols.mf = p.g.mf + (size_t)c0 * pitch + base;
     cols.lofs = (int)fss_perm((uint32_t)(x0 - 1)) - (int)base;
-    cols.rofs = (int)fss_perm((uint32_t)(x0 + 8)) - (int)base;
+    cols.rofs = (int)fss_perm((uint32_t)(x0 + K2_COLS)) - (int)base;
     int32_t* out = p.out + (size_t)c0 * pitch + base;
 
     // rows c0-1 and c1 exist: the zone lies FSS_ZONE_MARGIN rows inside the world and a strip stores FSS_HALO_ROWS ghost rows
