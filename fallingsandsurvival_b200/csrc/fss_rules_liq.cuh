@@ -238,38 +238,42 @@ struct WinWalk {
     }
 
     // ---- SAND, scan 1, world.cpp:1218-1337 (no reactions: liq_window_applies; no free fall: particles are off) ------------
+    // (one way out of every rule body below: each `return` in the middle of a body is a merge point at which the compiler
+    // shuffles the window registers into place again -- ncu counted 35 such moves per cell visit)
     template <int K>
     __device__ __forceinline__ void sand1(LRow& C, LRow& B, cidx_t irow, int r, uint32_t mf) {
         const uint32_t bmf = B.mf[K];
         const uint32_t blmf = K > 0 ? B.mf[K > 0 ? K - 1 : 0] : lb_mf;
         const uint32_t brmf = K < FSS_CHUNK_W - 1 ? B.mf[K < FSS_CHUNK_W - 1 ? K + 1 : 0] : rb_mf;
         const bool can_b = can_move_into(bmf, mf), can_l = can_move_into(blmf, mf), can_r = can_move_into(brmf, mf);
-        if(!can_b) return; // :1276, :1287
-        busy = true;
-        const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)(cx + K), (uint32_t)(cy + r));
-        if((can_l || can_r) && fss_rand(key, 1287, 0) % 20 == 0) return;
-        const cidx_t i = irow + 32 * K, ib = i + p.g.pitch;
-        uint32_t tile_mf = mf;
-        if(fss_rand(key, 1300, 0) % 2 == 0) tile_mf |= MF_MOVED;
-        exchange<K>(C, B, i, ib, sC, sB, tile_mf, C.dif[K]); // :1296-1306
-        B.fl |= LF_VIS << K;                         // :1308 tickVisited[x + (y + 1) * width]; row 16 is outside the chunk (ignored)
-        if(fss_rand(key, 1313, 0) % 2 == 0) { // :1313-1335 transmit movement
-            if(MF_IS(blmf, FSS_PHYS_SAND) && fss_rand(key, 1316, 0) % 2 == 0 && !(blmf & MF_MOVED)) {
-                if(K > 0) {
-                    B.mf[K > 0 ? K - 1 : 0] = blmf | MF_MOVED;
-                    B.fl |= LF_MF << (K > 0 ? K - 1 : 0);
-                } else {
-                    lb_mf = blmf | MF_MOVED;
-                    p.g.mf[irow + p.g.pitch + lofs] = lb_mf;
-                }
-            }
-            if(MF_IS(brmf, FSS_PHYS_SAND) && fss_rand(key, 1327, 0) % 2 == 0 && !(brmf & MF_MOVED)) {
-                if(K < FSS_CHUNK_W - 1) {
-                    B.mf[K < FSS_CHUNK_W - 1 ? K + 1 : 0] = brmf | MF_MOVED;
-                    B.fl |= LF_MF << (K < FSS_CHUNK_W - 1 ? K + 1 : 0);
-                } else {
-                    rb_mf = brmf | MF_MOVED;
-                    p.g.mf[irow + p.g.pitch + rofs] = rb_mf;
+        if(can_b) { // :1276, :1287
+            busy = true;
+            const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)(cx + K), (uint32_t)(cy + r));
+            if(!((can_l || can_r) && fss_rand(key, 1287, 0) % 20 == 0)) {
+                const cidx_t i = irow + 32 * K, ib = i + p.g.pitch;
+                uint32_t tile_mf = mf;
+                if(fss_rand(key, 1300, 0) % 2 == 0) tile_mf |= MF_MOVED;
+                exchange<K>(C, B, i, ib, sC, sB, tile_mf, C.dif[K]); // :1296-1306
+                B.fl |= LF_VIS << K;                                 // :1308 tickVisited[x + (y + 1) * width]; row 16 is outside the chunk (ignored)
+                if(fss_rand(key, 1313, 0) % 2 == 0) { // :1313-1335 transmit movement
+                    if(MF_IS(blmf, FSS_PHYS_SAND) && fss_rand(key, 1316, 0) % 2 == 0 && !(blmf & MF_MOVED)) {
+                        if(K > 0) {
+                            B.mf[K > 0 ? K - 1 : 0] = blmf | MF_MOVED;
+                            B.fl |= LF_MF << (K > 0 ? K - 1 : 0);
+                        } else {
+                            lb_mf = blmf | MF_MOVED;
+                            p.g.mf[irow + p.g.pitch + lofs] = lb_mf;
+                        }
+                    }
+                    if(MF_IS(brmf, FSS_PHYS_SAND) && fss_rand(key, 1327, 0) % 2 == 0 && !(brmf & MF_MOVED)) {
+                        if(K < FSS_CHUNK_W - 1) {
+                            B.mf[K < FSS_CHUNK_W - 1 ? K + 1 : 0] = brmf | MF_MOVED;
+                            B.fl |= LF_MF << (K < FSS_CHUNK_W - 1 ? K + 1 : 0);
+                        } else {
+                            rb_mf = brmf | MF_MOVED;
+                            p.g.mf[irow + p.g.pitch + rofs] = rb_mf;
+                        }
+                    }
                 }
             }
         }
@@ -279,26 +283,24 @@ struct WinWalk {
     template <int K>
     __device__ __forceinline__ void cell(LRow& A, LRow& C, LRow& B, LSide& L, LSide& R, cidx_t irow, int r) {
         const uint32_t mf = C.mf[K];
-        if(p.iter >= mf_iters(mf)) { // :1163-1166
-            C.fl |= LF_VIS << K;
-            return;
-        }
-        if(SAND && MF_IS(mf, FSS_PHYS_SAND)) {
-            sand1<K>(C, B, irow, r, mf);
-            return;
-        }
-        if(!MF_IS(mf, FSS_PHYS_SOUP)) return;
+        const bool spent = p.iter >= mf_iters(mf); // :1163-1166
+        if(spent) C.fl |= LF_VIS << K;
+        if(SAND && !spent && MF_IS(mf, FSS_PHYS_SAND)) sand1<K>(C, B, irow, r, mf);
         // ---- SOUP, world.cpp:1338-1537
         const float amt = C.amt[K];
-        if(amt == 0.0f) return;    // :1344
-        if(amt < FLUID_MinValue) { // :1346-1350
+        const bool soup = !spent && MF_IS(mf, FSS_PHYS_SOUP) && amt != 0.0f; // :1344
+        if(soup && amt < FLUID_MinValue) {                                   // :1346-1350
             busy = true;
             C.amt[K] = 0.0f;
             C.fl |= LF_AMT << K;
-            return;
+        } else if(soup && !(mf & MF_MOVED)) { // :1376 (moved == settled for liquids)
+            busy = true;                      // an unsettled liquid cell always changes: it flows, or its settle counter advances
+            soup1<K>(A, C, B, L, R, irow, r, mf, amt);
         }
-        if(mf & MF_MOVED) return; // :1376 (moved == settled for liquids)
-        busy = true;              // an unsettled liquid cell always changes: it flows, or its settle counter advances
+    }
+
+    template <int K>
+    __device__ __forceinline__ void soup1(LRow& A, LRow& C, LRow& B, LSide& L, LSide& R, cidx_t irow, int r, const uint32_t mf, const float amt) {
         const cidx_t pitch = p.g.pitch;
         const cidx_t i = irow + 32 * K;
         const uint32_t mat = mf_mat(mf);
@@ -312,6 +314,7 @@ struct WinWalk {
         const uint32_t bmf = B.mf[K], tmf = A.mf[K];
         // the by-value copies of the four neighbours decide the un-settling at the end (:1529-1535)
         const uint32_t lmf0 = lmf, rmf0 = rmf;
+        bool swapped = false; // ITER0: the cell changed places with a different liquid below / above and its visit is over
 
         const bool air_below = MF_IS(bmf, FSS_PHYS_AIR); // :1381
         if((air_below && p.iter <= 2) || mf_mat(bmf) == mat) { // :1384-1405
@@ -327,10 +330,10 @@ struct WinWalk {
             const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)(cx + K), (uint32_t)(cy + r));
             if(fss_rand(key, 1407, 0) % 10 == 0) {
                 exchange<K>(C, B, i, i + pitch, sC, sB, mf, C.dif[K]);
-                return;
+                swapped = true;
             }
         }
-        bool done = remaining < FLUID_MinValue; // :1414-1418
+        bool done = swapped || remaining < FLUID_MinValue; // :1414-1418
         if(!done) {
             // :1420-1424
             const bool can_left = (MF_IS(lmf0, FSS_PHYS_AIR) || mf_mat(lmf0) == mat) && !air_below;
@@ -377,44 +380,45 @@ struct WinWalk {
                     if(fss_rand(key, 1511, 0) % 10 == 0) {
                         if(SAND) wait_payload(); // (row r-1's words may still be on their way in)
                         exchange<K>(C, A, i, i - pitch, sC, sA, mf, tdif);
-                        return;
+                        swapped = true;
                     }
                 }
             }
         }
-        if(done) { // :1414-1418, :1450-1454, :1480-1484, :1518-1522
-            C.dif[K] = tdif - remaining;
+        if(!swapped) {
+            if(done) { // :1414-1418, :1450-1454, :1480-1484, :1518-1522
+                C.dif[K] = tdif - remaining;
+            } else {
+                if(start == remaining) { // :1524-1528
+                    const uint32_t settle = (mf_settle(mf) + 1u) & 0xFFu;
+                    uint32_t nmf = (mf & 0x00FFFFFFu) | (settle << MF_SETTLE_SHIFT);
+                    if(settle >= 10u) nmf |= MF_MOVED;
+                    C.mf[K] = nmf;
+                    C.fl |= LF_MF << K;
+                } else { // :1529-1535: the by-value copies decide (a neighbour seeded above still counts as AIR)
+                    if(MF_IS(tmf, FSS_PHYS_SOUP) && (tmf & MF_MOVED)) {
+                        A.mf[K] = tmf & ~MF_MOVED;
+                        A.fl |= LF_MF << K;
+                    }
+                    if(MF_IS(bmf, FSS_PHYS_SOUP) && (bmf & MF_MOVED)) {
+                        B.mf[K] = bmf & ~MF_MOVED;
+                        B.fl |= LF_MF << K;
+                    }
+                    if(MF_IS(lmf0, FSS_PHYS_SOUP) && (lmf0 & MF_MOVED)) {
+                        lmf = lmf0 & ~MF_MOVED;
+                        if(K > 0) C.fl |= LF_MF << (K > 0 ? K - 1 : 0);
+                        else p.g.mf[irow + lofs] = lmf;
+                    }
+                    if(MF_IS(rmf0, FSS_PHYS_SOUP) && (rmf0 & MF_MOVED)) {
+                        rmf = rmf0 & ~MF_MOVED;
+                        if(K < FSS_CHUNK_W - 1) C.fl |= LF_MF << (K < FSS_CHUNK_W - 1 ? K + 1 : 0);
+                        else p.g.mf[irow + rofs] = rmf;
+                    }
+                }
+                C.dif[K] = tdif; // :1537 `tiles[index] = tile`
+            }
             C.fl |= LF_DIF << K;
-            return;
         }
-        if(start == remaining) { // :1524-1528
-            const uint32_t settle = (mf_settle(mf) + 1u) & 0xFFu;
-            uint32_t nmf = (mf & 0x00FFFFFFu) | (settle << MF_SETTLE_SHIFT);
-            if(settle >= 10u) nmf |= MF_MOVED;
-            C.mf[K] = nmf;
-            C.fl |= LF_MF << K;
-        } else { // :1529-1535: the by-value copies decide (a neighbour seeded above still counts as AIR)
-            if(MF_IS(tmf, FSS_PHYS_SOUP) && (tmf & MF_MOVED)) {
-                A.mf[K] = tmf & ~MF_MOVED;
-                A.fl |= LF_MF << K;
-            }
-            if(MF_IS(bmf, FSS_PHYS_SOUP) && (bmf & MF_MOVED)) {
-                B.mf[K] = bmf & ~MF_MOVED;
-                B.fl |= LF_MF << K;
-            }
-            if(MF_IS(lmf0, FSS_PHYS_SOUP) && (lmf0 & MF_MOVED)) {
-                lmf = lmf0 & ~MF_MOVED;
-                if(K > 0) C.fl |= LF_MF << (K > 0 ? K - 1 : 0);
-                else p.g.mf[irow + lofs] = lmf;
-            }
-            if(MF_IS(rmf0, FSS_PHYS_SOUP) && (rmf0 & MF_MOVED)) {
-                rmf = rmf0 & ~MF_MOVED;
-                if(K < FSS_CHUNK_W - 1) C.fl |= LF_MF << (K < FSS_CHUNK_W - 1 ? K + 1 : 0);
-                else p.g.mf[irow + rofs] = rmf;
-            }
-        }
-        C.dif[K] = tdif; // :1537 `tiles[index] = tile`
-        C.fl |= LF_DIF << K;
     }
 
     // world.cpp:1075-1088, the three cases computed and selected (each case is the reference's own expression)
