@@ -7,14 +7,18 @@ One "step" = one full World::tick (6 iter x 4 tk checkerboard sub-steps x 3 scan
 the whole tick zone; workload c3 also runs World::tickTemperature every 4th step (Game.cpp:2759).
 metric = cell-updates/s = zone cells x steps / seconds, whole job (all ranks).
 
-N = 1   workload "c2" (BASELINE.json configs[1]): 16384 x 16384 zone, 25 % sand / 20 % water / 10 % stone.
-N > 1   weak scaling: every rank owns a 16384 x 16384 strip of a 16384 x (16384*N) zone, halo rows
-        exchanged over NCCL after tk 1 / tk 3 of every iter (one process per GPU under torchrun).
+N = 1   workload "c2" (BASELINE.json configs[1]): 16384 x 16384 zone, 25 % sand / 20 % water / 10 % stone; the line also
+        carries `extra.c3` (configs[2], with roofline_k2 for k_temperature) and `extra.c5` (configs[4] at 32768 x 32768,
+        early-out on and off), a few ticks each.
+N > 1   workload "c4" (configs[3]): ONE 65536 x 65536 zone cut into N row strips (strong scaling), halo rows exchanged
+        over NCCL after tk 1 / tk 3 of every iter (one process per GPU under torchrun).
+Every line carries `digest`: fss_hash of the grid after the timed ticks, summed over the ranks -- the same for every N.
 The grid is generated on the device (fss_fill_synthetic); "data": "synthetic".
 
 Besides `value` (grid resident in HBM) the line carries
-  e2e          the same metric through the C ABI with HOST buffers: every step uploads the whole grid from
-               pinned host memory, ticks, and downloads the whole grid (the reference-side shim's worst case)
+  e2e          the same metric through the C ABI with HOST buffers (fss_tick_host): every step the whole grid goes up
+               from pinned host memory, is ticked, and comes back (the reference-side shim's worst case), pipelined
+               in row bands so that both PCIe directions and the kernels overlap
   roofline     K1 (k_substep) against the measured HBM copy bandwidth, algorithmic bytes as DESIGN.md defines
   cpu_baseline the reference's own tick (oracle/_ref) or the oracle port on this box's host cores, N = 1 only
 `--impl reference` times only that CPU implementation (rank 0), same metric and unit.
@@ -87,12 +91,13 @@ class ClockSampler:
 
 
 def ncu_traffic(workload, size):
-    """dram__bytes_read.sum + dram__bytes_write.sum per k_substep launch from the committed ncu capture of this very
-    workload (profiles/r01k_*), or None when the capture does not match the run"""
+    """dram__bytes_read.sum + dram__bytes_write.sum per movement launch (mean over the 24 launches of one tick) from the
+    committed ncu capture of this very workload on this round's build (profiles/r02_k1_traffic.json; a number taken under a
+    profiler cannot be produced inside a timed run), or None when the capture does not match the run"""
     if workload != "c2" or size != ZONE_PER_GPU:
         return None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01k_k_substep_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_k1_traffic.json")) as f:
             d = json.load(f)
         return float(d["dram_bytes_per_launch_mean"]), d["source"]
     except (OSError, KeyError, ValueError):
@@ -376,7 +381,7 @@ def k1_roofline(k1_ms, zone_cells, workload, size):
     sweep = 2.0 * CELL_BYTES_PLANES * zone_cells / 4            # active micro-chunks read + written once, all planes
     traffic, traffic_src = ncu_traffic(workload, size)
     return {
-        "kernel": "k_substep (K1: k_substep<NOGAS> iters 0-1, k_substep_liq iters 2-5 on the c2 fill)", "bound": "hbm",
+        "kernel": "K1 movement sub-step: k_substep_win<SAND> (iters 0-1 of the c2 fill) and k_substep_win<liquid> (iters 2-5), mean over the 24 launches of a tick", "bound": "hbm",
         "achieved": algo / (avg / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
         "frac": algo / (avg / 1e3) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
         "dram_achieved": (traffic / (avg / 1e3) / 1e9) if traffic else None,
