@@ -690,6 +690,7 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
     if(p.ny <= 0 || p.nx <= 0) return FSS_OK;
     {
         dim3 grid((p.nx + K1_THREADS - 1) / K1_THREADS, p.ny);
+        uint32_t work_tiles_now = 0;
         p.work = nullptr;
         p.work_n = nullptr;
         // Mostly settled worlds: a small kernel lists the tiles that still hold a not-settled chunk and a fixed grid strides over
@@ -698,8 +699,9 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
         // plain, the count is refreshed once per tick.  (FSS_TRACK_DIRTY needs a note per skipped chunk: plain launches only.)
         static const bool no_worklist = getenv("FSS_NO_WORKLIST") != nullptr;
         static const bool always_worklist = getenv("FSS_WORKLIST_ALWAYS") != nullptr; // tests: every launch through the list
-        if(w->d_q && !w->d_qskip && !no_worklist && !w->edge_launch && grid.x <= 0xFFFu && grid.y <= 0xFFFFFu) {
-            const uint32_t tiles = grid.x * grid.y;
+        const uint32_t tiles_x = (uint32_t)(p.nx + 31) / 32; // warp tiles per chunk row
+        if(w->d_q && !w->d_qskip && !no_worklist && !w->edge_launch && tiles_x <= 0x3FFFu && grid.y <= 0x3FFFFu) {
+            const uint32_t tiles = tiles_x * grid.y;
             if(tiles > w->work_cap) {
                 CU(cudaStreamSynchronize(w->stream));
                 cudaFree(w->d_work);
@@ -717,14 +719,14 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
             if(always_worklist) w->work_mode = true;
             if(w->work_mode || (iter == 0 && tk == 0)) {
                 CU(cudaMemsetAsync(w->d_work_n, 0, sizeof(uint32_t), w->stream));
-                k_worklist<<<(tiles * 32 + 127) / 128, 128, 0, w->stream>>>(p.q, p.q_w, ofs_x, ofs_y, iter, p.nx, (int)grid.x, p.ny, w->d_work, w->d_work_n);
+                k_worklist<<<(tiles + 127) / 128, 128, 0, w->stream>>>(p.q, p.q_w, ofs_x, ofs_y, iter, p.nx, (int)tiles_x, p.ny, w->d_work, w->d_work_n);
                 CU(cudaMemcpyAsync((void*)w->h_work_n, w->d_work_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
                 w->work_tiles = tiles;
                 w->stats.kernel_launches++;
                 if(w->work_mode) {
                     p.work = w->d_work;
                     p.work_n = w->d_work_n;
-                    grid = dim3(std::min<uint32_t>(tiles, 148u * 8u), 1);
+                    work_tiles_now = tiles; // the grid is sized below, once the kernel (and how many of its CTAs fit an SM) is known
                 }
             }
         }
@@ -732,7 +734,22 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
         const int mode = no_spec ? K1_GENERAL : (iter >= w->liq_from_iter ? K1_LIQUID : (iter >= w->nogas_from_iter ? K1_NOGAS : K1_GENERAL));
         const bool flow = w->g.fx != nullptr;
         const bool dirty = w->g.dirty != nullptr;
-#define FSS_LAUNCH_K1(M, F, D) k_substep<M, F, D><<<grid, K1_THREADS, 0, w->stream>>>(p)
+        // with a worklist: exactly as many CTAs as are resident at once (a second wave would start when the first is nearly done)
+        auto persistent = [&](const void* kernel) -> dim3 {
+            if(!work_tiles_now) return grid;
+            static std::vector<std::pair<const void*, int>> per_sm; // per kernel: CTAs per SM
+            int n = 0;
+            for(auto& e : per_sm)
+                if(e.first == kernel) n = e.second;
+            if(!n) {
+                if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, K1_THREADS, 0) != cudaSuccess || n < 1) n = 4;
+                per_sm.push_back({kernel, n});
+            }
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
+            return dim3(std::min<uint32_t>((work_tiles_now + K1_WARPS - 1) / K1_WARPS, (uint32_t)(sms * n)), 1);
+        };
+#define FSS_LAUNCH_K1(M, F, D) k_substep<M, F, D><<<persistent((const void*)k_substep<M, F, D>), K1_THREADS, 0, w->stream>>>(p)
 #define FSS_LAUNCH_K1_MODE(M)                                                                      \
     do {                                                                                           \
         if(dirty) {                                                                                \
@@ -742,13 +759,15 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
         }                                                                                          \
     } while(0)
         if(liq_window_applies(mode, iter, w->cfg.flags, flow, dirty, w->sand_reacts)) {
+#define FSS_LAUNCH_WIN(S, I) k_substep_win<S, I><<<persistent((const void*)k_substep_win<S, I>), K1_THREADS, 0, w->stream>>>(p)
             if(mode == K1_LIQUID) {
-                if(iter == 0) k_substep_win<false, true><<<grid, K1_THREADS, 0, w->stream>>>(p);
-                else k_substep_win<false, false><<<grid, K1_THREADS, 0, w->stream>>>(p);
+                if(iter == 0) FSS_LAUNCH_WIN(false, true);
+                else FSS_LAUNCH_WIN(false, false);
             } else {
-                if(iter == 0) k_substep_win<true, true><<<grid, K1_THREADS, 0, w->stream>>>(p);
-                else k_substep_win<true, false><<<grid, K1_THREADS, 0, w->stream>>>(p);
+                if(iter == 0) FSS_LAUNCH_WIN(true, true);
+                else FSS_LAUNCH_WIN(true, false);
             }
+#undef FSS_LAUNCH_WIN
         } else if(mode == K1_LIQUID) FSS_LAUNCH_K1_MODE(K1_LIQUID);
         else if(mode == K1_NOGAS) FSS_LAUNCH_K1_MODE(K1_NOGAS);
         else FSS_LAUNCH_K1_MODE(K1_GENERAL);

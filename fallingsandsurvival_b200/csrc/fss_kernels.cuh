@@ -39,20 +39,26 @@ __global__ void k_code_pad(int* out) {
 #ifndef K1N_MIN_BLOCKS
 #define K1N_MIN_BLOCKS 7
 #endif
-// The tiles one CTA works on: its own (blockIdx) in a plain launch, or every gridDim.x-th entry of the worklist.
+// What one warp works on: 32 horizontally adjacent chunks of one active chunk row ("warp tile" wx, by).  In a plain launch
+// the warps of CTA (blockIdx.x, blockIdx.y) own the warp tiles 4 * blockIdx.x .. + 3 of chunk row blockIdx.y; with a worklist
+// every warp of the fixed grid strides over the list on its own (no CTA-wide step inside the loop), so a list that names one
+// live warp tile in every CTA-sized stretch of the world (a 256-cell-wide active pocket) still fills whole CTAs.
+#define K1_WARPS (K1_THREADS / 32)
 struct TileLoop {
     uint32_t t, n, stride;
     const uint32_t* work;
     __device__ __forceinline__ TileLoop(const SubstepParams& p) : work(p.work) {
-        t = work ? blockIdx.x : 0u;
+        const uint32_t warp = threadIdx.x >> 5;
+        t = work ? blockIdx.x * K1_WARPS + warp : 0u;
         n = work ? *p.work_n : 1u;
-        stride = gridDim.x;
+        stride = gridDim.x * K1_WARPS;
     }
-    __device__ __forceinline__ bool next(int& bx, int& by) {
+    // gi = this thread's chunk in its chunk row, by = the chunk row
+    __device__ __forceinline__ bool next(int& gi, int& by) {
         if(t >= n) return false;
-        const uint32_t e = work ? work[t] : ((uint32_t)blockIdx.y << 12 | blockIdx.x);
-        bx = (int)(e & 0xFFFu);
-        by = (int)(e >> 12);
+        const uint32_t e = work ? work[t] : ((uint32_t)blockIdx.y << 14 | (blockIdx.x * K1_WARPS + (threadIdx.x >> 5)));
+        gi = (int)(e & 0x3FFFu) * 32 + (int)(threadIdx.x & 31u);
+        by = (int)(e >> 14);
         t += work ? stride : 1u;
         return true;
     }
@@ -70,9 +76,8 @@ __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS
     }
     __syncthreads();
     TileLoop tiles(p);
-    int bx, by;
-    while(tiles.next(bx, by)) {
-        const int gi = bx * K1_THREADS + threadIdx.x;
+    int gi, by;
+    while(tiles.next(gi, by)) {
         bool live = gi < p.nx;
         uint8_t* qown = nullptr;
 #ifndef K1_NO_EARLY
@@ -119,9 +124,8 @@ __global__ void __launch_bounds__(K1_THREADS, SAND ? K1WS_MIN_BLOCKS : K1W_MIN_B
         __syncthreads();
     }
     TileLoop tiles(p);
-    int bx, by;
-    while(tiles.next(bx, by)) {
-        const int gi = bx * K1_THREADS + threadIdx.x;
+    int gi, by;
+    while(tiles.next(gi, by)) {
         bool live = gi < p.nx;
         uint8_t* qown = nullptr;
 #ifndef K1_NO_EARLY
@@ -138,21 +142,26 @@ __global__ void __launch_bounds__(K1_THREADS, SAND ? K1WS_MIN_BLOCKS : K1W_MIN_B
     }
 }
 
-// ---- the worklist of a sub-step: which tiles (K1_THREADS chunks of one active chunk row) hold a chunk that is not settled ----
-// One warp per tile; lane l looks at the flags of the tile's chunks 4l .. 4l+3.
+// ---- the worklist of a sub-step: which warp tiles (32 chunks of one active chunk row) hold a chunk that is not settled ----
+// One THREAD per warp tile (its 32 flags are 64 consecutive bytes); the list slots of a warp's live tiles come from one atomicAdd.
 __global__ void __launch_bounds__(128) k_worklist(const uint8_t* __restrict__ q, int q_w, int ofs_x, int ofs_y, int iter, int nx, int tiles_x, int ny,
                                                   uint32_t* __restrict__ work, uint32_t* __restrict__ work_n) {
-    const int tile = (int)((blockIdx.x * 128u + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if(tile >= tiles_x * ny) return;
-    const int bx = tile % tiles_x, by = tile / tiles_x;
-    const uint8_t* row = q + (size_t)(2 * by + ofs_y + 1) * q_w + (ofs_x + 1);
+    const int tile = (int)(blockIdx.x * 128u + threadIdx.x), lane = threadIdx.x & 31;
     bool active = false;
-#pragma unroll
-    for(int k = 0; k < K1_THREADS / 32; k++) {
-        const int gi = bx * K1_THREADS + lane * (K1_THREADS / 32) + k;
-        if(gi < nx && row[2 * gi] > (uint8_t)iter) active = true;
+    uint32_t entry = 0u;
+    if(tile < tiles_x * ny) {
+        const int wx = tile % tiles_x, by = tile / tiles_x;
+        const uint8_t* row = q + (size_t)(2 * by + ofs_y + 1) * q_w + (ofs_x + 1) + 2 * (size_t)wx * 32;
+        const int n = min(32, nx - wx * 32);
+        for(int l = 0; l < n; l++) active = active || row[2 * l] > (uint8_t)iter;
+        entry = ((uint32_t)by << 14) | (uint32_t)wx;
     }
-    if(__any_sync(0xFFFFFFFFu, active) && lane == 0) work[atomicAdd(work_n, 1u)] = ((uint32_t)by << 12) | (uint32_t)bx;
+    const unsigned live = __ballot_sync(0xFFFFFFFFu, active);
+    if(live == 0u) return;
+    uint32_t base = 0u;
+    if(lane == __ffs((int)live) - 1) base = atomicAdd(work_n, (uint32_t)__popc(live));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs((int)live) - 1);
+    if(active) work[base + __popc(live & ((1u << lane) - 1u))] = entry;
 }
 
 // ---- K2: temperature stencil ---------------------------------------------------------------------------

@@ -58,9 +58,9 @@ struct SubstepParams {
     uint8_t* qskip; // FSS_TRACK_DIRTY: per chunk the lowest iter whose visit was skipped since the last render (0xFF = none); same layout as q
     int q_w;      // flags per row of chunks (zone chunks + 2 guards)
     int ofs_x, ofs_y; // phase offsets in chunks: the chunk of thread (gi, by) is (2*gi + ofs_x, 2*by + ofs_y)
-    // Compacted worklist (mostly settled worlds): `work` = the tiles (K1_THREADS chunks of one chunk row: by << 12 | bx) that
-    // hold at least one chunk that is not verified settled, built by k_worklist right before the launch; a fixed grid of
-    // CTAs then strides over it.  nullptr = one CTA per tile of the (ceil(nx / K1_THREADS), ny) grid.
+    // Compacted worklist (mostly settled worlds): `work` = the warp tiles (32 chunks of one chunk row: by << 14 | wx) that
+    // hold at least one chunk that is not verified settled, built by k_worklist right before the launch; the warps of a fixed
+    // grid then stride over it.  nullptr = one CTA per K1_THREADS chunks of the (ceil(nx / K1_THREADS), ny) grid.
     const uint32_t* work;
     const uint32_t* work_n;
 };
