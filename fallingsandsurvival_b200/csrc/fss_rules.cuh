@@ -945,33 +945,23 @@ struct ChunkWalk {
     // cell below: none of them is stored to by this visit before the rule looks at it) instead of four dependent round
     // trips.  In the lock-step scan those chains hit lines the row prefetch has brought into L1; here every lane is at its
     // own position, most of them miss L1, and a lane's round is as long as its longest chain.
-    __device__ __forceinline__ void sand2_sparse(cidx_t i, int x, int y, uint32_t mf, unsigned long long bit) {
+    struct Sand2Batch { // what one scan-2 position can need, requested together (visit2_sparse)
+        Cell tile, dl, dr;
+        uint32_t bmf, lmf, rmf;
+    };
+    __device__ __forceinline__ void sand2_sparse(cidx_t i, int x, int y, const Sand2Batch& b, unsigned long long bit) {
         const Grid& g = p.g;
         const cidx_t pitch = g.pitch;
+        const uint32_t mf = b.tile.mf;
         const uint32_t mat = mf_mat(mf);
         const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
         if(!(mf & MF_MOVED) && busy) { // see sand2(): the draw cannot un-stick the cell whatever the probe counts
-            const uint32_t r = fss_rand(key, 1715, 0);
-            if(r % 500u && r % 333u && r % 250u && r % 200u && r % 166u && r % 142u && r % 125u && r % 111u && r % 100u) return;
+            if(!stopped_draw_can_hit(fss_rand(key, 1715, 0))) return;
         }
         const cidx_t ibl = il + pitch, ibr = ir + pitch, ib = i + pitch;
-        const uint32_t blmf = g.mf[ibl], brmf = g.mf[ibr], bmf = g.mf[ib], lmf = g.mf[il], rmf = g.mf[ir];
-        Cell tile, dl, dr;
-        tile.mf = mf;
-        tile.col = g.col[i];
-        tile.temp = g.temp[i];
-        tile.amt = g.amt[i];
-        tile.dif = g.dif[i];
-        dl.mf = blmf;
-        dl.col = g.col[ibl];
-        dl.temp = g.temp[ibl];
-        dl.amt = g.amt[ibl];
-        dl.dif = g.dif[ibl];
-        dr.mf = brmf;
-        dr.col = g.col[ibr];
-        dr.temp = g.temp[ibr];
-        dr.amt = g.amt[ibr];
-        dr.dif = g.dif[ibr];
+        const uint32_t blmf = b.dl.mf, brmf = b.dr.mf, bmf = b.bmf, lmf = b.lmf, rmf = b.rmf;
+        Cell tile = b.tile;
+        const Cell &dl = b.dl, &dr = b.dr;
         const bool can_l = can_move_into(blmf, mf), can_r = can_move_into(brmf, mf);
         if(!(can_l || can_r)) { // :1697-1734 with no open diagonal: `moved` ends up false
             if(mf & MF_MOVED) {
@@ -1036,8 +1026,43 @@ struct ChunkWalk {
     // lanes that still have one -- instead of all 64 positions in lock step with one or two lanes inside the SAND rule.
     // The order inside a chunk is per lane anyway; a visit never clears a bit, and the bits it sets lie at positions the
     // order has already passed (or its own), so the set of positions to visit only shrinks as the reference's does.
-    __device__ __forceinline__ void scan2_sparse() {
+    // `stopm`: positions that held an unvisited SAND cell with moved == false when scan 1 was done with them (WinWalk<true>::retire
+    // sees every word of the chunk on its way out of the window).  Such a word cannot change before its scan-2 visit: a visit
+    // at (x, y) writes its own cell, the cell below (row y+1: already passed, the order is bottom-up), a side cell only if that
+    // is AIR, and a diagonal in row y+1.  So the pillar draw of those positions -- which ends 19 visits in 20 before anything is
+    // loaded -- is evaluated here, lane by lane without touching memory, and only the positions that survive it take part in
+    // the warp's steps (2.5 of the 5.4 unvisited positions of a c2 chunk are stopped cells).  Only when `busy` is already set:
+    // see sand2().
+    // A step is ONE round trip: the position's own words are requested together with everything the SAND rule can need.
+    static __device__ __forceinline__ bool stopped_draw_can_hit(uint32_t r) {
+        return !(r % 500u && r % 333u && r % 250u && r % 200u && r % 166u && r % 142u && r % 125u && r % 111u && r % 100u);
+    }
+    __device__ __forceinline__ void visit2_sparse(int dx, int dy, unsigned long long bit) {
+        const Grid& g = p.g;
+        const cidx_t i = locate(dx, dy);
+        const cidx_t pitch = g.pitch, ibl = il + pitch, ibr = ir + pitch;
+        Sand2Batch b;
+        b.tile = ld_cell(g, i);
+        b.dl = ld_cell(g, ibl);
+        b.dr = ld_cell(g, ibr);
+        b.bmf = g.mf[i + pitch];
+        b.lmf = g.mf[il];
+        b.rmf = g.mf[ir];
+        if(MF_IS(b.tile.mf, FSS_PHYS_SAND)) sand2_sparse(i, cx + dx, cy + dy, b, bit);
+        else if(MF_IS(b.tile.mf, FSS_PHYS_SOUP)) soup_apply(i, b.tile.amt, b.tile.dif, bit); // :1808-1825
+    }
+    __device__ __forceinline__ void scan2_sparse(unsigned long long stopm = 0ull) {
         unsigned long long todo = ~vis;
+        if(busy) {
+            unsigned long long m = todo & stopm;
+            while(m != 0ull) {
+                const int pos = 63 - __clzll((long long)m);
+                const unsigned long long bit = 1ull << pos;
+                m &= ~bit;
+                const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)(cx + (pos & (FSS_CHUNK_W - 1))), (uint32_t)(cy + (pos >> 2)));
+                if(!stopped_draw_can_hit(fss_rand(key, 1715, 0))) todo &= ~bit;
+            }
+        }
         while(__any_sync(wmask, todo != 0ull)) {
             if(todo != 0ull) {
                 const int top = 63 - __clzll((long long)todo);          // highest row with an unvisited position
@@ -1046,12 +1071,7 @@ struct ChunkWalk {
                 const int dx = __ffs((int)nib) - 1;                     // its leftmost unvisited column
                 const unsigned long long bit = 1ull << (dy * FSS_CHUNK_W + dx);
                 todo &= ~bit;
-                if(!(vis & bit)) { // :1676 (a visit earlier in this scan may have marked it)
-                    const cidx_t i = locate(dx, dy);
-                    const uint32_t mf = p.g.mf[i];
-                    if(MF_IS(mf, FSS_PHYS_SAND)) sand2_sparse(i, cx + dx, cy + dy, mf, bit);
-                    else if(MF_IS(mf, FSS_PHYS_SOUP)) soup_apply(i, p.g.amt[i], p.g.dif[i], bit); // :1808-1825
-                }
+                if(!(vis & bit)) visit2_sparse(dx, dy, bit); // :1676 (a visit earlier in this scan may have marked it)
             }
         }
     }

@@ -102,6 +102,7 @@ struct WinWalk {
     cidx_t c0; // index of (cx, cy) in the planes
     bool busy; // this visit stored to the grid or drew a random number (else it was the identity); see SubstepParams::q
     unsigned long long vis; // SAND: tickVisited of the chunk as scan 2 finds it
+    unsigned long long stopm; // SAND: unvisited SAND cells with moved == false (ChunkWalk::scan2_sparse decides their pillar draw without a load)
     uint32_t lb_mf, rb_mf;  // SAND: mf of the outside cells of the row BELOW the one being scanned (a SAND cell's diagonals)
     unsigned wmask;
     // SAND: cells move, and their colour / temperature words move with them.  Those two planes of the three window rows live in
@@ -114,7 +115,7 @@ struct WinWalk {
 
     __device__ __forceinline__ WinWalk(const SubstepParams& p_, const uint32_t* si, int cx_, int cy_, unsigned wmask_, uint32_t* pay_ = nullptr,
                                        int pstride_ = 1)
-        : p(p_), sinfo(si), cx(cx_), cy(cy_), busy(false), vis(0ull), lb_mf(0u), rb_mf(0u), wmask(wmask_), pay(pay_), pstride(pstride_), sA(0), sC(1), sB(2) {
+        : p(p_), sinfo(si), cx(cx_), cy(cy_), busy(false), vis(0ull), stopm(0ull), lb_mf(0u), rb_mf(0u), wmask(wmask_), pay(pay_), pstride(pstride_), sA(0), sC(1), sB(2) {
         const uint32_t pb = fss_perm((uint32_t)cx);
         lofs = (int)fss_perm((uint32_t)(cx - 1)) - (int)pb;
         rofs = (int)fss_perm((uint32_t)(cx + FSS_CHUNK_W)) - (int)pb;
@@ -460,6 +461,7 @@ struct WinWalk {
             if(apply || (X.fl & (LF_AMT << k))) p.g.amt[i] = apply ? s : a;
             if(apply || (X.fl & (LF_DIF << k))) p.g.dif[i] = apply ? 0.0f : d;
             if(SAND && inside && (visited || (soup && !gone))) vis |= 1ull << (r * FSS_CHUNK_W + k);
+            if(SAND && inside && !visited && MF_IS(mf, FSS_PHYS_SAND) && !(mf & MF_MOVED)) stopm |= 1ull << (r * FSS_CHUNK_W + k);
         }
     }
 
@@ -530,7 +532,7 @@ struct WinWalk {
 #ifdef K1_SCAN2_LOCKSTEP
             w.scan2_rest();
 #else
-            w.scan2_sparse();
+            w.scan2_sparse(stopm);
 #endif
             busy = w.busy;
         }
