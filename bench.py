@@ -90,6 +90,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def pin_to_gpu_numa_node(local):
+    """Bind this rank's host threads to the CPUs next to its GPU (NVML's ideal CPU affinity = the GPU's NUMA node) BEFORE any
+    pinned host buffer is allocated: first touch then places the staging memory on that node, and N ranks stop sharing one
+    socket's memory controllers and one set of cores (round 1: every rank ran on CPUs 0-31 / NUMA node 0)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        try:
+            node = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            node = None
+        cpus = sorted(os.sched_getaffinity(0))
+        return {"numa_node": node, "cpus": f"{cpus[0]}-{cpus[-1]} ({len(cpus)})"}
+    except Exception as e:  # no NVML / not permitted in this container: run unpinned and say so
+        return {"numa_node": None, "cpus": f"unpinned: {type(e).__name__}"}
+
+
 def ncu_traffic(workload, size):
     """dram__bytes_read.sum + dram__bytes_write.sum per movement launch (mean over the 24 launches of one tick) from the
     committed ncu capture of this very workload on this round's build (profiles/r02_k1_traffic.json; a number taken under a
@@ -427,6 +446,7 @@ def main():
     n = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert n == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={n}: launch with torchrun --nproc-per-node {args.gpus}"
+    affinity = pin_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     if n > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -444,7 +464,7 @@ def main():
             "metric": "cell-updates/sec", "value": zone_cells * args.steps / (m["ms"] / 1e3), "unit": "cell-updates/s", "n_gpus": n, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps, "higher_is_better": True, "scaling": "strong" if workload == "c4" else "weak",
             "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic", "config": workload_config(workload, n, (ZW, ZH), early_out=not args.no_early_out),
-            "gpu_launches": int(m["launches"]), "clocks": m["clocks"],
+            "gpu_launches": int(m["launches"]), "clocks": m["clocks"], "host_affinity_rank0": affinity,
             "digest": m["digest"], "digest_what": f"fss_hash of the whole grid (sum over ranks mod 2^64) after {m['digest_after_ticks']} ticks; "
                                                   "identical for every --gpus N on the same workload",
         }

@@ -973,7 +973,8 @@ int fss_tick_temperature(fss_world* w) {
     p.own_lo = w->own_lo;
     p.own_hi = w->own_hi;
     const uint32_t slots = w->g.pitch / 8 * (8 / K2_COLS); // one thread per K2_COLS columns (pitch is a multiple of 256)
-    k_temperature<<<dim3((slots + TEMP_THREADS - 1) / TEMP_THREADS, (w->g.rows + TEMP_ROWS - 1) / TEMP_ROWS), TEMP_THREADS, 0, w->stream>>>(p);
+    const dim3 grid((slots + TEMP_THREADS - 1) / TEMP_THREADS, (w->g.rows + TEMP_ROWS - 1) / TEMP_ROWS);
+    k_temperature<<<grid, TEMP_THREADS, 0, w->stream>>>(p);
     w->stats.kernel_launches++;
     CU(cudaGetLastError());
     std::swap(w->g.temp, w->temp2);

@@ -165,28 +165,17 @@ __global__ void __launch_bounds__(128) k_worklist(const uint8_t* __restrict__ q,
 }
 
 // ---- K2: temperature stencil ---------------------------------------------------------------------------
-// World::tickTemperature, world.cpp:2043-2143.  One thread owns the 8 consecutive columns of one "group" (x >> 3) and
-// walks TEMP_ROWS stored rows top-down; lanes of a warp own consecutive groups, so each of a thread's loads is one fully
-// used 128-byte line per warp.  The per-neighbour terms
+// World::tickTemperature, world.cpp:2043-2143.  One thread owns four consecutive columns (half of one "group" x >> 3) and
+// walks TEMP_ROWS stored rows top-down; lanes of a warp own consecutive groups.  The per-neighbour terms
 //   factor = abs(T)/64.0f * conductionOther;  v += T*factor;  n += factor      (world.cpp:2072-2116)
 // depend only on the neighbour, so they are computed once per loaded cell and kept in registers for the three rows
 // they take part in; a cell with T == 0 contributes (+0.0f, +0.0f), which leaves the fp32 running sums bit-identical to
 // the reference's `if(T != 0)` skip.  The nine terms are added in the reference's order (x offset outer, y offset inner).
-// Output goes to the second temperature plane (Jacobi); cells outside tickZone are copied.
-//
-// Round 2: the kernel was latency-bound at 10 warps per SM -- every row iteration issued its 20 loads and
-// waited for them.  Now the raw words of row y+2 are requested BEFORE row y is computed (software pipelining: a full row
-// of arithmetic, ~400 instructions, covers the DRAM latency), row pointers are carried instead of recomputed, the
-// per-material terms (1 - conductionSelf, float(addTemp)) come from shared-memory tables, and the row loop is unrolled
-// by three so that the three-row register window rotates by renaming.
+// Output goes to the second temperature plane (Jacobi); cells outside tickZone are copied.  How the rows reach the
+// threads: see k_temperature below (bulk copies into a shared-memory ring).
 #define TEMP_ROWS 64
 #define TEMP_THREADS 128
-#ifndef K2_COLS
-#define K2_COLS 4 /* columns per thread: 8 (a whole group) or 4 (half a group: half the registers, twice the warps) */
-#endif
-#ifndef K2_MIN_BLOCKS
-#define K2_MIN_BLOCKS (K2_COLS == 4 ? 5 : 3)
-#endif
+#define K2_COLS 4
 
 struct TempParams {
     Grid g;
@@ -206,26 +195,6 @@ struct TempRow { // the conduction terms of one row, plus what the row needs whe
     int32_t t[K2_COLS];
     uint32_t mpk[K2_COLS / 4]; // material ids of the own columns, one byte each
 };
-
-struct TempCols {
-    const int32_t* t;   // the thread's first column in the current stored row (temperature plane)
-    const uint32_t* mf; // same cell, mf plane
-    int lofs, rofs;     // word offsets of the columns left / right of the thread's columns, relative to its first column
-};
-
-__device__ __forceinline__ void temp_request(const TempCols& c, size_t row_ofs, TempRaw& r) {
-    const int32_t* t = c.t + row_ofs;
-    const uint32_t* m = c.mf + row_ofs;
-    r.t[0] = t[c.lofs];
-    r.m[0] = m[c.lofs];
-#pragma unroll
-    for(int k = 0; k < K2_COLS; k++) {
-        r.t[k + 1] = t[32 * k];
-        r.m[k + 1] = m[32 * k];
-    }
-    r.t[K2_COLS + 1] = t[c.rofs];
-    r.m[K2_COLS + 1] = m[c.rofs];
-}
 
 __device__ __forceinline__ void temp_terms(const float* s_co, const TempRaw& r, TempRow& o) {
 #pragma unroll
@@ -252,7 +221,7 @@ __device__ __forceinline__ void temp_terms(const float* s_co, const TempRaw& r, 
 
 // the outputs of the row whose terms are in B (A = the row above, C = the row below)
 // s_self[m] = {conductionSelf, 1 - conductionSelf, float(addTemp), addTemp bits}
-__device__ __forceinline__ void temp_outputs(const float4* s_self, const TempRow& A, const TempRow& B, const TempRow& C, int32_t* out) {
+__device__ __forceinline__ void temp_outputs(const float4* s_self, const TempRow& A, const TempRow& B, const TempRow& C, int32_t* out, bool store = true) {
     // The two running sums of every cell are chains of nine dependent adds each (the reference's order is part of the result):
     // all the chains of the row are written out first, without a branch between them, so that they can be issued
     // interleaved instead of each waiting four cycles for its predecessor.
@@ -281,13 +250,60 @@ __device__ __forceinline__ void temp_outputs(const float4* s_self, const TempRow
         // one is selected (no branch: v != 0 almost everywhere a temperature is not zero)
         const int32_t warm = (int32_t)(self.z + (v[r] / n[r] * self.x) + (B.t[r] * self.y));
         const int32_t cold = (int32_t)(__float_as_uint(self.w) + (uint32_t)B.t[r]);
-        out[32 * r] = v[r] != 0 ? warm : cold;
+        if(store) out[32 * r] = v[r] != 0 ? warm : cold;
     }
 }
 
-__global__ void __launch_bounds__(TEMP_THREADS, K2_MIN_BLOCKS) k_temperature(const __grid_constant__ TempParams p) {
+// ---- K2, TMA-staged (sm_90+ bulk copies; the shipped form on sm_100a) -------------------------------------------------
+// In the permuted
+// layout the 512 columns a CTA owns (two aligned 256-column blocks) are 2 KB of CONTIGUOUS words per row and plane, and the
+// two halo columns are the words right before and right after them.  So one elected thread fetches a whole row of both planes
+// with two `cp.async.bulk` copies of 2 KB + 2 x 16 B into a ring of K2_STAGES shared-memory stages, each guarded by a "full"
+// mbarrier (the copy's complete_tx) and an "empty" one (every consumer arrives after it has read the stage); the consumers read
+// their 12 words per row from shared memory (lanes hit consecutive banks).  No thread issues a global load in the row loop, no
+// register is held for words in flight, and K2_STAGES - 1 rows are on their way while one is computed: the round-2 kernel had
+// one row in flight and was waiting for it a third of the time (ncu: long-scoreboard 3.7 per issue at 18 warps per SM).
+#define K2_STAGES 3 /* = the period of the three-row register window: stage numbers and window roles are static in the unrolled loop */
+#ifndef K2T_MIN_BLOCKS
+#define K2T_MIN_BLOCKS 7 /* 72 registers; 5 / 6 / 7 CTAs per SM: 0.855 / 0.851 / 0.818 ms at 16384^2 */
+#endif
+#define K2_STAGE_WORDS (4 + 512 + 4) /* 16 B of left halo, two 256-column blocks, 16 B of right halo */
+
+__device__ __forceinline__ uint32_t smem_u32(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "K2_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra K2_DONE;\n"
+        "bra K2_WAIT;\n"
+        "K2_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(TEMP_THREADS, K2T_MIN_BLOCKS) k_temperature(const __grid_constant__ TempParams p) {
+    static_assert(K2_COLS == 4 && TEMP_THREADS == 128, "a CTA owns two 256-column blocks: 128 threads x 4 columns");
     __shared__ float s_co[FSS_MAX_MATERIALS];
     __shared__ float4 s_self[FSS_MAX_MATERIALS];
+    __shared__ __align__(128) uint32_t s_stage[K2_STAGES][2][K2_STAGE_WORDS]; // [stage][temperature, mf][words]
+    __shared__ __align__(8) uint64_t s_full[K2_STAGES], s_empty[K2_STAGES];
     for(int m = threadIdx.x; m < FSS_MAX_MATERIALS; m += TEMP_THREADS) {
         const bool in = m < p.n_mat;
         const float cs = in ? p.mats[m].cond_self : 1.0f;
@@ -295,59 +311,126 @@ __global__ void __launch_bounds__(TEMP_THREADS, K2_MIN_BLOCKS) k_temperature(con
         s_co[m] = in ? p.mats[m].cond_other : 0.0f;
         s_self[m] = make_float4(cs, 1 - cs, (float)add, __uint_as_float(add));
     }
-    __syncthreads();
-    // thread -> (group of 8 columns, part of the group): the 32 lanes of a warp own 32 consecutive groups (one 128-byte line per
-    // column), the warps of a CTA alternate over the parts
-    constexpr int PARTS = 8 / K2_COLS;
+    // thread -> (group of 8 columns, half of the group), as in k_temperature
     const uint32_t slot = blockIdx.x * TEMP_THREADS + threadIdx.x;
-    const uint32_t grp = (slot / (32 * PARTS)) * 32 + (slot & 31u);
-    const int part = (int)((slot >> 5) % PARTS);
-    if(grp >= p.g.pitch / 8) return;
+    const uint32_t grp = (slot / 64u) * 32u + (slot & 31u);
+    const int part = (int)((slot >> 5) & 1u);
+    const bool active = grp < p.g.pitch / 8;
     const int x0 = (int)grp * 8 + part * K2_COLS;
     const int sr0 = blockIdx.y * TEMP_ROWS;
     const int sr1 = min(sr0 + TEMP_ROWS, p.g.rows);
     const size_t pitch = p.g.pitch;
     const uint32_t base = fss_perm((uint32_t)x0);
+    const uint32_t cta_base = blockIdx.x * 512u; // storage offset of the CTA's first column in a row
     const bool in_zone_x = x0 >= p.zx && x0 + K2_COLS <= p.zx + p.zw;
-    // stored rows [c0, c1) of this band are computed, the others copied
+    // stored rows [c0, c1) of this band are computed (the same for every thread of the CTA), the others copied
     const int y_lo = max(p.zy, p.own_lo), y_hi = min(p.zy + p.zh, p.own_hi);
-    int c0 = max(sr0, y_lo - p.g.sy0), c1 = min(sr1, y_hi - p.g.sy0);
-    if(!in_zone_x || c0 >= c1) c0 = c1 = sr1;
-    for(int sr = sr0; sr < sr1; sr++) {
-        if(sr >= c0 && sr < c1) continue;
-        const size_t rb = (size_t)sr * pitch + base;
+    const int c0 = max(sr0, y_lo - p.g.sy0), c1 = min(sr1, y_hi - p.g.sy0);
+    const bool consumer = active && in_zone_x && c0 < c1;
+    if(active) {
+        for(int sr = sr0; sr < sr1; sr++) {
+            if(consumer && sr >= c0 && sr < c1) continue;
+            const size_t rb = (size_t)sr * pitch + base;
 #pragma unroll
-        for(int r = 0; r < K2_COLS; r++) p.out[rb + r * 32] = p.g.temp[rb + r * 32];
+            for(int r = 0; r < K2_COLS; r++) p.out[rb + r * 32] = p.g.temp[rb + r * 32];
+        }
     }
-    if(c0 >= c1) return;
+    // Thread 0 issues the copies.  It always walks the row loop like a consumer (its stores are switched off when its own columns
+    // lie outside the zone), so that the loop body has no role tests in it.
+    const bool producer = threadIdx.x == 0;
+    const int n_cons = __syncthreads_count(consumer || producer); // (also orders the table stores above)
+    if(__syncthreads_count(consumer) == 0) return;
+    if(producer) {
+#pragma unroll
+        for(int s = 0; s < K2_STAGES; s++) {
+            mbar_init(&s_full[s], 1u);
+            mbar_init(&s_empty[s], (uint32_t)n_cons);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if(!consumer && !producer) return;
 
-    TempCols cols;
-    cols.t = p.g.temp + (size_t)c0 * pitch + base;
-    cols.mf = p.g.mf + (size_t)c0 * pitch + base;
-    cols.lofs = (int)fss_perm((uint32_t)(x0 - 1)) - (int)base;
-    cols.rofs = (int)fss_perm((uint32_t)(x0 + K2_COLS)) - (int)base;
+    // row j of the pipeline = stored row c0 - 1 + j, j = 0 .. n_rows - 1 (rows c0-1 and c1 exist: the zone lies FSS_ZONE_MARGIN
+    // rows inside the world and a strip stores FSS_HALO_ROWS ghost rows); row j lives in stage j % 3, whose k-th use has parity k & 1
+    const int n_rows = c1 - c0 + 2;
+    const uint32_t n_blk = min(2u, p.g.pitch / 256u - 2u * blockIdx.x);
+    const uint32_t bytes = n_blk * 1024u + 32u;
+    const int32_t* src_t = p.g.temp + (size_t)(c0 - 1) * pitch + cta_base - 4;
+    const uint32_t* src_m = p.g.mf + (size_t)(c0 - 1) * pitch + cta_base - 4;
+    auto issue = [&](int stage, int j) {
+        mbar_expect_tx(&s_full[stage], 2u * bytes);
+        tma_load_1d(&s_stage[stage][0][0], src_t + (size_t)j * pitch, bytes, &s_full[stage]);
+        tma_load_1d(&s_stage[stage][1][0], src_m + (size_t)j * pitch, bytes, &s_full[stage]);
+    };
+    if(producer) {
+        issue(0, 0);
+        issue(1, 1);
+        if(n_rows > 2) issue(2, 2);
+    }
+    // word offsets inside a stage: own column k at w0 + 32 k, the columns left / right of the thread's four at wl / wr
+    const int w0 = 4 + (int)(base - cta_base);
+    const int wl = 4 + (int)(fss_perm((uint32_t)(x0 - 1)) - cta_base), wr = 4 + (int)(fss_perm((uint32_t)(x0 + K2_COLS)) - cta_base);
+    // the terms of pipeline row j (in stage `stage`, use parity `par`); the stage is handed back as soon as its words are in
+    // registers, and the stage read one row ago (`prev`, parity `ppar`) is sent for row j + 2 once every consumer has arrived there
+    auto take = [&](int stage, uint32_t par, int prev, uint32_t ppar, int j, TempRow& o) {
+        mbar_wait(&s_full[stage], par);
+        TempRaw r;
+        const uint32_t* st = &s_stage[stage][0][0];
+        const uint32_t* sm = &s_stage[stage][1][0];
+        r.t[0] = (int32_t)st[wl];
+        r.m[0] = sm[wl];
+#pragma unroll
+        for(int k = 0; k < K2_COLS; k++) {
+            r.t[k + 1] = (int32_t)st[w0 + 32 * k];
+            r.m[k + 1] = sm[w0 + 32 * k];
+        }
+        r.t[K2_COLS + 1] = (int32_t)st[wr];
+        r.m[K2_COLS + 1] = sm[wr];
+        mbar_arrive(&s_empty[stage]);
+        temp_terms(s_co, r, o);
+        if(producer && j + 2 < n_rows) {
+            mbar_wait(&s_empty[prev], ppar);
+            issue(prev, j + 2);
+        }
+    };
     int32_t* out = p.out + (size_t)c0 * pitch + base;
-
-    // rows c0-1 and c1 exist: the zone lies FSS_ZONE_MARGIN rows inside the world and a strip stores FSS_HALO_ROWS ghost rows
     TempRow A, B, C;
-    TempRaw raw;
-    temp_request(cols, (size_t)0 - pitch, raw);
-    temp_terms(s_co, raw, A);
-    temp_request(cols, 0, raw);
-    temp_terms(s_co, raw, B);
-    temp_request(cols, pitch, raw);
-    // invariant at the top of an iteration for stored row sr: A, B = terms of rows sr-1, sr; `raw` = the words of row sr+1,
-    // requested while the previous row's outputs were computed
-#pragma unroll 3
-    for(int sr = c0; sr < c1; sr++) {
-        temp_terms(s_co, raw, C);
-        if(sr + 1 < c1) temp_request(cols, 2 * pitch, raw); // row sr+2, used by the next iteration: in flight during the outputs below
-        temp_outputs(s_self, A, B, C, out);
-        A = B;
-        B = C;
-        cols.t += pitch;
-        cols.mf += pitch;
-        out += pitch;
+    {   // rows 0 and 1: nothing to send behind row 0 (stages 0 .. 2 were sent above)
+        mbar_wait(&s_full[0], 0u);
+        TempRaw r;
+        r.t[0] = (int32_t)s_stage[0][0][wl];
+        r.m[0] = s_stage[0][1][wl];
+#pragma unroll
+        for(int k = 0; k < K2_COLS; k++) {
+            r.t[k + 1] = (int32_t)s_stage[0][0][w0 + 32 * k];
+            r.m[k + 1] = s_stage[0][1][w0 + 32 * k];
+        }
+        r.t[K2_COLS + 1] = (int32_t)s_stage[0][0][wr];
+        r.m[K2_COLS + 1] = s_stage[0][1][wr];
+        mbar_arrive(&s_empty[0]);
+        temp_terms(s_co, r, A);
+    }
+    take(1, 0u, 0, 0u, 1, B); // sends row 3 into stage 0
+    // loop turn i handles rows j = 2 + 3i (stage 2, use i), j + 1 (stage 0, use i + 1), j + 2 (stage 1, use i + 1)
+    int j = 2;
+    uint32_t par = 0u;
+    for(; j + 2 < n_rows; j += 3, par ^= 1u) {
+        take(2, par, 1, par, j, C);
+        temp_outputs(s_self, A, B, C, out, consumer);
+        take(0, par ^ 1u, 2, par, j + 1, A);
+        temp_outputs(s_self, B, C, A, out + pitch, consumer);
+        take(1, par ^ 1u, 0, par ^ 1u, j + 2, B);
+        temp_outputs(s_self, C, A, B, out + 2 * pitch, consumer);
+        out += 3 * pitch;
+    }
+    if(j < n_rows) {
+        take(2, par, 1, par, j, C);
+        temp_outputs(s_self, A, B, C, out, consumer);
+        if(j + 1 < n_rows) {
+            take(0, par ^ 1u, 2, par, j + 1, A);
+            temp_outputs(s_self, B, C, A, out + pitch, consumer);
+        }
     }
 }
 
