@@ -130,7 +130,8 @@ struct fss_world {
     uint8_t* d_present;
     int liq_from_iter;    // from this iter on only liquids can act
     int nogas_from_iter;  // from this iter on no GAS / fire can act
-    bool sand_reacts;     // a SAND material with reactions can be present (world.cpp:1251-1274): no register-window kernel
+    bool sand_reacts;     // a SAND material with reactions can be present (world.cpp:1251-1274): the general register-window kernel
+    int fire_iters;       // largest `iterations` of a fire material that can be present (0: none): fire acts while iter < this
     // World::particles (fss_particles.cuh): the list, its scratch copy and the per-particle round state, all `pl_cap` long
     fss_particle *pl_list, *pl_next;
     uint8_t *pl_decided, *pl_keep, *pl_sure, *pl_big;
@@ -208,8 +209,10 @@ static void recompute_liq(fss_world* w) {
     int from = 0;
     bool gas_or_fire = false;
     w->sand_reacts = false;
+    w->fire_iters = 0;
     for(int m = 0; m < w->n_mat; m++) {
         if(!pres[m]) continue;
+        if(w->h_mats[m].bits & MF_FIRE) w->fire_iters = std::max(w->fire_iters, std::min(mf_iters(w->h_mats[m].bits), 6));
         if(mf_type(w->h_mats[m].bits) == FSS_PHYS_SAND && w->h_mats[m].n_react > 0) w->sand_reacts = true;
         const int type = mf_type(w->h_mats[m].bits), iters = std::min(mf_iters(w->h_mats[m].bits), 6);
         const bool gf = type == FSS_PHYS_GAS || (w->h_mats[m].bits & MF_FIRE);
@@ -759,10 +762,15 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
         }                                                                                          \
     } while(0)
         if(liq_window_applies(mode, iter, w->cfg.flags, flow, dirty, w->sand_reacts)) {
-#define FSS_LAUNCH_WIN(S, I) k_substep_win<S, I><<<persistent((const void*)k_substep_win<S, I>), K1_THREADS, 0, w->stream>>>(p)
+#define FSS_LAUNCH_WIN(...) k_substep_win<__VA_ARGS__><<<persistent((const void*)k_substep_win<__VA_ARGS__>), K1_THREADS, 0, w->stream>>>(p)
             if(mode == K1_LIQUID) {
                 if(iter == 0) FSS_LAUNCH_WIN(false, true);
                 else FSS_LAUNCH_WIN(false, false);
+            } else if(liq_window_general(mode, w->sand_reacts)) {
+                // GAS / fire / SAND reactions can be present: the general window walk, with the liquid swaps and the fire rule only
+                // where they can act (iter 0; fire while iter < the largest `iterations` of a fire material that can be present)
+                if(iter == 0 || iter < w->fire_iters) FSS_LAUNCH_WIN(true, true, true);
+                else FSS_LAUNCH_WIN(true, false, true);
             } else {
                 if(iter == 0) FSS_LAUNCH_WIN(true, true);
                 else FSS_LAUNCH_WIN(true, false);

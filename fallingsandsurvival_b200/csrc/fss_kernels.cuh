@@ -110,8 +110,11 @@ __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS
 #ifndef K1WS_MIN_BLOCKS
 #define K1WS_MIN_BLOCKS 4
 #endif
-template <bool SAND, bool ITER0>
-__global__ void __launch_bounds__(K1_THREADS, SAND ? K1WS_MIN_BLOCKS : K1W_MIN_BLOCKS) k_substep_win(const __grid_constant__ SubstepParams p) {
+#ifndef K1WG_MIN_BLOCKS
+#define K1WG_MIN_BLOCKS 4
+#endif
+template <bool SAND, bool ITER0, bool GEN = false>
+__global__ void __launch_bounds__(K1_THREADS, GEN ? K1WG_MIN_BLOCKS : (SAND ? K1WS_MIN_BLOCKS : K1W_MIN_BLOCKS)) k_substep_win(const __grid_constant__ SubstepParams p) {
     __shared__ uint32_t sinfo[SAND ? FSS_MAX_MATERIALS : 1];
     __shared__ uint32_t spay[SAND ? WIN_PAY_WORDS * K1_THREADS : 1]; // WinWalk::pay: colour / temperature of the window rows
     if(SAND) {
@@ -135,8 +138,8 @@ __global__ void __launch_bounds__(K1_THREADS, SAND ? K1WS_MIN_BLOCKS : K1W_MIN_B
         }
 #endif
         if(live) {
-            WinWalk<SAND, ITER0> w(p, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * by, __activemask(), spay + threadIdx.x,
-                                   K1_THREADS);
+            WinWalk<SAND, ITER0, GEN> w(p, sinfo, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * by, __activemask(), spay + threadIdx.x,
+                                        K1_THREADS);
             w.run(qown);
         }
     }

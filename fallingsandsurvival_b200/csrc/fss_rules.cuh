@@ -197,9 +197,9 @@ __device__ __noinline__ unsigned long long rule_fire(const SubstepParams& p, int
 }
 
 // ---- SAND reactions, world.cpp:1251-1274 (only SAND evaluates them); true = the cell reacted ----------
-__device__ __noinline__ bool rule_sand_react(const SubstepParams& p, cidx_t i, int x, int y, uint32_t mf) {
+// sand_react_cell: what the cell turns into (`out`), given its temperature; rule_sand_react: the same through memory.
+__device__ __noinline__ bool sand_react_cell(const SubstepParams& p, int x, int y, uint32_t mf, int32_t temp, Cell& out) {
     const DMat& m = p.mats[mf_mat(mf)];
-    const int32_t temp = p.g.temp[i];
     const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
     bool react = false;
     uint32_t site_seen[FSS_MAX_REACTIONS];
@@ -211,14 +211,19 @@ __device__ __noinline__ bool rule_sand_react(const SubstepParams& p, cidx_t i, i
             uint32_t k = 0;
             for(int q = 0; q < r; q++) k += (site_seen[q] == site) ? 1u : 0u;
             site_seen[r] = site;
-            Cell c = create_cell(p, m.r_target[r], x, y, key, k);
-            c.temp = temp;
-            st_cell(p.g, i, c);
-            if(p.g.dirty) p.g.dirty[i] = 1; // :1259, :1267
+            out = create_cell(p, m.r_target[r], x, y, key, k); // (each matching reaction overwrites the cell: the last one stays)
+            out.temp = temp;
             react = true;
         }
     }
     return react;
+}
+__device__ __forceinline__ bool rule_sand_react(const SubstepParams& p, cidx_t i, int x, int y, uint32_t mf) {
+    Cell c;
+    if(!sand_react_cell(p, x, y, mf, p.g.temp[i], c)) return false;
+    st_cell(p.g, i, c);
+    if(p.g.dirty) p.g.dirty[i] = 1; // :1259, :1267
+    return true;
 }
 
 // ---- falling liquid leaves the grid as particles, world.cpp:1352-1374; false = no room for the records: the cell stays --
@@ -726,21 +731,26 @@ struct ChunkWalk {
 #endif
         } else if(MF_IS(mf, FSS_PHYS_SOUP)) { // :1808-1825
             soup_apply(i, g.amt[i], g.dif[i], bit);
-        } else if(GASFIRE && MF_IS(mf, FSS_PHYS_GAS)) { // :1879-1899
-            const cidx_t ial = il - g.pitch, iar = ir - g.pitch;
-            const bool al = MF_IS(g.mf[ial], FSS_PHYS_AIR), ar = MF_IS(g.mf[iar], FSS_PHYS_AIR);
-            if(al || ar) busy = true;
-            if(al && !(ar && fss_rand(fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y), 1884, 0) % 2 == 0)) {
-                swap_cells(i, ial);
-                D(i); // :1886, :1889
-                D(ial);
-                mark(x - 1, y - 1);
-            } else if(ar) {
-                swap_cells(i, iar);
-                D(i); // :1893, :1896
-                D(iar);
-                mark(x + 1, y - 1);
-            }
+        } else if(GASFIRE && MF_IS(mf, FSS_PHYS_GAS)) {
+            gas2(i, x, y);
+        }
+    }
+    // GAS in scan 2, world.cpp:1879-1899 (il / ir as locate() left them)
+    __device__ __forceinline__ void gas2(cidx_t i, int x, int y) {
+        const Grid& g = p.g;
+        const cidx_t ial = il - g.pitch, iar = ir - g.pitch;
+        const bool al = MF_IS(g.mf[ial], FSS_PHYS_AIR), ar = MF_IS(g.mf[iar], FSS_PHYS_AIR);
+        if(al || ar) busy = true;
+        if(al && !(ar && fss_rand(fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y), 1884, 0) % 2 == 0)) {
+            swap_cells(i, ial);
+            D(i); // :1886, :1889
+            D(ial);
+            mark(x - 1, y - 1);
+        } else if(ar) {
+            swap_cells(i, iar);
+            D(i); // :1893, :1896
+            D(iar);
+            mark(x + 1, y - 1);
         }
     }
 
@@ -1006,6 +1016,7 @@ struct ChunkWalk {
         const cidx_t idiag = go_left ? ibl : ibr, iside = go_left ? il : ir;
         const Cell diag = go_left ? dl : dr;
         const uint32_t smf = go_left ? lmf : rmf;
+        if(GASFIRE && MF_IS(diag.mf, FSS_PHYS_GAS)) maybe_gas = true; // (a GAS cell lands on a position that may be unvisited)
         if(MF_IS(smf, FSS_PHYS_AIR)) {
             st_cell(g, iside, diag);
             if(go_left) mark(x - 1, y);
@@ -1050,6 +1061,23 @@ struct ChunkWalk {
         b.rmf = g.mf[ir];
         if(MF_IS(b.tile.mf, FSS_PHYS_SAND)) sand2_sparse(i, cx + dx, cy + dy, b, bit);
         else if(MF_IS(b.tile.mf, FSS_PHYS_SOUP)) soup_apply(i, b.tile.amt, b.tile.dif, bit); // :1808-1825
+        else if(GASFIRE && MF_IS(b.tile.mf, FSS_PHYS_GAS)) gas2(i, cx + dx, cy + dy);
+    }
+    // Scan 3 (world.cpp:1905-1974: only GAS acts) by the visited bits, like scan2_sparse.  `gasm`: the positions that held a GAS
+    // cell when scan 1 was done with them; a GAS cell can only be somewhere else if scan 2 displaced one (maybe_gas, set by
+    // sand2_sparse) -- scan 2's own GAS moves end on positions they mark visited.
+    __device__ __forceinline__ void scan3_sparse(unsigned long long gasm) {
+        unsigned long long todo = ~vis & (maybe_gas ? ~0ull : gasm);
+        while(__any_sync(wmask, todo != 0ull)) {
+            if(todo != 0ull) {
+                const int top = 63 - __clzll((long long)todo);
+                const int dy = top >> 2;
+                const unsigned nib = (unsigned)(todo >> (dy * FSS_CHUNK_W)) & 0xFu;
+                const int dx = __ffs((int)nib) - 1;
+                todo &= ~(1ull << (dy * FSS_CHUNK_W + dx));
+                scan3_cell(dx, dy); // (tests the visited bit itself)
+            }
+        }
     }
     __device__ __forceinline__ void scan2_sparse(unsigned long long stopm = 0ull) {
         unsigned long long todo = ~vis;

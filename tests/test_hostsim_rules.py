@@ -120,6 +120,19 @@ def test_register_window_liquid_path_matches_oracle(hostsim, mix):
     _compare(hostsim, cells, zone, SPECIALISED[mix], 0, ticks=30, early_out=True)
 
 
+@pytest.mark.parametrize("mix", ["c3", "gas", "fire", "randmats", "liquids"])
+def test_register_window_general_path_matches_oracle(hostsim, mix):
+    """WinWalk<true, *, GEN = true> (csrc/fss_rules_liq.cuh): GAS rising as an exchange with the row above, scans 2 and 3 by the
+    visited bits, fire with its ignitions applied through memory (the "fire" mix sets several hundred cells alight in these
+    ticks), SAND reactions on the payload temperature (hot gold ore melts on its first visit).  Taken wherever particles are off
+    and no flow / dirty planes are kept; with and without the settled-chunk flags."""
+    cells, zone = make_world((200, 176), mix, seed=1000 + len(mix))
+    _compare(hostsim, cells, zone, [GENERAL] * 6, 0, ticks=24)
+    _compare(hostsim, cells, zone, [GENERAL] * 6, 0, ticks=40, early_out=True)
+    cells, zone = make_world((136, 240), mix, seed=77)
+    _compare(hostsim, cells, zone, [GENERAL, GENERAL, NOGAS, LIQUID, LIQUID, LIQUID] if mix == "liquids" else [GENERAL] * 6, 0, ticks=12)
+
+
 def test_rule_code_with_early_out(hostsim):
     """the settled-chunk flags as the rules maintain them (ChunkWalk::run): skipping must not change anything"""
     cells, zone = make_world((264, 208), "pockets", seed=9)
