@@ -761,18 +761,18 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
             if(flow) FSS_LAUNCH_K1(M, true, false); else FSS_LAUNCH_K1(M, false, false);           \
         }                                                                                          \
     } while(0)
-        if(liq_window_applies(mode, iter, w->cfg.flags, flow, dirty, w->sand_reacts)) {
+        if(liq_window_applies(mode, iter, w->cfg.flags, flow, dirty, w->sand_reacts, w->fire_iters)) {
 #define FSS_LAUNCH_WIN(...) k_substep_win<__VA_ARGS__><<<persistent((const void*)k_substep_win<__VA_ARGS__>), K1_THREADS, 0, w->stream>>>(p)
             if(mode == K1_LIQUID) {
                 if(iter == 0) FSS_LAUNCH_WIN(false, true);
                 else FSS_LAUNCH_WIN(false, false);
             } else if(liq_window_general(mode, w->sand_reacts)) {
-                // GAS / fire / SAND reactions can be present: the general window walk, with the liquid swaps and the fire rule only
-                // where they can act (iter 0; fire while iter < the largest `iterations` of a fire material that can be present)
-                if(iter == 0 || iter < w->fire_iters) FSS_LAUNCH_WIN(true, true, true);
+                // GAS / SAND reactions can be present (and fire that cannot act any more): the general window walk
+                if(iter == 0) FSS_LAUNCH_WIN(true, true, true);
                 else FSS_LAUNCH_WIN(true, false, true);
             } else {
-                if(iter == 0) FSS_LAUNCH_WIN(true, true);
+                static const bool force_iter0 = getenv("FSS_FORCE_ITER0_KERNEL") != nullptr; // measurements: the larger kernel (a superset, exact) for every iter
+                if(iter == 0 || force_iter0) FSS_LAUNCH_WIN(true, true);
                 else FSS_LAUNCH_WIN(true, false);
             }
 #undef FSS_LAUNCH_WIN

@@ -36,11 +36,17 @@
 //   liquid rule) and the liquid half of scan 2 on the window, then ChunkWalk<K1_NOGAS>::scan2_rest() runs scan 2's SAND rule
 //   through L1 as before.  `sand_reacts`: a SAND material with reactions (world.cpp:1251-1274: reads the temperature plane and
 //   re-creates the cell) can be present -- those worlds stay on ChunkWalk.
-//   K1_GENERAL sub-steps and SAND materials with reactions (round 2, second half): WinWalk<true, *, GEN = true> adds GAS (rising
-//   in scan 1 is an exchange with the row above; scans 2 and 3 by the visited bits), fire (5 x 5 gather by the whole warp,
-//   ignitions through memory with the window written back and re-read: one in a few thousand visits) and SAND reactions
-//   (the temperature travels with the cell in the shared-memory payload).
-__host__ __device__ __forceinline__ bool liq_window_applies(int mode, int iter, uint32_t cfg_flags, bool flow, bool dirty, bool sand_reacts = false) {
+//   K1_GENERAL sub-steps in which no fire material can act, and SAND materials with reactions (round 2, second half):
+//   WinWalk<true, *, GEN = true> adds GAS (rising in scan 1 is an exchange with the row above; scans 2 and 3 by the visited
+//   bits) and SAND reactions (the temperature travels with the cell in the shared-memory payload).  Sub-steps in which fire
+//   acts (iter < the fire material's `iterations`: iter 0 with the reference's table) stay on ChunkWalk<K1_GENERAL>: the fire
+//   rule was built on the window too (5 x 5 gather by the whole warp, ignitions through memory with the window written back and
+//   re-read) and was exact, but the kernel grew to 105 KB of code and ran c3's iter 0 in 27.1 ms against 21.9 ms
+//   (instruction-cache misses: 4 stalled warps per issue); see profiles/r02_tuning_log.md section 10 and the commit before
+//   this one.
+// `fire_iters`: the largest `iterations` of a fire material that can be present (0: none)
+__host__ __device__ __forceinline__ bool liq_window_applies(int mode, int iter, uint32_t cfg_flags, bool flow, bool dirty, bool sand_reacts = false,
+                                                            int fire_iters = 0) {
 #ifdef K1_NO_LIQ_WINDOW
     return false;
 #else
@@ -50,7 +56,7 @@ __host__ __device__ __forceinline__ bool liq_window_applies(int mode, int iter, 
 #elif defined(K1_NO_GEN_WINDOW)
     return mode == K1_LIQUID || (mode == K1_NOGAS && !sand_reacts);
 #else
-    return true;
+    return mode != K1_GENERAL || iter >= fire_iters;
 #endif
 #endif
 }
@@ -99,13 +105,11 @@ struct LSide { // the cell left / right of the row being scanned (outside the ch
 // ITER0: the sub-step is an iter-0 one: only then can two different liquids change places (world.cpp:1406-1412, :1510-1516);
 //        compiled out of the other five iters' kernels (their code is a tenth shorter: instruction-cache misses are a
 //        measurable part of this kernel's stalls)
-// GEN:   GAS, fire and SAND reactions can be present (SAND must be true).  With GEN, ITER0 also stands for "a fire material can
-//        act in this sub-step" (fire acts while iter < its `iterations`, 1 in the reference's table): <true, false, true> has
-//        neither the liquid swaps nor the fire rule.
+// GEN:   GAS and SAND reactions can be present (SAND must be true); fire materials too, as long as none of them can act in the
+//        sub-step (liq_window_applies): a spent fire cell is an inert PASSABLE cell.
 template <bool SAND, bool ITER0 = true, bool GEN = false>
 struct WinWalk {
     static_assert(SAND || !GEN, "the general window walk includes the SAND rules");
-    static constexpr bool FIRE = GEN && ITER0;
     const SubstepParams& p;
     const uint32_t* sinfo;
     int cx, cy;
@@ -117,8 +121,6 @@ struct WinWalk {
     unsigned long long vis; // SAND: tickVisited of the chunk as scan 2 finds it
     unsigned long long stopm; // SAND: unvisited SAND cells with moved == false (ChunkWalk::scan2_sparse decides their pillar draw without a load)
     unsigned long long gasm;  // GEN: positions holding a GAS cell when scan 1 was done with them (ChunkWalk::scan3_sparse)
-    uint32_t pend_ign;        // FIRE: the 5 x 5 neighbours the fire cell just visited sets alight (bit q = (q/5 - 2, q%5 - 2)), applied right after its visit
-    int pend_col;             //       its column
     uint32_t lb_mf, rb_mf;  // SAND: mf of the outside cells of the row BELOW the one being scanned (a SAND cell's diagonals)
     unsigned wmask;
     // SAND: cells move, and their colour / temperature words move with them.  Those two planes of the three window rows live in
@@ -131,7 +133,7 @@ struct WinWalk {
 
     __device__ __forceinline__ WinWalk(const SubstepParams& p_, const uint32_t* si, int cx_, int cy_, unsigned wmask_, uint32_t* pay_ = nullptr,
                                        int pstride_ = 1)
-        : p(p_), sinfo(si), cx(cx_), cy(cy_), busy(false), vis(0ull), stopm(0ull), gasm(0ull), pend_ign(0u), pend_col(0), lb_mf(0u), rb_mf(0u), wmask(wmask_), pay(pay_), pstride(pstride_), sA(0), sC(1), sB(2) {
+        : p(p_), sinfo(si), cx(cx_), cy(cy_), busy(false), vis(0ull), stopm(0ull), gasm(0ull), lb_mf(0u), rb_mf(0u), wmask(wmask_), pay(pay_), pstride(pstride_), sA(0), sC(1), sB(2) {
         const uint32_t pb = fss_perm((uint32_t)cx);
         lofs = (int)fss_perm((uint32_t)(cx - 1)) - (int)pb;
         rofs = (int)fss_perm((uint32_t)(cx + FSS_CHUNK_W)) - (int)pb;
@@ -269,9 +271,7 @@ struct WinWalk {
                 C.dif[K] = c.dif;
                 P(sC, 0, K) = c.col;
                 P(sC, 1, K) = (uint32_t)c.temp;
-                // written through: memory then knows whether the product is SOLID, which is all the fire gather asks of cells
-                // that are still in the window (every other change in the window turns non-SOLID cells into non-SOLID cells)
-                st_cell(p.g, irow + 32 * K, c);
+                C.fl |= (LF_ALL | LF_PAY) << K;
                 C.fl |= LF_VIS << K; // (a product is marked visited, so even a GAS product gets no scan 2 / 3 visit)
                 reacted = true;
             }
@@ -319,14 +319,12 @@ struct WinWalk {
 
     // ---- scan 1 of one cell, world.cpp:1154-1665, on the window: A / C / B = rows r-1 / r / r+1, L / R = the outside cells of row r
     template <int K>
-    // `fire_dies` (FIRE): the cell is an active fire cell and fire1() has decided that it goes out
-    __device__ __forceinline__ void cell(LRow& A, LRow& C, LRow& B, LSide& L, LSide& R, const LSide& Ln, const LSide& Rn, cidx_t irow, int r, bool fire_dies = false) {
+    __device__ __forceinline__ void cell(LRow& A, LRow& C, LRow& B, LSide& L, LSide& R, const LSide& Ln, const LSide& Rn, cidx_t irow, int r) {
         const uint32_t mf = C.mf[K];
-        // GEN: a GAS cell that rose into this position, a neighbour a fire cell set alight: already visited (:1161)
+        // GEN: a GAS cell that rose into this position: already visited (:1161)
         const bool seen = GEN && (C.fl & (LF_VIS << K)) != 0u;
         const bool spent = seen || p.iter >= mf_iters(mf); // :1163-1166
         if(spent) C.fl |= LF_VIS << K;
-        if(FIRE && fire_dies) kill<K>(C); // (a fire material is PASSABLE: no other rule below applies)
         if(SAND && !spent && MF_IS(mf, FSS_PHYS_SAND)) sand1<K>(C, B, irow, r, mf);
         if(GEN && !spent && MF_IS(mf, FSS_PHYS_GAS)) gas1<K>(A, C, Ln, Rn, irow, r, mf);
         // ---- SOUP, world.cpp:1338-1537
@@ -358,55 +356,6 @@ struct WinWalk {
                 A.fl |= LF_VIS << K; // :1661 tickVisited[x + (y - 1) * width]; row -1 is outside the chunk (ignored)
             }
         }
-    }
-
-    // ---- FIRE, world.cpp:1171-1216 (ChunkWalk's rule_fire, on the window).  Without FSS_PARTICLES_EMIT the recolour and the
-    // particle draws (:1172-1189) have no effect (draws are keyed by site: skipping them shifts nothing).
-    // `solid_nb`: which of the 25 neighbours are SOLID, gathered through memory.  Memory is right about that for every cell:
-    // whatever the window holds that memory does not yet is a non-SOLID cell in a non-SOLID cell's place (moves, flows,
-    // deletions); reaction products and ignitions are written through.
-    __device__ __forceinline__ uint32_t coop_fire_scan(unsigned fire_lanes, int x, int y) const {
-        const int lane = threadIdx.x & 31;
-        const int rank = __popc(wmask & ((1u << lane) - 1u)), n = __popc(wmask);
-        uint32_t mine = 0u;
-        while(fire_lanes) {
-            const int src = __ffs(fire_lanes) - 1;
-            fire_lanes &= fire_lanes - 1;
-            const int fx = __shfl_sync(wmask, x, src), fy = __shfl_sync(wmask, y, src);
-            uint32_t part = 0u;
-            for(int q = rank; q < 25; q += n)
-                if(MF_IS(p.g.mf[p.g.idx(fx + q / 5 - 2, fy + q % 5 - 2)], FSS_PHYS_SOLID)) part |= 1u << q;
-            const uint32_t all = __reduce_or_sync(wmask, part);
-            if(lane == src) mine = all;
-        }
-        return mine;
-    }
-    template <int K>
-    __device__ __forceinline__ void kill(LRow& C) { // `tiles[index] = Tiles::NOTHING`
-        const Cell n = cell_nothing(p.nothing_mf);
-        C.mf[K] = n.mf;
-        C.amt[K] = n.amt;
-        C.dif[K] = n.dif;
-        P(sC, 0, K) = n.col;
-        P(sC, 1, K) = (uint32_t)n.temp;
-        C.fl |= (LF_ALL | LF_PAY | LF_VIS) << K;
-    }
-    // the visit of the active fire cell in column k of row r; true = it goes out (the caller's cell<K> removes it)
-    __device__ __forceinline__ bool fire1(int k, int r, uint32_t solid_nb) {
-        busy = true;
-        const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)(cx + k), (uint32_t)(cy + r));
-        bool dies = fss_rand(key, 1191, 0) % 150 == 0; // :1191-1196
-        if(!dies) {
-            uint32_t k1202 = 0u, ign = 0u;
-            for(uint32_t rest = solid_nb; rest; rest &= rest - 1) // :1198-1208, in the reference's order (xx outer, yy inner)
-                if(fss_rand(key, 1202, k1202++) % 500 == 0) ign |= rest & (0u - rest);
-            if(ign) { // applied by scans() right after this cell's visit: apply_ignitions()
-                pend_ign = ign;
-                pend_col = k;
-            }
-            dies = !solid_nb && fss_rand(key, 1210, 0) % 120 == 0; // :1210-1214
-        }
-        return dies;
     }
 
     template <int K>
@@ -575,69 +524,6 @@ struct WinWalk {
         }
     }
 
-    // FIRE: a row of the window goes back to memory as it is (no scan-2 step, unlike retire) / is read again (visited marks stay)
-    __device__ __forceinline__ void flush_row(LRow& X, cidx_t irow, int slot) {
-#pragma unroll
-        for(int k = 0; k < FSS_CHUNK_W; k++) {
-            const cidx_t i = irow + 32 * k;
-            if(X.fl & (LF_PAY << k)) {
-                p.g.col[i] = P(slot, 0, k);
-                p.g.temp[i] = (int32_t)P(slot, 1, k);
-            }
-            if(X.fl & (LF_MF << k)) p.g.mf[i] = X.mf[k];
-            if(X.fl & (LF_AMT << k)) p.g.amt[i] = X.amt[k];
-            if(X.fl & (LF_DIF << k)) p.g.dif[i] = X.dif[k];
-        }
-        X.fl &= 0xFu * LF_VIS;
-    }
-    __device__ __forceinline__ void reload_row(LRow& X, cidx_t irow) {
-        const uint32_t keep = X.fl;
-        load_row(X, irow);
-        X.fl = keep;
-    }
-    // The ignitions of the fire cell at (pend_col, r), world.cpp:1198-1208: `tiles[...] = Tiles::createFire()` for the chosen
-    // SOLID neighbours, up to two rows and two columns away -- inside the window, in the row that is prefetched, in rows that
-    // have left it, in the outside columns.  One visit in a few thousand gets here, so it goes the plain way: the window is
-    // written back, the cells are created in memory, and everything the thread holds is read again.  ir = column 0 of row r.
-    __device__ __forceinline__ void apply_ignitions(LRow& A, LRow& C, LRow& B, LRow& N, LSide& L, LSide& R, LSide& Ln, LSide& Rn, cidx_t ir, int r) {
-        const cidx_t pitch = p.g.pitch;
-        wait_payload();
-        flush_row(A, ir - pitch, sA);
-        flush_row(C, ir, sC);
-        flush_row(B, ir + pitch, sB);
-        const int x = cx + pend_col, y = cy + r;
-        const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
-        uint32_t kcreate = 0u;
-        for(uint32_t rest = pend_ign; rest; rest &= rest - 1) {
-            const int q = __ffs((int)rest) - 1, xx = q / 5 - 2, yy = q % 5 - 2;
-            st_cell(p.g, p.g.idx(x + xx, y + yy), create_cell(p, p.fire_id, x + xx, y + yy, key, kcreate++)); // Tiles::createFire()
-            const int dx = pend_col + xx, ry = r + yy;
-            if(dx >= 0 && dx < FSS_CHUNK_W && ry >= 0 && ry < FSS_CHUNK_H) { // :1205 tickVisited, inside the chunk
-                const uint32_t bit = LF_VIS << dx;
-                if(yy == -2) N.fl |= bit; // (r >= 2 here: N holds row r-2)
-                else if(yy == -1) A.fl |= bit;
-                else if(yy == 0) C.fl |= bit;
-                else if(yy == 1) B.fl |= bit;
-                else vis |= 1ull << (ry * FSS_CHUNK_W + dx); // row r+2 has left the window
-            }
-        }
-        pend_ign = 0u;
-        reload_row(A, ir - pitch);
-        reload_row(C, ir);
-        reload_row(B, ir + pitch);
-        if(r >= 1) reload_row(N, ir - 2 * pitch);
-        load_side(L, ir + lofs);
-        load_side(R, ir + rofs);
-        load_side(Ln, ir - pitch + lofs);
-        load_side(Rn, ir - pitch + rofs);
-        lb_mf = p.g.mf[ir + pitch + lofs];
-        rb_mf = p.g.mf[ir + pitch + rofs];
-        fetch_payload(sA, ir - pitch);
-        fetch_payload(sC, ir);
-        fetch_payload(sB, ir + pitch);
-        wait_payload();
-    }
-
     __device__ __forceinline__ void scans() {
         LRow A, C, B, N;
         LSide L, R, Ln, Rn;
@@ -668,31 +554,10 @@ struct WinWalk {
                 load_side(Ln, ir - pitch + lofs);
                 load_side(Rn, ir - pitch + rofs);
             }
-            if(FIRE) {
-                // one code site for what follows a fire cell's visit: the columns in a loop that is not unrolled
-#pragma unroll 1
-                for(int k = 0; k < FSS_CHUNK_W; k++) {
-                    // every lane of the warp is here: the 5 x 5 neighbourhoods of the warp's fire cells are gathered together
-                    const uint32_t mfk = k == 0 ? C.mf[0] : (k == 1 ? C.mf[1] : (k == 2 ? C.mf[2] : C.mf[3]));
-                    const bool fire = !(C.fl & (LF_VIS << k)) && p.iter < mf_iters(mfk) && (mfk & MF_FIRE);
-                    const unsigned fire_lanes = __ballot_sync(wmask, fire);
-                    bool dies = false;
-                    if(fire_lanes) {
-                        const uint32_t solid_nb = coop_fire_scan(fire_lanes, cx + k, cy + r);
-                        if(fire) dies = fire1(k, r, solid_nb);
-                    }
-                    if(k == 0) cell<0>(A, C, B, L, R, Ln, Rn, ir, r, dies);
-                    else if(k == 1) cell<1>(A, C, B, L, R, Ln, Rn, ir, r, dies);
-                    else if(k == 2) cell<2>(A, C, B, L, R, Ln, Rn, ir, r, dies);
-                    else cell<3>(A, C, B, L, R, Ln, Rn, ir, r, dies);
-                    if(pend_ign) apply_ignitions(A, C, B, N, L, R, Ln, Rn, ir, r);
-                }
-            } else {
-                cell<0>(A, C, B, L, R, Ln, Rn, ir, r);
-                cell<1>(A, C, B, L, R, Ln, Rn, ir, r);
-                cell<2>(A, C, B, L, R, Ln, Rn, ir, r);
-                cell<3>(A, C, B, L, R, Ln, Rn, ir, r);
-            }
+            cell<0>(A, C, B, L, R, Ln, Rn, ir, r);
+            cell<1>(A, C, B, L, R, Ln, Rn, ir, r);
+            cell<2>(A, C, B, L, R, Ln, Rn, ir, r);
+            cell<3>(A, C, B, L, R, Ln, Rn, ir, r);
             retire(B, ir + pitch, r + 1, r < FSS_CHUNK_H - 1, sB);
             B = C;
             C = A;

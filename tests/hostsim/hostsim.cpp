@@ -56,13 +56,13 @@ static void run_launch(HostWorld* w, const SubstepParams& p) {
                 if(*qown <= (uint8_t)p.iter) continue;
             }
             const int cx = p.x_begin + 2 * FSS_CHUNK_W * gi, cy = p.y_begin + 2 * FSS_CHUNK_H * by;
-            if(liq_window_applies(MODE, p.iter, p.flags, FLOW, DIRTY, sand_reacts)) { // launch_substep's choice (csrc/fss_abi.cu)
+            int fire_iters = 0; // (fire_iters of fss_abi.cu restated)
+            for(int m = 0; m < w->n_mat; m++)
+                if(w->mats[m].bits & MF_FIRE) fire_iters = std::max(fire_iters, std::min(mf_iters(w->mats[m].bits), 6));
+            if(liq_window_applies(MODE, p.iter, p.flags, FLOW, DIRTY, sand_reacts, fire_iters)) { // launch_substep's choice (csrc/fss_abi.cu)
                 uint32_t pay[WIN_PAY_WORDS]; // the kernel's shared-memory slice of this thread
-                if(liq_window_general(MODE, sand_reacts)) { // (fire_iters of fss_abi.cu restated: the table's fire acts at iter 0 only)
-                    int fire_iters = 0;
-                    for(int m = 0; m < w->n_mat; m++)
-                        if(w->mats[m].bits & MF_FIRE) fire_iters = std::max(fire_iters, std::min(mf_iters(w->mats[m].bits), 6));
-                    if(p.iter == 0 || p.iter < fire_iters) {
+                if(liq_window_general(MODE, sand_reacts)) {
+                    if(p.iter == 0) {
                         WinWalk<true, true, true> walk(p, w->sinfo, cx, cy, 1u, pay, 1);
                         walk.run(qown);
                     } else {
