@@ -132,6 +132,7 @@ struct fss_world {
     int nogas_from_iter;  // from this iter on no GAS / fire can act
     bool sand_reacts;     // a SAND material with reactions can be present (world.cpp:1251-1274): the general register-window kernel
     int fire_iters;       // largest `iterations` of a fire material that can be present (0: none): fire acts while iter < this
+    bool one_liquid;      // at most one SOUP material can be present: two different liquids never meet (world.cpp:1406-1412, :1510-1516)
     // World::particles (fss_particles.cuh): the list, its scratch copy and the per-particle round state, all `pl_cap` long
     fss_particle *pl_list, *pl_next;
     uint8_t *pl_decided, *pl_keep, *pl_sure, *pl_big;
@@ -210,8 +211,10 @@ static void recompute_liq(fss_world* w) {
     bool gas_or_fire = false;
     w->sand_reacts = false;
     w->fire_iters = 0;
+    int liquids = 0;
     for(int m = 0; m < w->n_mat; m++) {
         if(!pres[m]) continue;
+        if(mf_type(w->h_mats[m].bits) == FSS_PHYS_SOUP) liquids++;
         if(w->h_mats[m].bits & MF_FIRE) w->fire_iters = std::max(w->fire_iters, std::min(mf_iters(w->h_mats[m].bits), 6));
         if(mf_type(w->h_mats[m].bits) == FSS_PHYS_SAND && w->h_mats[m].n_react > 0) w->sand_reacts = true;
         const int type = mf_type(w->h_mats[m].bits), iters = std::min(mf_iters(w->h_mats[m].bits), 6);
@@ -222,6 +225,7 @@ static void recompute_liq(fss_world* w) {
     // While SAND moves, a GAS cell it displaces lands on an unvisited position and is then run by scans 2 and 3 whatever its
     // own `iterations` (they have no such gate): the no-gas kernel is only exact when no GAS / fire material is present at all.
     // The liquid-only kernel has no such case: nothing moves a cell there (SOUP-SOUP swaps at iter 0 aside).
+    w->one_liquid = liquids <= 1;
     w->nogas_from_iter = gas_or_fire ? 99 : 0;
     w->liq_from_iter = from;
     if(getenv("FSS_DEBUG")) {
@@ -763,16 +767,20 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
     } while(0)
         if(liq_window_applies(mode, iter, w->cfg.flags, flow, dirty, w->sand_reacts, w->fire_iters)) {
 #define FSS_LAUNCH_WIN(...) k_substep_win<__VA_ARGS__><<<persistent((const void*)k_substep_win<__VA_ARGS__>), K1_THREADS, 0, w->stream>>>(p)
+            // the kernels with the iter-0 code (two different liquids changing places) are a superset and exact for every iter, but
+            // 7 KB longer, and K1's speed follows its code size (same sub-step, 56 KB against 63 KB of code: 7.78 against 8.59 ms):
+            // they run at iter 0 only, and not at all while at most one liquid material can be present
+            static const bool force_iter0 = getenv("FSS_FORCE_ITER0_KERNEL") != nullptr; // measurements
+            const bool swaps = (iter == 0 && !w->one_liquid) || force_iter0;
             if(mode == K1_LIQUID) {
-                if(iter == 0) FSS_LAUNCH_WIN(false, true);
+                if(swaps) FSS_LAUNCH_WIN(false, true);
                 else FSS_LAUNCH_WIN(false, false);
             } else if(liq_window_general(mode, w->sand_reacts)) {
                 // GAS / SAND reactions can be present (and fire that cannot act any more): the general window walk
-                if(iter == 0) FSS_LAUNCH_WIN(true, true, true);
+                if(swaps) FSS_LAUNCH_WIN(true, true, true);
                 else FSS_LAUNCH_WIN(true, false, true);
             } else {
-                static const bool force_iter0 = getenv("FSS_FORCE_ITER0_KERNEL") != nullptr; // measurements: the larger kernel (a superset, exact) for every iter
-                if(iter == 0 || force_iter0) FSS_LAUNCH_WIN(true, true);
+                if(swaps) FSS_LAUNCH_WIN(true, true);
                 else FSS_LAUNCH_WIN(true, false);
             }
 #undef FSS_LAUNCH_WIN

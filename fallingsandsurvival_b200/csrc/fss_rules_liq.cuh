@@ -287,14 +287,15 @@ struct WinWalk {
         if(can_b) { // :1276, :1287
             busy = true;
             const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)(cx + K), (uint32_t)(cy + r));
-            if(!((can_l || can_r) && fss_rand(key, 1287, 0) % 20 == 0)) {
+#define SAND1_DRAW(bit, site, mod) (fss_rand(key, site, 0) % (mod) == 0)
+            if(!((can_l || can_r) && SAND1_DRAW(0, 1287, 20))) {
                 const cidx_t i = irow + 32 * K, ib = i + p.g.pitch;
                 uint32_t tile_mf = mf;
-                if(fss_rand(key, 1300, 0) % 2 == 0) tile_mf |= MF_MOVED;
+                if(SAND1_DRAW(1, 1300, 2)) tile_mf |= MF_MOVED;
                 exchange<K>(C, B, i, ib, sC, sB, tile_mf, C.dif[K]); // :1296-1306
                 B.fl |= LF_VIS << K;                                 // :1308 tickVisited[x + (y + 1) * width]; row 16 is outside the chunk (ignored)
-                if(fss_rand(key, 1313, 0) % 2 == 0) { // :1313-1335 transmit movement
-                    if(MF_IS(blmf, FSS_PHYS_SAND) && fss_rand(key, 1316, 0) % 2 == 0 && !(blmf & MF_MOVED)) {
+                if(SAND1_DRAW(2, 1313, 2)) { // :1313-1335 transmit movement
+                    if(MF_IS(blmf, FSS_PHYS_SAND) && SAND1_DRAW(3, 1316, 2) && !(blmf & MF_MOVED)) {
                         if(K > 0) {
                             B.mf[K > 0 ? K - 1 : 0] = blmf | MF_MOVED;
                             B.fl |= LF_MF << (K > 0 ? K - 1 : 0);
@@ -303,7 +304,7 @@ struct WinWalk {
                             p.g.mf[irow + p.g.pitch + lofs] = lb_mf;
                         }
                     }
-                    if(MF_IS(brmf, FSS_PHYS_SAND) && fss_rand(key, 1327, 0) % 2 == 0 && !(brmf & MF_MOVED)) {
+                    if(MF_IS(brmf, FSS_PHYS_SAND) && SAND1_DRAW(4, 1327, 2) && !(brmf & MF_MOVED)) {
                         if(K < FSS_CHUNK_W - 1) {
                             B.mf[K < FSS_CHUNK_W - 1 ? K + 1 : 0] = brmf | MF_MOVED;
                             B.fl |= LF_MF << (K < FSS_CHUNK_W - 1 ? K + 1 : 0);
@@ -314,6 +315,7 @@ struct WinWalk {
                     }
                 }
             }
+#undef SAND1_DRAW
         }
     }
 
