@@ -164,6 +164,9 @@ struct fss_world {
     uint32_t* d_work;
     uint32_t* d_work_n;
     volatile uint32_t* h_work_n; // pinned: the latest count the device has reported (read without synchronising: a hint only)
+    uint32_t* d_work_n_host;     // its device address
+    uint8_t* h_seen;             // fss_tick_host: pinned + mapped, 32 bands x FSS_MAX_MATERIALS bytes (which materials each band held)
+    uint8_t* d_seen_host;
     size_t work_cap;
     uint32_t work_tiles;         // tiles of the launch that count belongs to
     bool work_mode;              // launches go through the worklist
@@ -411,6 +414,7 @@ int fss_destroy(fss_world* w) {
     cudaFree(w->d_work);
     cudaFree(w->d_work_n);
     if(w->h_work_n) cudaFreeHost((void*)w->h_work_n);
+    if(w->h_seen) cudaFreeHost(w->h_seen);
     particles_free(w);
     if(w->own_stream) cudaStreamDestroy(w->own_stream);
     delete w;
@@ -718,7 +722,10 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
                 w->work_cap = tiles;
                 if(!w->d_work_n) {
                     CU(cudaMalloc(&w->d_work_n, sizeof(uint32_t)));
-                    CU(cudaHostAlloc((void**)&w->h_work_n, sizeof(uint32_t), cudaHostAllocDefault));
+                    // mapped: the count is written by a one-thread kernel, not by a copy (a cudaMemcpyAsync would queue behind the
+                    // 256 MB passes of fss_tick_host's download on the device -> host copy engine and stall this stream)
+                    CU(cudaHostAlloc((void**)&w->h_work_n, sizeof(uint32_t), cudaHostAllocMapped));
+                    CU(cudaHostGetDevicePointer((void**)&w->d_work_n_host, (void*)w->h_work_n, 0));
                     *w->h_work_n = 0xFFFFFFFFu;
                 }
             }
@@ -727,7 +734,7 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
             if(w->work_mode || (iter == 0 && tk == 0)) {
                 CU(cudaMemsetAsync(w->d_work_n, 0, sizeof(uint32_t), w->stream));
                 k_worklist<<<(tiles + 127) / 128, 128, 0, w->stream>>>(p.q, p.q_w, ofs_x, ofs_y, iter, p.nx, (int)tiles_x, p.ny, w->d_work, w->d_work_n);
-                CU(cudaMemcpyAsync((void*)w->h_work_n, w->d_work_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+                k_copy_words<<<1, 32, 0, w->stream>>>(w->d_work_n, w->d_work_n_host, 1);
                 w->work_tiles = tiles;
                 w->stats.kernel_launches++;
                 if(w->work_mode) {
@@ -924,6 +931,8 @@ int fss_tick_host(fss_world* w, uint32_t tick_ct, fss_cell* cells, size_t pitch_
             CU(cudaEventCreateWithFlags(&w->ev_wave[k], cudaEventDisableTiming));
         }
         CU(cudaEventCreateWithFlags(&w->ev_stage_free, cudaEventDisableTiming));
+        CU(cudaHostAlloc((void**)&w->h_seen, 32 * FSS_MAX_MATERIALS, cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer((void**)&w->d_seen_host, (void*)w->h_seen, 0));
     }
     // whatever the world's stream still has queued comes first
     CU(cudaEventRecord(w->ev_stage_free, w->stream));
@@ -933,11 +942,13 @@ int fss_tick_host(fss_world* w, uint32_t tick_ct, fss_cell* cells, size_t pitch_
     auto K = [&](int b) { return b >= n_bands ? zbands : (int)((long long)zbands * b / n_bands); };   // band b ends before 32-row band K(b+1)
     auto row_end = [&](int b) { return b + 1 >= n_bands ? y0 + rows : w->zy + K(b + 1) * FSS_ZONE_ALIGN_Y; }; // first stored row after band b
     auto front = [&](int b, int s) { return b < 0 ? 0 : (b + 1 >= n_bands ? zbands : std::max(0, K(b + 1) - (s + 1))); };
-    std::vector<uint8_t> seen(FSS_MAX_MATERIALS * (size_t)n_bands);
+    // (written by a small kernel into mapped host memory: a device -> host copy on the upload stream would wait in the copy
+    // engine's queue behind the download stream's 256 MB passes, and the next band's upload behind it)
+    const uint8_t* seen = w->h_seen;
     auto upload_band = [&](int b) -> int {
         const int lo = b == 0 ? y0 : row_end(b - 1), hi = row_end(b);
         if(int r = host_copy_rows(w, w->up_stream, w->d_stage, lo, hi - lo, cells, pitch_cells, true)) return r;
-        CU(cudaMemcpyAsync(seen.data() + (size_t)b * FSS_MAX_MATERIALS, w->d_present, FSS_MAX_MATERIALS, cudaMemcpyDeviceToHost, w->up_stream));
+        k_copy_words<<<1, 64, 0, w->up_stream>>>((const uint32_t*)w->d_present, (uint32_t*)(w->d_seen_host + (size_t)b * FSS_MAX_MATERIALS), FSS_MAX_MATERIALS / 4);
         CU(cudaEventRecord(w->ev_up[b], w->up_stream));
         return FSS_OK;
     };

@@ -167,6 +167,11 @@ __global__ void __launch_bounds__(128) k_worklist(const uint8_t* __restrict__ q,
     if(active) work[base + __popc(live & ((1u << lane) - 1u))] = entry;
 }
 
+// a few words device -> mapped host memory (or anywhere) without the copy engines
+__global__ void k_copy_words(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int n) {
+    for(int k = threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
+}
+
 // ---- K2: temperature stencil ---------------------------------------------------------------------------
 // World::tickTemperature, world.cpp:2043-2143.  One thread owns four consecutive columns (half of one "group" x >> 3) and
 // walks TEMP_ROWS stored rows top-down; lanes of a warp own consecutive groups.  The per-neighbour terms
