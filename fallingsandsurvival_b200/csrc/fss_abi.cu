@@ -1739,21 +1739,103 @@ int fss_clear_flow(fss_world* w) {
     return FSS_OK;
 }
 
-int fss_shift_grid(fss_world* w, int change_x, int change_y) {
-    if(!w) return fail(FSS_ERR_INVALID, "null world");
-    if(w->sharded) return fail(FSS_ERR_STATE, "fss_shift_grid on a strip-sharded world is not supported (rows would cross strips)");
-    if(change_x == 0 && change_y == 0) return FSS_OK;
-    if(use_device(w)) return FSS_ERR_CUDA;
-    // every plane goes through the spare temperature plane: shift into it, then swap the two pointers
+static void plane_ptrs(fss_world* w, void* ptr[5]);
+
+// Strip-sharded worlds: only the rows a strip owns are current in its planes (the halo exchange refreshes just the ghost rows
+// the rules look at), so the sources of its stored rows [s0, s1) that lie outside [own_lo, own_hi) come from the neighbours:
+// `u` from the upper strip, `l` from the lower one; `gd` / `gu` = what the lower / upper neighbour needs of this strip's rows.
+struct ShiftRows {
+    int u_lo, u_hi, l_lo, l_hi;
+    int gd_lo, gd_hi, gu_lo, gu_hi;
+};
+static ShiftRows shift_rows(const fss_world* w, int change_y, bool has_upper, bool has_lower) {
+    ShiftRows r = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int s0 = w->g.sy0, s1 = w->g.sy0 + w->g.rows, height = (int)w->cfg.height;
+    if(has_upper) {
+        r.u_lo = std::max(0, s0 - change_y), r.u_hi = w->own_lo;
+        r.gu_lo = w->own_lo, r.gu_hi = std::min(height, w->own_lo + FSS_HALO_ROWS - change_y); // the upper strip's storage ends at own_lo + 16
+    }
+    if(has_lower) {
+        r.l_lo = w->own_hi, r.l_hi = std::min(height, s1 - change_y);
+        r.gd_lo = std::max(0, w->own_hi - FSS_HALO_ROWS - change_y), r.gd_hi = w->own_hi; // the lower strip's storage starts at own_hi - 16
+    }
+    if(r.u_hi < r.u_lo) r.u_hi = r.u_lo;
+    if(r.l_hi < r.l_lo) r.l_hi = r.l_lo;
+    if(r.gu_hi < r.gu_lo) r.gu_hi = r.gu_lo;
+    if(r.gd_hi < r.gd_lo) r.gd_hi = r.gd_lo;
+    return r;
+}
+
+// every plane goes through the spare temperature plane: shift into it, then swap the two pointers.  `foreign`: the five planes of
+// the rows r.u of the upper strip, then the five planes of the rows r.l of the lower one (nullptr: an undivided world)
+static int shift_planes(fss_world* w, int change_x, int change_y, const uint32_t* foreign, const ShiftRows& r) {
     uint32_t** planes[5] = {&w->g.mf, &w->g.col, (uint32_t**)&w->g.temp, (uint32_t**)&w->g.amt, (uint32_t**)&w->g.dif};
     uint32_t* spare = (uint32_t*)w->temp2;
+    const size_t u_words = (size_t)(r.u_hi - r.u_lo) * w->g.pitch, l_words = (size_t)(r.l_hi - r.l_lo) * w->g.pitch;
+    ShiftParams p;
+    p.pitch = w->g.pitch;
+    p.rows = w->g.rows;
+    p.width = (int)w->cfg.width;
+    p.change_x = change_x;
+    p.change_y = change_y;
+    p.sy0 = w->g.sy0;
+    p.height = (int)w->cfg.height;
+    p.own_lo = foreign ? w->own_lo : w->g.sy0;
+    p.own_hi = foreign ? w->own_hi : w->g.sy0 + w->g.rows;
+    p.u_lo = r.u_lo, p.u_hi = foreign ? r.u_hi : r.u_lo;
+    p.l_lo = r.l_lo, p.l_hi = foreign ? r.l_hi : r.l_lo;
     for(int k = 0; k < 5; k++) {
-        k_shift<<<dim3(w->g.rows, w->g.pitch / 256), 256, 0, w->stream>>>(*planes[k], spare, w->g.pitch, w->g.rows, (int)w->cfg.width, change_x, change_y);
+        p.fu = foreign ? foreign + k * u_words : nullptr;
+        p.fl = foreign ? foreign + 5 * u_words + k * l_words : nullptr;
+        k_shift<<<dim3(w->g.rows, w->g.pitch / 256), 256, 0, w->stream>>>(*planes[k], spare, p);
         w->stats.kernel_launches++;
         std::swap(*planes[k], spare);
     }
     w->temp2 = (int32_t*)spare;
     CU(cudaGetLastError());
+    return dirty_chunks(w, 0, 0, -1, -1);
+}
+
+int fss_shift_grid(fss_world* w, int change_x, int change_y) {
+    if(!w) return fail(FSS_ERR_INVALID, "null world");
+    if(change_x == 0 && change_y == 0) return FSS_OK;
+    if(use_device(w)) return FSS_ERR_CUDA;
+    if(w->sharded) {
+        // rows cross strip boundaries: collective over the communicator (every rank makes the same call).  Each strip first
+        // fetches the rows of its neighbours that its stored rows take their new content from, then shifts.
+        if(!w->comm) return fail(FSS_ERR_STATE, "fss_shift_grid on a strip-sharded world needs a communicator (or fss_shift_grid_peer inside one process)");
+        const int d = std::abs(change_y);
+        if(d > (int)w->cfg.strip_rows - FSS_HALO_ROWS)
+            return fail(FSS_ERR_RANGE, "fss_shift_grid: |change_y| = %d exceeds the strip's %u rows less %d (rows would have to skip a strip)", d, w->cfg.strip_rows, FSS_HALO_ROWS);
+        const ShiftRows r = shift_rows(w, change_y, w->rank > 0, w->rank + 1 < w->n_ranks);
+        uint32_t* foreign = nullptr;
+        const size_t u_words = (size_t)(r.u_hi - r.u_lo) * w->g.pitch, l_words = (size_t)(r.l_hi - r.l_lo) * w->g.pitch;
+        CU(cudaMalloc(&foreign, std::max<size_t>(1, u_words + l_words) * 5 * sizeof(uint32_t)));
+        int rc = FSS_OK;
+        {
+            void* ptr[5];
+            plane_ptrs(w, ptr);
+            const int up = w->rank - 1, down = w->rank + 1;
+            if(g_nccl.group_start() != 0) rc = fail(FSS_ERR_COMM, "ncclGroupStart");
+            for(int k = 0; k < 5 && !rc; k++) {
+                auto rows_at = [&](int lo) { return (char*)ptr[k] + (size_t)(lo - w->g.sy0) * w->g.pitch * 4; };
+                if(r.gd_hi > r.gd_lo && g_nccl.send(rows_at(r.gd_lo), (size_t)(r.gd_hi - r.gd_lo) * w->g.pitch, NCCL_UINT32, down, w->comm, w->stream) != 0) rc = fail(FSS_ERR_COMM, "ncclSend");
+                if(!rc && r.gu_hi > r.gu_lo && g_nccl.send(rows_at(r.gu_lo), (size_t)(r.gu_hi - r.gu_lo) * w->g.pitch, NCCL_UINT32, up, w->comm, w->stream) != 0) rc = fail(FSS_ERR_COMM, "ncclSend");
+                if(!rc && u_words && g_nccl.recv(foreign + k * u_words, u_words, NCCL_UINT32, up, w->comm, w->stream) != 0) rc = fail(FSS_ERR_COMM, "ncclRecv");
+                if(!rc && l_words && g_nccl.recv(foreign + 5 * u_words + k * l_words, l_words, NCCL_UINT32, down, w->comm, w->stream) != 0) rc = fail(FSS_ERR_COMM, "ncclRecv");
+            }
+            const std::string first_error = rc ? g_err : std::string(); // (the group is always closed: see fss_exchange_halo)
+            const int end = g_nccl.group_end();
+            if(rc) fail(rc, "%s", first_error.c_str());
+            else if(end != 0) rc = fail(FSS_ERR_COMM, "ncclGroupEnd: %s", g_nccl.err_string ? g_nccl.err_string(end) : "nccl error");
+            w->stats.kernel_launches++;
+        }
+        if(!rc) rc = shift_planes(w, change_x, change_y, foreign, r);
+        cudaStreamSynchronize(w->stream);
+        cudaFree(foreign);
+        return rc;
+    }
+    if(int rc = shift_planes(w, change_x, change_y, nullptr, ShiftRows{0, 0, 0, 0, 0, 0, 0, 0})) return rc;
     if(w->pl_used) { // world.cpp:2729-2731: the particles move with the grid (what the ticks so far spawned is in the list by then)
         if(int rc = particles_adopt(w)) return rc;
         if(w->pl_n) {
@@ -1762,7 +1844,58 @@ int fss_shift_grid(fss_world* w, int change_x, int change_y) {
             w->stats.kernel_launches++;
         }
     }
-    return dirty_chunks(w, 0, 0, -1, -1);
+    return FSS_OK;
+}
+
+// the same for the strips of ONE process (top to bottom), rows fetched by peer copies
+int fss_shift_grid_peer(fss_world** strips, int n, int change_x, int change_y) {
+    if(!strips || n < 1) return fail(FSS_ERR_INVALID, "null argument");
+    for(int k = 0; k < n; k++) {
+        if(!strips[k] || !strips[k]->sharded) return fail(FSS_ERR_INVALID, "strip %d is not a strip-sharded world", k);
+        if(k && (strips[k - 1]->own_hi != strips[k]->own_lo || strips[k - 1]->g.pitch != strips[k]->g.pitch)) return fail(FSS_ERR_INVALID, "worlds are not adjacent strips");
+        if(std::abs(change_y) > (int)strips[k]->cfg.strip_rows - FSS_HALO_ROWS)
+            return fail(FSS_ERR_RANGE, "|change_y| = %d exceeds the %u rows of strip %d less %d", std::abs(change_y), strips[k]->cfg.strip_rows, k, FSS_HALO_ROWS);
+    }
+    if(change_x == 0 && change_y == 0) return FSS_OK;
+    // every strip's foreign rows are copied out of the neighbours BEFORE any strip shifts
+    std::vector<uint32_t*> foreign((size_t)n, nullptr);
+    std::vector<ShiftRows> rows((size_t)n);
+    int rc = FSS_OK;
+    for(int k = 0; k < n; k++) cudaStreamSynchronize(strips[k]->stream); // what the strips still have queued comes first
+    for(int k = 0; k < n && !rc; k++) {
+        fss_world* w = strips[k];
+        const ShiftRows& r = rows[k] = shift_rows(w, change_y, k > 0, k + 1 < n);
+        const size_t u_words = (size_t)(r.u_hi - r.u_lo) * w->g.pitch, l_words = (size_t)(r.l_hi - r.l_lo) * w->g.pitch;
+        if(cudaSetDevice(w->device) != cudaSuccess || cudaMalloc(&foreign[k], std::max<size_t>(1, u_words + l_words) * 5 * sizeof(uint32_t)) != cudaSuccess) {
+            rc = fail(FSS_ERR_CUDA, "fss_shift_grid_peer: staging rows");
+            break;
+        }
+        for(int side = 0; side < 2 && !rc; side++) {
+            const size_t words = side ? l_words : u_words;
+            if(!words) continue;
+            fss_world* src = strips[side ? k + 1 : k - 1];
+            const int lo = side ? r.l_lo : r.u_lo;
+            void* ps[5];
+            plane_ptrs(src, ps);
+            for(int q = 0; q < 5; q++) {
+                const char* a = (const char*)ps[q] + (size_t)(lo - src->g.sy0) * src->g.pitch * 4;
+                uint32_t* dst = foreign[k] + (side ? 5 * u_words : 0) + q * words;
+                if(cudaMemcpyPeerAsync(dst, w->device, a, src->device, words * 4, w->stream) != cudaSuccess) rc = fail(FSS_ERR_CUDA, "peer copy");
+            }
+        }
+        cudaStreamSynchronize(w->stream);
+    }
+    for(int k = 0; k < n && !rc; k++) {
+        if(use_device(strips[k])) rc = FSS_ERR_CUDA;
+        else rc = shift_planes(strips[k], change_x, change_y, foreign[k], rows[k]);
+    }
+    for(int k = 0; k < n; k++)
+        if(foreign[k]) {
+            cudaSetDevice(strips[k]->device);
+            cudaStreamSynchronize(strips[k]->stream);
+            cudaFree(foreign[k]);
+        }
+    return rc;
 }
 
 int fss_get_stats(fss_world* w, fss_stats* out) {

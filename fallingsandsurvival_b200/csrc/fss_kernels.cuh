@@ -583,16 +583,31 @@ __global__ void __launch_bounds__(256) k_fill(const __grid_constant__ FillParams
 // ---- grid shift when the camera moves: World::tickChunks, world.cpp:2617-2630 ---------------------------------
 // tiles[new] = tiles[new - change] wherever the source lies inside the grid; every other cell keeps its content
 // (the reference's in-place loop never clears the vacated band).  One plane per launch, out of place.
-__global__ void __launch_bounds__(256) k_shift(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t pitch, int rows, int width,
-                                               int change_x, int change_y) {
+// Strip-sharded worlds: `rows` stored rows starting at global row sy0 of a world `height` rows high.  Only the rows a strip OWNS
+// are current in its planes (of its ghost rows the halo exchange refreshes the 2 above and the 10 below that the rules look
+// at), so a source row outside [own_lo, own_hi) comes from the neighbour that owns it: `fu` = rows [u_lo, u_hi) of the upper
+// strip, `fl` = rows [l_lo, l_hi) of the lower one, fetched before the shift (fss_abi.cu).  Every stored row, ghost rows
+// included, is current afterwards.
+struct ShiftParams {
+    uint32_t pitch;
+    int rows, width, change_x, change_y, sy0, height, own_lo, own_hi;
+    const uint32_t *fu, *fl;
+    int u_lo, u_hi, l_lo, l_hi;
+};
+__global__ void __launch_bounds__(256) k_shift(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const ShiftParams p) {
     const uint32_t pcol = blockIdx.y * 256u + threadIdx.x;
     const int y = blockIdx.x;
-    if(pcol >= pitch) return;
+    if(pcol >= p.pitch) return;
     const int x = (int)fss_unperm(pcol);
-    const int ox = x - change_x, oy = y - change_y;
-    const size_t i = (size_t)y * pitch + pcol;
+    const int ox = x - p.change_x, oy = p.sy0 + y - p.change_y; // global source row
+    const size_t i = (size_t)y * p.pitch + pcol;
     uint32_t v = in[i];
-    if(x < width && ox >= 0 && ox < width && oy >= 0 && oy < rows) v = in[(size_t)oy * pitch + fss_perm((uint32_t)ox)];
+    if(x < p.width && ox >= 0 && ox < p.width && oy >= 0 && oy < p.height) {
+        const uint32_t po = fss_perm((uint32_t)ox);
+        if(oy >= p.own_lo && oy < p.own_hi) v = in[(size_t)(oy - p.sy0) * p.pitch + po];
+        else if(oy >= p.u_lo && oy < p.u_hi) v = p.fu[(size_t)(oy - p.u_lo) * p.pitch + po];
+        else if(oy >= p.l_lo && oy < p.l_hi) v = p.fl[(size_t)(oy - p.l_lo) * p.pitch + po];
+    }
     out[i] = v;
 }
 

@@ -82,6 +82,7 @@ def load():
         "fss_exchange_halo": [vp, i32],
         "fss_exchange_halo_temperature": [vp],
         "fss_exchange_halo_peer": [vp, vp, i32],
+        "fss_shift_grid_peer": [vp, i32, i32, i32],
         "fss_exchange_halo_temperature_peer": [vp, vp],
         "fss_get_stats": [vp, C.POINTER(abi.Stats)],
     }
@@ -392,6 +393,11 @@ class StripWorld:
             p.tick_temperature()
         for a, b in zip(self.parts[:-1], self.parts[1:]):
             _check(self.L, self.L.fss_exchange_halo_temperature_peer(a.h_, b.h_))
+
+    def shift_grid(self, change_x, change_y):
+        """World::tickChunks' camera shift (world.cpp:2617-2630) across the strips: rows that cross a boundary come from the neighbour"""
+        arr = (C.c_void_p * len(self.parts))(*[p.h_ for p in self.parts])
+        _check(self.L, self.L.fss_shift_grid_peer(arr, len(self.parts), change_x, change_y))
 
     def cells(self):
         out = np.zeros((self.h, self.w), dtype=abi.CELL_DTYPE)

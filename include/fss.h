@@ -222,8 +222,13 @@ int fss_lz4_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, s
 /* World::tickChunks' grid shift when the camera moves (world.cpp:2617-2630): every cell moves by (change_x, change_y);
  * cells whose source would lie outside the grid keep their content, exactly like the reference's in-place loop.  The
  * caller then uploads the freshly loaded chunks into the vacated band.  A device-resident particle list moves with the grid
- * (world.cpp:2729-2731).  Not available on strip-sharded worlds. */
+ * (world.cpp:2729-2731).
+ * Strip-sharded worlds: rows cross strip boundaries, so the call is COLLECTIVE -- every rank of the communicator makes it with
+ * the same arguments (each strip fetches the |change_y| rows of its neighbour that become its first / last stored rows, NCCL
+ * send / recv, then shifts); fss_shift_grid_peer does the same for the strips of one process (`strips` ordered top to bottom).
+ * |change_y| must not exceed any strip's rows less the 16 ghost rows (FSS_ERR_RANGE: nothing was moved). */
 int fss_shift_grid(fss_world* w, int change_x, int change_y);
+int fss_shift_grid_peer(fss_world** strips, int n, int change_x, int change_y);
 
 /* ---- the hot path ---------------------------------------------------------------------------- */
 /* one World::tick(): 6 iter x 4 tk checkerboard sub-steps x 3 scans (world.cpp:1108-2011);

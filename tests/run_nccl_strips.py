@@ -26,10 +26,13 @@ def main():
     ticks = 12
     cells, zone = helpers.make_world(size, "c3", seed=31)
     rw = strips.RankWorld(size, zone, rank, n, local, cells=cells, defs=helpers.full_table(), particles=True)
+    shifts = {3: (5, 40), 7: (-9, -70), 9: (0, 17)}  # World::tickChunks' camera shift, collective over the ranks (rows cross strips)
     for t in range(ticks):
         rw.tick(t)
         if t % 4 == 2:
             rw.tick_temperature()
+        if t in shifts:
+            rw.shift_grid(*shifts[t])
     y0, rows = rw.strip
     mine = rw.world.download(0, y0, size[0], rows)
     digest = torch.tensor([rw.world.hash() & 0x7FFFFFFFFFFFFFFF, rw.world.hash() >> 63], dtype=torch.int64, device="cuda")
@@ -43,6 +46,8 @@ def main():
             whole.tick(t)
             if t % 4 == 2:
                 whole.tick_temperature()
+            if t in shifts:
+                whole.shift_grid(*shifts[t])
         ref = whole.cells()
         out = np.zeros_like(ref)
         hsum = 0

@@ -458,6 +458,36 @@ def test_shift_grid_matches_reference_loop(change):
     o.close()
 
 
+@pytest.mark.parametrize("n_strips", [2, 3])
+def test_shift_grid_on_strips_equals_whole_world(n_strips):
+    """World::tickChunks' shift (world.cpp:2617-2630) on a strip-sharded world: rows that cross a strip boundary come from the
+    neighbouring strip (fss_shift_grid_peer here; the NCCL form of the same exchange is driven by tests/run_nccl_strips.py).
+    Shifts in all directions, larger than the ghost rows, ticks in between; a shift longer than a strip is refused whole."""
+    from fallingsandsurvival_b200 import world
+    cells, zone = make_world((264, 400), "c3", seed=12)
+    whole = gpu_world(cells, zone, particles=True)
+    parts = world.StripWorld(cells, zone, n_strips, defs=full_table(), particles=True)
+    t = 0
+    for cx, cy in [(3, 5), (-7, -40), (0, 33), (11, -1), (-2, 64), (0, 0), (40, -70)]:
+        whole.shift_grid(cx, cy)
+        parts.shift_grid(cx, cy)
+        a, b = whole.cells(), parts.cells()
+        assert a.tobytes() == b.tobytes(), f"shift ({cx}, {cy}): " + diff_report(a, b)
+        for _ in range(2):
+            whole.tick(t)
+            parts.tick(t)
+            t += 1
+        a, b = whole.cells(), parts.cells()
+        assert a.tobytes() == b.tobytes(), f"ticks after shift ({cx}, {cy}): " + diff_report(a, b)
+    before = parts.cells()
+    with pytest.raises(world.FssError) as e:
+        parts.shift_grid(0, 300)
+    assert e.value.code == -6
+    assert parts.cells().tobytes() == before.tobytes()
+    whole.close()
+    parts.close()
+
+
 def test_kernel_specialisation_follows_the_materials_present():
     """k_substep<K1_LIQUID / K1_NOGAS / K1_GENERAL> are picked per iter from the set of materials that can be in the world.
     Start with water + stone only (every iter runs the liquid-only kernel), then paint sand, then steam and fire through the
