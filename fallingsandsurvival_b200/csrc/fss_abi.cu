@@ -165,6 +165,7 @@ struct fss_world {
     uint32_t* d_work_n;
     volatile uint32_t* h_work_n; // pinned: the latest count the device has reported (read without synchronising: a hint only)
     uint32_t* d_work_n_host;     // its device address
+    uint8_t* d_dirty_halo;       // strip-sharded + FSS_TRACK_DIRTY: the marks received with a halo exchange (2 rows of bytes)
     uint8_t* h_seen;             // fss_tick_host: pinned + mapped, 32 bands x FSS_MAX_MATERIALS bytes (which materials each band held)
     uint8_t* d_seen_host;
     size_t work_cap;
@@ -340,10 +341,7 @@ int fss_create(const fss_config* cfg, fss_world** out) {
         CUX(cudaMemsetAsync(w->g.fy, 0, n * 4, w->stream));
     }
     if(cfg->flags & FSS_TRACK_DIRTY) {
-        if(w->sharded) { // the marks a strip leaves in its ghost rows would have to travel with the halo exchange
-            fss_destroy(w);
-            return fail(FSS_ERR_INVALID, "FSS_TRACK_DIRTY is not available on strip-sharded worlds");
-        }
+        // (strip-sharded worlds: the marks a strip leaves in its ghost rows travel with the halo exchange, dirty_halo_*)
         CUX(cudaMalloc(&w->g.dirty, n));
         CUX(cudaMemsetAsync(w->g.dirty, 0, n, w->stream));
     }
@@ -415,6 +413,7 @@ int fss_destroy(fss_world* w) {
     cudaFree(w->d_work_n);
     if(w->h_work_n) cudaFreeHost((void*)w->h_work_n);
     if(w->h_seen) cudaFreeHost(w->h_seen);
+    cudaFree(w->d_dirty_halo);
     particles_free(w);
     if(w->own_stream) cudaStreamDestroy(w->own_stream);
     delete w;
@@ -1378,14 +1377,14 @@ static int skipped_marks(fss_world* w) {
 static int dirty_ready(fss_world* w) {
     if(!w) return fail(FSS_ERR_INVALID, "null world");
     if(!w->g.dirty) return fail(FSS_ERR_STATE, "the world was created without FSS_TRACK_DIRTY");
-    if(w->sharded) return fail(FSS_ERR_STATE, "dirty -> pixels is not available on strip-sharded worlds");
     return use_device(w);
 }
 
 int fss_mark_dirty(fss_world* w, int x, int y, int width, int height) {
     if(int rc = dirty_ready(w)) return rc;
     // like the reference's own writes, cells outside the world are skipped
-    const int x0 = std::max(x, 0), y0 = std::max(y, 0), x1 = std::min<long long>((long long)x + width, w->cfg.width), y1 = std::min<long long>((long long)y + height, w->cfg.height);
+    // (a strip marks the rows it owns: the same call on the neighbouring strip marks the rest)
+    const int x0 = std::max(x, 0), y0 = std::max(y, w->own_lo), x1 = std::min<long long>((long long)x + width, w->cfg.width), y1 = std::min<long long>((long long)y + height, w->own_hi);
     if(x1 <= x0 || y1 <= y0) return FSS_OK;
     const long long cells = (long long)(x1 - x0) * (y1 - y0);
     if(cells > 0x7FFFFFFFll) return fail(FSS_ERR_RANGE, "rectangle of %lld cells", cells);
@@ -1402,8 +1401,8 @@ int fss_mark_dirty_list(fss_world* w, const fss_rect* rects, size_t n) {
     std::vector<int4> v;
     long long biggest = 0;
     for(size_t i = 0; i < n; i++) {
-        const int x0 = std::max(rects[i].x, 0), y0 = std::max(rects[i].y, 0);
-        const int x1 = (int)std::min<long long>((long long)rects[i].x + rects[i].w, w->cfg.width), y1 = (int)std::min<long long>((long long)rects[i].y + rects[i].h, w->cfg.height);
+        const int x0 = std::max(rects[i].x, 0), y0 = std::max(rects[i].y, w->own_lo);
+        const int x1 = (int)std::min<long long>((long long)rects[i].x + rects[i].w, w->cfg.width), y1 = (int)std::min<long long>((long long)rects[i].y + rects[i].h, w->own_hi);
         if(x1 <= x0 || y1 <= y0) continue;
         v.push_back(make_int4(x0, y0, x1 - x0, y1 - y0));
         biggest = std::max(biggest, (long long)(x1 - x0) * (y1 - y0));
@@ -1426,7 +1425,7 @@ int fss_render_dirty(fss_world* w, uint64_t* moving_tiles, int n_materials, fss_
     if(!w->mats_set) return fail(FSS_ERR_STATE, "fss_set_materials first");
     if(n_materials < 0 || n_materials > FSS_MAX_MATERIALS) return fail(FSS_ERR_INVALID, "%d materials", n_materials);
     if(int rc = skipped_marks(w)) return rc;
-    const size_t cells = plane_cells(w), pixels = (size_t)w->cfg.width * w->cfg.height;
+    const size_t cells = plane_cells(w), pixels = (size_t)w->cfg.width * w->g.rows; // the layers hold the rows this world stores
     if(!w->px[0]) {
         for(int k = 0; k < 4; k++) {
             CU(cudaMalloc(&w->px[k], pixels * 4));
@@ -1463,6 +1462,8 @@ int fss_render_dirty(fss_world* w, uint64_t* moving_tiles, int n_materials, fss_
     p.moving = w->d_rinfo;
     p.info = (uint32_t*)(w->d_rinfo + FSS_MAX_MATERIALS);
     p.cells = cells;
+    p.own_lo = w->own_lo;
+    p.own_hi = w->own_hi;
     k_render_dirty<<<(unsigned)((cells + 255) / 256), 256, 0, w->stream>>>(p);
     CU(cudaGetLastError());
     w->stats.kernel_launches++;
@@ -1484,10 +1485,10 @@ int fss_download_pixels(fss_world* w, int layer, int x, int y, int width, int he
     if(int rc = dirty_ready(w)) return rc;
     if(!rgba || layer < 0 || layer > 3) return fail(FSS_ERR_INVALID, "bad argument");
     if(!w->px[0]) return fail(FSS_ERR_STATE, "fss_render_dirty first");
-    if(width <= 0 || height <= 0 || x < 0 || y < 0 || (uint32_t)(x + width) > w->cfg.width || (uint32_t)(y + height) > w->cfg.height)
-        return fail(FSS_ERR_RANGE, "rectangle (%d,%d,%d,%d) outside the %ux%u world", x, y, width, height, w->cfg.width, w->cfg.height);
+    if(width <= 0 || height <= 0 || x < 0 || y < w->own_lo || (uint32_t)(x + width) > w->cfg.width || y + height > w->own_hi)
+        return fail(FSS_ERR_RANGE, "rectangle (%d,%d,%d,%d) outside the rows [%d, %d) this world renders (width %u)", x, y, width, height, w->own_lo, w->own_hi, w->cfg.width);
     if(pitch_bytes < (size_t)width * 4) return fail(FSS_ERR_INVALID, "pitch %zu < %d pixels", pitch_bytes, width);
-    CU(cudaMemcpy2DAsync(rgba, pitch_bytes, w->px[layer] + (size_t)y * w->cfg.width + x, (size_t)w->cfg.width * 4, (size_t)width * 4, (size_t)height,
+    CU(cudaMemcpy2DAsync(rgba, pitch_bytes, w->px[layer] + (size_t)(y - w->g.sy0) * w->cfg.width + x, (size_t)w->cfg.width * 4, (size_t)width * 4, (size_t)height,
                          cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
     return FSS_OK;
@@ -1920,6 +1921,29 @@ static void plane_ptrs(fss_world* w, void* ptr[5]) {
     ptr[4] = w->g.dif;
 }
 
+// World::dirty on strip-sharded worlds.  A strip's kernels also mark cells of the two ghost rows next to its boundary (moves reach
+// one row, fire ignition two): those marks belong to the neighbour that owns the rows.  They travel with the halo exchange that
+// carries the cells they stand for -- after tk 1 the upper strip's marks of rows [B, B+2) go down, after tk 3 the lower strip's
+// marks of rows [B-2, B) go up -- are OR-ed into the owner's plane, and are cleared where they came from (sent once: the owner
+// may have rendered and cleared its plane before the next exchange).
+static const int DIRTY_HALO_ROWS = 2;
+static int dirty_halo_buffer(fss_world* w) {
+    if(!w->d_dirty_halo) CU(cudaMalloc(&w->d_dirty_halo, (size_t)DIRTY_HALO_ROWS * w->g.pitch));
+    return FSS_OK;
+}
+static uint8_t* dirty_rows(fss_world* w, int lo) { return w->g.dirty + (size_t)(lo - w->g.sy0) * w->g.pitch; }
+// after the transfer: the received marks join the owner's, the sent ones are dropped
+static int dirty_halo_finish(fss_world* w, bool received, int recv_lo, bool sent, int sent_lo, cudaStream_t st) {
+    const size_t bytes = (size_t)DIRTY_HALO_ROWS * w->g.pitch;
+    if(received) {
+        k_or_words<<<(unsigned)((bytes / 4 + 255) / 256), 256, 0, st>>>((uint32_t*)dirty_rows(w, recv_lo), (const uint32_t*)w->d_dirty_halo, (int)(bytes / 4));
+        CU(cudaGetLastError());
+        w->stats.kernel_launches++;
+    }
+    if(sent) CU(cudaMemsetAsync(dirty_rows(w, sent_lo), 0, bytes, st));
+    return FSS_OK;
+}
+
 int fss_exchange_halo_peer(fss_world* upper, fss_world* lower, int tk) {
     if(!upper || !lower) return fail(FSS_ERR_INVALID, "null world");
     if(upper->own_hi != lower->own_lo || upper->g.pitch != lower->g.pitch) return fail(FSS_ERR_INVALID, "worlds are not adjacent strips");
@@ -1944,10 +1968,19 @@ int fss_exchange_halo_peer(fss_world* upper, fss_world* lower, int tk) {
         CU(cudaMemcpyPeerAsync(d, dst->device, s, src->device, (size_t)(hi - lo) * src->g.pitch * 4, dst->stream));
     }
     if(dirty_chunks(dst, 0, lo, (int)dst->cfg.width, hi - lo)) return FSS_ERR_CUDA;
+    const bool marks = src->g.dirty && dst->g.dirty; // World::dirty: the marks the source left in the rows the destination owns
+    const int mlo = tk == 1 ? B : B - DIRTY_HALO_ROWS;
+    if(marks) {
+        if(int rc = dirty_halo_buffer(dst)) return rc;
+        CU(cudaMemcpyPeerAsync(dst->d_dirty_halo, dst->device, dirty_rows(src, mlo), src->device, (size_t)DIRTY_HALO_ROWS * src->g.pitch, dst->stream));
+        if(int rc = dirty_halo_finish(dst, true, mlo, false, 0, dst->stream)) return rc;
+    }
     CU(cudaEventRecord(ev, dst->stream));
     CU(cudaSetDevice(src->device));
     CU(cudaStreamWaitEvent(src->stream, ev, 0)); // the source must not overwrite the rows while they are copied
     CU(cudaEventDestroy(ev));
+    if(marks)
+        if(int rc = dirty_halo_finish(src, false, 0, true, mlo, src->stream)) return rc;
     return FSS_OK;
 }
 
@@ -2024,14 +2057,22 @@ static int halo_received(fss_world* w, int tk) {
 
 static int exchange_halo_on(fss_world* w, int tk, cudaStream_t st) {
     const bool has_upper = w->rank > 0, has_lower = w->rank + 1 < w->n_ranks;
+    const bool marks = w->g.dirty != nullptr;
+    const size_t mark_words = (size_t)DIRTY_HALO_ROWS * w->g.pitch / 4;
+    if(marks)
+        if(int rc0 = dirty_halo_buffer(w)) return rc0;
     int rc = FSS_OK;
     NC(g_nccl.group_start());
     if(tk == 1) { // data flows down
         if(has_lower) rc = nccl_rows(w, true, w->rank + 1, w->own_hi + DOWN_LO, w->own_hi + DOWN_HI, false, st);
         if(!rc && has_upper) rc = nccl_rows(w, false, w->rank - 1, w->own_lo + DOWN_LO, w->own_lo + DOWN_HI, false, st);
+        if(!rc && marks && has_lower && g_nccl.send(dirty_rows(w, w->own_hi), mark_words, NCCL_UINT32, w->rank + 1, w->comm, st) != 0) rc = fail(FSS_ERR_COMM, "ncclSend");
+        if(!rc && marks && has_upper && g_nccl.recv(w->d_dirty_halo, mark_words, NCCL_UINT32, w->rank - 1, w->comm, st) != 0) rc = fail(FSS_ERR_COMM, "ncclRecv");
     } else { // data flows up
         if(has_upper) rc = nccl_rows(w, true, w->rank - 1, w->own_lo + UP_LO, w->own_lo + UP_HI, false, st);
         if(!rc && has_lower) rc = nccl_rows(w, false, w->rank + 1, w->own_hi + UP_LO, w->own_hi + UP_HI, false, st);
+        if(!rc && marks && has_upper && g_nccl.send(dirty_rows(w, w->own_lo - DIRTY_HALO_ROWS), mark_words, NCCL_UINT32, w->rank - 1, w->comm, st) != 0) rc = fail(FSS_ERR_COMM, "ncclSend");
+        if(!rc && marks && has_lower && g_nccl.recv(w->d_dirty_halo, mark_words, NCCL_UINT32, w->rank + 1, w->comm, st) != 0) rc = fail(FSS_ERR_COMM, "ncclRecv");
     }
     // the group is always closed, also after a failed send / recv: an open group would leave the communicator unusable and the
     // neighbour blocked.  A communicator error is fatal for the world (the strips are out of step): destroy and re-create it.
@@ -2040,6 +2081,10 @@ static int exchange_halo_on(fss_world* w, int tk, cudaStream_t st) {
     if(rc) return fail(rc, "%s", first_error.c_str());
     if(end != 0) return fail(FSS_ERR_COMM, "ncclGroupEnd: %s", g_nccl.err_string ? g_nccl.err_string(end) : "nccl error");
     w->stats.kernel_launches++; // one fused NCCL send/recv kernel per group
+    if(marks) {
+        if(tk == 1) rc = dirty_halo_finish(w, has_upper, w->own_lo, has_lower, w->own_hi, st);
+        else rc = dirty_halo_finish(w, has_lower, w->own_hi - DIRTY_HALO_ROWS, has_upper, w->own_lo - DIRTY_HALO_ROWS, st);
+    }
     return rc;
 }
 

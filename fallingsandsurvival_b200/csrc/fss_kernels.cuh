@@ -167,6 +167,11 @@ __global__ void __launch_bounds__(128) k_worklist(const uint8_t* __restrict__ q,
     if(active) work[base + __popc(live & ((1u << lane) - 1u))] = entry;
 }
 
+__global__ void __launch_bounds__(256) k_or_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int n) {
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if(k < n) dst[k] |= src[k];
+}
+
 // a few words device -> mapped host memory (or anywhere) without the copy engines
 __global__ void k_copy_words(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int n) {
     for(int k = threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];

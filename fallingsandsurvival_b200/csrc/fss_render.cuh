@@ -18,11 +18,12 @@ struct RenderParams {
     const DLook* looks;
     int n_mat;
     int width;
-    uint32_t* px[4]; // main, fire, emission, flow: row-major width * height, bytes r g b a
+    uint32_t* px[4]; // main, fire, emission, flow: row-major width * stored rows, bytes r g b a
     float *prev_fx, *prev_fy;
     unsigned long long* moving; // n_mat counters
     uint32_t* info;             // hadDirty, hadFire, hadFlow
     size_t cells;               // stored cells (rows * pitch)
+    int own_lo, own_hi;         // global rows this world renders: a strip's ghost rows belong to its neighbours
 };
 
 __device__ __forceinline__ uint32_t rgba_bytes(uint32_t r, uint32_t g, uint32_t b, uint32_t a) { return r | (g << 8) | (b << 16) | (a << 24); }
@@ -36,13 +37,13 @@ __global__ void __launch_bounds__(256) k_render_dirty(const __grid_constant__ Re
     uint32_t my_mat = 0xFFFFFFFFu; // material of this thread's dirty cell
     if(i < p.cells && p.g.dirty[i]) {
         const uint32_t row = (uint32_t)(i / p.g.pitch), x = fss_unperm((uint32_t)(i % p.g.pitch));
-        if((int)x < p.width) {
+        if((int)x < p.width && (int)row + p.g.sy0 >= p.own_lo && (int)row + p.g.sy0 < p.own_hi) {
             any = true;
             p.g.dirty[i] = 0; // Game.cpp:2751: the memset after the job, for the cells that were set
             const uint32_t mf = p.g.mf[i];
             const uint32_t mat = mf_mat(mf);
             my_mat = mat;
-            const size_t o = (size_t)(row + p.g.sy0) * p.width + x;
+            const size_t o = (size_t)row * p.width + x; // the layers hold the stored rows
             if(MF_IS(mf, FSS_PHYS_AIR)) { // :2590-2607
                 p.px[0][o] = 0u;
                 p.px[1][o] = 0u;

@@ -394,6 +394,44 @@ class StripWorld:
         for a, b in zip(self.parts[:-1], self.parts[1:]):
             _check(self.L, self.L.fss_exchange_halo_temperature_peer(a.h_, b.h_))
 
+    # ---- World::dirty and the dirty -> pixels job: every strip keeps, renders and hands out the rows it owns ----
+    def dirty(self):
+        out = np.zeros((self.h, self.w), dtype=np.uint8)
+        for p, (y0, rows) in zip(self.parts, self.plan):
+            out[y0:y0 + rows] = p.dirty(0, y0, self.w, rows)
+        return out
+
+    def mark_dirty(self, x, y, w, h):
+        for p in self.parts:
+            p.mark_dirty(x, y, w, h)
+
+    def render_dirty(self):
+        moving, info = None, (0, 0, 0)
+        for p in self.parts:
+            m, i = p.render_dirty()
+            moving = m if moving is None else moving + m
+            info = tuple(a | b for a, b in zip(info, i))
+        return moving, info
+
+    def pixels(self, layer):
+        out = np.zeros((self.h, self.w, 4), dtype=np.uint8)
+        for p, (y0, rows) in zip(self.parts, self.plan):
+            out[y0:y0 + rows] = p.pixels(layer, 0, y0, self.w, rows)
+        return out
+
+    def flow(self):
+        fx = np.zeros((self.h, self.w), dtype=np.float32)
+        fy = np.zeros((self.h, self.w), dtype=np.float32)
+        for p, (y0, rows) in zip(self.parts, self.plan):
+            a, b = p.flow()  # the stored rows
+            lo = y0 - p.stored[0]
+            fx[y0:y0 + rows], fy[y0:y0 + rows] = a[lo:lo + rows], b[lo:lo + rows]
+        return fx, fy
+
+    def set_material_looks(self, alpha, emit):
+        for p in self.parts:
+            p.set_material_looks(alpha, emit)
+
     def shift_grid(self, change_x, change_y):
         """World::tickChunks' camera shift (world.cpp:2617-2630) across the strips: rows that cross a boundary come from the neighbour"""
         arr = (C.c_void_p * len(self.parts))(*[p.h_ for p in self.parts])

@@ -132,7 +132,9 @@ typedef struct fss_material {
                                  fss_render_dirty.  One more byte per cell; a compile-time kernel variant, off by default.  Works with
                                  the settled-chunk early-out: the reference re-marks every liquid cell in every sub-step
                                  (world.cpp:1814, :1823), so for a chunk whose visit is skipped the kernel notes the iter and the
-                                 marks are added before World::dirty is next looked at.  Not available on strip-sharded worlds. */
+                                 marks are added before World::dirty is next looked at.  Strip-sharded worlds: the marks a strip
+                                 leaves in the ghost rows next to its boundary travel with the halo exchange to the strip that
+                                 owns the rows; every strip marks, renders and hands out the rows it owns. */
 
 typedef struct fss_config {
     uint32_t struct_size; /* sizeof(fss_config), for ABI evolution */
@@ -263,7 +265,10 @@ int fss_clear_flow(fss_world* w);
  *          if the material is fire; liquids: prevFlow += (flow - prevFlow) * 0.25 (negative y halved), flow pixel =
  *          clamp(prevFlow * (3.0 / iterations + 0.5) / 4.0 + 0.5, 0, 1) * 255 in double like the reference; flow := 0.
  * The four RGBA layers (byte order r, g, b, a as the reference writes them) live on the device, row-major, and only change where
- * cells were dirty; fss_download_pixels copies a rectangle of one layer to the host.  dirty is cleared afterwards. */
+ * cells were dirty; fss_download_pixels copies a rectangle of one layer to the host.  dirty is cleared afterwards.
+ * Strip-sharded worlds: each strip renders and counts the rows it owns (fss_download_pixels: rectangles inside those rows;
+ * moving_tiles and the three flags of the whole world = the sums / ORs over the strips); fss_mark_dirty marks the owned part of
+ * a rectangle, so host edits are marked on every strip they touch. */
 typedef struct fss_render_info {
     uint32_t had_dirty, had_fire, had_flow; /* Game.cpp:2588, :2626, :2639 */
 } fss_render_info;

@@ -25,7 +25,7 @@ def main():
     size = (520, 64 * 4 * n + 32)
     ticks = 12
     cells, zone = helpers.make_world(size, "c3", seed=31)
-    rw = strips.RankWorld(size, zone, rank, n, local, cells=cells, defs=helpers.full_table(), particles=True)
+    rw = strips.RankWorld(size, zone, rank, n, local, cells=cells, defs=helpers.full_table(), particles=True, track_dirty=True, track_flow=True)
     shifts = {3: (5, 40), 7: (-9, -70), 9: (0, 17)}  # World::tickChunks' camera shift, collective over the ranks (rows cross strips)
     for t in range(ticks):
         rw.tick(t)
@@ -33,32 +33,54 @@ def main():
             rw.tick_temperature()
         if t in shifts:
             rw.shift_grid(*shifts[t])
+        if t == 5:
+            rw.render_dirty()  # consumes the marks so far: what is gathered below is what the later ticks left
     y0, rows = rw.strip
+    # World::dirty on strips: the marks of the ghost rows travelled with the halo exchange; every strip renders the rows it owns
+    marks = rw.world.dirty(0, y0, size[0], rows)
+    moving, info = rw.render_dirty()
+    layers = [rw.world.pixels(k, 0, y0, size[0], rows) for k in range(4)]
     mine = rw.world.download(0, y0, size[0], rows)
     digest = torch.tensor([rw.world.hash() & 0x7FFFFFFFFFFFFFFF, rw.world.hash() >> 63], dtype=torch.int64, device="cuda")
     parts = rw.world.drain_particles()
     gathered = [None] * n
-    dist.all_gather_object(gathered, (y0, rows, mine.tobytes(), rw.world.hash(), parts.tobytes()))
+    dist.all_gather_object(gathered, (y0, rows, mine.tobytes(), rw.world.hash(), parts.tobytes(), marks.tobytes(), moving, info, [a.tobytes() for a in layers]))
     ok = True
     if rank == 0:
-        whole = world.World(cells, zone, defs=helpers.full_table(), particles=True, device=local)
+        whole = world.World(cells, zone, defs=helpers.full_table(), particles=True, device=local, track_dirty=True, track_flow=True)
         for t in range(ticks):
             whole.tick(t)
             if t % 4 == 2:
                 whole.tick_temperature()
             if t in shifts:
                 whole.shift_grid(*shifts[t])
+            if t == 5:
+                whole.render_dirty()
         ref = whole.cells()
+        ref_marks = whole.dirty()
+        ref_moving, ref_info = whole.render_dirty()
+        ref_layers = [whole.pixels(k) for k in range(4)]
+        got_marks = np.zeros_like(ref_marks)
+        got_moving, got_info = np.zeros_like(ref_moving), (0, 0, 0)
+        got_layers = [np.zeros_like(a) for a in ref_layers]
         out = np.zeros_like(ref)
         hsum = 0
         recs = []
-        for gy0, grows, raw, h, praw in gathered:
+        for gy0, grows, raw, h, praw, mraw, mov, inf, lraw in gathered:
             out[gy0:gy0 + grows] = np.frombuffer(raw, dtype=abi.CELL_DTYPE).reshape(grows, size[0])
+            got_marks[gy0:gy0 + grows] = np.frombuffer(mraw, dtype=np.uint8).reshape(grows, size[0])
+            got_moving = got_moving + mov
+            got_info = tuple(a | b for a, b in zip(got_info, inf))
+            for k in range(4):
+                got_layers[k][gy0:gy0 + grows] = np.frombuffer(lraw[k], dtype=np.uint8).reshape(grows, size[0], 4)
             hsum = (hsum + h) & 0xFFFFFFFFFFFFFFFF
             recs.append(np.frombuffer(praw, dtype=abi.PARTICLE_DTYPE))
         recs = np.concatenate(recs)
         recs = recs[abi.spawn_order(recs, zone)]
-        ok = out.tobytes() == ref.tobytes() and hsum == whole.hash() and recs.tobytes() == whole.drain_particles().tobytes()
+        dirty_ok = (got_marks.tobytes() == ref_marks.tobytes() and np.array_equal(got_moving, ref_moving) and got_info == ref_info
+                    and all(a.tobytes() == b.tobytes() for a, b in zip(got_layers, ref_layers)))
+        ok = out.tobytes() == ref.tobytes() and hsum == whole.hash() and recs.tobytes() == whole.drain_particles().tobytes() and dirty_ok
+        print(f"World::dirty ({int(ref_marks.sum())} marks), pixel layers, counts over the strips {'==' if dirty_ok else '!='} single GPU", flush=True)
         print(f"nccl strips n={n}: cells {'==' if out.tobytes() == ref.tobytes() else '!='} single GPU, digest sum {hsum:016x} vs {whole.hash():016x}, "
               f"{len(recs)} particle records -> {'OK' if ok else 'MISMATCH'}", flush=True)
         whole.close()

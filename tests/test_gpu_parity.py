@@ -913,6 +913,45 @@ def test_device_dirty_and_pixels_match_oracle(mix, early_out):
     o.close()
 
 
+@pytest.mark.parametrize("n_strips,early_out", [(2, True), (3, False), (3, True)])
+def test_dirty_and_pixels_on_strips_equal_whole_world(n_strips, early_out):
+    """World::dirty on a strip-sharded world: the marks a strip leaves in its ghost rows travel with the halo exchange and are
+    OR-ed into the owner's plane; every strip renders the rows it owns.  Marks every tick, the four layers, the flags, the
+    per-material counts (summed over the strips) and the consumed flow accumulators against the undivided world."""
+    from fallingsandsurvival_b200 import world
+    cells, zone = make_world((264, 400), "c3", seed=21)
+    alpha, emit = _looks()
+    whole = gpu_world(cells, zone, particles=True, track_dirty=True, track_flow=True, early_out=early_out)
+    parts = world.StripWorld(cells, zone, n_strips, defs=full_table(), particles=True, track_dirty=True, track_flow=True, early_out=early_out)
+    whole.set_material_looks(alpha, emit)
+    parts.set_material_looks(alpha, emit)
+    for t in range(18):
+        whole.tick(t)
+        parts.tick(t)
+        if t == 4:  # a host edit across a strip boundary
+            whole.mark_dirty(20, 100, 60, 150)
+            parts.mark_dirty(20, 100, 60, 150)
+        if t % 4 == 2:
+            whole.tick_temperature()
+            parts.tick_temperature()
+        da, db = whole.dirty(), parts.dirty()
+        assert da.tobytes() == db.tobytes(), f"tick {t}: dirty differs in {int((da != db).sum())} cells, first {np.argwhere(da != db)[0]}"
+        if t % 3 == 1:
+            ma, ia = whole.render_dirty()
+            mb, ib = parts.render_dirty()
+            assert ia == ib and np.array_equal(ma, mb), f"tick {t}: {ia} vs {ib}"
+            for layer in range(4):
+                a, b = whole.pixels(layer), parts.pixels(layer)
+                assert a.tobytes() == b.tobytes(), f"tick {t}: layer {layer} differs in {int((a != b).any(axis=2).sum())} pixels"
+            assert not parts.dirty().any()
+            fa, fb = whole.flow(), parts.flow()
+            assert fa[0].tobytes() == fb[0].tobytes() and fa[1].tobytes() == fb[1].tobytes()
+        a, b = whole.cells(), parts.cells()
+        assert a.tobytes() == b.tobytes(), f"tick {t}: " + diff_report(a, b)
+    whole.close()
+    parts.close()
+
+
 def test_device_dirty_error_paths():
     from fallingsandsurvival_b200 import world
     cells, zone = make_world((264, 240), "c2", seed=1)
@@ -922,8 +961,16 @@ def test_device_dirty_error_paths():
     with pytest.raises(world.FssError):
         g.mark_dirty(0, 0, 8, 8)
     g.close()
+    s = world.World(cells, zone, defs=full_table(), strip=(0, 144), track_dirty=True)  # a strip renders the rows it owns
     with pytest.raises(world.FssError):
-        world.World(cells, zone, defs=full_table(), strip=(0, 128), track_dirty=True)  # no dirty plane on strips
+        s.tick_particles()  # device particles stay refused on strips
+    s.mark_dirty(0, 100, 10, 60)  # the owned part of the rectangle
+    assert int(s.dirty(0, 0, 264, 160).sum()) == 10 * 44
+    s.render_dirty()
+    with pytest.raises(world.FssError) as e:
+        s.pixels(0, 0, 130, 10, 20)  # reaches into the neighbour's rows
+    assert e.value.code == -6
+    s.close()
     g = gpu_world(cells, zone, track_dirty=True)
     with pytest.raises(world.FssError):
         g.pixels(0)  # before the first render
