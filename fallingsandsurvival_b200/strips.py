@@ -63,6 +63,27 @@ def tick_schedule():
                 yield ("exchange", it, tk)
 
 
+def shift_rows(height: int, plan, rank: int, change_y: int):
+    """World::tickChunks' grid shift (world.cpp:2617-2630) on strips: new[y] = old[y - change_y].  Only the rows a strip OWNS are
+    current in its storage (the halo exchange refreshes just the ghost rows the rules look at), so the sources of its stored rows
+    that lie outside its owned rows come from the neighbours.  Returns the global row ranges
+      (fetch_from_upper, fetch_from_lower, give_to_lower, give_to_upper)
+    as (lo, hi) pairs (empty: lo == hi), the same arithmetic as shift_rows() in csrc/fss_abi.cu; |change_y| must not exceed
+    any strip's rows less HALO_ROWS."""
+    n = len(plan)
+    own_lo, own_hi = plan[rank][0], plan[rank][0] + plan[rank][1]
+    s0, s1 = stored_rows(height, plan[rank])
+    if abs(change_y) > min(r for _, r in plan) - HALO_ROWS:
+        raise ValueError("shift longer than the shortest strip less its ghost rows")
+    empty = (0, 0)
+    u = (max(0, s0 - change_y), own_lo) if rank > 0 else empty
+    gu = (own_lo, min(height, own_lo + HALO_ROWS - change_y)) if rank > 0 else empty
+    lo_ = (own_hi, min(height, s1 - change_y)) if rank + 1 < n else empty
+    gd = (max(0, own_hi - HALO_ROWS - change_y), own_hi) if rank + 1 < n else empty
+    fix = lambda r: r if r[1] > r[0] else (r[0], r[0])
+    return fix(u), fix(lo_), fix(gd), fix(gu)
+
+
 class RankWorld:
     """One rank's strip of a world sharded over torch.distributed ranks (one process per GPU, NCCL).
 

@@ -128,6 +128,88 @@ def test_gloo_ranks_reproduce_the_undivided_world(n, tmp_path):
     assert parts.tobytes() == whole.drain_particles().tobytes()
 
 
+def _shift_worker(rank, n, port, out_dir, shifts):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=n)
+    cells, zone = make_world(SIZE, "c3", seed=5)
+    H, W = cells.shape
+    plan = strips.plan_strips(H, zone, n)
+    own_lo, own_hi = plan[rank][0], plan[rank][0] + plan[rank][1]
+    s_lo, s_hi = strips.stored_rows(H, plan[rank])
+    local = cells.copy()
+    for k, (cx, cy) in enumerate(shifts):
+        # only the owned rows are current: everything else (ghost rows included) is poisoned before every shift
+        stale = np.ones(H, dtype=bool)
+        stale[own_lo:own_hi] = False
+        local["material"][stale] = 2
+        local["color"][stale] = 0xDEAD0000 + k
+        u, lw, gd, gu = strips.shift_rows(H, plan, rank, cy)
+        reqs, recvs = [], []
+        for (a, b), peer in ((gd, rank + 1), (gu, rank - 1)):
+            if b > a:
+                reqs.append(dist.isend(_rows_tensor(local, a, b), peer))
+        for (a, b), peer in ((u, rank - 1), (lw, rank + 1)):
+            if b > a:
+                t = torch.empty((b - a) * W * abi.CELL_DTYPE.itemsize, dtype=torch.uint8)
+                recvs.append((t, a, b))
+                reqs.append(dist.irecv(t, peer))
+        for r in reqs:
+            r.wait()
+        src = local.copy()
+        for t, a, b in recvs:
+            src[a:b] = t.numpy().view(abi.CELL_DTYPE).reshape(b - a, W)
+        valid = np.zeros(H, dtype=bool)  # what k_shift may read: the owned rows and what was fetched
+        valid[own_lo:own_hi] = True
+        for _, a, b in recvs:
+            valid[a:b] = True
+        new = local.copy()
+        ys, xs = np.mgrid[s_lo:s_hi, 0:W]
+        oy, ox = ys - cy, xs - cx
+        ok = (ox >= 0) & (ox < W) & (oy >= 0) & (oy < H)
+        assert valid[oy[ok]].all(), f"rank {rank}, shift {(cx, cy)}: a source row is neither owned nor fetched"
+        new[ys[ok], xs[ok]] = src[oy[ok], ox[ok]]
+        local = new
+        np.save(os.path.join(out_dir, f"shift{k}_rank{rank}.npy"), local[s_lo:s_hi])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_gloo_shift_grid_across_strips(n, tmp_path):
+    """fss_shift_grid on strips, the row arithmetic (strips.shift_rows == shift_rows() of csrc/fss_abi.cu) with gloo as the
+    transport: every STORED row of every rank, ghost rows included, must come out as the undivided shift leaves it"""
+    shifts = [(3, 5), (-7, -40), (0, 33), (11, -1), (-2, 64), (40, -70), (0, 16), (5, -16)]
+    port = _free_port()
+    mp.spawn(_shift_worker, args=(n, port, str(tmp_path), shifts), nprocs=n, join=True)
+    cells, zone = make_world(SIZE, "c3", seed=5)
+    H, W = cells.shape
+    plan = strips.plan_strips(H, zone, n)
+    ref = cells.copy()
+    for k, (cx, cy) in enumerate(shifts):
+        ys, xs = np.mgrid[0:H, 0:W]
+        oy, ox = ys - cy, xs - cx
+        ok = (ox >= 0) & (ox < W) & (oy >= 0) & (oy < H)
+        new = ref.copy()
+        new[ok] = ref[oy[ok], ox[ok]]
+        ref = new
+        for r in range(n):
+            s_lo, s_hi = strips.stored_rows(H, plan[r])
+            got = np.load(tmp_path / f"shift{k}_rank{r}.npy")
+            own_lo, own_hi = plan[r][0], plan[r][0] + plan[r][1]
+            # rows whose source lies outside the world keep their content: owned rows keep real cells, ghost rows keep the poison
+            a, b = got[own_lo - s_lo:own_hi - s_lo], ref[own_lo:own_hi]
+            assert a.tobytes() == b.tobytes(), f"shift {k} {(cx, cy)}, rank {r}: {int((a != b).sum())} owned cells differ"
+            keep = np.zeros(H, dtype=bool)
+            keep[max(0, cy):min(H, H + cy)] = True  # rows that have a source inside the world
+            rows = np.arange(s_lo, s_hi)
+            sel = keep[rows]
+            a, b = got[sel][:, max(0, cx):min(W, W + cx)], ref[rows[sel]][:, max(0, cx):min(W, W + cx)]
+            assert a.tobytes() == b.tobytes(), f"shift {k} {(cx, cy)}, rank {r}: {int((a != b).sum())} stored cells with a source differ"
+    with pytest.raises(ValueError):
+        strips.shift_rows(H, plan, 0, 400)
+
+
 def test_plan_strips_properties():
     zone = (16, 16, 16384, 16384 * 8)
     plan = strips.plan_strips(16384 * 8 + 32, zone, 8)
