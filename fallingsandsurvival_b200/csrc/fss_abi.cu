@@ -165,6 +165,8 @@ struct fss_world {
     uint32_t* d_work_n;
     volatile uint32_t* h_work_n; // pinned: the latest count the device has reported (read without synchronising: a hint only)
     uint32_t* d_work_n_host;     // its device address
+    int work_flip;               // which of the two counters d_work_n[0 / 1] the next list is counted in
+    bool work_zeroed;            // ... and whether the last tick kernel has already zeroed it
     uint8_t* d_dirty_halo;       // strip-sharded + FSS_TRACK_DIRTY: the marks received with a halo exchange (2 rows of bytes)
     uint8_t* h_seen;             // fss_tick_host: pinned + mapped, 32 bands x FSS_MAX_MATERIALS bytes (which materials each band held)
     uint8_t* d_seen_host;
@@ -720,7 +722,8 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
                 CU(cudaMalloc(&w->d_work, (size_t)tiles * sizeof(uint32_t)));
                 w->work_cap = tiles;
                 if(!w->d_work_n) {
-                    CU(cudaMalloc(&w->d_work_n, sizeof(uint32_t)));
+                    CU(cudaMalloc(&w->d_work_n, 2 * sizeof(uint32_t)));
+                    CU(cudaMemsetAsync(w->d_work_n, 0, 2 * sizeof(uint32_t), w->stream));
                     // mapped: the count is written by a one-thread kernel, not by a copy (a cudaMemcpyAsync would queue behind the
                     // 256 MB passes of fss_tick_host's download on the device -> host copy engine and stall this stream)
                     CU(cudaHostAlloc((void**)&w->h_work_n, sizeof(uint32_t), cudaHostAllocMapped));
@@ -731,15 +734,24 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
             if(w->work_tiles && *w->h_work_n != 0xFFFFFFFFu) w->work_mode = (double)*w->h_work_n < 0.5 * (double)w->work_tiles;
             if(always_worklist) w->work_mode = true;
             if(w->work_mode || (iter == 0 && tk == 0)) {
-                CU(cudaMemsetAsync(w->d_work_n, 0, sizeof(uint32_t), w->stream));
-                k_worklist<<<(tiles + 127) / 128, 128, 0, w->stream>>>(p.q, p.q_w, ofs_x, ofs_y, iter, p.nx, (int)tiles_x, p.ny, w->d_work, w->d_work_n);
-                k_copy_words<<<1, 32, 0, w->stream>>>(w->d_work_n, w->d_work_n_host, 1);
+                // two counters take turns: the tick kernel that strides over list i zeroes the counter of list i+1 and reports its
+                // own count to the host, so a launch through the list is two launches (list, tick kernel), not four
+                uint32_t* cnt = w->d_work_n + w->work_flip;
+                if(!w->work_zeroed) CU(cudaMemsetAsync(cnt, 0, sizeof(uint32_t), w->stream));
+                k_worklist<<<(tiles + 127) / 128, 128, 0, w->stream>>>(p.q, p.q_w, ofs_x, ofs_y, iter, p.nx, (int)tiles_x, p.ny, w->d_work, cnt);
                 w->work_tiles = tiles;
                 w->stats.kernel_launches++;
                 if(w->work_mode) {
                     p.work = w->d_work;
-                    p.work_n = w->d_work_n;
+                    p.work_n = cnt;
+                    p.work_n_host = w->d_work_n_host;
+                    p.work_n_next = w->d_work_n + (w->work_flip ^ 1);
+                    w->work_flip ^= 1;
+                    w->work_zeroed = true;
                     work_tiles_now = tiles; // the grid is sized below, once the kernel (and how many of its CTAs fit an SM) is known
+                } else { // a plain launch follows: the count only refreshes the hint (once per tick)
+                    k_copy_words<<<1, 32, 0, w->stream>>>(cnt, w->d_work_n_host, 1);
+                    w->work_zeroed = false;
                 }
             }
         }

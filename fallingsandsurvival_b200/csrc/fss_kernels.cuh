@@ -52,6 +52,10 @@ struct TileLoop {
         t = work ? blockIdx.x * K1_WARPS + warp : 0u;
         n = work ? *p.work_n : 1u;
         stride = gridDim.x * K1_WARPS;
+        if(work && blockIdx.x == 0 && threadIdx.x == 0) {
+            *p.work_n_host = n;
+            *p.work_n_next = 0u;
+        }
     }
     // gi = this thread's chunk in its chunk row, by = the chunk row
     __device__ __forceinline__ bool next(int& gi, int& by) {

@@ -63,6 +63,10 @@ struct SubstepParams {
     // grid then stride over it.  nullptr = one CTA per K1_THREADS chunks of the (ceil(nx / K1_THREADS), ny) grid.
     const uint32_t* work;
     const uint32_t* work_n;
+    // with a worklist: thread 0 of CTA 0 reports the count to the host (mapped memory, a hint for the next launch's choice) and
+    // zeroes the counter the NEXT list will be counted in -- instead of a memset and a copy kernel around every launch
+    uint32_t* work_n_host;
+    uint32_t* work_n_next;
 };
 
 __device__ __forceinline__ Cell cell_nothing(uint32_t nothing_mf) {
