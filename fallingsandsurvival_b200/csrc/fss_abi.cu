@@ -52,6 +52,7 @@ typedef int (*nccl_comm_init_rank_t)(void**, int, NcclId, int);
 typedef int (*nccl_comm_destroy_t)(void*);
 typedef int (*nccl_send_t)(const void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*nccl_recv_t)(void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_all_reduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*nccl_group_t)(void);
 typedef const char* (*nccl_err_t)(int);
 static struct {
@@ -61,10 +62,13 @@ static struct {
     nccl_comm_destroy_t comm_destroy;
     nccl_send_t send;
     nccl_recv_t recv;
+    nccl_all_reduce_t all_reduce;
     nccl_group_t group_start, group_end;
     nccl_err_t err_string;
 } g_nccl;
 #define NCCL_UINT32 3 /* ncclUint32, nccl.h */
+#define NCCL_UINT8 1  /* ncclUint8 */
+#define NCCL_MAX 2    /* ncclMax */
 
 static int nccl_bind() {
     if(g_nccl.lib) return FSS_OK;
@@ -78,10 +82,11 @@ static int nccl_bind() {
     g_nccl.comm_destroy = (nccl_comm_destroy_t)dlsym(h, "ncclCommDestroy");
     g_nccl.send = (nccl_send_t)dlsym(h, "ncclSend");
     g_nccl.recv = (nccl_recv_t)dlsym(h, "ncclRecv");
+    g_nccl.all_reduce = (nccl_all_reduce_t)dlsym(h, "ncclAllReduce");
     g_nccl.group_start = (nccl_group_t)dlsym(h, "ncclGroupStart");
     g_nccl.group_end = (nccl_group_t)dlsym(h, "ncclGroupEnd");
     g_nccl.err_string = (nccl_err_t)dlsym(h, "ncclGetErrorString");
-    if(!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.send || !g_nccl.recv || !g_nccl.group_start || !g_nccl.group_end)
+    if(!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.send || !g_nccl.recv || !g_nccl.all_reduce || !g_nccl.group_start || !g_nccl.group_end)
         return fail(FSS_ERR_COMM, "libnccl.so.2 lacks a required symbol");
     g_nccl.lib = h;
     return FSS_OK;
@@ -167,6 +172,7 @@ struct fss_world {
     uint32_t* d_work_n_host;     // its device address
     int work_flip;               // which of the two counters d_work_n[0 / 1] the next list is counted in
     bool work_zeroed;            // ... and whether the last tick kernel has already zeroed it
+    uint8_t *h_present_mask, *d_present_mask; // strip-sharded with a communicator: which materials ANY strip can hold (share_present)
     uint8_t* d_dirty_halo;       // strip-sharded + FSS_TRACK_DIRTY: the marks received with a halo exchange (2 rows of bytes)
     uint8_t* h_seen;             // fss_tick_host: pinned + mapped, 32 bands x FSS_MAX_MATERIALS bytes (which materials each band held)
     uint8_t* d_seen_host;
@@ -201,7 +207,9 @@ static void owned_bands(const fss_world* w, int& j_lo, int& j_hi) {
 // can turn into: reaction targets, condensed steam, fire), the liquid-only kernel k_substep<true> gives identical results.
 static void recompute_liq(fss_world* w) {
     bool pres[FSS_MAX_MATERIALS];
-    for(int m = 0; m < FSS_MAX_MATERIALS; m++) pres[m] = m < w->n_mat && (w->present_all || w->present[m]);
+    // (a strip without a communicator cannot know what the other strips hold: everything; with one, share_present() tells it)
+    const bool unknown = w->present_all || (w->sharded && !w->comm);
+    for(int m = 0; m < FSS_MAX_MATERIALS; m++) pres[m] = m < w->n_mat && (unknown || w->present[m]);
     for(bool grew = true; grew;) {
         grew = false;
         for(int m = 0; m < w->n_mat; m++) {
@@ -416,6 +424,8 @@ int fss_destroy(fss_world* w) {
     if(w->h_work_n) cudaFreeHost((void*)w->h_work_n);
     if(w->h_seen) cudaFreeHost(w->h_seen);
     cudaFree(w->d_dirty_halo);
+    cudaFree(w->d_present_mask);
+    if(w->h_present_mask) cudaFreeHost(w->h_present_mask);
     particles_free(w);
     if(w->own_stream) cudaStreamDestroy(w->own_stream);
     delete w;
@@ -639,7 +649,6 @@ static int rect_copy(fss_world* w, int x, int y, int rw, int rh, fss_cell* host,
     CU(cudaStreamSynchronize(w->stream)); // the caller owns `host` again when we return
     if(upload) {
         for(int m = 0; m < FSS_MAX_MATERIALS; m++) w->present[m] = w->present[m] || seen[m];
-        if(w->sharded) w->present_all = true; // what the other strips hold is unknown here
         recompute_liq(w);
     }
     return FSS_OK;
@@ -812,10 +821,13 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
     return FSS_OK;
 }
 
+static int share_present(fss_world* w);
+
 int fss_substep(fss_world* w, uint32_t tick_ct, int iter, int tk) {
     int rc = ready(w);
     if(rc) return rc;
     if(iter < 0 || iter > 5 || tk < 0 || tk > 3) return fail(FSS_ERR_INVALID, "sub-step (iter %d, tk %d)", iter, tk);
+    if(w->comm && iter == 0 && tk == 0 && (rc = share_present(w))) return rc; // (a caller that drives the schedule itself: once per tick)
     rc = launch_substep(w, tick_ct, iter, tk);
     if(rc) return rc;
     CU(cudaGetLastError());
@@ -827,6 +839,7 @@ int fss_tick(fss_world* w, uint32_t tick_ct) {
     if(rc) return rc;
     if(w->sharded && !w->comm) return fail(FSS_ERR_STATE, "strip-sharded world without communicator: attach one, or drive fss_substep + fss_exchange_halo_peer");
     static const bool serial_halo = getenv("FSS_SERIAL_HALO") != nullptr; // measurements: exchange on the compute stream
+    if(w->comm && (rc = share_present(w))) return rc;
     if(w->comm && !w->comm_stream) {
         int prio_lo = 0, prio_hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -1633,7 +1646,6 @@ static int chunk_records(fss_world* w, int x0, int y0, int cw, int ch, fss_tile_
         CU(cudaMemcpyAsync(seen, w->d_present, FSS_MAX_MATERIALS, cudaMemcpyDeviceToHost, w->stream));
         CU(cudaStreamSynchronize(w->stream));
         for(int m = 0; m < FSS_MAX_MATERIALS; m++) w->present[m] = w->present[m] || seen[m];
-        if(w->sharded) w->present_all = true;
         recompute_liq(w);
     } else {
         k_read_records<<<blocks, 256, 0, w->stream>>>(p);
@@ -2031,6 +2043,29 @@ int fss_comm_attach(fss_world* w, const void* id128, int rank, int n_ranks) {
     NC(g_nccl.comm_init_rank(&w->comm, n_ranks, id, rank));
     w->rank = rank;
     w->n_ranks = n_ranks;
+    recompute_liq(w); // (from here on the strips tell each other which materials they hold: share_present)
+    return FSS_OK;
+}
+
+// Strip-sharded worlds over a communicator: which kernel specialisation is exact depends on the materials that can be present, and a
+// material uploaded into one strip reaches the others through the halo rows.  Once per tick the strips OR their sets (a 256-byte
+// all-reduce and a host read: tens of microseconds against ticks of tens of milliseconds); collective like fss_tick itself.
+static int share_present(fss_world* w) {
+    if(!w->comm) return FSS_OK;
+    if(!w->d_present_mask) {
+        CU(cudaMalloc(&w->d_present_mask, FSS_MAX_MATERIALS));
+        CU(cudaHostAlloc((void**)&w->h_present_mask, FSS_MAX_MATERIALS, cudaHostAllocDefault));
+    }
+    for(int m = 0; m < FSS_MAX_MATERIALS; m++) w->h_present_mask[m] = (w->present_all || w->present[m]) ? 1 : 0;
+    CU(cudaMemcpyAsync(w->d_present_mask, w->h_present_mask, FSS_MAX_MATERIALS, cudaMemcpyHostToDevice, w->stream));
+    NC(g_nccl.all_reduce(w->d_present_mask, w->d_present_mask, FSS_MAX_MATERIALS, NCCL_UINT8, NCCL_MAX, w->comm, w->stream));
+    CU(cudaMemcpyAsync(w->h_present_mask, w->d_present_mask, FSS_MAX_MATERIALS, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    w->stats.kernel_launches++;
+    bool grew = false;
+    for(int m = 0; m < w->n_mat; m++)
+        if(w->h_present_mask[m] && !w->present[m]) w->present[m] = grew = true;
+    if(grew) recompute_liq(w);
     return FSS_OK;
 }
 

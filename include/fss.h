@@ -234,7 +234,9 @@ int fss_shift_grid_peer(fss_world** strips, int n, int change_x, int change_y);
 
 /* ---- the hot path ---------------------------------------------------------------------------- */
 /* one World::tick(): 6 iter x 4 tk checkerboard sub-steps x 3 scans (world.cpp:1108-2011);
- * `tick_ct` is World::tickCt (world.cpp:2017), the RNG key.  Asynchronous.  For a strip-sharded
+ * `tick_ct` is World::tickCt (world.cpp:2017), the RNG key.  Asynchronous (strip-sharded worlds with a communicator: the strips
+ * first tell each other which materials they hold -- a 256-byte all-reduce and a host read -- so that a material uploaded into one
+ * strip switches the kernels of all of them before it can cross a boundary).  For a strip-sharded
  * world with a communicator attached this also performs the per-sub-step halo exchange. */
 int fss_tick(fss_world* w, uint32_t tick_ct);
 /* One World::tick() for a caller that keeps `tiles[]` on the host (the shim's worst case: the whole grid crosses PCIe both

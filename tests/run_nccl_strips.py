@@ -24,10 +24,29 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     size = (520, 64 * 4 * n + 32)
     ticks = 12
-    cells, zone = helpers.make_world(size, "c3", seed=31)
+    # a sand / water / stone world plus lava and hot gold ore; steam and fire arrive later, in ONE strip only (see below)
+    from fallingsandsurvival_b200 import materials as M
+    cells, zone = helpers.make_world(size, [(M.TEST_SAND, 25), (M.WATER, 20), (M.COBBLE_STONE, 10), (M.LAVA, 3), (M.GOLD_ORE, 3)], seed=31)
+    cells["temperature"][cells["material"] == M.GOLD_ORE] = 600
     rw = strips.RankWorld(size, zone, rank, n, local, cells=cells, defs=helpers.full_table(), particles=True, track_dirty=True, track_flow=True)
     shifts = {3: (5, 40), 7: (-9, -70), 9: (0, 17)}  # World::tickChunks' camera shift, collective over the ranks (rows cross strips)
+
+    def paint(w, t):
+        # a host edit that only the LAST strip sees: steam and fire painted just below its upper boundary.  The steam rises into the
+        # strip above, whose kernels were specialised for a world without GAS: the strips tell each other once per tick
+        # (share_present in csrc/fss_abi.cu), so the upper strip switches kernels before the first steam cell reaches it
+        if t != 4:
+            return
+        y = strips.plan_strips(size[1], zone, n)[-1][0] + 17  # (outside the 16 ghost rows the strip above stores: an edit inside them is made on both strips)
+        patch = w.download(40, y, 200, 24)
+        sel = (np.add.outer(np.arange(24), np.arange(200)) % 3) == 0
+        patch["material"][sel] = M.STEAM
+        patch["material"][~sel & ((np.add.outer(np.arange(24), np.arange(200)) % 7) == 0)] = M.FIRE
+        w.upload(40, y, patch)
+
     for t in range(ticks):
+        if rank == n - 1:
+            paint(rw.world, t)
         rw.tick(t)
         if t % 4 == 2:
             rw.tick_temperature()
@@ -49,6 +68,7 @@ def main():
     if rank == 0:
         whole = world.World(cells, zone, defs=helpers.full_table(), particles=True, device=local, track_dirty=True, track_flow=True)
         for t in range(ticks):
+            paint(whole, t)
             whole.tick(t)
             if t % 4 == 2:
                 whole.tick_temperature()

@@ -142,6 +142,27 @@ def test_gpu_matches_oracle_larger(mix, size, ticks):
     o.close()
 
 
+@pytest.mark.parametrize("size,zone", [((264, 112), None), ((1288, 208), None), ((520, 400), (24, 48, 456, 288)), ((776, 336), (264, 16, 256, 64)),
+                                       ((300, 176), (16, 32, 264, 96))])
+def test_temperature_geometries(size, zone):
+    """k_temperature (rows arrive as bulk copies into a three-stage ring): CTAs that own one 256-column block instead of two (an
+    odd number of blocks per row), zones that start inside a CTA's columns, row bands of every length modulo the ring's three
+    stages, CTAs with no column in the zone at all"""
+    cells, dzone = make_world(size, "c3", seed=66)
+    zone = zone or dzone
+    rng = np.random.default_rng(1)
+    cells["temperature"] = rng.integers(-1100, 1100, cells.shape).astype(np.int32) * (rng.random(cells.shape) < 0.7)
+    g = gpu_world(cells, zone)
+    o = oracle_world(cells, zone)
+    for k in range(5):
+        g.tick_temperature()
+        o.tick_temperature()
+        a, b = o.cells(), g.cells()
+        assert a.tobytes() == b.tobytes(), f"pass {k}: " + diff_report(a["temperature"], b["temperature"])
+    g.close()
+    o.close()
+
+
 def test_temperature_only_many_passes():
     cells, zone = make_world((520, 272), "c3", seed=6)
     rng = np.random.default_rng(0)
