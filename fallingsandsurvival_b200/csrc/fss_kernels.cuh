@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS
 // Same grid and chunk ownership as k_substep; launched instead of k_substep<K1_LIQUID> (SAND = false) or k_substep<K1_NOGAS>
 // (SAND = true) where liq_window_applies().
 #ifndef K1W_MIN_BLOCKS
-#define K1W_MIN_BLOCKS 5
+#define K1W_MIN_BLOCKS (K1_NROW_SMEM ? 6 : 5)
 #endif
 #ifndef K1WS_MIN_BLOCKS
 #define K1WS_MIN_BLOCKS 4
@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS
 template <bool SAND, bool ITER0, bool GEN = false>
 __global__ void __launch_bounds__(K1_THREADS, GEN ? K1WG_MIN_BLOCKS : (SAND ? K1WS_MIN_BLOCKS : K1W_MIN_BLOCKS)) k_substep_win(const __grid_constant__ SubstepParams p) {
     __shared__ uint32_t sinfo[SAND ? FSS_MAX_MATERIALS : 1];
-    __shared__ uint32_t spay[SAND ? WIN_PAY_WORDS * K1_THREADS : 1]; // WinWalk::pay: colour / temperature of the window rows
+    // WinWalk::pay: colour / temperature of the window rows (SAND), or the two buffers of the row requested ahead (K1_NROW_SMEM)
+    __shared__ uint32_t spay[(SAND || K1_NROW_SMEM) ? WIN_SMEM_WORDS(SAND) * K1_THREADS : 1];
     if(SAND) {
         for(int m = threadIdx.x; m < p.n_mat; m += K1_THREADS) {
             const DMat& d = p.mats[m];

@@ -92,6 +92,11 @@ struct LRow { // one grid row of the chunk's four columns
 #define LF_PAY 0x1000u /* bits 12-15: the colour / temperature words in shared memory differ from memory (SAND) */
 #define LF_VIS 0x10000u
 #define WIN_PAY_WORDS (3 * 2 * FSS_CHUNK_W) /* per thread: 3 window rows x {colour, temperature} x 4 columns */
+#ifndef K1_NROW_SMEM
+#define K1_NROW_SMEM 1 /* liquid-only kernels: the row requested ahead waits in shared memory (cp.async) instead of in 13 registers */
+#endif
+#define WIN_NB_WORDS (2 * 3 * FSS_CHUNK_W) /* per thread: two buffers of {mf, amt, dif} x 4 columns */
+#define WIN_SMEM_WORDS(SAND_) ((SAND_) ? WIN_PAY_WORDS : WIN_NB_WORDS)
 
 struct LSide { // the cell left / right of the row being scanned (outside the chunk)
     uint32_t mf;
@@ -168,6 +173,43 @@ struct WinWalk {
 #ifdef __CUDA_ARCH__
         __pipeline_commit();
 #endif
+    }
+    // !SAND with K1_NROW_SMEM: the row requested one iteration ahead (mf, amt, dif of the four columns) lands in one of two
+    // buffers of the thread's shared-memory slice instead of in the registers of `N`: 96 -> 80 registers, six CTAs per SM
+    // instead of five, 3.24 -> 3.00 ms per liquid iter of c2.  (The same in the SAND kernel, with five CTAs instead of four, is
+    // slower: 7.8 -> 8.05 ms; the outside cells through shared memory as well change nothing.  profiles/r02_tuning_log.md 15)
+    static constexpr bool NSM = !SAND && K1_NROW_SMEM != 0;
+    __device__ __forceinline__ uint32_t& NB(int buf, int plane, int k) const { return pay[((buf * 3 + plane) * FSS_CHUNK_W + k) * pstride]; }
+    __device__ __forceinline__ void fetch_row_async(int buf, cidx_t i) const {
+#pragma unroll
+        for(int k = 0; k < FSS_CHUNK_W; k++) {
+#ifdef __CUDA_ARCH__
+            __pipeline_memcpy_async(&NB(buf, 0, k), p.g.mf + i + 32 * k, 4);
+            __pipeline_memcpy_async(&NB(buf, 1, k), p.g.amt + i + 32 * k, 4);
+            __pipeline_memcpy_async(&NB(buf, 2, k), p.g.dif + i + 32 * k, 4);
+#else
+            NB(buf, 0, k) = p.g.mf[i + 32 * k];
+            memcpy(&NB(buf, 1, k), &p.g.amt[i + 32 * k], 4);
+            memcpy(&NB(buf, 2, k), &p.g.dif[i + 32 * k], 4);
+#endif
+        }
+#ifdef __CUDA_ARCH__
+        __pipeline_commit();
+#endif
+    }
+    __device__ __forceinline__ void take_row(LRow& R, int buf) const {
+#pragma unroll
+        for(int k = 0; k < FSS_CHUNK_W; k++) {
+            R.mf[k] = NB(buf, 0, k);
+#ifdef __CUDA_ARCH__
+            R.amt[k] = __uint_as_float(NB(buf, 1, k));
+            R.dif[k] = __uint_as_float(NB(buf, 2, k));
+#else
+            memcpy(&R.amt[k], &NB(buf, 1, k), 4);
+            memcpy(&R.dif[k], &NB(buf, 2, k), 4);
+#endif
+        }
+        R.fl = 0u;
     }
     static __device__ __forceinline__ void wait_payload() {
 #ifdef __CUDA_ARCH__
@@ -533,7 +575,9 @@ struct WinWalk {
         const cidx_t pitch = p.g.pitch;
         load_row(B, ir + pitch);
         load_row(C, ir);
-        load_row(N, ir - pitch);
+        int nbuf = 0;
+        if(NSM) fetch_row_async(0, ir - pitch);
+        else load_row(N, ir - pitch);
         load_side(L, ir + lofs);
         load_side(R, ir + rofs);
         if(SAND) {
@@ -546,12 +590,19 @@ struct WinWalk {
         Rn = R;
 #pragma unroll 1
         for(int r = FSS_CHUNK_H - 1; r >= 0; r--) {
-            A = N;
+            if(NSM) {
+                wait_payload();
+                take_row(A, nbuf);
+                nbuf ^= 1;
+                if(r >= 1) fetch_row_async(nbuf, ir - 2 * pitch);
+            } else {
+                A = N;
+            }
             if(SAND) { // rows r and r+1 have arrived (requested an iteration ago); row r-1 is needed from the next iteration on
                 wait_payload();
                 fetch_payload(sA, ir - pitch);
             }
-            if(r >= 1) load_row(N, ir - 2 * pitch); // requested a whole row of arithmetic ahead of their use
+            if(r >= 1 && !NSM) load_row(N, ir - 2 * pitch); // requested a whole row of arithmetic ahead of their use
             if(r >= 1 || GEN) { // (GEN: a GAS cell of row 0 looks at the outside cells of row -1)
                 load_side(Ln, ir - pitch + lofs);
                 load_side(Rn, ir - pitch + rofs);

@@ -60,7 +60,7 @@ static void run_launch(HostWorld* w, const SubstepParams& p) {
             for(int m = 0; m < w->n_mat; m++)
                 if(w->mats[m].bits & MF_FIRE) fire_iters = std::max(fire_iters, std::min(mf_iters(w->mats[m].bits), 6));
             if(liq_window_applies(MODE, p.iter, p.flags, FLOW, DIRTY, sand_reacts, fire_iters)) { // launch_substep's choice (csrc/fss_abi.cu)
-                uint32_t pay[WIN_PAY_WORDS]; // the kernel's shared-memory slice of this thread
+                uint32_t pay[WIN_PAY_WORDS > WIN_NB_WORDS ? WIN_PAY_WORDS : WIN_NB_WORDS]; // the kernel's shared-memory slice of this thread
                 if(liq_window_general(MODE, sand_reacts)) {
                     if(p.iter == 0) {
                         WinWalk<true, true, true> walk(p, w->sinfo, cx, cy, 1u, pay, 1);
