@@ -137,6 +137,8 @@ struct fss_world {
     int nogas_from_iter;  // from this iter on no GAS / fire can act
     bool sand_reacts;     // a SAND material with reactions can be present (world.cpp:1251-1274): the general register-window kernel
     int fire_iters;       // largest `iterations` of a fire material that can be present (0: none): fire acts while iter < this
+    bool fire_static;     // fire can be split off into k_fire_prepass: no SAND material denser than a fire material, no SAND reaction with a SOLID product
+    uint8_t* d_fire_verdict; // one byte per stored cell (allocated when the first such sub-step runs)
     bool one_liquid;      // at most one SOUP material can be present: two different liquids never meet (world.cpp:1406-1412, :1510-1516)
     // World::particles (fss_particles.cuh): the list, its scratch copy and the per-particle round state, all `pl_cap` long
     fss_particle *pl_list, *pl_next;
@@ -240,6 +242,22 @@ static void recompute_liq(fss_world* w) {
     // own `iterations` (they have no such gate): the no-gas kernel is only exact when no GAS / fire material is present at all.
     // The liquid-only kernel has no such case: nothing moves a cell there (SOUP-SOUP swaps at iter 0 aside).
     w->one_liquid = liquids <= 1;
+    // fire_prepass_chunk's two conditions (fss_rules_liq.cuh), over the materials that can be present
+    {
+        uint32_t sand_rank = 0, fire_rank = 0xFFFFFFFFu;
+        bool solid_product = false;
+        for(int m = 0; m < w->n_mat; m++) {
+            if(!pres[m]) continue;
+            const DMat& d = w->h_mats[m];
+            if(mf_type(d.bits) == FSS_PHYS_SAND) {
+                sand_rank = std::max(sand_rank, d.bits & MF_RANK_MASK);
+                for(int r = 0; r < d.n_react; r++)
+                    if(mf_type(w->h_mats[d.r_target[r]].bits) == FSS_PHYS_SOLID) solid_product = true;
+            }
+            if(d.bits & MF_FIRE) fire_rank = std::min(fire_rank, d.bits & MF_RANK_MASK);
+        }
+        w->fire_static = sand_rank <= fire_rank && !solid_product;
+    }
     w->nogas_from_iter = gas_or_fire ? 99 : 0;
     w->liq_from_iter = from;
     if(getenv("FSS_DEBUG")) {
@@ -424,6 +442,7 @@ int fss_destroy(fss_world* w) {
     if(w->h_work_n) cudaFreeHost((void*)w->h_work_n);
     if(w->h_seen) cudaFreeHost(w->h_seen);
     cudaFree(w->d_dirty_halo);
+    cudaFree(w->d_fire_verdict);
     cudaFree(w->d_present_mask);
     if(w->h_present_mask) cudaFreeHost(w->h_present_mask);
     particles_free(w);
@@ -714,6 +733,7 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
         uint32_t work_tiles_now = 0;
         p.work = nullptr;
         p.work_n = nullptr;
+        p.fire_verdict = w->d_fire_verdict;
         // Mostly settled worlds: a small kernel lists the tiles that still hold a not-settled chunk and a fixed grid strides over
         // that list, so settled regions cost neither CTAs nor flag loads.  Whether a launch goes through the list is decided from
         // the last count the device reported (a hint read without synchronising: both ways give the same cells); while launches are
@@ -792,19 +812,29 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
             if(flow) FSS_LAUNCH_K1(M, true, false); else FSS_LAUNCH_K1(M, false, false);           \
         }                                                                                          \
     } while(0)
-        if(liq_window_applies(mode, iter, w->cfg.flags, flow, dirty, w->sand_reacts, w->fire_iters)) {
+        if(liq_window_applies(mode, iter, w->cfg.flags, flow, dirty, w->sand_reacts, w->fire_iters, w->fire_static)) {
 #define FSS_LAUNCH_WIN(...) k_substep_win<__VA_ARGS__><<<persistent((const void*)k_substep_win<__VA_ARGS__>), K1_THREADS, 0, w->stream>>>(p)
             // the kernels with the iter-0 code (two different liquids changing places) are a superset and exact for every iter, but
             // 7 KB longer, and K1's speed follows its code size (same sub-step, 56 KB against 63 KB of code: 7.78 against 8.59 ms):
             // they run at iter 0 only, and not at all while at most one liquid material can be present
             static const bool force_iter0 = getenv("FSS_FORCE_ITER0_KERNEL") != nullptr; // measurements
             const bool swaps = (iter == 0 && !w->one_liquid) || force_iter0;
+            const bool fire_acts = mode == K1_GENERAL && iter < w->fire_iters; // (only here with fire_static: liq_window_applies)
+            if(fire_acts) { // the fire cells' visits are decided first (fire_prepass_chunk), the window kernel applies the verdicts
+                if(!w->d_fire_verdict) {
+                    CU(cudaMalloc(&w->d_fire_verdict, plane_cells(w)));
+                    CU(cudaMemsetAsync(w->d_fire_verdict, 0, plane_cells(w), w->stream));
+                }
+                p.fire_verdict = w->d_fire_verdict;
+                k_fire_prepass<<<dim3((p.nx + 127) / 128, p.ny), 128, 0, w->stream>>>(p);
+                w->stats.kernel_launches++;
+            }
             if(mode == K1_LIQUID) {
                 if(swaps) FSS_LAUNCH_WIN(false, true);
                 else FSS_LAUNCH_WIN(false, false);
             } else if(liq_window_general(mode, w->sand_reacts)) {
                 // GAS / SAND reactions can be present (and fire that cannot act any more): the general window walk
-                if(swaps) FSS_LAUNCH_WIN(true, true, true);
+                if(swaps || fire_acts) FSS_LAUNCH_WIN(true, true, true);
                 else FSS_LAUNCH_WIN(true, false, true);
             } else {
                 if(swaps) FSS_LAUNCH_WIN(true, true);

@@ -150,6 +150,18 @@ __global__ void __launch_bounds__(K1_THREADS, GEN ? K1WG_MIN_BLOCKS : (SAND ? K1
     }
 }
 
+// ---- fire for the window path: one thread per active chunk walks the chunk's active fire cells (fire_prepass_chunk) ----------
+// Same chunk ownership and the same settled-chunk test as the kernel that follows; always the plain grid (a settled chunk has no
+// active fire cell: a fire cell's visit is never idle).
+__global__ void __launch_bounds__(128) k_fire_prepass(const __grid_constant__ SubstepParams p) {
+    const int gi = (int)(blockIdx.x * 128u + threadIdx.x), by = (int)blockIdx.y;
+    if(gi >= p.nx) return;
+#ifndef K1_NO_EARLY
+    if(p.q && p.q[(size_t)(2 * by + p.ofs_y + 1) * p.q_w + (2 * gi + p.ofs_x + 1)] <= (uint8_t)p.iter) return;
+#endif
+    fire_prepass_chunk(p, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * by);
+}
+
 // ---- the worklist of a sub-step: which warp tiles (32 chunks of one active chunk row) hold a chunk that is not settled ----
 // One THREAD per warp tile (its 32 flags are 64 consecutive bytes); the list slots of a warp's live tiles come from one atomicAdd.
 __global__ void __launch_bounds__(128) k_worklist(const uint8_t* __restrict__ q, int q_w, int ofs_x, int ofs_y, int iter, int nx, int tiles_x, int ny,

@@ -67,7 +67,12 @@ struct SubstepParams {
     // zeroes the counter the NEXT list will be counted in -- instead of a memset and a copy kernel around every launch
     uint32_t* work_n_host;
     uint32_t* work_n_next;
+    // Fire on the register-window path (fss_rules_liq.cuh, fire_prepass_chunk): one byte per stored cell, written by k_fire_prepass
+    // right before the sub-step's kernel and consumed (zeroed again) by it.  0 = nothing to do, FIRE_DIES, FIRE_NEW.
+    uint8_t* fire_verdict;
 };
+#define FIRE_DIES 1u /* the fire cell goes out at its scan-1 visit (world.cpp:1191-1196, :1210-1214) */
+#define FIRE_NEW 2u  /* the cell was set alight in this sub-step: visited (world.cpp:1205), it does not act */
 
 __device__ __forceinline__ Cell cell_nothing(uint32_t nothing_mf) {
     // Tiles::NOTHING, Tiles.cpp:7; fluidAmount keeps the constructor default 2.0f (MaterialInstance.hpp:21)

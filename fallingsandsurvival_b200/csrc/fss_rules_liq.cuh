@@ -44,9 +44,10 @@
 //   re-read) and was exact, but the kernel grew to 105 KB of code and ran c3's iter 0 in 27.1 ms against 21.9 ms
 //   (instruction-cache misses: 4 stalled warps per issue); see profiles/r02_tuning_log.md section 10 and the commit before
 //   this one.
-// `fire_iters`: the largest `iterations` of a fire material that can be present (0: none)
+// `fire_iters`: the largest `iterations` of a fire material that can be present (0: none); `fire_static`: the conditions under which
+// the fire rule can be split off into k_fire_prepass hold (fire_prepass_chunk below)
 __host__ __device__ __forceinline__ bool liq_window_applies(int mode, int iter, uint32_t cfg_flags, bool flow, bool dirty, bool sand_reacts = false,
-                                                            int fire_iters = 0) {
+                                                            int fire_iters = 0, bool fire_static = false) {
 #ifdef K1_NO_LIQ_WINDOW
     return false;
 #else
@@ -56,7 +57,7 @@ __host__ __device__ __forceinline__ bool liq_window_applies(int mode, int iter, 
 #elif defined(K1_NO_GEN_WINDOW)
     return mode == K1_LIQUID || (mode == K1_NOGAS && !sand_reacts);
 #else
-    return mode != K1_GENERAL || iter >= fire_iters;
+    return mode != K1_GENERAL || iter >= fire_iters || fire_static;
 #endif
 #endif
 }
@@ -76,6 +77,61 @@ __host__ __device__ __forceinline__ float fdiv_const(float x, float c, float rc)
     const float r = fmaf(-c, q, x);
     return fmaf(r, rc, q);
 #endif
+}
+
+// ---- FIRE for the register-window path, world.cpp:1171-1216 -----------------------------------------------------------------
+// The fire rule does not fit the window kernel (its code made the kernel a third longer and a quarter slower, tuning log 10), and
+// it does not have to be there.  What a fire cell's visit does: draw (RNG keys of the cell), look which of its 25 neighbours are
+// SOLID, set some of those alight (`tiles[...] = Tiles::createFire()`, marked visited), go out.  Under two conditions on the
+// materials that can be present (fss_abi.cu, `fire_static`):
+//   (a) no SAND material is denser than a fire material -- then nothing ever moves a fire cell (SAND displaces what is lighter,
+//       liquids flow into AIR or their own kind, GAS rises into AIR), and no movement rule can tell a SOLID cell from a fire cell
+//       (neither can be moved into);
+//   (b) no SAND reaction produces a SOLID material -- then SOLID cells only change by being set alight;
+// which neighbours are SOLID at the time of the visit depends on the grid at the START of the sub-step and on the ignitions of the
+// fire cells of the same chunk that scan 1 reaches earlier, and WHEN within the sub-step a SOLID cell turns into fire makes no
+// difference to anybody but later fire cells of the same chunk.  So one thread per active chunk walks the chunk's active fire cells
+// in scan-1 order BEFORE the sub-step's kernel: it sets the chosen neighbours alight in memory right away (its own later gathers
+// see them), notes FIRE_NEW for those inside the chunk (visited: they do not act when scan 1 reaches them) and FIRE_DIES for a
+// fire cell that goes out.  Going out has to happen at the cell's own visit (cells scanned later see AIR, earlier ones saw
+// fire): the window kernel does that from the note.  Without FSS_PARTICLES_EMIT the recolour and the particle draws
+// (:1172-1189) have no effect.
+__device__ __forceinline__ void fire_prepass_chunk(const SubstepParams& p, int cx, int cy) {
+    const Grid& g = p.g;
+#pragma unroll 1
+    for(int r = FSS_CHUNK_H - 1; r >= 0; r--) {
+        const cidx_t irow = (cidx_t)(cy + r - g.sy0) * g.pitch + fss_perm((uint32_t)cx);
+        uint32_t m[FSS_CHUNK_W];
+#pragma unroll
+        for(int k = 0; k < FSS_CHUNK_W; k++) m[k] = g.mf[irow + 32 * k];
+#pragma unroll 1
+        for(int k = 0; k < FSS_CHUNK_W; k++) {
+            const uint32_t mf = k == 0 ? m[0] : (k == 1 ? m[1] : (k == 2 ? m[2] : m[3]));
+            const cidx_t i = irow + 32 * k;
+            if(!(mf & MF_FIRE) || p.iter >= mf_iters(mf) || p.fire_verdict[i] == FIRE_NEW) continue; // (set alight a moment ago by this thread)
+            const int x = cx + k, y = cy + r;
+            const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
+            bool dies = fss_rand(key, 1191, 0) % 150 == 0; // :1191-1196
+            if(!dies) {
+                uint32_t solid_nb = 0u; // bit q = the neighbour (q/5 - 2, q%5 - 2) is SOLID: the reference's loop order (xx outer, yy inner)
+#pragma unroll
+                for(int q = 0; q < 25; q++)
+                    if(MF_IS(g.mf[g.idx(x + q / 5 - 2, y + q % 5 - 2)], FSS_PHYS_SOLID)) solid_nb |= 1u << q;
+                uint32_t k1202 = 0u, kcreate = 0u;
+                for(uint32_t rest = solid_nb; rest; rest &= rest - 1) { // :1198-1208
+                    if(fss_rand(key, 1202, k1202++) % 500 == 0) {
+                        const int q = __ffs((int)rest) - 1, xx = q / 5 - 2, yy = q % 5 - 2;
+                        const cidx_t j = g.idx(x + xx, y + yy);
+                        st_cell(g, j, create_cell(p, p.fire_id, x + xx, y + yy, key, kcreate++)); // Tiles::createFire()
+                        const unsigned dx = (unsigned)(x + xx - cx), dy = (unsigned)(y + yy - cy);
+                        if(dx < (unsigned)FSS_CHUNK_W && dy < (unsigned)FSS_CHUNK_H) p.fire_verdict[j] = FIRE_NEW; // :1205, inside the chunk
+                    }
+                }
+                dies = !solid_nb && fss_rand(key, 1210, 0) % 120 == 0; // :1210-1214
+            }
+            if(dies) p.fire_verdict[i] = FIRE_DIES;
+        }
+    }
 }
 
 struct LRow { // one grid row of the chunk's four columns
@@ -115,6 +171,7 @@ struct LSide { // the cell left / right of the row being scanned (outside the ch
 template <bool SAND, bool ITER0 = true, bool GEN = false>
 struct WinWalk {
     static_assert(SAND || !GEN, "the general window walk includes the SAND rules");
+    static constexpr bool FIRE = GEN && ITER0; // the instantiation that also serves the sub-steps in which fire acts (fire_prepass_chunk)
     const SubstepParams& p;
     const uint32_t* sinfo;
     int cx, cy;
@@ -369,6 +426,23 @@ struct WinWalk {
         const bool seen = GEN && (C.fl & (LF_VIS << K)) != 0u;
         const bool spent = seen || p.iter >= mf_iters(mf); // :1163-1166
         if(spent) C.fl |= LF_VIS << K;
+        if(FIRE && !spent && (mf & MF_FIRE)) { // an active fire cell: k_fire_prepass has decided its visit (fire_prepass_chunk)
+            busy = true;
+            const uint32_t v = p.fire_verdict[irow + 32 * K];
+            if(v) {
+                p.fire_verdict[irow + 32 * K] = 0;
+                if(v == FIRE_DIES) { // `tiles[index] = Tiles::NOTHING`, visited
+                    const Cell n = cell_nothing(p.nothing_mf);
+                    C.mf[K] = n.mf;
+                    C.amt[K] = n.amt;
+                    C.dif[K] = n.dif;
+                    P(sC, 0, K) = n.col;
+                    P(sC, 1, K) = (uint32_t)n.temp;
+                    C.fl |= (LF_ALL | LF_PAY) << K;
+                }
+                C.fl |= LF_VIS << K; // (FIRE_NEW: set alight in this sub-step, :1205)
+            }
+        }
         if(SAND && !spent && MF_IS(mf, FSS_PHYS_SAND)) sand1<K>(C, B, irow, r, mf);
         if(GEN && !spent && MF_IS(mf, FSS_PHYS_GAS)) gas1<K>(A, C, Ln, Rn, irow, r, mf);
         // ---- SOUP, world.cpp:1338-1537

@@ -39,15 +39,62 @@ struct HostWorld {
     unsigned long long part_count[2] = {0, 0};
     std::vector<uint8_t> q;
     int q_w = 0, q_h = 0;
+    std::vector<uint8_t> fire_verdict; // k_fire_prepass -> window kernel (csrc/fss_rules_liq.cuh fire_prepass_chunk)
 };
 
+// recompute_liq of csrc/fss_abi.cu restated from the grid's content: can fire be split off into the pre-pass?
+static bool fire_static(const HostWorld* w) {
+    std::vector<bool> pres((size_t)w->n_mat, false);
+    for(size_t i = 0; i < w->mf.size(); i++) pres[mf_mat(w->mf[i])] = true;
+    if(w->fire_id >= 0) pres[(size_t)w->fire_id] = true;
+    for(bool grew = true; grew;) {
+        grew = false;
+        for(int m = 0; m < w->n_mat; m++) {
+            if(!pres[m]) continue;
+            const DMat& d = w->mats[m];
+            if(mf_type(d.bits) == FSS_PHYS_SAND)
+                for(int r = 0; r < d.n_react; r++)
+                    if(!pres[d.r_target[r]]) pres[d.r_target[r]] = grew = true;
+            if((d.flags & FSS_MAT_IS_STEAM) && w->condense >= 0 && !pres[w->condense]) pres[w->condense] = grew = true;
+        }
+    }
+    uint32_t sand_rank = 0, fire_rank = 0xFFFFFFFFu;
+    bool solid_product = false;
+    for(int m = 0; m < w->n_mat; m++) {
+        if(!pres[m]) continue;
+        const DMat& d = w->mats[m];
+        if(mf_type(d.bits) == FSS_PHYS_SAND) {
+            sand_rank = std::max(sand_rank, d.bits & MF_RANK_MASK);
+            for(int r = 0; r < d.n_react; r++)
+                if(mf_type(w->mats[d.r_target[r]].bits) == FSS_PHYS_SOLID) solid_product = true;
+        }
+        if(d.bits & MF_FIRE) fire_rank = std::min(fire_rank, d.bits & MF_RANK_MASK);
+    }
+    return sand_rank <= fire_rank && !solid_product;
+}
+
 template <int MODE, bool FLOW, bool DIRTY>
-static void run_launch(HostWorld* w, const SubstepParams& p) {
+static void run_launch(HostWorld* w, const SubstepParams& p0) {
+    SubstepParams p = p0;
+    if(w->fire_verdict.size() != w->mf.size()) w->fire_verdict.assign(w->mf.size(), 0);
+    p.fire_verdict = w->fire_verdict.data();
     // fss_abi.cu keeps track of which materials can be present; here the grid itself is asked: is there a SAND cell whose
     // material has reactions (world.cpp:1251-1274)?  Without one no reaction can create one during the launch.
     bool sand_reacts = false;
     for(size_t i = 0; i < w->mf.size() && !sand_reacts; i++)
         sand_reacts = MF_IS(w->mf[i], FSS_PHYS_SAND) && w->mats[mf_mat(w->mf[i])].n_react > 0;
+    int fire_iters = 0; // (fire_iters of fss_abi.cu restated)
+    for(int m = 0; m < w->n_mat; m++)
+        if(w->mats[m].bits & MF_FIRE) fire_iters = std::max(fire_iters, std::min(mf_iters(w->mats[m].bits), 6));
+    const bool fstatic = fire_static(w);
+    const bool window = liq_window_applies(MODE, p.iter, p.flags, FLOW, DIRTY, sand_reacts, fire_iters, fstatic); // launch_substep's choice (csrc/fss_abi.cu)
+    if(window && MODE == K1_GENERAL && p.iter < fire_iters) { // k_fire_prepass
+        for(int by = 0; by < p.ny; by++)
+            for(int gi = 0; gi < p.nx; gi++) {
+                if(p.q && p.q[(size_t)(2 * by + p.ofs_y + 1) * p.q_w + (2 * gi + p.ofs_x + 1)] <= (uint8_t)p.iter) continue;
+                fire_prepass_chunk(p, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * by);
+            }
+    }
     for(int by = 0; by < p.ny; by++) {
         for(int gi = 0; gi < p.nx; gi++) {
             uint8_t* qown = nullptr;
@@ -56,13 +103,10 @@ static void run_launch(HostWorld* w, const SubstepParams& p) {
                 if(*qown <= (uint8_t)p.iter) continue;
             }
             const int cx = p.x_begin + 2 * FSS_CHUNK_W * gi, cy = p.y_begin + 2 * FSS_CHUNK_H * by;
-            int fire_iters = 0; // (fire_iters of fss_abi.cu restated)
-            for(int m = 0; m < w->n_mat; m++)
-                if(w->mats[m].bits & MF_FIRE) fire_iters = std::max(fire_iters, std::min(mf_iters(w->mats[m].bits), 6));
-            if(liq_window_applies(MODE, p.iter, p.flags, FLOW, DIRTY, sand_reacts, fire_iters)) { // launch_substep's choice (csrc/fss_abi.cu)
+            if(window) {
                 uint32_t pay[WIN_PAY_WORDS > WIN_NB_WORDS ? WIN_PAY_WORDS : WIN_NB_WORDS]; // the kernel's shared-memory slice of this thread
                 if(liq_window_general(MODE, sand_reacts)) {
-                    if(p.iter == 0) {
+                    if(p.iter == 0 || (MODE == K1_GENERAL && p.iter < fire_iters)) {
                         WinWalk<true, true, true> walk(p, w->sinfo, cx, cy, 1u, pay, 1);
                         walk.run(qown);
                     } else {
