@@ -155,11 +155,12 @@ __global__ void __launch_bounds__(K1_THREADS, GEN ? K1WG_MIN_BLOCKS : (SAND ? K1
 // active fire cell: a fire cell's visit is never idle).
 __global__ void __launch_bounds__(128) k_fire_prepass(const __grid_constant__ SubstepParams p) {
     const int gi = (int)(blockIdx.x * 128u + threadIdx.x), by = (int)blockIdx.y;
-    if(gi >= p.nx) return;
+    bool live = gi < p.nx;
 #ifndef K1_NO_EARLY
-    if(p.q && p.q[(size_t)(2 * by + p.ofs_y + 1) * p.q_w + (2 * gi + p.ofs_x + 1)] <= (uint8_t)p.iter) return;
+    if(live && p.q && p.q[(size_t)(2 * by + p.ofs_y + 1) * p.q_w + (2 * gi + p.ofs_x + 1)] <= (uint8_t)p.iter) live = false;
 #endif
-    fire_prepass_chunk(p, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * by);
+    if(!__any_sync(0xFFFFFFFFu, live)) return;
+    fire_prepass_chunk(p, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * by, live, 0xFFFFFFFFu);
 }
 
 // ---- the worklist of a sub-step: which warp tiles (32 chunks of one active chunk row) hold a chunk that is not settled ----

@@ -91,45 +91,64 @@ __host__ __device__ __forceinline__ float fdiv_const(float x, float c, float rc)
 // which neighbours are SOLID at the time of the visit depends on the grid at the START of the sub-step and on the ignitions of the
 // fire cells of the same chunk that scan 1 reaches earlier, and WHEN within the sub-step a SOLID cell turns into fire makes no
 // difference to anybody but later fire cells of the same chunk.  So one thread per active chunk walks the chunk's active fire cells
-// in scan-1 order BEFORE the sub-step's kernel: it sets the chosen neighbours alight in memory right away (its own later gathers
+// in scan-1 order BEFORE the sub-step's kernel: it sets the chosen neighbours alight in memory right away (its later gathers
 // see them), notes FIRE_NEW for those inside the chunk (visited: they do not act when scan 1 reaches them) and FIRE_DIES for a
 // fire cell that goes out.  Going out has to happen at the cell's own visit (cells scanned later see AIR, earlier ones saw
 // fire): the window kernel does that from the note.  Without FSS_PARTICLES_EMIT the recolour and the particle draws
 // (:1172-1189) have no effect.
-__device__ __forceinline__ void fire_prepass_chunk(const SubstepParams& p, int cx, int cy) {
+// `live`: this lane has a chunk to walk (every lane of the warp goes through the loops: the 25 neighbours of a fire cell are
+// gathered by the whole warp, lane q loading neighbour q, like ChunkWalk::coop_fire_scan); `wmask`: the lanes of the warp.
+__device__ __forceinline__ void fire_prepass_chunk(const SubstepParams& p, int cx, int cy, bool live, unsigned wmask) {
     const Grid& g = p.g;
+    const int lane = (int)(threadIdx.x & 31u);
+    const int rank = __popc(wmask & ((1u << lane) - 1u)), n = __popc(wmask);
 #pragma unroll 1
     for(int r = FSS_CHUNK_H - 1; r >= 0; r--) {
-        const cidx_t irow = (cidx_t)(cy + r - g.sy0) * g.pitch + fss_perm((uint32_t)cx);
+        const cidx_t irow = live ? (cidx_t)(cy + r - g.sy0) * g.pitch + fss_perm((uint32_t)cx) : 0;
         uint32_t m[FSS_CHUNK_W];
 #pragma unroll
-        for(int k = 0; k < FSS_CHUNK_W; k++) m[k] = g.mf[irow + 32 * k];
+        for(int k = 0; k < FSS_CHUNK_W; k++) m[k] = live ? g.mf[irow + 32 * k] : 0u;
 #pragma unroll 1
         for(int k = 0; k < FSS_CHUNK_W; k++) {
             const uint32_t mf = k == 0 ? m[0] : (k == 1 ? m[1] : (k == 2 ? m[2] : m[3]));
             const cidx_t i = irow + 32 * k;
-            if(!(mf & MF_FIRE) || p.iter >= mf_iters(mf) || p.fire_verdict[i] == FIRE_NEW) continue; // (set alight a moment ago by this thread)
             const int x = cx + k, y = cy + r;
-            const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
-            bool dies = fss_rand(key, 1191, 0) % 150 == 0; // :1191-1196
-            if(!dies) {
-                uint32_t solid_nb = 0u; // bit q = the neighbour (q/5 - 2, q%5 - 2) is SOLID: the reference's loop order (xx outer, yy inner)
-#pragma unroll
-                for(int q = 0; q < 25; q++)
-                    if(MF_IS(g.mf[g.idx(x + q / 5 - 2, y + q % 5 - 2)], FSS_PHYS_SOLID)) solid_nb |= 1u << q;
-                uint32_t k1202 = 0u, kcreate = 0u;
-                for(uint32_t rest = solid_nb; rest; rest &= rest - 1) { // :1198-1208
-                    if(fss_rand(key, 1202, k1202++) % 500 == 0) {
-                        const int q = __ffs((int)rest) - 1, xx = q / 5 - 2, yy = q % 5 - 2;
-                        const cidx_t j = g.idx(x + xx, y + yy);
-                        st_cell(g, j, create_cell(p, p.fire_id, x + xx, y + yy, key, kcreate++)); // Tiles::createFire()
-                        const unsigned dx = (unsigned)(x + xx - cx), dy = (unsigned)(y + yy - cy);
-                        if(dx < (unsigned)FSS_CHUNK_W && dy < (unsigned)FSS_CHUNK_H) p.fire_verdict[j] = FIRE_NEW; // :1205, inside the chunk
-                    }
-                }
-                dies = !solid_nb && fss_rand(key, 1210, 0) % 120 == 0; // :1210-1214
+            // an active fire cell that was not set alight a moment ago by this very thread
+            bool fire = live && (mf & MF_FIRE) && p.iter < mf_iters(mf);
+            if(fire) fire = p.fire_verdict[i] != FIRE_NEW;
+            unsigned fire_lanes = __ballot_sync(wmask, fire);
+            if(!fire_lanes) continue;
+            // bit q = the neighbour (q/5 - 2, q%5 - 2) is SOLID, in the reference's loop order (xx outer, yy inner)
+            uint32_t solid_nb = 0u;
+            while(fire_lanes) {
+                const int src = __ffs((int)fire_lanes) - 1;
+                fire_lanes &= fire_lanes - 1;
+                const int fx = __shfl_sync(wmask, x, src), fy = __shfl_sync(wmask, y, src);
+                uint32_t part = 0u;
+                for(int q = rank; q < 25; q += n)
+                    if(MF_IS(g.mf[g.idx(fx + q / 5 - 2, fy + q % 5 - 2)], FSS_PHYS_SOLID)) part |= 1u << q;
+                const uint32_t all = __reduce_or_sync(wmask, part);
+                if(lane == src) solid_nb = all;
             }
-            if(dies) p.fire_verdict[i] = FIRE_DIES;
+            if(fire) {
+                const uint32_t key = fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y);
+                bool dies = fss_rand(key, 1191, 0) % 150 == 0; // :1191-1196
+                if(!dies) {
+                    uint32_t k1202 = 0u, kcreate = 0u;
+                    for(uint32_t rest = solid_nb; rest; rest &= rest - 1) { // :1198-1208
+                        if(fss_rand(key, 1202, k1202++) % 500 == 0) {
+                            const int q = __ffs((int)rest) - 1, xx = q / 5 - 2, yy = q % 5 - 2;
+                            const cidx_t j = g.idx(x + xx, y + yy);
+                            st_cell(g, j, create_cell(p, p.fire_id, x + xx, y + yy, key, kcreate++)); // Tiles::createFire()
+                            const unsigned dx = (unsigned)(x + xx - cx), dy = (unsigned)(y + yy - cy);
+                            if(dx < (unsigned)FSS_CHUNK_W && dy < (unsigned)FSS_CHUNK_H) p.fire_verdict[j] = FIRE_NEW; // :1205, inside the chunk
+                        }
+                    }
+                    dies = !solid_nb && fss_rand(key, 1210, 0) % 120 == 0; // :1210-1214
+                }
+                if(dies) p.fire_verdict[i] = FIRE_DIES;
+            }
+            __syncwarp(wmask); // what this lane has just set alight is read by the other lanes on its behalf in its later gathers
         }
     }
 }

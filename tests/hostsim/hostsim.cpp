@@ -92,7 +92,7 @@ static void run_launch(HostWorld* w, const SubstepParams& p0) {
         for(int by = 0; by < p.ny; by++)
             for(int gi = 0; gi < p.nx; gi++) {
                 if(p.q && p.q[(size_t)(2 * by + p.ofs_y + 1) * p.q_w + (2 * gi + p.ofs_x + 1)] <= (uint8_t)p.iter) continue;
-                fire_prepass_chunk(p, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * by);
+                fire_prepass_chunk(p, p.x_begin + 2 * FSS_CHUNK_W * gi, p.y_begin + 2 * FSS_CHUNK_H * by, true, 1u);
             }
     }
     for(int by = 0; by < p.ny; by++) {
