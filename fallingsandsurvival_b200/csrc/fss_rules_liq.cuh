@@ -36,14 +36,12 @@
 //   liquid rule) and the liquid half of scan 2 on the window, then ChunkWalk<K1_NOGAS>::scan2_rest() runs scan 2's SAND rule
 //   through L1 as before.  `sand_reacts`: a SAND material with reactions (world.cpp:1251-1274: reads the temperature plane and
 //   re-creates the cell) can be present -- those worlds stay on ChunkWalk.
-//   K1_GENERAL sub-steps in which no fire material can act, and SAND materials with reactions (round 2, second half):
-//   WinWalk<true, *, GEN = true> adds GAS (rising in scan 1 is an exchange with the row above; scans 2 and 3 by the visited
-//   bits) and SAND reactions (the temperature travels with the cell in the shared-memory payload).  Sub-steps in which fire
-//   acts (iter < the fire material's `iterations`: iter 0 with the reference's table) stay on ChunkWalk<K1_GENERAL>: the fire
-//   rule was built on the window too (5 x 5 gather by the whole warp, ignitions through memory with the window written back and
-//   re-read) and was exact, but the kernel grew to 105 KB of code and ran c3's iter 0 in 27.1 ms against 21.9 ms
-//   (instruction-cache misses: 4 stalled warps per issue); see profiles/r02_tuning_log.md section 10 and the commit before
-//   this one.
+//   K1_GENERAL sub-steps and SAND materials with reactions (round 2, second half): WinWalk<true, *, GEN = true> adds GAS (rising
+//   in scan 1 is an exchange with the row above; scans 2 and 3 by the visited bits) and SAND reactions (the temperature travels
+//   with the cell in the shared-memory payload).  Fire: its rule is NOT in the window kernel (built there it was exact, but the
+//   kernel grew to 105 KB of code and ran c3's iter 0 in 27.1 ms against 21.9 ms; profiles/r02_tuning_log.md section 10); where
+//   the material table allows it (`fire_static`) the fire cells' visits are decided by k_fire_prepass before the kernel
+//   (fire_prepass_chunk below), otherwise sub-steps in which fire acts stay on ChunkWalk<K1_GENERAL>.
 // `fire_iters`: the largest `iterations` of a fire material that can be present (0: none); `fire_static`: the conditions under which
 // the fire rule can be split off into k_fire_prepass hold (fire_prepass_chunk below)
 __host__ __device__ __forceinline__ bool liq_window_applies(int mode, int iter, uint32_t cfg_flags, bool flow, bool dirty, bool sand_reacts = false,
