@@ -509,6 +509,35 @@ def test_shift_grid_on_strips_equals_whole_world(n_strips):
     parts.close()
 
 
+@pytest.mark.parametrize("table", ["reference", "dense sand", "sand turns to stone"])
+def test_fire_paths_match_oracle(table):
+    """Fire without particle emission: with the reference's table the fire cells' visits are decided by k_fire_prepass and applied by
+    the register-window kernel; a SAND material denser than fire (it displaces fire cells) or a SAND reaction with a SOLID product
+    switch that off (fss_abi.cu `fire_static`) and the sub-steps in which fire acts run on the lock-step kernel.  All three against
+    the oracle, every tick, with and without the settled-chunk flags."""
+    import copy
+    from fallingsandsurvival_b200 import world
+    from oracle import oraclesim
+    defs = copy.deepcopy(full_table())
+    if table == "dense sand":
+        defs[M.TEST_SAND].density = 30.0
+    elif table == "sand turns to stone":
+        defs[M.GOLD_ORE].reactions = [(abi.REACT_TEMPERATURE_ABOVE, 512, M.COBBLE_STONE)]
+    mix = [(M.FIRE, 6), (M.SOFT_DIRT, 18), (M.COBBLE_STONE, 8), (M.TEST_SAND, 15), (M.GOLD_ORE, 5), (M.WATER, 12), (M.LAVA, 3), (M.STEAM, 3)]
+    cells, zone = make_world((328, 272), mix, seed=91, defs=defs)
+    cells["temperature"][cells["material"] == M.GOLD_ORE] = 600
+    for early_out in (False, True):
+        g = world.World(cells, zone, defs=defs, early_out=early_out)
+        o = oraclesim.OracleWorld(cells, zone, defs=defs)
+        for t in range(20):
+            g.tick(t)
+            o.tick(t)
+            a, b = o.cells(), g.cells()
+            assert a.tobytes() == b.tobytes(), f"{table}, early-out {early_out}, tick {t}: " + diff_report(a, b)
+        g.close()
+        o.close()
+
+
 def test_kernel_specialisation_follows_the_materials_present():
     """k_substep<K1_LIQUID / K1_NOGAS / K1_GENERAL> are picked per iter from the set of materials that can be in the world.
     Start with water + stone only (every iter runs the liquid-only kernel), then paint sand, then steam and fire through the

@@ -133,6 +133,24 @@ def test_register_window_general_path_matches_oracle(hostsim, mix):
     _compare(hostsim, cells, zone, [GENERAL, GENERAL, NOGAS, LIQUID, LIQUID, LIQUID] if mix == "liquids" else [GENERAL] * 6, 0, ticks=12)
 
 
+@pytest.mark.parametrize("table", ["reference", "dense sand", "sand turns to stone"])
+def test_fire_prepass_and_its_conditions(hostsim, table):
+    """fire_prepass_chunk + the window walk applying its verdicts (the reference's table), and the two conditions that switch the
+    pre-pass off (csrc/fss_abi.cu `fire_static`, restated in tests/hostsim): a SAND material denser than fire displaces fire
+    cells, a SAND reaction with a SOLID product changes which neighbours are SOLID in the middle of a sub-step"""
+    import copy
+    defs = copy.deepcopy(full_table())
+    if table == "dense sand":
+        defs[M.TEST_SAND].density = 30.0
+    elif table == "sand turns to stone":
+        defs[M.GOLD_ORE].reactions = [(abi.REACT_TEMPERATURE_ABOVE, 512, M.COBBLE_STONE)]
+    mix = [(M.FIRE, 6), (M.SOFT_DIRT, 18), (M.COBBLE_STONE, 8), (M.TEST_SAND, 15), (M.GOLD_ORE, 5), (M.WATER, 12), (M.LAVA, 3), (M.STEAM, 3)]
+    cells, zone = make_world((200, 176), mix, seed=91, defs=defs)
+    cells["temperature"][cells["material"] == M.GOLD_ORE] = 600
+    _compare(hostsim, cells, zone, [GENERAL] * 6, 0, ticks=16, defs=defs)
+    _compare(hostsim, cells, zone, [GENERAL] * 6, 0, ticks=24, early_out=True, defs=defs)
+
+
 def test_rule_code_with_early_out(hostsim):
     """the settled-chunk flags as the rules maintain them (ChunkWalk::run): skipping must not change anything"""
     cells, zone = make_world((264, 208), "pockets", seed=9)
@@ -141,8 +159,8 @@ def test_rule_code_with_early_out(hostsim):
     _compare(hostsim, cells, zone, [GENERAL] * 6, abi.PARTICLES_EMIT, ticks=16, early_out=True)
 
 
-def _compare(L, cells, zone, modes, flags, ticks, early_out=False):
-    defs = full_table()
+def _compare(L, cells, zone, modes, flags, ticks, early_out=False, defs=None):
+    defs = defs or full_table()
     hs = HostSim(L, cells, zone, defs, flags, early_out=early_out)
     o = oraclesim.OracleWorld(cells, zone, defs=defs, particles=bool(flags & abi.PARTICLES_EMIT))
     for t in range(ticks):
