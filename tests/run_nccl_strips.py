@@ -104,6 +104,25 @@ def main():
         print(f"nccl strips n={n}: cells {'==' if out.tobytes() == ref.tobytes() else '!='} single GPU, digest sum {hsum:016x} vs {whole.hash():016x}, "
               f"{len(recs)} particle records -> {'OK' if ok else 'MISMATCH'}", flush=True)
         whole.close()
+    # the same world without particle emission: the register-window kernels (fire through its pre-pass) on strips, the edge band
+    # beside the interior bands
+    rw2 = strips.RankWorld(size, zone, rank, n, local, cells=cells, defs=helpers.full_table())
+    if rank == n - 1:
+        paint(rw2.world, 4)
+    for t in range(8):
+        rw2.tick(t)
+    h2 = [None] * n
+    dist.all_gather_object(h2, rw2.world.hash())
+    if rank == 0:
+        whole2 = world.World(cells, zone, defs=helpers.full_table(), device=local)
+        paint(whole2, 4)
+        for t in range(8):
+            whole2.tick(t)
+        ok2 = (sum(h2) & 0xFFFFFFFFFFFFFFFF) == whole2.hash()
+        print(f"without particle emission (window kernels): digest sum {(sum(h2) & 0xFFFFFFFFFFFFFFFF):016x} vs {whole2.hash():016x} -> {'OK' if ok2 else 'MISMATCH'}", flush=True)
+        ok = ok and ok2
+        whole2.close()
+    rw2.world.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     rw.world.close()
