@@ -763,61 +763,6 @@ struct ChunkWalk {
         }
     }
 
-#ifdef K1_DECOUPLED_SCAN2
-    // EXPERIMENT (off by default, not yet measured on the GPU; its logic is checked on the host by tests/test_hostsim_rules.py):
-    // scan 2 with one cursor per lane.  In lock step the SAND rule of scan 2 runs at 1.7-2.7 of 32 lanes (only the lanes whose
-    // cell at this very (dx, dy) is an unvisited SAND cell; profiles/r01o_k_substep_nogas_source_lines.txt).  The order inside a
-    // chunk only matters per lane, so every lane walks ahead on its own to its next unvisited SAND cell (handling the cheap
-    // SOUP / GAS cells on the way, in order), and the rule body then runs with all lanes that found one.
-    __device__ __forceinline__ void scan2_decoupled() {
-        const Grid& g = p.g;
-        int k = 0; // position in scan order: dy = 15 - k / 4, dx = k % 4
-        for(;;) {
-            uint32_t mf = 0u;
-            cidx_t i = 0;
-            int dx = 0, dy = 0;
-            bool have = false;
-            while(k < FSS_CHUNK_W * FSS_CHUNK_H) {
-                dy = FSS_CHUNK_H - 1 - k / FSS_CHUNK_W;
-                dx = k % FSS_CHUNK_W;
-                const unsigned long long bit = 1ull << (dy * FSS_CHUNK_W + dx);
-                if(!(vis & bit)) { // :1676
-                    i = locate(dx, dy);
-                    mf = g.mf[i];
-                    if(MF_IS(mf, FSS_PHYS_SAND)) {
-                        have = true;
-                        break;
-                    }
-                    const int x = cx + dx, y = cy + dy;
-                    if(MF_IS(mf, FSS_PHYS_SOUP)) { // :1808-1825
-                        soup_apply(i, g.amt[i], g.dif[i], bit);
-                    } else if(GASFIRE && MF_IS(mf, FSS_PHYS_GAS)) { // :1879-1899
-                        const cidx_t ial = il - g.pitch, iar = ir - g.pitch;
-                        const bool al = MF_IS(g.mf[ial], FSS_PHYS_AIR), ar = MF_IS(g.mf[iar], FSS_PHYS_AIR);
-                        if(al || ar) busy = true;
-                        if(al && !(ar && fss_rand(fss_rng_cell_key(p.tkey, (uint32_t)x, (uint32_t)y), 1884, 0) % 2 == 0)) {
-                            swap_cells(i, ial);
-                            D(i); // :1886, :1889
-                            D(ial);
-                            mark(x - 1, y - 1);
-                        } else if(ar) {
-                            swap_cells(i, iar);
-                            D(i); // :1893, :1896
-                            D(iar);
-                            mark(x + 1, y - 1);
-                        }
-                    }
-                }
-                k++;
-            }
-            if(!__any_sync(wmask, have)) break;
-            if(have) {
-                sand2(i, cx + dx, cy + dy, mf, 1ull << (dy * FSS_CHUNK_W + dx));
-                k++;
-            }
-        }
-    }
-#endif
 
     // Scan 2's SOUP step (`fluidAmount += fluidAmountDiff`, :1808-1825) for chunk row r, run right after scan 1 has finished
     // row r-1, while the row's amt / dif lines are still in L1 (by scan 2 proper they have been evicted and come back from
@@ -1151,16 +1096,12 @@ struct ChunkWalk {
             }
             // no GAS can be active: scan 3 has nothing to do
         } else {
-#ifdef K1_DECOUPLED_SCAN2
-            scan2_decoupled();
-#else
 #pragma unroll 1
             for(int dy = FSS_CHUNK_H - 1; dy >= 0; dy--) {
                 if(dy >= K1_PF2) prefetch_row(dy - K1_PF2);
 #pragma unroll 1
                 for(int dx = 0; dx < FSS_CHUNK_W; dx++) scan2_cell(dx, dy);
             }
-#endif
             if(GASFIRE) scan3();
         }
     }

@@ -43,12 +43,6 @@ def hostsim(tmp_path_factory):
     return _build(tmp_path_factory, "hostsim")
 
 
-@pytest.fixture(scope="module")
-def hostsim_decoupled(tmp_path_factory):
-    """the rules with the scan-2 experiment of fss_rules.cuh switched on (-DK1_DECOUPLED_SCAN2; off in the product build)"""
-    return _build(tmp_path_factory, "hostsim_dec", ["-DK1_DECOUPLED_SCAN2"])
-
-
 class HostSim:
     def __init__(self, L, cells, zone, defs, flags, early_out=False):
         self.L = L
@@ -178,12 +172,3 @@ def _compare(L, cells, zone, modes, flags, ticks, early_out=False, defs=None):
             assert hs.drain().tobytes() == o.drain_particles().tobytes(), f"tick {t}: spawn records differ"
     hs.close()
     o.close()
-
-
-@pytest.mark.parametrize("mix", ["c2", "c3", "sand", "gas", "fire", "randmats"])
-def test_decoupled_scan2_experiment_matches_oracle(hostsim_decoupled, mix):
-    """the one-cursor-per-lane scan 2 (an experiment that is not in the product build): its order of operations inside a chunk"""
-    cells, zone = make_world((200, 176), mix, seed=800 + len(mix))
-    _compare(hostsim_decoupled, cells, zone, [GENERAL] * 6, abi.PARTICLES_EMIT | abi.TRACK_FLOW | abi.TRACK_DIRTY, ticks=10)
-    if mix in SPECIALISED:
-        _compare(hostsim_decoupled, cells, zone, SPECIALISED[mix], abi.PARTICLES_EMIT, ticks=10)
