@@ -136,6 +136,7 @@ struct fss_world {
     int liq_from_iter;    // from this iter on only liquids can act
     int nogas_from_iter;  // from this iter on no GAS / fire can act
     bool sand_reacts;     // a SAND material with reactions can be present (world.cpp:1251-1274): the general register-window kernel
+    int gas_iters;        // largest `iterations` of a GAS material that can be present (0: none): GAS acts in scan 1 while iter < this
     int fire_iters;       // largest `iterations` of a fire material that can be present (0: none): fire acts while iter < this
     bool fire_static;     // fire can be split off into k_fire_prepass: no SAND material denser than a fire material, no SAND reaction with a SOLID product
     uint8_t* d_fire_verdict; // one byte per stored cell (allocated when the first such sub-step runs)
@@ -227,11 +228,13 @@ static void recompute_liq(fss_world* w) {
     bool gas_or_fire = false;
     w->sand_reacts = false;
     w->fire_iters = 0;
+    w->gas_iters = 0;
     int liquids = 0;
     for(int m = 0; m < w->n_mat; m++) {
         if(!pres[m]) continue;
         if(mf_type(w->h_mats[m].bits) == FSS_PHYS_SOUP) liquids++;
         if(w->h_mats[m].bits & MF_FIRE) w->fire_iters = std::max(w->fire_iters, std::min(mf_iters(w->h_mats[m].bits), 6));
+        if(mf_type(w->h_mats[m].bits) == FSS_PHYS_GAS) w->gas_iters = std::max(w->gas_iters, std::min(mf_iters(w->h_mats[m].bits), 6));
         if(mf_type(w->h_mats[m].bits) == FSS_PHYS_SAND && w->h_mats[m].n_react > 0) w->sand_reacts = true;
         const int type = mf_type(w->h_mats[m].bits), iters = std::min(mf_iters(w->h_mats[m].bits), 6);
         const bool gf = type == FSS_PHYS_GAS || (w->h_mats[m].bits & MF_FIRE);
@@ -834,8 +837,9 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
                 else FSS_LAUNCH_WIN(false, false);
             } else if(liq_window_general(mode, w->sand_reacts)) {
                 // GAS / SAND reactions can be present (and fire that cannot act any more): the general window walk
-                if(swaps || fire_acts) FSS_LAUNCH_WIN(true, true, true);
-                else FSS_LAUNCH_WIN(true, false, true);
+                if(swaps || fire_acts) FSS_LAUNCH_WIN(true, true, 2);
+                else if(iter < w->gas_iters) FSS_LAUNCH_WIN(true, false, 2);
+                else FSS_LAUNCH_WIN(true, false, 1); // no GAS material acts in scan 1 any more: the shorter kernel
             } else {
                 if(swaps) FSS_LAUNCH_WIN(true, true);
                 else FSS_LAUNCH_WIN(true, false);

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(K1_THREADS, MODE == K1_LIQUID ? K1L_MIN_BLOCKS
 #ifndef K1WG_MIN_BLOCKS
 #define K1WG_MIN_BLOCKS 4
 #endif
-template <bool SAND, bool ITER0, bool GEN = false>
+template <bool SAND, bool ITER0, int GEN = 0>
 __global__ void __launch_bounds__(K1_THREADS, GEN ? K1WG_MIN_BLOCKS : (SAND ? K1WS_MIN_BLOCKS : K1W_MIN_BLOCKS)) k_substep_win(const __grid_constant__ SubstepParams p) {
     __shared__ uint32_t sinfo[SAND ? FSS_MAX_MATERIALS : 1];
     // WinWalk::pay: colour / temperature of the window rows (SAND), or the two buffers of the row requested ahead (K1_NROW_SMEM)

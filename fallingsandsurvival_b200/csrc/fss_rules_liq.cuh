@@ -185,7 +185,10 @@ struct LSide { // the cell left / right of the row being scanned (outside the ch
 //        measurable part of this kernel's stalls)
 // GEN:   GAS and SAND reactions can be present (SAND must be true); fire materials too, as long as none of them can act in the
 //        sub-step (liq_window_applies): a spent fire cell is an inert PASSABLE cell.
-template <bool SAND, bool ITER0 = true, bool GEN = false>
+// GEN is a level: 0 = SAND + SOUP only; 1 = GAS and SAND reactions can be present but no GAS material can act in scan 1 any more
+// (iter >= its `iterations`: GAS then only moves in scans 2 / 3, where it does whatever its `iterations`); 2 = everything.
+// Level 1 exists because the kernel's speed follows its code size: it is 7 KB shorter than level 2.
+template <bool SAND, bool ITER0 = true, int GEN = 0>
 struct WinWalk {
     static_assert(SAND || !GEN, "the general window walk includes the SAND rules");
     static constexpr bool FIRE = GEN && ITER0; // the instantiation that also serves the sub-steps in which fire acts (fire_prepass_chunk)
@@ -461,7 +464,7 @@ struct WinWalk {
             }
         }
         if(SAND && !spent && MF_IS(mf, FSS_PHYS_SAND)) sand1<K>(C, B, irow, r, mf);
-        if(GEN && !spent && MF_IS(mf, FSS_PHYS_GAS)) gas1<K>(A, C, Ln, Rn, irow, r, mf);
+        if(GEN == 2 && !spent && MF_IS(mf, FSS_PHYS_GAS)) gas1<K>(A, C, Ln, Rn, irow, r, mf);
         // ---- SOUP, world.cpp:1338-1537
         const float amt = C.amt[K];
         const bool soup = !spent && MF_IS(mf, FSS_PHYS_SOUP) && amt != 0.0f; // :1344
@@ -694,7 +697,7 @@ struct WinWalk {
                 fetch_payload(sA, ir - pitch);
             }
             if(r >= 1 && !NSM) load_row(N, ir - 2 * pitch); // requested a whole row of arithmetic ahead of their use
-            if(r >= 1 || GEN) { // (GEN: a GAS cell of row 0 looks at the outside cells of row -1)
+            if(r >= 1 || GEN == 2) { // (a GAS cell of row 0 looks at the outside cells of row -1)
                 load_side(Ln, ir - pitch + lofs);
                 load_side(Rn, ir - pitch + rofs);
             }

@@ -106,11 +106,17 @@ static void run_launch(HostWorld* w, const SubstepParams& p0) {
             if(window) {
                 uint32_t pay[WIN_PAY_WORDS > WIN_NB_WORDS ? WIN_PAY_WORDS : WIN_NB_WORDS]; // the kernel's shared-memory slice of this thread
                 if(liq_window_general(MODE, sand_reacts)) {
+                    int gas_iters = 0; // (gas_iters of fss_abi.cu restated)
+                    for(int m = 0; m < w->n_mat; m++)
+                        if(mf_type(w->mats[m].bits) == FSS_PHYS_GAS) gas_iters = std::max(gas_iters, std::min(mf_iters(w->mats[m].bits), 6));
                     if(p.iter == 0 || (MODE == K1_GENERAL && p.iter < fire_iters)) {
-                        WinWalk<true, true, true> walk(p, w->sinfo, cx, cy, 1u, pay, 1);
+                        WinWalk<true, true, 2> walk(p, w->sinfo, cx, cy, 1u, pay, 1);
+                        walk.run(qown);
+                    } else if(p.iter < gas_iters) {
+                        WinWalk<true, false, 2> walk(p, w->sinfo, cx, cy, 1u, pay, 1);
                         walk.run(qown);
                     } else {
-                        WinWalk<true, false, true> walk(p, w->sinfo, cx, cy, 1u, pay, 1);
+                        WinWalk<true, false, 1> walk(p, w->sinfo, cx, cy, 1u, pay, 1);
                         walk.run(qown);
                     }
                 } else if(p.iter == 0) {
