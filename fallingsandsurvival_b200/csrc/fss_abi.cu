@@ -815,7 +815,9 @@ static int launch_substep(fss_world* w, uint32_t tick_ct, int iter, int tk, int 
             if(flow) FSS_LAUNCH_K1(M, true, false); else FSS_LAUNCH_K1(M, false, false);           \
         }                                                                                          \
     } while(0)
-        if(liq_window_applies(mode, iter, w->cfg.flags, flow, dirty, w->sand_reacts, w->fire_iters, w->fire_static)) {
+        // (FSS_NO_WINDOW, read at every launch: the lock-step kernels for everything -- the cross-check of the two kernel families at
+        // sizes the oracle does not reach, tests/test_gpu_parity.py::test_full_size_kernel_families_agree)
+        if(liq_window_applies(mode, iter, w->cfg.flags, flow, dirty, w->sand_reacts, w->fire_iters, w->fire_static) && !getenv("FSS_NO_WINDOW")) {
 #define FSS_LAUNCH_WIN(...) k_substep_win<__VA_ARGS__><<<persistent((const void*)k_substep_win<__VA_ARGS__>), K1_THREADS, 0, w->stream>>>(p)
             // the kernels with the iter-0 code (two different liquids changing places) are a superset and exact for every iter, but
             // 7 KB longer, and K1's speed follows its code size (same sub-step, 56 KB against 63 KB of code: 7.78 against 8.59 ms):

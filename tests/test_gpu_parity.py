@@ -401,6 +401,39 @@ def test_c1_full_size_thousand_ticks_against_the_reference_build():
     g.close()
 
 
+@pytest.mark.parametrize("mix", ["c2", "c3"])
+def test_full_size_kernel_families_agree(mix, monkeypatch):
+    """c2 / c3 (BASELINE configs[1] / [2]: + fire, lava, steam, gold ore) at 16384 x 16384, where the oracle is out of reach: the
+    register-window kernels (general walk, fire through its pre-pass) and the lock-step kernels (FSS_NO_WINDOW) are two
+    implementations of the same rules and must leave the same grid, tick after tick, temperature included"""
+    import torch
+    from fallingsandsurvival_b200 import world
+    free, _ = torch.cuda.mem_get_info()
+    S = 16384 if free > 60e9 else 4096
+    size = (S + 32, S + 32)
+    zone = (16, 16, S, S)
+    a = world.World(None, zone, defs=full_table(), size=size)
+    b = world.World(None, zone, defs=full_table(), size=size)
+    for w in (a, b):
+        w.fill_synthetic(MIXES[mix], seed=0xF55)
+    assert a.hash() == b.hash()
+    for t in range(4):
+        a.tick(t)
+        a.sync()
+        monkeypatch.setenv("FSS_NO_WINDOW", "1")
+        b.tick(t)
+        b.sync()
+        monkeypatch.delenv("FSS_NO_WINDOW")
+        if t == 2:
+            a.tick_temperature()
+            b.tick_temperature()
+        assert a.hash() == b.hash(), f"tick {t}: window kernels {a.hash():016x} != lock-step kernels {b.hash():016x}"
+    la, lb = a.stats().kernel_launches, b.stats().kernel_launches
+    assert mix == "c2" or la > lb  # (c3: the window path launched its fire pre-passes: the two worlds did take different kernels)
+    a.close()
+    b.close()
+
+
 def test_full_size_properties():
     """at BASELINE's 16384 x 16384 the oracle is out of reach; check what does not need it: the digest of a 2-strip
     run equals the undivided run, early-out on equals off, and SAND / SOLID counts are conserved"""
