@@ -434,6 +434,32 @@ def test_full_size_kernel_families_agree(mix, monkeypatch):
     b.close()
 
 
+def test_full_size_tick_host_equals_resident_ticks():
+    """fss_tick_host at the benchmark's size (16384 x 16384: 16 bands of 1024 rows, 5.4 GB each way per tick): the grid that comes
+    back to the host, and the one left on the device, equal the grid of a world that stayed resident"""
+    import torch
+    from fallingsandsurvival_b200 import world
+    free, _ = torch.cuda.mem_get_info()
+    S = 16384 if free > 60e9 else 4096
+    size = (S + 32, S + 32)
+    zone = (16, 16, S, S)
+    a = world.World(None, zone, defs=full_table(), size=size)
+    b = world.World(None, zone, defs=full_table(), size=size)
+    for w in (a, b):
+        w.fill_synthetic(worlds.MIX_C2, seed=0xF55)
+    host = torch.empty((size[1], size[0], 20), dtype=torch.uint8, pin_memory=True).numpy().view(abi.CELL_DTYPE).reshape(size[1], size[0])
+    a.download(0, 0, size[0], size[1], out=host)
+    for t in range(2):
+        a.tick_host(host, t)
+        b.tick(t)
+        assert a.hash() == b.hash(), f"tick {t}: device grid after fss_tick_host differs from the resident world"
+    back = torch.empty((size[1], size[0], 20), dtype=torch.uint8, pin_memory=True).numpy().view(abi.CELL_DTYPE).reshape(size[1], size[0])
+    b.download(0, 0, size[0], size[1], out=back)
+    assert np.array_equal(host.view(np.uint8), back.view(np.uint8)), "the grid fss_tick_host handed back differs from the resident world's"
+    a.close()
+    b.close()
+
+
 def test_full_size_properties():
     """at BASELINE's 16384 x 16384 the oracle is out of reach; check what does not need it: the digest of a 2-strip
     run equals the undivided run, early-out on equals off, and SAND / SOLID counts are conserved"""
