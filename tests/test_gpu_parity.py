@@ -460,6 +460,30 @@ def test_full_size_tick_host_equals_resident_ticks():
     b.close()
 
 
+def test_full_size_mostly_settled_world_early_out():
+    """BASELINE configs[4] at its stated size (32768 x 32768, the lower nine tenths stone with pockets of the c2 mix, sparse sand
+    above): the settled-chunk flags and the compacted worklist skip most of the world; the grid must equal the one every
+    chunk visit produced (FSS_NO_EARLY_OUT), tick after tick"""
+    import torch
+    from fallingsandsurvival_b200 import world
+    free, _ = torch.cuda.mem_get_info()
+    S = 32768 if free > 90e9 else 4096
+    size = (S + 32, S + 32)
+    zone = (16, 16, S, S)
+    on = world.World(None, zone, defs=full_table(), size=size, early_out=True)
+    off = world.World(None, zone, defs=full_table(), size=size, early_out=False)
+    for w in (on, off):
+        w.fill_synthetic(worlds.MIX_C2, seed=0xF55, border=16, solid_from_row=int(size[1] * 0.1), n_boxes=64 if S >= 4096 else 4, box_size=256,
+                         sparse_material=M.TEST_SAND, sparse_per_mille=1)
+    for t in range(8):
+        on.tick(t)
+        off.tick(t)
+        assert on.hash() == off.hash(), f"tick {t}"
+    assert on.stats().kernel_launches > off.stats().kernel_launches  # (the worklist kernels ran)
+    on.close()
+    off.close()
+
+
 def test_full_size_properties():
     """at BASELINE's 16384 x 16384 the oracle is out of reach; check what does not need it: the digest of a 2-strip
     run equals the undivided run, early-out on equals off, and SAND / SOLID counts are conserved"""
